@@ -1,0 +1,240 @@
+"""datagen/tpch.py -- synthetic TPC-H tables as pyarrow Tables (dbgen-exact for the generated columns).
+
+Neither product nor oracle: fabricates inputs for tests and bench.py.  The C generator
+(datagen/tpch_dbgen.c) is compiled on first use into datagen/_build/ (built by
+__graft_entry__.build() so it travels to the GPU box prebuilt).
+
+Arrow layout mirrors what Sail hands its operators for Parquet-backed TPC-H tables (SURVEY.md
+section 8a): keys Int64, money Decimal128(15,2), dates Date32, strings Utf8View (Sail reads Parquet
+strings as views: crates/sail-common/src/config/application.yaml:375-381) or Utf8
+(`strings="utf8"`, what `spark.createDataFrame(pandas)` yields in test_tpch.py:19-24).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pyarrow as pa
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libtpch_dbgen.so")
+_lib = None
+
+MKTSEGMENT = ["AUTOMOBILE", "BUILDING", "FURNITURE", "MACHINERY", "HOUSEHOLD"]
+ORDERPRIORITY = ["1-URGENT", "2-HIGH", "3-MEDIUM", "4-NOT SPECIFIED", "5-LOW"]
+SHIPINSTRUCT = ["DELIVER IN PERSON", "COLLECT COD", "NONE", "TAKE BACK RETURN"]
+SHIPMODE = ["REG AIR", "AIR", "RAIL", "TRUCK", "MAIL", "FOB", "SHIP"]   # codes 5,6 pinned by golden Q12
+NATIONS = [("ALGERIA", 0), ("ARGENTINA", 1), ("BRAZIL", 1), ("CANADA", 1), ("EGYPT", 4),
+           ("ETHIOPIA", 0), ("FRANCE", 3), ("GERMANY", 3), ("INDIA", 2), ("INDONESIA", 2),
+           ("IRAN", 4), ("IRAQ", 4), ("JAPAN", 2), ("JORDAN", 4), ("KENYA", 0), ("MOROCCO", 0),
+           ("MOZAMBIQUE", 0), ("PERU", 1), ("CHINA", 2), ("ROMANIA", 3), ("SAUDI ARABIA", 4),
+           ("VIETNAM", 2), ("RUSSIA", 3), ("UNITED KINGDOM", 3), ("UNITED STATES", 1)]
+REGIONS = ["AFRICA", "AMERICA", "ASIA", "EUROPE", "MIDDLE EAST"]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "tpch_dbgen.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", _SO, src])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.tpch_gen_orders.restype = ctypes.c_int64
+    return _lib
+
+
+def counts(sf: float) -> dict:
+    out = (ctypes.c_int64 * 4)()
+    lib().tpch_counts_get(ctypes.c_double(sf), out)
+    return {"part": out[0], "supplier": out[1], "customer": out[2], "orders": out[3]}
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+# ---- numpy -> Arrow column builders (zero Python loops over rows) --------------------------------
+def decimal_from_int64(v: np.ndarray, precision: int = 15, scale: int = 2) -> pa.Array:
+    n = len(v)
+    raw = np.empty((n, 2), dtype=np.int64)
+    raw[:, 0] = v
+    raw[:, 1] = v >> 63
+    return pa.Array.from_buffers(pa.decimal128(precision, scale), n, [None, pa.py_buffer(raw)])
+
+
+def date32(v: np.ndarray) -> pa.Array:
+    return pa.Array.from_buffers(pa.date32(), len(v), [None, pa.py_buffer(np.ascontiguousarray(v, dtype=np.int32))])
+
+
+def strings_from_codes(codes: np.ndarray, values: list, kind: str = "view") -> pa.Array:
+    """Dictionary codes -> Utf8View (views share one data buffer; <=12-byte strings inline) or Utf8."""
+    n = len(codes)
+    enc = [s.encode() for s in values]
+    if kind == "utf8":
+        lens = np.array([len(s) for s in enc], dtype=np.int64)
+        offsets = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum(lens[codes], out=offsets[1:])
+        width = int(lens.max())
+        mat = np.zeros((len(enc), width), dtype=np.uint8)
+        for i, s in enumerate(enc):
+            mat[i, : len(s)] = np.frombuffer(s, dtype=np.uint8)
+        rows = mat[codes]
+        mask = np.arange(width)[None, :] < lens[codes][:, None]
+        data = rows[mask]
+        return pa.Array.from_buffers(pa.string(), n, [None, pa.py_buffer(offsets), pa.py_buffer(data.tobytes())])
+    heap = b"".join(enc)
+    table = np.zeros((len(enc), 16), dtype=np.uint8)
+    off = 0
+    for i, s in enumerate(enc):
+        table[i, 0:4] = np.frombuffer(np.int32(len(s)).tobytes(), dtype=np.uint8)
+        if len(s) <= 12:
+            table[i, 4:4 + len(s)] = np.frombuffer(s, dtype=np.uint8)
+        else:
+            table[i, 4:8] = np.frombuffer(s[:4], dtype=np.uint8)
+            table[i, 8:12] = np.frombuffer(np.int32(0).tobytes(), dtype=np.uint8)
+            table[i, 12:16] = np.frombuffer(np.int32(off).tobytes(), dtype=np.uint8)
+        off += len(s)
+    views = np.ascontiguousarray(table[codes])
+    bufs = [None, pa.py_buffer(views)]
+    if any(len(s) > 12 for s in enc):
+        bufs.append(pa.py_buffer(heap))
+    return pa.Array.from_buffers(pa.string_view(), n, bufs)
+
+
+def chars(v: np.ndarray, kind: str = "view") -> pa.Array:
+    """single-byte flag column (l_returnflag, l_linestatus, o_orderstatus) -> string array"""
+    n = len(v)
+    if kind == "utf8":
+        offsets = np.arange(n + 1, dtype=np.int32)
+        return pa.Array.from_buffers(pa.string(), n, [None, pa.py_buffer(offsets), pa.py_buffer(np.ascontiguousarray(v))])
+    views = np.zeros((n, 16), dtype=np.uint8)
+    views[:, 0] = 1
+    views[:, 4] = v
+    return pa.Array.from_buffers(pa.string_view(), n, [None, pa.py_buffer(views)])
+
+
+# ---- tables --------------------------------------------------------------------------------------
+LINEITEM_ALL = ["l_orderkey", "l_partkey", "l_suppkey", "l_linenumber", "l_quantity", "l_extendedprice",
+                "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate", "l_commitdate",
+                "l_receiptdate", "l_shipinstruct", "l_shipmode"]
+ORDERS_ALL = ["o_orderkey", "o_custkey", "o_orderstatus", "o_totalprice", "o_orderdate",
+              "o_orderpriority", "o_clerk", "o_shippriority"]
+
+
+def _gen_orders_chunk(sf, first, n, want_o, want_l):
+    dt = {"o_orderkey": "i8", "o_custkey": "i8", "o_orderstatus": "u1", "o_totalprice": "i8", "o_orderdate": "i4",
+          "o_orderpriority": "u1", "o_clerk": "i8", "o_shippriority": "i4",
+          "l_orderkey": "i8", "l_partkey": "i8", "l_suppkey": "i8", "l_linenumber": "i4", "l_quantity": "i8",
+          "l_extendedprice": "i8", "l_discount": "i8", "l_tax": "i8", "l_returnflag": "u1", "l_linestatus": "u1",
+          "l_shipdate": "i4", "l_commitdate": "i4", "l_receiptdate": "i4", "l_shipinstruct": "u1", "l_shipmode": "u1"}
+    arrs = {}
+    for name in ORDERS_ALL:
+        arrs[name] = np.empty(n, dtype=dt[name]) if name in want_o else None
+    for name in LINEITEM_ALL:
+        arrs[name] = np.empty(7 * n, dtype=dt[name]) if name in want_l else None
+    nl = lib().tpch_gen_orders(ctypes.c_double(sf), ctypes.c_int64(first), ctypes.c_int64(n),
+                               *[_p(arrs[k]) for k in ORDERS_ALL + LINEITEM_ALL])
+    for name in LINEITEM_ALL:
+        if arrs[name] is not None:
+            arrs[name] = arrs[name][:nl]
+    return arrs
+
+
+def gen_orders_lineitem_numpy(sf: float, orders_cols=(), lineitem_cols=(), first: int = 0, n: int | None = None,
+                              threads: int | None = None) -> dict:
+    """Raw numpy columns (money in int64 cents, dates as int32 days, flags as bytes, categoricals as codes)."""
+    total = counts(sf)["orders"]
+    if n is None:
+        n = total - first
+    threads = threads or min(32, os.cpu_count() or 1)
+    chunk = max(1, min(n, max(100_000, (n + threads - 1) // threads)))
+    jobs = [(first + s, min(chunk, n - s)) for s in range(0, n, chunk)]
+    if len(jobs) == 1:
+        parts = [_gen_orders_chunk(sf, jobs[0][0], jobs[0][1], set(orders_cols), set(lineitem_cols))]
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            parts = list(ex.map(lambda j: _gen_orders_chunk(sf, j[0], j[1], set(orders_cols), set(lineitem_cols)), jobs))
+    out = {}
+    for name in list(orders_cols) + list(lineitem_cols):
+        out[name] = np.concatenate([p[name] for p in parts]) if len(parts) > 1 else parts[0][name]
+    return out
+
+
+def _to_arrow(name: str, v: np.ndarray, strings: str) -> pa.Array:
+    if name in ("l_quantity", "l_extendedprice", "o_totalprice", "c_acctbal", "s_acctbal", "p_retailprice"):
+        return decimal_from_int64(v)
+    if name in ("l_discount", "l_tax"):
+        return decimal_from_int64(v)          # already hundredths: 0.05 == 5
+    if name.endswith("date"):
+        return date32(v)
+    if name in ("l_returnflag", "l_linestatus", "o_orderstatus"):
+        return chars(v, strings)
+    if name == "o_orderpriority":
+        return strings_from_codes(v, ORDERPRIORITY, strings)
+    if name == "l_shipinstruct":
+        return strings_from_codes(v, SHIPINSTRUCT, strings)
+    if name == "l_shipmode":
+        return strings_from_codes(v, SHIPMODE, strings)
+    if name == "c_mktsegment":
+        return strings_from_codes(v, MKTSEGMENT, strings)
+    if v.dtype == np.int32:
+        return pa.array(v, type=pa.int32())
+    return pa.array(v, type=pa.int64())
+
+
+def lineitem(sf: float, columns=None, strings: str = "view", **kw) -> pa.Table:
+    columns = list(columns or LINEITEM_ALL)
+    raw = gen_orders_lineitem_numpy(sf, (), columns, **kw)
+    return pa.table([_to_arrow(c, raw[c], strings) for c in columns], names=columns)
+
+
+def orders(sf: float, columns=None, strings: str = "view", **kw) -> pa.Table:
+    columns = list(columns or ORDERS_ALL)
+    raw = gen_orders_lineitem_numpy(sf, columns, (), **kw)
+    return pa.table([_to_arrow(c, raw[c], strings) for c in columns], names=columns)
+
+
+def customer(sf: float, columns=None, strings: str = "view") -> pa.Table:
+    n = counts(sf)["customer"]
+    a = {"c_custkey": np.empty(n, "i8"), "c_nationkey": np.empty(n, "i8"), "c_acctbal": np.empty(n, "i8"),
+         "c_mktsegment": np.empty(n, "u1")}
+    lib().tpch_gen_customer(ctypes.c_double(sf), ctypes.c_int64(0), ctypes.c_int64(n),
+                            _p(a["c_custkey"]), _p(a["c_nationkey"]), _p(a["c_acctbal"]), _p(a["c_mktsegment"]))
+    columns = list(columns or a.keys())
+    return pa.table([_to_arrow(c, a[c], strings) for c in columns], names=columns)
+
+
+def supplier(sf: float, columns=None, strings: str = "view") -> pa.Table:
+    n = counts(sf)["supplier"]
+    a = {"s_suppkey": np.empty(n, "i8"), "s_nationkey": np.empty(n, "i8"), "s_acctbal": np.empty(n, "i8")}
+    lib().tpch_gen_supplier(ctypes.c_double(sf), ctypes.c_int64(0), ctypes.c_int64(n),
+                            _p(a["s_suppkey"]), _p(a["s_nationkey"]), _p(a["s_acctbal"]))
+    columns = list(columns or a.keys())
+    return pa.table([_to_arrow(c, a[c], strings) for c in columns], names=columns)
+
+
+def nation(strings: str = "view") -> pa.Table:
+    keys = np.arange(25, dtype=np.int64)
+    names = strings_from_codes(np.arange(25), [n for n, _ in NATIONS], strings)
+    return pa.table([pa.array(keys), names, pa.array(np.array([r for _, r in NATIONS], dtype=np.int64))],
+                    names=["n_nationkey", "n_name", "n_regionkey"])
+
+
+def region(strings: str = "view") -> pa.Table:
+    return pa.table([pa.array(np.arange(5, dtype=np.int64)), strings_from_codes(np.arange(5), REGIONS, strings)],
+                    names=["r_regionkey", "r_name"])
+
+
+def tables(sf: float, strings: str = "view") -> dict:
+    """All generated tables (small scale factors only)."""
+    return {"lineitem": lineitem(sf, strings=strings), "orders": orders(sf, strings=strings),
+            "customer": customer(sf, strings=strings), "supplier": supplier(sf, strings=strings),
+            "nation": nation(strings), "region": region(strings)}

@@ -1,5 +1,6 @@
 /*
- * oracle/tpch_dbgen.c -- TEST INFRASTRUCTURE (data generator for the oracle and the bench).
+ * datagen/tpch_dbgen.c -- synthetic-data generator (TPC-H dbgen restatement) used by tests and bench.py.
+ * It is neither the product path nor the oracle: it only fabricates input tables.
  *
  * A from-scratch restatement of the TPC-H dbgen (v3) algorithm for the columns the hot path
  * consumes.  The reference's golden vectors (python/pysail/tests/spark/test_tpch.py:11-26,

@@ -1,0 +1,259 @@
+"""Physical plans of the BASELINE.json workloads, written as trees of operator specs.
+
+Each node is the JSON object a Rust `ExecutionPlan` shim would hand to `sailgpu_op_create`
+(include/sailgpu.h) for the DataFusion operator it replaces.  The shapes follow the reference's
+plan snapshots (python/pysail/tests/spark/__snapshots__/test_tpch.plan.yaml): Q1 `:3-19`,
+Q3 `:72-97`, Q4 `:99-118`, Q5 `:120-156`, Q6, Q12 -- minus the rename-only ProjectionExecs and
+the RoundRobinBatch fan-out that pre-sharded tables make unnecessary.
+
+The tree is engine-agnostic: `execute(plan, tables, run_op)` drives it with any callable that maps
+(spec, *input tables) -> table.  tests/ drive it with the oracle and with the CUDA engine and diff
+the two.
+"""
+from __future__ import annotations
+
+import datetime
+from dataclasses import dataclass, field
+
+
+def days(iso: str) -> int:
+    return (datetime.date.fromisoformat(iso) - datetime.date(1970, 1, 1)).days
+
+
+# ---- expression helpers (column refs by NAME here; resolved to indices when the node is built) ----
+def col(name):
+    return {"col": name}
+
+
+def lit(value, type_):
+    return {"lit": value, "type": type_}
+
+
+def dec(unscaled: int, p: int, s: int):
+    return {"lit": str(int(unscaled)), "type": f"Decimal128({p},{s})"}
+
+
+def date(iso: str):
+    return {"lit": days(iso), "type": "Date32"}
+
+
+def string(v: str, type_="Utf8View"):
+    return {"lit": v, "type": type_}
+
+
+def binop(op, l, r):
+    return {"op": op, "l": l, "r": r}
+
+
+def and_(*xs):
+    out = xs[0]
+    for x in xs[1:]:
+        out = binop("and", out, x)
+    return out
+
+
+def or_(*xs):
+    out = xs[0]
+    for x in xs[1:]:
+        out = binop("or", out, x)
+    return out
+
+
+def resolve(e, names):
+    """replace {"col": "name"} by {"col": index}"""
+    if isinstance(e, dict):
+        if "col" in e and isinstance(e["col"], str):
+            return {"col": names.index(e["col"])}
+        return {k: resolve(v, names) for k, v in e.items()}
+    if isinstance(e, list):
+        return [resolve(x, names) for x in e]
+    return e
+
+
+@dataclass
+class Node:
+    spec: dict
+    inputs: list = field(default_factory=list)
+    names: list = field(default_factory=list)
+
+
+def scan(table: str, columns: list) -> Node:
+    return Node({"op": "scan", "table": table, "columns": list(columns)}, [], list(columns))
+
+
+def filter_(child: Node, predicate, projection=None) -> Node:
+    proj = None if projection is None else [child.names.index(c) for c in projection]
+    names = child.names if proj is None else list(projection)
+    return Node({"op": "filter", "predicate": resolve(predicate, child.names), "projection": proj}, [child], list(names))
+
+
+def project(child: Node, exprs: list) -> Node:
+    """exprs: list of (expr, name) or column names"""
+    items = []
+    for e in exprs:
+        if isinstance(e, str):
+            e = (col(e), e)
+        items.append({"expr": resolve(e[0], child.names), "name": e[1]})
+    return Node({"op": "projection", "exprs": items}, [child], [i["name"] for i in items])
+
+
+def aggregate(child: Node, mode: str, group_by: list, aggs: list) -> Node:
+    """group_by: column names or (expr, name); aggs: (fn, arg_expr|None, name, input_type)"""
+    gb = []
+    for g in group_by:
+        if isinstance(g, str):
+            g = (col(g), g)
+        gb.append({"expr": resolve(g[0], child.names), "name": g[1]})
+    merging = mode in ("final", "final_partitioned")
+    specs, names = [], [g["name"] for g in gb]
+    for fn, arg, name, in_type in aggs:
+        a = {"fn": fn, "name": name, "input_type": in_type}
+        if not merging:
+            a["args"] = [] if arg is None else [resolve(arg, child.names)]
+        specs.append(a)
+        if mode == "partial":
+            names += [f"{name}[count]", f"{name}[sum]"] if fn == "avg" else [f"{name}[{fn}]"]
+        else:
+            names.append(name)
+    return Node({"op": "aggregate", "mode": mode, "group_by": gb, "aggs": specs}, [child], names)
+
+
+def two_phase(child: Node, group_by: list, aggs: list) -> Node:
+    """AggregateExec Partial -> [RepartitionExec Hash(group keys)] -> FinalPartitioned"""
+    part = aggregate(child, "partial", group_by, aggs)
+    gnames = [g if isinstance(g, str) else g[1] for g in group_by]
+    return aggregate(part, "final_partitioned" if gnames else "final", gnames, aggs)
+
+
+def hash_join(build: Node, probe: Node, on: list, join_type="inner", projection=None, filter=None) -> Node:
+    names = {"left_semi": build.names, "left_anti": build.names,
+             "right_semi": probe.names, "right_anti": probe.names}.get(join_type, build.names + probe.names)
+    spec = {"op": "hash_join", "join_type": join_type, "mode": "collect_left",
+            "on": [[build.names.index(a), probe.names.index(b)] for a, b in on],
+            "filter": None if filter is None else resolve(filter, build.names + probe.names),
+            "projection": None if projection is None else [names.index(c) for c in projection]}
+    return Node(spec, [build, probe], list(names if projection is None else projection))
+
+
+def sort(child: Node, keys: list, fetch=None) -> Node:
+    """keys: (column name, asc) -- Spark default null ordering: ASC NULLS FIRST / DESC NULLS LAST"""
+    ks = [{"expr": resolve(col(k), child.names), "asc": asc, "nulls_first": asc} for k, asc in keys]
+    return Node({"op": "sort", "keys": ks, "fetch": fetch}, [child], list(child.names))
+
+
+def execute(node: Node, tables: dict, run_op):
+    if node.spec["op"] == "scan":
+        return tables[node.spec["table"]].select(node.spec["columns"])
+    ins = [execute(c, tables, run_op) for c in node.inputs]
+    return run_op(node.spec, *ins)
+
+
+# ---- TPC-H ------------------------------------------------------------------------------------------
+ONE = dec(1, 10, 0)     # `Int32(1)` coerced by DataFusion to Decimal128(10,0): test_tpch.plan.yaml:15
+D152 = "Decimal128(15,2)"
+DISC_PRICE = binop("*", col("l_extendedprice"), binop("-", ONE, col("l_discount")))   # Decimal128(32,4)
+
+
+def q1(strings="Utf8View") -> Node:
+    li = scan("lineitem", ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag",
+                           "l_linestatus", "l_shipdate"])
+    f = filter_(li, binop("<=", col("l_shipdate"), date("1998-09-24")),
+                ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus"])
+    p = project(f, [(DISC_PRICE, "__common_expr_1"), "l_quantity", "l_extendedprice", "l_discount", "l_tax",
+                    "l_returnflag", "l_linestatus"])
+    charge = binop("*", col("__common_expr_1"), binop("+", ONE, col("l_tax")))
+    aggs = [("sum", col("l_quantity"), "sum_qty", D152),
+            ("sum", col("l_extendedprice"), "sum_base_price", D152),
+            ("sum", col("__common_expr_1"), "sum_disc_price", "Decimal128(32,4)"),
+            ("sum", charge, "sum_charge", "Decimal128(38,6)"),
+            ("avg", col("l_quantity"), "avg_qty", D152),
+            ("avg", col("l_extendedprice"), "avg_price", D152),
+            ("avg", col("l_discount"), "avg_disc", D152),
+            ("count", None, "count_order", None)]
+    a = two_phase(p, ["l_returnflag", "l_linestatus"], aggs)
+    return sort(a, [("l_returnflag", True), ("l_linestatus", True)])
+
+
+def q6() -> Node:
+    li = scan("lineitem", ["l_quantity", "l_extendedprice", "l_discount", "l_shipdate"])
+    pred = and_(binop(">=", col("l_shipdate"), date("1994-01-01")),
+                binop("<", col("l_shipdate"), date("1995-01-01")),
+                binop(">=", col("l_discount"), dec(3, 15, 2)),
+                binop("<=", col("l_discount"), dec(5, 15, 2)),
+                binop("<", col("l_quantity"), dec(2400, 15, 2)))
+    f = filter_(li, pred, ["l_extendedprice", "l_discount"])
+    p = project(f, [(binop("*", col("l_extendedprice"), col("l_discount")), "rev")])
+    return two_phase(p, [], [("sum", col("rev"), "revenue", "Decimal128(31,4)")])
+
+
+def q3(strings="Utf8View") -> Node:
+    cust = filter_(scan("customer", ["c_custkey", "c_mktsegment"]),
+                   binop("=", col("c_mktsegment"), string("BUILDING", strings)), ["c_custkey"])
+    ords = filter_(scan("orders", ["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"]),
+                   binop("<", col("o_orderdate"), date("1995-03-15")))
+    j1 = hash_join(cust, ords, [("c_custkey", "o_custkey")], projection=["o_orderkey", "o_orderdate", "o_shippriority"])
+    li = filter_(scan("lineitem", ["l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"]),
+                 binop(">", col("l_shipdate"), date("1995-03-15")), ["l_orderkey", "l_extendedprice", "l_discount"])
+    j2 = hash_join(j1, li, [("o_orderkey", "l_orderkey")],
+                   projection=["o_orderdate", "o_shippriority", "l_orderkey", "l_extendedprice", "l_discount"])
+    a = two_phase(j2, ["l_orderkey", "o_orderdate", "o_shippriority"],
+                  [("sum", DISC_PRICE, "revenue", "Decimal128(32,4)")])
+    p = project(a, ["l_orderkey", "revenue", "o_orderdate", "o_shippriority"])
+    return sort(p, [("revenue", False), ("o_orderdate", True)], fetch=10)
+
+
+def q4(strings="Utf8View") -> Node:
+    li = filter_(scan("lineitem", ["l_orderkey", "l_commitdate", "l_receiptdate"]),
+                 binop(">", col("l_receiptdate"), col("l_commitdate")), ["l_orderkey"])
+    ords = filter_(scan("orders", ["o_orderkey", "o_orderdate", "o_orderpriority"]),
+                   and_(binop(">=", col("o_orderdate"), date("1995-04-01")),
+                        binop("<", col("o_orderdate"), date("1995-07-01"))), ["o_orderkey", "o_orderpriority"])
+    j = hash_join(li, ords, [("l_orderkey", "o_orderkey")], join_type="right_semi", projection=["o_orderpriority"])
+    a = two_phase(j, ["o_orderpriority"], [("count", None, "order_count", None)])
+    return sort(a, [("o_orderpriority", True)])
+
+
+def q5(strings="Utf8View") -> Node:
+    cust = scan("customer", ["c_custkey", "c_nationkey"])
+    ords = filter_(scan("orders", ["o_orderkey", "o_custkey", "o_orderdate"]),
+                   and_(binop(">=", col("o_orderdate"), date("1994-01-01")),
+                        binop("<", col("o_orderdate"), date("1995-01-01"))), ["o_orderkey", "o_custkey"])
+    j1 = hash_join(cust, ords, [("c_custkey", "o_custkey")], projection=["c_nationkey", "o_orderkey"])
+    li = scan("lineitem", ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"])
+    j2 = hash_join(j1, li, [("o_orderkey", "l_orderkey")],
+                   projection=["c_nationkey", "l_suppkey", "l_extendedprice", "l_discount"])
+    supp = scan("supplier", ["s_suppkey", "s_nationkey"])
+    j3 = hash_join(supp, j2, [("s_suppkey", "l_suppkey"), ("s_nationkey", "c_nationkey")],
+                   projection=["s_nationkey", "l_extendedprice", "l_discount"])
+    nat = scan("nation", ["n_nationkey", "n_name", "n_regionkey"])
+    j4 = hash_join(j3, nat, [("s_nationkey", "n_nationkey")],
+                   projection=["l_extendedprice", "l_discount", "n_name", "n_regionkey"])
+    reg = filter_(scan("region", ["r_regionkey", "r_name"]),
+                  binop("=", col("r_name"), string("AFRICA", strings)), ["r_regionkey"])
+    j5 = hash_join(reg, j4, [("r_regionkey", "n_regionkey")], projection=["l_extendedprice", "l_discount", "n_name"])
+    a = two_phase(j5, ["n_name"], [("sum", DISC_PRICE, "revenue", "Decimal128(32,4)")])
+    return sort(a, [("revenue", False)])
+
+
+def q12(strings="Utf8View") -> Node:
+    li = filter_(scan("lineitem", ["l_orderkey", "l_shipdate", "l_commitdate", "l_receiptdate", "l_shipmode"]),
+                 and_(or_(binop("=", col("l_shipmode"), string("FOB", strings)),
+                          binop("=", col("l_shipmode"), string("SHIP", strings))),
+                      binop(">", col("l_receiptdate"), col("l_commitdate")),
+                      binop("<", col("l_shipdate"), col("l_commitdate")),
+                      binop(">=", col("l_receiptdate"), date("1995-01-01")),
+                      binop("<", col("l_receiptdate"), date("1996-01-01"))), ["l_orderkey", "l_shipmode"])
+    ords = scan("orders", ["o_orderkey", "o_orderpriority"])
+    j = hash_join(li, ords, [("l_orderkey", "o_orderkey")], projection=["l_shipmode", "o_orderpriority"])
+    urgent = or_(binop("=", col("o_orderpriority"), string("1-URGENT", strings)),
+                 binop("=", col("o_orderpriority"), string("2-HIGH", strings)))
+    other = and_(binop("!=", col("o_orderpriority"), string("1-URGENT", strings)),
+                 binop("!=", col("o_orderpriority"), string("2-HIGH", strings)))
+    one, zero = lit(1, "Int64"), lit(0, "Int64")
+    a = two_phase(j, ["l_shipmode"],
+                  [("sum", {"case": [[urgent, one]], "else": zero}, "high_line_count", "Int64"),
+                   ("sum", {"case": [[other, one]], "else": zero}, "low_line_count", "Int64")])
+    return sort(a, [("l_shipmode", True)])
+
+
+TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q12": q12}
