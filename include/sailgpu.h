@@ -1,0 +1,194 @@
+/*
+ * sailgpu.h -- C ABI of libsailgpu.so: the B200-native replacement for the DataFusion physical
+ * operators on Sail's hot path.
+ *
+ * Who binds this.  A Rust shim crate inside Sail implements
+ * `datafusion::physical_plan::ExecutionPlan` once per replaced operator and drives this API from
+ * the `SendableRecordBatchStream` it returns from `execute(partition, ctx)`:
+ *
+ *   reference interface this replaces (file:line under lakehq/sail)         entry points here
+ *   ---------------------------------------------------------------------   ---------------------------
+ *   ExecutionPlan::execute(partition, Arc<TaskContext>)                      sailgpu_op_create
+ *     crates/sail-execution/src/plan/shuffle_write.rs:146-206 (shape),
+ *     crates/sail-physical-plan/src/streaming/filter.rs:104-116
+ *   RecordBatchStream::poll_next: pull child batch, hand it to the operator  sailgpu_op_push[_device],
+ *     crates/sail-execution/src/plan/shuffle_write.rs:226-232                sailgpu_op_finish_input
+ *   RecordBatchStream::poll_next: yield Result<RecordBatch>                  sailgpu_op_pull[_device]
+ *   RecordBatchStream::schema() / ExecutionPlan::schema()                    out_schema of op_create
+ *   ExecutionPlan::metrics() (names in crates/sail-telemetry/src/execution/  sailgpu_op_metrics
+ *     metrics/{default,filter,join,projection}.rs)
+ *   drop(stream) == cancellation (repartition.rs:104-119)                    sailgpu_op_destroy
+ *   DataFusionError travelling as a stream item (stream/error.rs:38-70)      int32 status +
+ *                                                                            sailgpu_last_error
+ *   LocalJobRunner::execute / TaskRunner::execute_plan rewrite hook          (shim side; no C call)
+ *     crates/sail-execution/src/job_runner.rs:63, task_runner/core.rs:110
+ *   shuffle_write / shuffle_read for Partitioning::Hash                      op kind "repartition" +
+ *     crates/sail-execution/src/plan/shuffle_write.rs:209-267,               sailgpu_ctx_comm_init,
+ *     plan/shuffle_read.rs:107-117                                           sailgpu_exchange
+ *
+ * Data crosses the boundary as Arrow C Data Interface structs (host memory; the library copies
+ * host<->HBM itself from/to pinned staging) or Arrow C *Device* Data Interface structs
+ * (ARROW_DEVICE_CUDA: buffers already in HBM, zero copy -- how consecutive GPU operators chain
+ * without bouncing through the host).  No torch types, no C++ types: plain pointers and sizes.
+ *
+ * Operator specs are small JSON documents (UTF-8) mirroring DataFusion's plan-node fields:
+ *   {"op":"filter","predicate":E,"projection":[i,...]|null}
+ *   {"op":"projection","exprs":[{"expr":E,"name":"..."},...]}
+ *   {"op":"aggregate","mode":"partial|final|final_partitioned|single",
+ *    "group_by":[{"expr":E,"name":".."}],"aggs":[{"fn":"sum|avg|count|min|max","args":[E],
+ *    "name":"..","input_type":"T"}]}
+ *   {"op":"hash_join","join_type":"inner|left|right_semi|...","on":[[l,r],...],"filter":E|null,
+ *    "projection":[...]|null}              (input 0 = build = LEFT child, input 1 = probe)
+ *   {"op":"sort","keys":[{"expr":E,"asc":bool,"nulls_first":bool}],"fetch":k|null}
+ *   {"op":"repartition","scheme":"hash","exprs":[E],"n":N}
+ *   {"op":"pipeline","stages":[spec,...]}  (fused chain of filter/projection ending in at most one
+ *                                           aggregate: one kernel, one pass over HBM)
+ * Expressions E: {"col":i} {"lit":v,"type":"T"} {"op":"+|-|*|/|%|=|!=|<|<=|>|>=|and|or","l":E,"r":E}
+ *   {"not":E} {"neg":E} {"is_null":E} {"is_not_null":E} {"cast":E,"to":"T"}
+ *   {"case":[[E,E],...],"else":E|null} {"in":E,"set":[lit,...],"negated":b}
+ *   {"like":E,"pattern":"..","negated":b} {"fn":"date_part|substr",...}
+ * Types T: Boolean Int8..Int64 UInt8..UInt64 Float32 Float64 Date32 Decimal128(p,s) Utf8 Utf8View
+ *
+ * Threading: calls on different handles may run concurrently from any
+ * thread; calls on one handle must not overlap.  No thread affinity (the device is set per call).
+ * There is NO CPU fallback: every function fails with SAILGPU_ERR_NO_DEVICE if CUDA is unusable.
+ */
+#ifndef SAILGPU_H
+#define SAILGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ---- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+
+/* ---- Arrow C Device Data Interface ---- */
+#ifndef ARROW_C_DEVICE_DATA_INTERFACE
+#define ARROW_C_DEVICE_DATA_INTERFACE
+typedef int32_t ArrowDeviceType;
+#define ARROW_DEVICE_CPU 1
+#define ARROW_DEVICE_CUDA 2
+#define ARROW_DEVICE_CUDA_HOST 3
+struct ArrowDeviceArray {
+  struct ArrowArray array;   /* buffer pointers are device pointers */
+  int64_t device_id;
+  ArrowDeviceType device_type;
+  void* sync_event;          /* cudaEvent_t* or NULL */
+  int64_t reserved[3];
+};
+#endif
+
+#if defined(__GNUC__)
+#define SAILGPU_API __attribute__((visibility("default")))
+#else
+#define SAILGPU_API
+#endif
+
+typedef struct sailgpu_ctx sailgpu_ctx; /* per process+device: stream pool, HBM pool, pinned staging, NCCL comm */
+typedef struct sailgpu_op sailgpu_op;   /* one operator instance for one partition */
+
+enum {
+  SAILGPU_OK = 0,
+  SAILGPU_ERR_INVALID = 1,      /* bad argument / malformed spec            -> DataFusionError::Plan      */
+  SAILGPU_ERR_UNSUPPORTED = 2,  /* type/expression not implemented on GPU   -> DataFusionError::NotImplemented */
+  SAILGPU_ERR_CUDA = 3,         /* CUDA / NCCL runtime failure              -> DataFusionError::Execution */
+  SAILGPU_ERR_ARITHMETIC = 4,   /* divide by zero / decimal overflow        -> ArrowError::DivideByZero / ArithmeticOverflow */
+  SAILGPU_ERR_NO_DEVICE = 5,    /* no usable CUDA device: there is no CPU fallback */
+  SAILGPU_ERR_STATE = 6         /* call sequence violation (push after finish, ...) -> DataFusionError::Internal */
+};
+
+/* library / ABI version: major<<16 | minor */
+SAILGPU_API uint32_t sailgpu_version(void);
+
+/* Context on CUDA device `device` (ordinal visible to this process). */
+SAILGPU_API int32_t sailgpu_ctx_create(int32_t device, sailgpu_ctx** out);
+SAILGPU_API void sailgpu_ctx_destroy(sailgpu_ctx* ctx);
+/* last error message of a failed ctx-level call (thread-local copy, valid until next call) */
+SAILGPU_API const char* sailgpu_ctx_last_error(const sailgpu_ctx* ctx);
+
+/* NCCL communicator for the hash-repartition exchange (one rank per GPU/process).
+ * unique_id: 128 bytes obtained from sailgpu_comm_unique_id on rank 0 and distributed out of band
+ * (the Rust shim sends it in the RunTask message; tests use torch.distributed's store). */
+SAILGPU_API int32_t sailgpu_comm_unique_id(uint8_t* out128);
+SAILGPU_API int32_t sailgpu_ctx_comm_init(sailgpu_ctx* ctx, const uint8_t* unique_id128, int32_t rank, int32_t world_size);
+
+/* Create an operator.  `input_schemas[i]` is the Arrow schema (struct of fields) of input i;
+ * on success *out_schema is filled with the operator's output schema (caller releases it). */
+SAILGPU_API int32_t sailgpu_op_create(sailgpu_ctx* ctx, const char* spec_json, size_t spec_len,
+                          const struct ArrowSchema* const* input_schemas, int32_t n_inputs,
+                          int32_t partition, sailgpu_op** out, struct ArrowSchema* out_schema);
+
+/* Hand one input batch (struct array, host memory) to the operator.  Takes ownership: the library
+ * calls batch->release when it no longer needs the host buffers (after the H2D copy). */
+SAILGPU_API int32_t sailgpu_op_push(sailgpu_op* op, int32_t input_idx, struct ArrowArray* batch);
+/* Same for a batch whose buffers are already in HBM (zero copy; released when consumed). */
+SAILGPU_API int32_t sailgpu_op_push_device(sailgpu_op* op, int32_t input_idx, struct ArrowDeviceArray* batch);
+/* End of stream on input `input_idx`. */
+SAILGPU_API int32_t sailgpu_op_finish_input(sailgpu_op* op, int32_t input_idx);
+
+/* Next output batch.  *has_more == 0 and out->length == 0 together mean end of stream.  A batch
+ * with has_more == 1 and length == 0 is legal (DataFusion permits empty batches).  When the
+ * operator needs more input before it can produce output it returns length 0, has_more 1. */
+SAILGPU_API int32_t sailgpu_op_pull(sailgpu_op* op, struct ArrowArray* out, int32_t* has_more);
+SAILGPU_API int32_t sailgpu_op_pull_device(sailgpu_op* op, struct ArrowDeviceArray* out, int32_t* has_more);
+
+/* For "repartition" operators: output batches of partition `part` only. */
+SAILGPU_API int32_t sailgpu_op_pull_partition(sailgpu_op* op, int32_t part, struct ArrowDeviceArray* out, int32_t* has_more);
+
+/* All-to-all exchange of the n = world_size device batches in `send` (batch p goes to rank p);
+ * on return `recv` holds the concatenation of what every rank sent to this rank.  NCCL
+ * send/recv groups over NVLink; counts are exchanged first.  world_size 1 degenerates to a move. */
+SAILGPU_API int32_t sailgpu_exchange(sailgpu_ctx* ctx, const struct ArrowSchema* schema,
+                         struct ArrowDeviceArray* send, int32_t n, struct ArrowDeviceArray* recv);
+
+/* Metrics as a JSON object with DataFusion's metric names (output_rows, elapsed_compute [ns],
+ * output_batches, input_rows, build_time, join_time, ...) plus gpu.* extras
+ * (gpu.kernel_ns, gpu.h2d_bytes, gpu.d2h_bytes, gpu.kernel_launches).  Returns bytes needed. */
+SAILGPU_API int64_t sailgpu_op_metrics(sailgpu_op* op, char* json_buf, size_t cap);
+
+/* UTF-8 message of the last failed call on this handle ("" if none). */
+SAILGPU_API const char* sailgpu_last_error(const sailgpu_op* op);
+
+/* Idempotent; legal at any time (== dropping the RecordBatchStream: cancels and frees HBM). */
+SAILGPU_API void sailgpu_op_destroy(sailgpu_op* op);
+
+/* Pinned host memory for callers that want zero-staging H2D (the shim's scan adapter). */
+SAILGPU_API int32_t sailgpu_host_alloc(sailgpu_ctx* ctx, size_t bytes, void** out);
+SAILGPU_API void sailgpu_host_free(sailgpu_ctx* ctx, void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAILGPU_H */

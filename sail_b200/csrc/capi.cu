@@ -1,0 +1,189 @@
+// capi.cu -- the extern "C" surface declared in include/sailgpu.h.
+#include <cstdio>
+
+#include "engine.hpp"
+
+using namespace sg;
+
+struct sailgpu_ctx {
+  Ctx ctx;
+};
+struct sailgpu_op {
+  std::unique_ptr<Op> op;
+  sailgpu_ctx* owner = nullptr;
+  std::string last_error;
+  std::vector<bool> input_finished;
+};
+
+namespace {
+thread_local std::string g_ctx_error;
+
+template <typename F>
+int32_t guard(std::string* err, F&& f) {
+  try {
+    f();
+    return SAILGPU_OK;
+  } catch (const Error& e) {
+    if (err) *err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    if (err) *err = std::string("internal error: ") + e.what();
+    return SAILGPU_ERR_CUDA;
+  }
+}
+void set_device(const Ctx& c) { SG_CUDA(cudaSetDevice(c.device)); }
+}  // namespace
+
+extern "C" {
+
+SAILGPU_API uint32_t sailgpu_version(void) { return (0u << 16) | 1u; }
+
+SAILGPU_API int32_t sailgpu_ctx_create(int32_t device, sailgpu_ctx** out) {
+  return guard(&g_ctx_error, [&] {
+    SG_CHECK(out != nullptr, SAILGPU_ERR_INVALID, "out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      fail(SAILGPU_ERR_NO_DEVICE, std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); libsailgpu has no CPU fallback");
+    SG_CHECK(device >= 0 && device < n, SAILGPU_ERR_INVALID, "device ordinal out of range");
+    auto c = std::make_unique<sailgpu_ctx>();
+    c->ctx.device = device;
+    SG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SG_CUDA(cudaGetDeviceProperties(&prop, device));
+    SG_CHECK(prop.major >= 10, SAILGPU_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100-class; this library only carries sm_100a code");
+    c->ctx.sm_count = prop.multiProcessorCount;
+    c->ctx.max_smem = prop.sharedMemPerBlockOptin;
+    SG_CUDA(cudaStreamCreateWithFlags(&c->ctx.stream, cudaStreamNonBlocking));
+    SG_CUDA(cudaStreamCreateWithFlags(&c->ctx.copy_stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    SG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;   // keep freed HBM in the pool: operators re-allocate the same sizes every batch
+    SG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    *out = c.release();
+  });
+}
+
+SAILGPU_API void sailgpu_ctx_destroy(sailgpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx.device);
+  if (c->ctx.stream) { cudaStreamSynchronize(c->ctx.stream); cudaStreamDestroy(c->ctx.stream); }
+  if (c->ctx.copy_stream) cudaStreamDestroy(c->ctx.copy_stream);
+  delete c;
+}
+
+SAILGPU_API const char* sailgpu_ctx_last_error(const sailgpu_ctx*) { return g_ctx_error.c_str(); }
+
+SAILGPU_API int32_t sailgpu_op_create(sailgpu_ctx* c, const char* spec_json, size_t spec_len, const struct ArrowSchema* const* input_schemas,
+                          int32_t n_inputs, int32_t partition, sailgpu_op** out, struct ArrowSchema* out_schema) {
+  return guard(&g_ctx_error, [&] {
+    SG_CHECK(c && spec_json && out && out_schema, SAILGPU_ERR_INVALID, "null argument");
+    set_device(c->ctx);
+    Json spec = JsonParser(spec_json, spec_len).parse();
+    std::vector<Schema> ins;
+    for (int i = 0; i < n_inputs; ++i) ins.push_back(schema_from_arrow(input_schemas[i]));
+    auto h = std::make_unique<sailgpu_op>();
+    h->owner = c;
+    h->op = make_op(&c->ctx, spec, ins, partition);
+    h->input_finished.assign((size_t)n_inputs, false);
+    schema_to_arrow(h->op->out_schema, out_schema);
+    *out = h.release();
+  });
+}
+
+SAILGPU_API int32_t sailgpu_op_push(sailgpu_op* h, int32_t input_idx, struct ArrowArray* batch) {
+  if (!h) return SAILGPU_ERR_INVALID;
+  return guard(&h->last_error, [&] {
+    set_device(h->owner->ctx);
+    SG_CHECK(input_idx >= 0 && input_idx < (int)h->op->in_schemas.size(), SAILGPU_ERR_INVALID, "input index out of range");
+    SG_CHECK(!h->input_finished[(size_t)input_idx], SAILGPU_ERR_STATE, "push after finish_input");
+    BatchPtr b = import_host_batch(&h->owner->ctx, h->op->in_schemas[(size_t)input_idx], batch);
+    h->op->push(input_idx, b);
+  });
+}
+
+SAILGPU_API int32_t sailgpu_op_push_device(sailgpu_op* h, int32_t input_idx, struct ArrowDeviceArray* batch) {
+  if (!h) return SAILGPU_ERR_INVALID;
+  return guard(&h->last_error, [&] {
+    set_device(h->owner->ctx);
+    SG_CHECK(input_idx >= 0 && input_idx < (int)h->op->in_schemas.size(), SAILGPU_ERR_INVALID, "input index out of range");
+    SG_CHECK(!h->input_finished[(size_t)input_idx], SAILGPU_ERR_STATE, "push after finish_input");
+    SG_CHECK(batch && batch->array.release, SAILGPU_ERR_INVALID, "batch is null or released");
+    BatchPtr b = take_internal_batch(batch);
+    if (!b) b = import_device_batch(&h->owner->ctx, h->op->in_schemas[(size_t)input_idx], batch);
+    h->op->push(input_idx, b);
+  });
+}
+
+SAILGPU_API int32_t sailgpu_op_finish_input(sailgpu_op* h, int32_t input_idx) {
+  if (!h) return SAILGPU_ERR_INVALID;
+  return guard(&h->last_error, [&] {
+    set_device(h->owner->ctx);
+    SG_CHECK(input_idx >= 0 && input_idx < (int)h->op->in_schemas.size(), SAILGPU_ERR_INVALID, "input index out of range");
+    if (h->input_finished[(size_t)input_idx]) return;
+    h->input_finished[(size_t)input_idx] = true;
+    h->op->finish(input_idx);
+  });
+}
+
+static int32_t pull_common(sailgpu_op* h, int part, struct ArrowArray* host_out, struct ArrowDeviceArray* dev_out, int32_t* has_more) {
+  if (!h) return SAILGPU_ERR_INVALID;
+  return guard(&h->last_error, [&] {
+    set_device(h->owner->ctx);
+    SG_CHECK(has_more && (host_out || dev_out), SAILGPU_ERR_INVALID, "null argument");
+    BatchPtr b;
+    const bool more = part >= 0 ? h->op->pull_partition(part, &b) : h->op->pull(&b);
+    *has_more = more ? 1 : 0;
+    if (!b) b = empty_batch(&h->owner->ctx, h->op->out_schema);
+    if (host_out) export_host_batch(&h->owner->ctx, h->op->out_schema, b, host_out);
+    else export_device_batch(&h->owner->ctx, h->op->out_schema, b, dev_out);
+  });
+}
+
+SAILGPU_API int32_t sailgpu_op_pull(sailgpu_op* h, struct ArrowArray* out, int32_t* has_more) { return pull_common(h, -1, out, nullptr, has_more); }
+SAILGPU_API int32_t sailgpu_op_pull_device(sailgpu_op* h, struct ArrowDeviceArray* out, int32_t* has_more) { return pull_common(h, -1, nullptr, out, has_more); }
+SAILGPU_API int32_t sailgpu_op_pull_partition(sailgpu_op* h, int32_t part, struct ArrowDeviceArray* out, int32_t* has_more) {
+  if (part < 0) return SAILGPU_ERR_INVALID;
+  return pull_common(h, part, nullptr, out, has_more);
+}
+
+SAILGPU_API int64_t sailgpu_op_metrics(sailgpu_op* h, char* json_buf, size_t cap) {
+  if (!h) return -1;
+  const Metrics& m = h->op->m;
+  char tmp[1024];
+  int n = snprintf(tmp, sizeof(tmp),
+                   "{\"output_rows\":%llu,\"output_batches\":%llu,\"input_rows\":%llu,\"input_batches\":%llu,"
+                   "\"elapsed_compute\":%llu,\"build_input_rows\":%llu,\"build_input_batches\":%llu,\"build_time\":%llu,"
+                   "\"join_time\":%llu,\"gpu.kernel_launches\":%llu,\"gpu.h2d_bytes\":%llu,\"gpu.d2h_bytes\":%llu}",
+                   (unsigned long long)m.output_rows, (unsigned long long)m.output_batches, (unsigned long long)m.input_rows,
+                   (unsigned long long)m.input_batches, (unsigned long long)m.elapsed_compute_ns, (unsigned long long)m.build_input_rows,
+                   (unsigned long long)m.build_input_batches, (unsigned long long)m.build_time_ns, (unsigned long long)m.join_time_ns,
+                   (unsigned long long)m.kernel_launches, (unsigned long long)h->owner->ctx.h2d_bytes.load(),
+                   (unsigned long long)h->owner->ctx.d2h_bytes.load());
+  if (json_buf && cap) { size_t k = std::min<size_t>((size_t)n, cap - 1); memcpy(json_buf, tmp, k); json_buf[k] = 0; }
+  return n + 1;
+}
+
+SAILGPU_API const char* sailgpu_last_error(const sailgpu_op* h) { return h ? h->last_error.c_str() : "null handle"; }
+
+SAILGPU_API void sailgpu_op_destroy(sailgpu_op* h) {
+  if (!h) return;
+  cudaSetDevice(h->owner->ctx.device);
+  cudaStreamSynchronize(h->owner->ctx.stream);
+  delete h;
+}
+
+SAILGPU_API int32_t sailgpu_host_alloc(sailgpu_ctx* c, size_t bytes, void** out) {
+  return guard(&g_ctx_error, [&] {
+    SG_CHECK(c && out, SAILGPU_ERR_INVALID, "null argument");
+    set_device(c->ctx);
+    SG_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  });
+}
+SAILGPU_API void sailgpu_host_free(sailgpu_ctx* c, void* p) {
+  if (!c || !p) return;
+  cudaSetDevice(c->ctx.device);
+  cudaFreeHost(p);
+}
+
+}  // extern "C"

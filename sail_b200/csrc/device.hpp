@@ -1,0 +1,96 @@
+// device.hpp -- context, HBM buffers, device-resident columns/batches and Arrow C (Device) Data
+// Interface import/export.  Data layout in HBM is Arrow's own (values buffers, LSB bitmaps,
+// 16-byte string views) so an imported device batch is used in place; the only normalisation is
+// that string views longer than 12 bytes carry an absolute device pointer in their last 8 bytes
+// ("resolved views") so kernels can dereference them without a buffer table.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <functional>
+#include <mutex>
+
+#include "common.hpp"
+
+namespace sg {
+
+#define SG_CUDA(call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t _e = (call);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      ::sg::fail(SAILGPU_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #call); \
+  } while (0)
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  size_t max_smem = 227 * 1024;
+  cudaStream_t stream = nullptr;        // compute stream
+  cudaStream_t copy_stream = nullptr;   // H2D / D2H stream
+  std::string last_error;
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+  // metrics shared by all ops of the context
+  std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};
+};
+
+// A reference-counted HBM allocation (stream-ordered pool) or a borrowed foreign pointer.
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  Ctx* ctx = nullptr;
+  std::function<void()> on_release;   // borrowed buffers: drop the producer's reference
+  ~DevBuf() {
+    if (on_release) on_release();
+    else if (ptr && ctx) cudaFreeAsync(ptr, ctx->stream);
+  }
+};
+using BufPtr = std::shared_ptr<DevBuf>;
+
+inline BufPtr dev_alloc(Ctx* ctx, size_t bytes) {
+  auto b = std::make_shared<DevBuf>();
+  b->ctx = ctx;
+  b->bytes = bytes;
+  const size_t padded = ((bytes + 255) & ~(size_t)255) + 256;   // room for 16-byte over-reads of tails
+  SG_CUDA(cudaMallocAsync(&b->ptr, padded, ctx->stream));
+  return b;
+}
+inline BufPtr dev_alloc_zero(Ctx* ctx, size_t bytes) {
+  BufPtr b = dev_alloc(ctx, bytes);
+  SG_CUDA(cudaMemsetAsync(b->ptr, 0, ((bytes + 255) & ~(size_t)255) + 256, ctx->stream));
+  return b;
+}
+
+struct DevColumn {
+  DataType type;
+  int64_t length = 0;
+  BufPtr data;                 // values / views (Utf8 columns are converted to resolved views)
+  BufPtr validity;             // Arrow bitmap (bit i at offset 0) or null when no nulls
+  int64_t null_count = 0;
+  std::vector<BufPtr> heaps;   // keep-alive for string bytes the views point into
+  bool arrow_is_utf8 = false;  // the Arrow-facing type is Utf8 (export converts views back)
+};
+
+struct DevBatch {
+  std::vector<DevColumn> cols;
+  int64_t rows = 0;
+};
+using BatchPtr = std::shared_ptr<DevBatch>;
+
+// ---- Arrow import / export (device.cu) -------------------------------------------------------------
+Schema schema_from_arrow(const ArrowSchema* s);
+void schema_to_arrow(const Schema& s, ArrowSchema* out);
+
+// Host ArrowArray (struct) -> HBM.  Copies on ctx->copy_stream, then makes ctx->stream wait.
+BatchPtr import_host_batch(Ctx* ctx, const Schema& schema, ArrowArray* arr);
+// Device ArrowDeviceArray -> batch without copying values (string views are copied + resolved).
+BatchPtr import_device_batch(Ctx* ctx, const Schema& schema, ArrowDeviceArray* arr);
+// HBM -> host ArrowArray (malloc'ed buffers released by the consumer).
+void export_host_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, ArrowArray* out);
+// HBM -> ArrowDeviceArray sharing the buffers.
+void export_device_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, ArrowDeviceArray* out);
+
+BatchPtr concat_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts);
+BatchPtr empty_batch(Ctx* ctx, const Schema& schema);
+
+}  // namespace sg

@@ -1,0 +1,1554 @@
+// pipeline.cu -- the fused tile-pipeline kernel (see vm.h) and its helper kernels.
+//
+// Replaces, in one pass over HBM, the DataFusion operator chain
+//   FilterExec -> ProjectionExec -> AggregateExec(Partial|Single|Final*)      
+// that Sail drives per 8192-row batch (reference call sites: crates/sail-execution/src/
+// job_runner.rs:64 `execute_stream`, crates/sail-physical-plan/src/streaming/filter.rs:104-116,
+// crates/sail-plan/src/function/aggregate.rs:51-72,302-353,678-710).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "dev_util.cuh"
+#include "kernels.hpp"
+#include "vm.h"
+
+namespace sg {
+
+struct Smem {
+  uint64_t full[2];        // TMA "tile landed" barriers, one per stage
+  int32_t tile[2];
+  int32_t hot_n;           // groups in the CTA-local hot dictionary
+  int32_t elect;
+  unsigned long long tile_base;   // COMPACT: exclusive prefix of this tile
+  uint32_t warp_sums[33];
+};
+constexpr int SMEM_HDR = 256;
+
+struct TileCtx {
+  uint8_t* arena;
+  uint32_t stage_off;      // added to stage-relative (bit 31) offsets
+  int nrows;               // valid rows of this tile
+  int64_t row0;
+};
+__device__ __forceinline__ uint32_t eff(const TileCtx& c, uint32_t off) {
+  return (off & 0x7FFFFFFFu) + ((off >> 31) ? c.stage_off : 0u);
+}
+
+// ================================================================================================
+// tile VM
+// ================================================================================================
+template <typename T> struct ImmOf;
+template <> struct ImmOf<int32_t> { static __device__ __forceinline__ int32_t get(const VmInst& I) { return (int32_t)I.imm0; } };
+template <> struct ImmOf<int64_t> { static __device__ __forceinline__ int64_t get(const VmInst& I) { return (int64_t)I.imm0; } };
+template <> struct ImmOf<double> { static __device__ __forceinline__ double get(const VmInst& I) { return __longlong_as_double((long long)I.imm0); } };
+template <> struct ImmOf<i128> { static __device__ __forceinline__ i128 get(const VmInst& I) { return (i128)(((u128)I.imm1 << 64) | I.imm0); } };
+template <> struct ImmOf<uint8_t> { static __device__ __forceinline__ uint8_t get(const VmInst& I) { return (uint8_t)I.imm0; } };
+
+struct OpAdd { template <typename T> static __device__ __forceinline__ T f(T a, T b) { return a + b; } };
+struct OpSub { template <typename T> static __device__ __forceinline__ T f(T a, T b) { return a - b; } };
+struct OpMul { template <typename T> static __device__ __forceinline__ T f(T a, T b) { return a * b; } };
+template <> __device__ __forceinline__ int32_t OpAdd::f<int32_t>(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+template <> __device__ __forceinline__ int32_t OpSub::f<int32_t>(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+template <> __device__ __forceinline__ int32_t OpMul::f<int32_t>(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+template <> __device__ __forceinline__ int64_t OpAdd::f<int64_t>(int64_t a, int64_t b) { return (int64_t)((uint64_t)a + (uint64_t)b); }
+template <> __device__ __forceinline__ int64_t OpSub::f<int64_t>(int64_t a, int64_t b) { return (int64_t)((uint64_t)a - (uint64_t)b); }
+template <> __device__ __forceinline__ int64_t OpMul::f<int64_t>(int64_t a, int64_t b) { return (int64_t)((uint64_t)a * (uint64_t)b); }
+template <> __device__ __forceinline__ i128 OpAdd::f<i128>(i128 a, i128 b) { return (i128)((u128)a + (u128)b); }
+template <> __device__ __forceinline__ i128 OpSub::f<i128>(i128 a, i128 b) { return (i128)((u128)a - (u128)b); }
+template <> __device__ __forceinline__ i128 OpMul::f<i128>(i128 a, i128 b) { return (i128)((u128)a * (u128)b); }
+
+struct CmpEq { template <typename T> static __device__ __forceinline__ bool f(T a, T b) { return a == b; } };
+struct CmpNe { template <typename T> static __device__ __forceinline__ bool f(T a, T b) { return a != b; } };
+struct CmpLt { template <typename T> static __device__ __forceinline__ bool f(T a, T b) { return a < b; } };
+struct CmpLe { template <typename T> static __device__ __forceinline__ bool f(T a, T b) { return a <= b; } };
+struct CmpGt { template <typename T> static __device__ __forceinline__ bool f(T a, T b) { return a > b; } };
+struct CmpGe { template <typename T> static __device__ __forceinline__ bool f(T a, T b) { return a >= b; } };
+
+template <int RPT, typename T, typename F>
+__device__ __forceinline__ void vm_bin(const VmInst& I, const TileCtx& c) {
+  const T imm = ImmOf<T>::get(I);
+  const uint8_t* pa = c.arena + eff(c, I.a);
+  const uint8_t* pb = c.arena + eff(c, I.b);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    T a = (I.flags & F_IMM_A) ? imm : lds<T>(pa + r * I.sa);
+    T b = (I.flags & F_IMM_B) ? imm : lds<T>(pb + r * I.sb);
+    sts<T>(pd + r * (int)sizeof(T), F::template f<T>(a, b));
+  }
+}
+template <int RPT, typename T, typename F>
+__device__ __forceinline__ void vm_cmp(const VmInst& I, const TileCtx& c) {
+  const T imm = ImmOf<T>::get(I);
+  const uint8_t* pa = c.arena + eff(c, I.a);
+  const uint8_t* pb = c.arena + eff(c, I.b);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    T a = (I.flags & F_IMM_A) ? imm : lds<T>(pa + r * I.sa);
+    T b = (I.flags & F_IMM_B) ? imm : lds<T>(pb + r * I.sb);
+    pd[r] = F::template f<T>(a, b) ? 1 : 0;
+  }
+}
+template <int RPT, typename F>
+__device__ __forceinline__ void vm_bin_kind(const VmInst& I, int kind, const TileCtx& c) {
+  switch (kind) {
+    case K_I32: vm_bin<RPT, int32_t, F>(I, c); break;
+    case K_I64: vm_bin<RPT, int64_t, F>(I, c); break;
+    case K_F64: vm_bin<RPT, double, F>(I, c); break;
+    case K_I128: vm_bin<RPT, i128, F>(I, c); break;
+    default: break;
+  }
+}
+template <int RPT, typename F>
+__device__ __forceinline__ void vm_cmp_kind(const VmInst& I, int kind, const TileCtx& c) {
+  switch (kind) {
+    case K_B: vm_cmp<RPT, uint8_t, F>(I, c); break;
+    case K_I32: vm_cmp<RPT, int32_t, F>(I, c); break;
+    case K_I64: vm_cmp<RPT, int64_t, F>(I, c); break;
+    case K_F64: vm_cmp<RPT, double, F>(I, c); break;
+    case K_I128: vm_cmp<RPT, i128, F>(I, c); break;
+    default: break;
+  }
+}
+
+// views: equality only (ordering comparisons on strings are rejected by the compiler)
+template <int RPT>
+__device__ __forceinline__ void vm_view_eq(const VmInst& I, const TileCtx& c, bool negate) {
+  const uint8_t* pa = c.arena + eff(c, I.a);
+  const uint8_t* pb = c.arena + eff(c, I.b);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+  ulonglong2 imm; imm.x = I.imm0; imm.y = I.imm1;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    ulonglong2 a = (I.flags & F_IMM_A) ? imm : *reinterpret_cast<const ulonglong2*>(pa + r * I.sa);
+    ulonglong2 b = (I.flags & F_IMM_B) ? imm : *reinterpret_cast<const ulonglong2*>(pb + r * I.sb);
+    bool eq = view_equal(a, b);
+    pd[r] = (eq != negate) ? 1 : 0;
+  }
+}
+
+template <typename T> __device__ __forceinline__ T trunc_div(T a, T b) { return a / b; }
+
+template <int RPT, typename T, bool REM>
+__device__ __forceinline__ void vm_div(const VmInst& I, const TileCtx& c, uint32_t* err) {
+  const T imm = ImmOf<T>::get(I);
+  const uint8_t* pa = c.arena + eff(c, I.a);
+  const uint8_t* pb = c.arena + eff(c, I.b);
+  const uint8_t* pg = I.c == NO_SLOT ? nullptr : c.arena + eff(c, I.c);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    T a = (I.flags & F_IMM_A) ? imm : lds<T>(pa + r * I.sa);
+    T b = (I.flags & F_IMM_B) ? imm : lds<T>(pb + r * I.sb);
+    bool live = r < c.nrows && (pg == nullptr || pg[r]);
+    T q = 0;
+    if (b == 0) {
+      if (live) atomicOr(err, ERR_DIV_ZERO);
+    } else {
+      q = REM ? (T)(a % b) : (T)(a / b);
+    }
+    sts<T>(pd + r * (int)sizeof(T), q);
+  }
+}
+template <int RPT>
+__device__ __forceinline__ void vm_div_f64(const VmInst& I, const TileCtx& c, bool rem) {
+  const double imm = ImmOf<double>::get(I);
+  const uint8_t* pa = c.arena + eff(c, I.a);
+  const uint8_t* pb = c.arena + eff(c, I.b);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    double a = (I.flags & F_IMM_A) ? imm : lds<double>(pa + r * I.sa);
+    double b = (I.flags & F_IMM_B) ? imm : lds<double>(pb + r * I.sb);
+    sts<double>(pd + r * 8, rem ? fmod(a, b) : a / b);
+  }
+}
+
+// decimal rescale down: round half away from zero (arrow `rescale_decimal`)
+template <int RPT, typename T>
+__device__ __forceinline__ void vm_divround(const VmInst& I, const TileCtx& c) {
+  const T d = ImmOf<T>::get(I);
+  const uint8_t* pa = c.arena + eff(c, I.a);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    T a = lds<T>(pa + r * I.sa);
+    T q = a / d, rem = a % d;
+    T twice = rem < 0 ? -rem * 2 : rem * 2;
+    if (twice >= d) q += (a < 0 ? -1 : 1);
+    sts<T>(pd + r * (int)sizeof(T), q);
+  }
+}
+
+
+template <int RPT>
+__device__ __forceinline__ void vm_cvt(const VmInst& I, int dkind, const TileCtx& c) {
+  const uint8_t* pa = c.arena + eff(c, I.a);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    const uint8_t* p = pa + r * I.sa;
+    i128 iv = 0; double fv = 0.0; bool isf = false;
+    switch (I.aux) {
+      case SRC_I8: iv = lds<int8_t>(p); break;
+      case SRC_I16: iv = lds<int16_t>(p); break;
+      case SRC_U8: iv = lds<uint8_t>(p); break;
+      case SRC_U16: iv = lds<uint16_t>(p); break;
+      case SRC_U32: iv = lds<uint32_t>(p); break;
+      case SRC_I32: iv = lds<int32_t>(p); break;
+      case SRC_I64: iv = lds<int64_t>(p); break;
+      case SRC_I128: iv = lds<i128>(p); break;
+      case SRC_B: iv = lds<uint8_t>(p) ? 1 : 0; break;
+      case SRC_F32: fv = lds<float>(p); isf = true; break;
+      case SRC_F64: fv = lds<double>(p); isf = true; break;
+    }
+    switch (dkind) {
+      case K_I32: sts<int32_t>(pd + r * 4, isf ? (int32_t)fv : (int32_t)iv); break;
+      case K_I64: sts<int64_t>(pd + r * 8, isf ? (int64_t)fv : (int64_t)iv); break;
+      case K_I128: sts<i128>(pd + r * 16, isf ? (i128)(int64_t)fv : iv); break;
+      case K_F64: sts<double>(pd + r * 8, isf ? fv : (I.aux == SRC_I128 ? (double)iv : (double)(int64_t)iv)); break;
+      case K_B: pd[r] = isf ? (fv != 0.0) : (iv != 0); break;
+    }
+  }
+}
+
+template <int RPT, typename T>
+__device__ __forceinline__ void vm_select(const VmInst& I, const TileCtx& c) {
+  const T imm = ImmOf<T>::get(I);
+  const uint8_t* pa = c.arena + eff(c, I.a);
+  const uint8_t* pb = c.arena + eff(c, I.b);
+  const uint8_t* pc = c.arena + eff(c, I.c);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    T a = (I.flags & F_IMM_A) ? imm : lds<T>(pa + r * I.sa);
+    T b = (I.flags & F_IMM_B) ? imm : lds<T>(pb + r * I.sb);
+    sts<T>(pd + r * (int)sizeof(T), pc[r] ? a : b);
+  }
+}
+template <int RPT>
+__device__ __forceinline__ void vm_select_v16(const VmInst& I, const TileCtx& c) {
+  const uint8_t* pa = c.arena + eff(c, I.a);
+  const uint8_t* pb = c.arena + eff(c, I.b);
+  const uint8_t* pc = c.arena + eff(c, I.c);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+  ulonglong2 imm; imm.x = I.imm0; imm.y = I.imm1;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    ulonglong2 a = (I.flags & F_IMM_A) ? imm : *reinterpret_cast<const ulonglong2*>(pa + r * I.sa);
+    ulonglong2 b = (I.flags & F_IMM_B) ? imm : *reinterpret_cast<const ulonglong2*>(pb + r * I.sb);
+    *reinterpret_cast<ulonglong2*>(pd + r * 16) = pc[r] ? a : b;
+  }
+}
+
+// days since 1970-01-01 -> civil (year, month, day)
+__device__ __forceinline__ void civil_from_days(int32_t z0, int& y, int& m, int& d) {
+  int64_t z = (int64_t)z0 + 719468;
+  int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+  int64_t doe = z - era * 146097;
+  int64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  int64_t yy = yoe + era * 400;
+  int64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  int64_t mp = (5 * doy + 2) / 153;
+  d = (int)(doy - (153 * mp + 2) / 5 + 1);
+  m = (int)(mp < 10 ? mp + 3 : mp - 9);
+  y = (int)(m <= 2 ? yy + 1 : yy);
+}
+
+__device__ __forceinline__ bool like_match(const uint8_t* s, uint32_t n, const uint8_t* p, uint32_t m, int cls) {
+  switch (cls) {
+    case LIKE_EXACT:
+      if (n != m) return false;
+      for (uint32_t i = 0; i < m; ++i) if (s[i] != p[i]) return false;
+      return true;
+    case LIKE_PREFIX:
+      if (n < m) return false;
+      for (uint32_t i = 0; i < m; ++i) if (s[i] != p[i]) return false;
+      return true;
+    case LIKE_SUFFIX:
+      if (n < m) return false;
+      for (uint32_t i = 0; i < m; ++i) if (s[n - m + i] != p[i]) return false;
+      return true;
+    case LIKE_CONTAINS:
+      if (n < m) return false;
+      for (uint32_t st = 0; st + m <= n; ++st) {
+        uint32_t i = 0;
+        while (i < m && s[st + i] == p[i]) ++i;
+        if (i == m) return true;
+      }
+      return false;
+    default: {
+      // generic %/_ matcher with single backtrack point (pattern bytes: '%' any run, '_' one byte, '\\' escape)
+      uint32_t si = 0, pi = 0, star_p = 0xFFFFFFFFu, star_s = 0;
+      while (si < n) {
+        if (pi < m && p[pi] == '\\' && pi + 1 < m && p[pi + 1] == s[si]) { pi += 2; ++si; }
+        else if (pi < m && p[pi] != '%' && p[pi] != '\\' && (p[pi] == '_' || p[pi] == s[si])) { ++pi; ++si; }
+        else if (pi < m && p[pi] == '%') { star_p = pi++; star_s = si; }
+        else if (star_p != 0xFFFFFFFFu) { pi = star_p + 1; si = ++star_s; }
+        else return false;
+      }
+      while (pi < m && p[pi] == '%') ++pi;
+      return pi == m;
+    }
+  }
+}
+
+template <int RPT>
+__device__ __noinline__ void vm_like(const VmInst& I, const TileCtx& c) {
+  const uint8_t* pa = c.arena + eff(c, I.a);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+  const uint8_t* pat = reinterpret_cast<const uint8_t*>(I.imm1);
+  const uint32_t plen = (uint32_t)I.imm0;
+  const int cls = I.aux & 0xFF;
+  const bool negate = (I.aux >> 8) & 1;
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    bool hit = false;
+    if (r < c.nrows) {
+      const uint8_t* vp = pa + r * I.sa;
+      ulonglong2 v = *reinterpret_cast<const ulonglong2*>(vp);
+      hit = like_match(view_ptr(v, vp), (uint32_t)v.x, pat, plen, cls);
+    }
+    pd[r] = (hit != negate) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// join probe (OP_PROBE): open-addressing lookup of the probe key in the build table
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t load_key_word(const uint8_t* p, int width) {
+  switch (width) {
+    case 1: return *p;
+    case 4: return (uint64_t)(uint32_t)lds<int32_t>(p);   // zero-extended: equality domain only
+    default: return lds<uint64_t>(p);
+  }
+}
+
+struct KeyRegs { uint64_t w[MAX_KEY_WORDS]; };
+
+// Packs the key columns of row r into 8-byte words; returns the combined hash.  *has_null is set
+// when any key is NULL.  Views are kept as their 16 raw bytes (view_equal/view_hash resolve long
+// strings through the absolute pointer stored by the importer).
+template <int NKMAX>
+__device__ __forceinline__ uint64_t pack_key(const KeyDesc* keys, int n_keys, int has_null_word, const TileCtx& c, int r,
+                                             KeyRegs& k, bool* has_null) {
+  uint64_t h = 0x243F6A8885A308D3ull;
+  uint64_t nullmask = 0;
+  int w = has_null_word ? 1 : 0;
+#pragma unroll
+  for (int i = 0; i < NKMAX; ++i) {
+    if (i < n_keys) {
+      const KeyDesc& d = keys[i];
+      const uint8_t* p = c.arena + eff(c, d.slot) + r * d.stride;
+      bool isnull = d.valid_slot != NO_SLOT && c.arena[eff(c, d.valid_slot) + r] == 0;
+      if (isnull) nullmask |= 1ull << i;
+      if (d.width == 16) {
+        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+        if (isnull) { v.x = 0; v.y = 0; }
+        k.w[w] = v.x; k.w[w + 1] = v.y;
+        h = mix64(h ^ (d.is_view ? view_hash(v) : mix64(v.x ^ mix64(v.y))));
+        w += 2;
+      } else {
+        uint64_t v = isnull ? 0 : load_key_word(p, d.width);
+        k.w[w] = v;
+        h = mix64(h ^ v);
+        w += 1;
+      }
+    }
+  }
+  if (has_null_word) { k.w[0] = nullmask; h = mix64(h ^ nullmask); }
+  *has_null = nullmask != 0;
+  return h;
+}
+
+__device__ __forceinline__ bool key_words_equal(const KeyDesc* keys, int n_keys, int has_null_word, const uint64_t* a,
+                                                const KeyRegs& b) {
+  int w = 0;
+  if (has_null_word) { if (a[0] != b.w[0]) return false; w = 1; }
+  for (int i = 0; i < n_keys; ++i) {
+    if (keys[i].width == 16) {
+      if (keys[i].is_view) {
+        ulonglong2 x, y; x.x = a[w]; x.y = a[w + 1]; y.x = b.w[w]; y.y = b.w[w + 1];
+        if (!view_equal(x, y)) return false;
+      } else if (a[w] != b.w[w] || a[w + 1] != b.w[w + 1]) return false;
+      w += 2;
+    } else {
+      if (a[w] != b.w[w]) return false;
+      w += 1;
+    }
+  }
+  return true;
+}
+
+// join table slot: { u64 tag (0 = empty; hash | 1), i64 row }
+template <int RPT>
+__device__ __noinline__ void vm_probe(const ProbeParams& P, const TileCtx& c, uint32_t mask_slot) {
+  uint8_t* pm = c.arena + eff(c, P.match_slot);
+  uint8_t* prow = c.arena + eff(c, P.rowid_slot);
+  const uint8_t* pact = mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, mask_slot);
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    int64_t row = -1;
+    bool live = r < c.nrows && (pact == nullptr || pact[r]);
+    if (live) {
+      KeyRegs key; bool has_null;
+      uint64_t h = pack_key<MAX_KEYS>(P.keys, P.n_keys, 0, c, r, key, &has_null);
+      if (!has_null) {   // NullEqualsNothing
+        uint64_t tag = h | 1ull;
+        uint64_t idx = (h >> 1) & P.capacity_mask;
+        for (;;) {
+          const ulonglong2 s = *reinterpret_cast<const ulonglong2*>(P.table + idx * 16);
+          if (s.x == 0) break;
+          if (s.x == tag) {
+            // verify against the build-side key columns
+            const int64_t cand = (int64_t)s.y;
+            bool eq = true;
+            int w = 0;
+            for (int i = 0; i < P.n_keys && eq; ++i) {
+              const KeyDesc& d = P.keys[i];
+              const uint8_t* bp = P.build_keys[i] + cand * d.width;
+              if (d.width == 16) {
+                ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bp);
+                if (d.is_view) { ulonglong2 pv; pv.x = key.w[w]; pv.y = key.w[w + 1]; eq = view_equal(bv, pv); }
+                else eq = bv.x == key.w[w] && bv.y == key.w[w + 1];
+                w += 2;
+              } else {
+                eq = load_key_word(bp, d.width) == key.w[w];
+                w += 1;
+              }
+            }
+            if (eq) { row = cand; break; }
+          }
+          idx = (idx + 1) & P.capacity_mask;
+        }
+      }
+    }
+    if (row >= 0 && P.visited) P.visited[row] = 1;
+    pm[r] = row >= 0 ? 1 : 0;
+    sts<int64_t>(prow + r * 8, row);
+  }
+}
+
+template <int RPT>
+__device__ __forceinline__ void vm_gather(const VmInst& I, const TileCtx& c) {
+  const uint8_t* prow = c.arena + eff(c, I.a);
+  uint8_t* pd = c.arena + eff(c, I.dst);
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(I.imm1);
+  const int w = I.aux;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    int64_t row = lds<int64_t>(prow + r * 8);
+    if (w == 16) {
+      ulonglong2 v; v.x = 0; v.y = 0;
+      if (row >= 0) v = *reinterpret_cast<const ulonglong2*>(src + row * 16);
+      *reinterpret_cast<ulonglong2*>(pd + r * 16) = v;
+    } else if (w == 8) {
+      sts<uint64_t>(pd + r * 8, row >= 0 ? *reinterpret_cast<const uint64_t*>(src + row * 8) : 0ull);
+    } else if (w == 4) {
+      sts<uint32_t>(pd + r * 4, row >= 0 ? *reinterpret_cast<const uint32_t*>(src + row * 4) : 0u);
+    } else {   // bytes (validity / booleans stored one byte per row on the build side)
+      pd[r] = row >= 0 ? src[row] : 0;
+    }
+  }
+}
+
+template <int RPT>
+__device__ __forceinline__ void vm_exec(const VmInst* prog, int n_inst, const TileCtx& c, const PipelineParams& P,
+                                        const PipelineAux* aux) {
+  for (int pc = 0; pc < n_inst; ++pc) {
+    const VmInst I = prog[pc];
+    const int base = I.op & 0xFF, kind = I.op >> 8;
+    switch (base) {
+      case OP_UNPACK_BITS: {
+        const uint8_t* pa = c.arena + eff(c, I.a);
+        uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int r = threadIdx.x + k * NT;
+          pd[r] = (pa[r >> 3] >> (r & 7)) & 1;
+        }
+        break;
+      }
+      case OP_CONST: {
+        uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int r = threadIdx.x + k * NT;
+          switch (kind) {
+            case K_B: pd[r] = (uint8_t)I.imm0; break;
+            case K_I32: sts<int32_t>(pd + r * 4, (int32_t)I.imm0); break;
+            case K_I64: case K_F64: sts<uint64_t>(pd + r * 8, I.imm0); break;
+            default: { ulonglong2 v; v.x = I.imm0; v.y = I.imm1; *reinterpret_cast<ulonglong2*>(pd + r * 16) = v; }
+          }
+        }
+        break;
+      }
+      case OP_MOV: {
+        const uint8_t* pa = c.arena + eff(c, I.a);
+        uint8_t* pd = c.arena + eff(c, I.dst);
+        const int w = kind_width(kind);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int r = threadIdx.x + k * NT;
+          if (w == 16) *reinterpret_cast<ulonglong2*>(pd + r * 16) = *reinterpret_cast<const ulonglong2*>(pa + r * I.sa);
+          else if (w == 8) sts<uint64_t>(pd + r * 8, lds<uint64_t>(pa + r * I.sa));
+          else if (w == 4) sts<uint32_t>(pd + r * 4, lds<uint32_t>(pa + r * I.sa));
+          else pd[r] = pa[r * I.sa];
+        }
+        break;
+      }
+      case OP_CVT: vm_cvt<RPT>(I, kind, c); break;
+      case OP_ADD: vm_bin_kind<RPT, OpAdd>(I, kind, c); break;
+      case OP_SUB: vm_bin_kind<RPT, OpSub>(I, kind, c); break;
+      case OP_MUL: vm_bin_kind<RPT, OpMul>(I, kind, c); break;
+      case OP_DIV:
+      case OP_REM:
+        if (kind == K_F64) vm_div_f64<RPT>(I, c, base == OP_REM);
+        else if (kind == K_I32) { if (base == OP_DIV) vm_div<RPT, int32_t, false>(I, c, P.error_flag); else vm_div<RPT, int32_t, true>(I, c, P.error_flag); }
+        else if (kind == K_I64) { if (base == OP_DIV) vm_div<RPT, int64_t, false>(I, c, P.error_flag); else vm_div<RPT, int64_t, true>(I, c, P.error_flag); }
+        else { if (base == OP_DIV) vm_div<RPT, i128, false>(I, c, P.error_flag); else vm_div<RPT, i128, true>(I, c, P.error_flag); }
+        break;
+      case OP_NEG: {
+        const uint8_t* pa = c.arena + eff(c, I.a);
+        uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int r = threadIdx.x + k * NT;
+          switch (kind) {
+            case K_I32: sts<int32_t>(pd + r * 4, (int32_t)(0u - (uint32_t)lds<int32_t>(pa + r * I.sa))); break;
+            case K_I64: sts<int64_t>(pd + r * 8, (int64_t)(0ull - (uint64_t)lds<int64_t>(pa + r * I.sa))); break;
+            case K_F64: sts<double>(pd + r * 8, -lds<double>(pa + r * I.sa)); break;
+            default: sts<i128>(pd + r * 16, (i128)((u128)0 - (u128)lds<i128>(pa + r * I.sa)));
+          }
+        }
+        break;
+      }
+      case OP_MULW: {
+        const int64_t imm = (int64_t)I.imm0;
+        const uint8_t* pa = c.arena + eff(c, I.a);
+        const uint8_t* pb = c.arena + eff(c, I.b);
+        uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int r = threadIdx.x + k * NT;
+          int64_t a = (I.flags & F_IMM_A) ? imm : lds<int64_t>(pa + r * I.sa);
+          int64_t b = (I.flags & F_IMM_B) ? imm : lds<int64_t>(pb + r * I.sb);
+          ulonglong2 w;
+          w.x = (unsigned long long)a * (unsigned long long)b;
+          w.y = (unsigned long long)__mul64hi((long long)a, (long long)b);
+          *reinterpret_cast<ulonglong2*>(pd + r * 16) = w;
+        }
+        break;
+      }
+      case OP_MUL128_64: {
+        const int64_t imm = (int64_t)I.imm0;
+        const uint8_t* pa = c.arena + eff(c, I.a);
+        const uint8_t* pb = c.arena + eff(c, I.b);
+        uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int r = threadIdx.x + k * NT;
+          ulonglong2 a = *reinterpret_cast<const ulonglong2*>(pa + r * I.sa);
+          int64_t b = (I.flags & F_IMM_B) ? imm : lds<int64_t>(pb + r * I.sb);
+          // (ahi:alo) * sext(b)  mod 2^128
+          unsigned long long ub = (unsigned long long)b;
+          ulonglong2 w;
+          w.x = a.x * ub;
+          w.y = __umul64hi(a.x, ub) + a.y * ub - (b < 0 ? a.x : 0ull);
+          *reinterpret_cast<ulonglong2*>(pd + r * 16) = w;
+        }
+        break;
+      }
+      case OP_DIVROUND:
+        if (kind == K_I64) vm_divround<RPT, int64_t>(I, c); else vm_divround<RPT, i128>(I, c);
+        break;
+      case OP_EQ: if (kind == K_V16) vm_view_eq<RPT>(I, c, false); else vm_cmp_kind<RPT, CmpEq>(I, kind, c); break;
+      case OP_NE: if (kind == K_V16) vm_view_eq<RPT>(I, c, true); else vm_cmp_kind<RPT, CmpNe>(I, kind, c); break;
+      case OP_LT: vm_cmp_kind<RPT, CmpLt>(I, kind, c); break;
+      case OP_LE: vm_cmp_kind<RPT, CmpLe>(I, kind, c); break;
+      case OP_GT: vm_cmp_kind<RPT, CmpGt>(I, kind, c); break;
+      case OP_GE: vm_cmp_kind<RPT, CmpGe>(I, kind, c); break;
+      case OP_AND: case OP_OR: case OP_ANDNOT: case OP_NOT: {
+        const uint8_t* pa = c.arena + eff(c, I.a);
+        const uint8_t* pb = c.arena + eff(c, I.b);
+        uint8_t* pd = c.arena + eff(c, I.dst);
+        const uint8_t imm = (uint8_t)I.imm0;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int r = threadIdx.x + k * NT;
+          uint8_t a = (I.flags & F_IMM_A) ? imm : pa[r];
+          uint8_t b = (base == OP_NOT) ? 0 : ((I.flags & F_IMM_B) ? imm : pb[r]);
+          uint8_t v = base == OP_AND ? (a & b) : base == OP_OR ? (a | b) : base == OP_ANDNOT ? (a & (b ^ 1)) : (a ^ 1);
+          pd[r] = v & 1;
+        }
+        break;
+      }
+      case OP_SELECT:
+        switch (kind) {
+          case K_B: vm_select<RPT, uint8_t>(I, c); break;
+          case K_I32: vm_select<RPT, int32_t>(I, c); break;
+          case K_I64: vm_select<RPT, int64_t>(I, c); break;
+          case K_F64: vm_select<RPT, double>(I, c); break;
+          case K_I128: vm_select<RPT, i128>(I, c); break;
+          default: vm_select_v16<RPT>(I, c);
+        }
+        break;
+      case OP_STR_EQ_LONG: {
+        // literal longer than 12 bytes: imm0 = len | prefix << 32, imm1 = device pointer to the bytes
+        ulonglong2 lit; lit.x = I.imm0; lit.y = I.imm1;
+        const uint8_t* pa = c.arena + eff(c, I.a);
+        uint8_t* pd = c.arena + eff(c, I.dst);
+        for (int k = 0; k < RPT; ++k) {
+          const int r = threadIdx.x + k * NT;
+          ulonglong2 a = *reinterpret_cast<const ulonglong2*>(pa + r * I.sa);
+          bool eq = r < c.nrows && view_equal(a, lit);
+          pd[r] = (eq != (bool)(I.aux & 1)) ? 1 : 0;
+        }
+        break;
+      }
+      case OP_STR_LIKE: vm_like<RPT>(I, c); break;
+      case OP_DATE_PART: {
+        const uint8_t* pa = c.arena + eff(c, I.a);
+        uint8_t* pd = c.arena + eff(c, I.dst);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int r = threadIdx.x + k * NT;
+          int y, m, d;
+          civil_from_days(lds<int32_t>(pa + r * I.sa), y, m, d);
+          sts<int32_t>(pd + r * 4, I.aux == 0 ? y : I.aux == 1 ? m : d);
+        }
+        break;
+      }
+      case OP_PROBE: vm_probe<RPT>(aux->probe[I.aux], c, I.c); break;
+      case OP_GATHER: vm_gather<RPT>(I, c); break;
+      default: break;
+    }
+  }
+}
+
+// ================================================================================================
+// tile loading
+// ================================================================================================
+__device__ __forceinline__ uint32_t tile_bytes_of(const InputCol& in, int tile_rows) {
+  return in.width ? (uint32_t)in.width * tile_rows : (uint32_t)(tile_rows >> 3);
+}
+
+// cooperative copy (partial / unaligned tiles): zero-fills rows >= nrows
+__device__ __forceinline__ void load_tile_generic(const PipelineParams& P, uint8_t* arena, uint32_t stage_off, int64_t row0, int nrows) {
+  for (int i = 0; i < P.n_inputs; ++i) {
+    const InputCol& in = P.in[i];
+    uint8_t* dst = arena + (in.slot & 0x7FFFFFFFu) + ((in.slot >> 31) ? stage_off : 0u);
+    const uint32_t total = tile_bytes_of(in, P.tile_rows);
+    const uint32_t valid = in.width ? (uint32_t)in.width * nrows : (uint32_t)((nrows + 7) >> 3);
+    const uint8_t* src = in.data + (in.width ? (int64_t)in.width * row0 : (row0 >> 3));
+    if (in.tma_ok && (valid & 15u) == 0) {
+      for (uint32_t o = threadIdx.x * 16; o < total; o += NT * 16) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (o < valid) v = *reinterpret_cast<const uint4*>(src + o);
+        *reinterpret_cast<uint4*>(dst + o) = v;
+      }
+    } else {
+      for (uint32_t o = threadIdx.x; o < total; o += NT) dst[o] = o < valid ? src[o] : 0;
+    }
+  }
+}
+
+// ================================================================================================
+// aggregation: global table
+// ================================================================================================
+enum : uint32_t { ST_EMPTY = 0, ST_LOCKED = 1, ST_READY = 2 };
+
+__host__ __device__ inline uint64_t acc_identity(int op, int word_in_acc);
+__host__ __device__ inline int acc_words_of(int op);
+
+__device__ __forceinline__ uint64_t* agg_find_or_insert(const AggParams& A, const KeyRegs& key, uint64_t h, uint32_t* err) {
+  const uint32_t tag = (uint32_t)(h >> 32);
+  uint64_t idx = h & A.capacity_mask;
+  uint64_t probes = 0;
+  while (probes <= A.capacity_mask) {
+    uint64_t* e = reinterpret_cast<uint64_t*>(A.table) + idx * A.entry_words;
+    uint32_t* st = A.state + idx;
+    uint32_t s = ld_acquire_u32(st);
+    if (s == ST_EMPTY) {
+      s = atomicCAS(st, ST_EMPTY, ST_LOCKED);
+      if (s == ST_EMPTY) {
+        e[0] = tag;
+        e[1] = 0;                                                   // seen
+        for (int w = 0; w < A.key_words; ++w) e[2 + w] = key.w[w];
+        for (int j = 0; j < A.n_accs; ++j)
+          for (int w = 0; w < acc_words_of(A.accs[j].op); ++w)
+            e[2 + A.key_words + A.accs[j].word + w] = acc_identity(A.accs[j].op, w);
+        __threadfence();
+        st_release_u32(st, ST_READY);
+        atomicAdd(A.n_groups, 1ull);
+        return e;
+      }
+    }
+    if (s == ST_LOCKED) continue;     // another thread is publishing this slot: look again
+    if ((uint32_t)e[0] == tag && key_words_equal(A.keys, A.n_keys, A.has_null_word, e + 2, key)) return e;
+    idx = (idx + 1) & A.capacity_mask;
+    ++probes;
+  }
+  atomicOr(err, ERR_TABLE_FULL);
+  return nullptr;
+}
+
+// hash of an already packed key (same value pack_key() returns for the row it was packed from)
+__device__ __forceinline__ uint64_t hash_packed_key(const AggParams& A, const KeyRegs& key) {
+  uint64_t h = 0x243F6A8885A308D3ull;
+  int w = A.has_null_word ? 1 : 0;
+  for (int i = 0; i < A.n_keys; ++i) {
+    if (A.keys[i].width == 16) {
+      ulonglong2 v; v.x = key.w[w]; v.y = key.w[w + 1];
+      h = mix64(h ^ (A.keys[i].is_view ? view_hash(v) : mix64(v.x ^ mix64(v.y))));
+      w += 2;
+    } else { h = mix64(h ^ key.w[w]); w += 1; }
+  }
+  if (A.has_null_word) h = mix64(h ^ key.w[0]);
+  return h;
+}
+
+struct AccVal { i128 i; double f; bool valid; };
+
+__device__ __forceinline__ AccVal load_acc_value(const AccDesc& d, const TileCtx& c, int r) {
+  AccVal v; v.i = 0; v.f = 0.0; v.valid = true;
+  if (d.valid_slot != NO_SLOT) v.valid = c.arena[eff(c, d.valid_slot) + r] != 0;
+  if (d.value_slot == NO_SLOT) return v;
+  const uint8_t* p = c.arena + eff(c, d.value_slot) + r * d.stride;
+  switch (d.vkind) {
+    case K_I32: v.i = lds<int32_t>(p); break;
+    case K_I64: v.i = lds<int64_t>(p); break;
+    case K_I128: v.i = lds<i128>(p); break;
+    case K_F64: v.f = lds<double>(p); break;
+    case K_B: v.i = *p; break;
+    default: break;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void atomic_add_i128(uint64_t* w, i128 v) {
+  unsigned long long lo = (unsigned long long)(u128)v, hi = (unsigned long long)((u128)v >> 64);
+  unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(w), lo);
+  unsigned long long carry = (old + lo) < old ? 1ull : 0ull;
+  if (hi + carry) atomicAdd(reinterpret_cast<unsigned long long*>(w + 1), hi + carry);
+}
+__device__ __forceinline__ void atomic_minmax_i128(uint64_t* w, i128 v, bool is_min) {
+  u128 cur = ((u128)w[1] << 64) | w[0];
+  for (;;) {
+    i128 c = (i128)cur;
+    if (is_min ? (c <= v) : (c >= v)) return;
+    u128 prev = atomic_cas_128(w, cur, (u128)v);
+    if (prev == cur) return;
+    cur = prev;
+  }
+}
+__device__ __forceinline__ void atomic_minmax_f64(uint64_t* w, double v, bool is_min) {
+  unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(w);
+  for (;;) {
+    double c = __longlong_as_double((long long)cur);
+    if (is_min ? (c <= v) : (c >= v)) return;
+    unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(w), cur, (unsigned long long)__double_as_longlong(v));
+    if (prev == cur) return;
+    cur = prev;
+  }
+}
+
+// apply one accumulator update to a GLOBAL table entry (atomics)
+__device__ __forceinline__ void acc_global(uint64_t* e, const AggParams& A, int j, const AccVal& v) {
+  const AccDesc& d = A.accs[j];
+  uint64_t* w = e + 2 + A.key_words + d.word;
+  if (d.op == ACC_COUNT) { if (v.valid) atomicAdd(reinterpret_cast<unsigned long long*>(w), 1ull); return; }
+  if (!v.valid) return;
+  switch (d.op) {
+    case ACC_SUM_I64: atomicAdd(reinterpret_cast<unsigned long long*>(w), (unsigned long long)(int64_t)v.i); break;
+    case ACC_SUM_I128: atomic_add_i128(w, v.i); break;
+    case ACC_SUM_F64: atomicAdd(reinterpret_cast<double*>(w), v.f); break;
+    case ACC_MIN_I32: case ACC_MIN_I64: atomicMin(reinterpret_cast<long long*>(w), (long long)(int64_t)v.i); break;
+    case ACC_MAX_I32: case ACC_MAX_I64: atomicMax(reinterpret_cast<long long*>(w), (long long)(int64_t)v.i); break;
+    case ACC_MIN_I128: atomic_minmax_i128(w, v.i, true); break;
+    case ACC_MAX_I128: atomic_minmax_i128(w, v.i, false); break;
+    case ACC_MIN_F64: atomic_minmax_f64(w, v.f, true); break;
+    case ACC_MAX_F64: atomic_minmax_f64(w, v.f, false); break;
+    default: break;
+  }
+  if (d.track_seen) {
+    unsigned long long bit = 1ull << j;
+    if (!(*reinterpret_cast<volatile unsigned long long*>(e + 1) & bit)) atomicOr(reinterpret_cast<unsigned long long*>(e + 1), bit);
+  }
+}
+
+// identity of accumulator word `word_in_acc` (0 or 1)
+__host__ __device__ inline uint64_t acc_identity(int op, int word_in_acc) {
+  switch (op) {
+    case ACC_MIN_I32: case ACC_MIN_I64: return 0x7FFFFFFFFFFFFFFFull;
+    case ACC_MAX_I32: case ACC_MAX_I64: return 0x8000000000000000ull;
+    case ACC_MIN_I128: return word_in_acc ? 0x7FFFFFFFFFFFFFFFull : 0xFFFFFFFFFFFFFFFFull;
+    case ACC_MAX_I128: return word_in_acc ? 0x8000000000000000ull : 0ull;
+    case ACC_MIN_F64: return 0x7FF0000000000000ull;   // +inf
+    case ACC_MAX_F64: return 0xFFF0000000000000ull;   // -inf
+    default: return 0ull;
+  }
+}
+__host__ __device__ inline int acc_words_of(int op) {
+  return (op == ACC_SUM_I128 || op == ACC_MIN_I128 || op == ACC_MAX_I128) ? 2 : 1;
+}
+
+// combine value into a (private or CTA-total) accumulator held in plain memory words
+__device__ __forceinline__ void acc_combine_words(int op, uint64_t& w0, uint64_t& w1, uint64_t v0, uint64_t v1) {
+  switch (op) {
+    case ACC_SUM_I64: case ACC_COUNT: w0 += v0; break;
+    case ACC_SUM_I128: { uint64_t s = w0 + v0; w1 += v1 + (s < w0 ? 1ull : 0ull); w0 = s; break; }
+    case ACC_SUM_F64: w0 = (uint64_t)__double_as_longlong(__longlong_as_double((long long)w0) + __longlong_as_double((long long)v0)); break;
+    case ACC_MIN_I32: case ACC_MIN_I64: if ((int64_t)v0 < (int64_t)w0) w0 = v0; break;
+    case ACC_MAX_I32: case ACC_MAX_I64: if ((int64_t)v0 > (int64_t)w0) w0 = v0; break;
+    case ACC_MIN_I128: { i128 a = (i128)(((u128)w1 << 64) | w0), b = (i128)(((u128)v1 << 64) | v0); if (b < a) { w0 = v0; w1 = v1; } break; }
+    case ACC_MAX_I128: { i128 a = (i128)(((u128)w1 << 64) | w0), b = (i128)(((u128)v1 << 64) | v0); if (b > a) { w0 = v0; w1 = v1; } break; }
+    case ACC_MIN_F64: if (__longlong_as_double((long long)v0) < __longlong_as_double((long long)w0)) w0 = v0; break;
+    case ACC_MAX_F64: if (__longlong_as_double((long long)v0) > __longlong_as_double((long long)w0)) w0 = v0; break;
+    default: break;
+  }
+}
+
+// Hot-path scratch in shared memory (offsets relative to arena + A.hot_smem_off):
+//   u32  tags[G]            (padded to 8 bytes)
+//   u64  keys[G][key_words]
+//   u64  entry[G]           (global entry pointers, filled at flush)
+//   u64  priv[(G * pw + w) * NT + tid]   pw = 1 + acc_words  (word 0 = seen mask)
+struct HotView {
+  uint32_t* tags; uint64_t* keys; uint64_t* entry; uint64_t* priv; int G; int pw;
+};
+__device__ __forceinline__ HotView hot_view(const AggParams& A, uint8_t* arena) {
+  HotView h; h.G = A.hot_groups; h.pw = 1 + A.acc_words;
+  uint8_t* p = arena + A.hot_smem_off;
+  h.tags = reinterpret_cast<uint32_t*>(p); p += ((h.G * 4 + 7) & ~7);
+  h.keys = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * A.key_words * 8;
+  h.entry = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * 8;
+  h.priv = reinterpret_cast<uint64_t*>(p);
+  return h;
+}
+
+__device__ __forceinline__ int hot_lookup(const AggParams& A, const HotView& H, int hot_n, const KeyRegs& key, uint64_t h) {
+  const uint32_t tag = (uint32_t)(h >> 32);
+  for (int g = 0; g < hot_n; ++g)
+    if (H.tags[g] == tag && key_words_equal(A.keys, A.n_keys, A.has_null_word, H.keys + (size_t)g * A.key_words, key)) return g;
+  return -1;
+}
+
+template <int RPT>
+__device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParams& A, const TileCtx& c, Smem* sm) {
+  const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, P.mask_slot);
+  HotView H = hot_view(A, c.arena);
+  int8_t gid[RPT];
+  bool live[RPT];
+  if (A.hot_groups > 0) {
+    // phase A: look every live row up in the CTA-local dictionary
+    bool miss = false;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const int r = threadIdx.x + k * NT;
+      live[k] = r < c.nrows && (pact == nullptr || pact[r]);
+      gid[k] = -1;
+      if (live[k]) {
+        KeyRegs key; bool hn;
+        uint64_t h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
+        gid[k] = (int8_t)hot_lookup(A, H, sm->hot_n, key, h);
+        miss |= gid[k] < 0;
+      }
+    }
+    // phase B: grow the dictionary one group per round while there is room (rare after warm-up)
+    while (__syncthreads_or(miss && sm->hot_n < A.hot_groups)) {
+      if (threadIdx.x == 0) sm->elect = NT;
+      __syncthreads();
+      const bool want = miss && sm->hot_n < A.hot_groups;
+      if (want) atomicMin(&sm->elect, (int)threadIdx.x);
+      __syncthreads();
+      if (want && sm->elect == (int)threadIdx.x) {
+        for (int k = 0; k < RPT; ++k) {
+          if (live[k] && gid[k] < 0) {
+            const int r = threadIdx.x + k * NT;
+            KeyRegs key; bool hn;
+            uint64_t h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
+            const int g = sm->hot_n;
+            for (int w = 0; w < A.key_words; ++w) H.keys[(size_t)g * A.key_words + w] = key.w[w];
+            H.tags[g] = (uint32_t)(h >> 32);
+            sm->hot_n = g + 1;
+            break;
+          }
+        }
+      }
+      __syncthreads();
+      miss = false;
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        if (live[k] && gid[k] < 0) {
+          const int r = threadIdx.x + k * NT;
+          KeyRegs key; bool hn;
+          uint64_t h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
+          gid[k] = (int8_t)hot_lookup(A, H, sm->hot_n, key, h);
+          miss |= gid[k] < 0;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const int r = threadIdx.x + k * NT;
+      live[k] = r < c.nrows && (pact == nullptr || pact[r]);
+      gid[k] = -1;
+    }
+  }
+  // phase C: accumulate
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    if (!live[k]) continue;
+    const int r = threadIdx.x + k * NT;
+    if (gid[k] >= 0) {
+      uint64_t* base = H.priv + ((size_t)gid[k] * H.pw) * NT + threadIdx.x;
+      uint64_t seen = 0;
+      for (int j = 0; j < A.n_accs; ++j) {
+        const AccDesc& d = A.accs[j];
+        AccVal v = load_acc_value(d, c, r);
+        if (!v.valid) continue;
+        uint64_t* w0p = base + (size_t)(1 + d.word) * NT;
+        uint64_t w0 = *w0p, w1 = 0;
+        const bool wide = acc_words_of(d.op) == 2;
+        if (wide) w1 = w0p[NT];
+        uint64_t v0, v1 = 0;
+        if (d.op == ACC_COUNT) v0 = 1;
+        else if (d.op == ACC_SUM_F64 || d.op == ACC_MIN_F64 || d.op == ACC_MAX_F64) v0 = (uint64_t)__double_as_longlong(v.f);
+        else { v0 = (uint64_t)(u128)v.i; v1 = (uint64_t)((u128)v.i >> 64); }
+        acc_combine_words(d.op, w0, w1, v0, v1);
+        *w0p = w0;
+        if (wide) w0p[NT] = w1;
+        if (d.track_seen) seen |= 1ull << j;
+      }
+      if (seen) base[0] |= seen;
+    } else {
+      KeyRegs key; bool hn;
+      uint64_t h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
+      uint64_t* e = agg_find_or_insert(A, key, h, P.error_flag);
+      if (e) {
+        for (int j = 0; j < A.n_accs; ++j) acc_global(e, A, j, load_acc_value(A.accs[j], c, r));
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void hot_init(const AggParams& A, uint8_t* arena) {
+  if (A.hot_groups <= 0) return;
+  HotView H = hot_view(A, arena);
+  for (int g = 0; g < H.G; ++g) {
+    H.priv[((size_t)g * H.pw) * NT + threadIdx.x] = 0;   // seen
+    for (int j = 0; j < A.n_accs; ++j) {
+      const AccDesc& d = A.accs[j];
+      for (int w = 0; w < acc_words_of(d.op); ++w)
+        H.priv[((size_t)g * H.pw + 1 + d.word + w) * NT + threadIdx.x] = acc_identity(d.op, w);
+    }
+  }
+}
+
+// end of kernel: fold the NT thread-private copies of every hot group into the global table
+__device__ __forceinline__ void hot_flush(const PipelineParams& P, const AggParams& A, uint8_t* arena, Smem* sm) {
+  if (A.hot_groups <= 0) return;
+  __syncthreads();
+  HotView H = hot_view(A, arena);
+  const int n = sm->hot_n;
+  for (int g = threadIdx.x; g < n; g += NT) {
+    KeyRegs key;
+    for (int w = 0; w < A.key_words; ++w) key.w[w] = H.keys[(size_t)g * A.key_words + w];
+    const uint64_t h = hash_packed_key(A, key);
+    H.entry[g] = reinterpret_cast<uint64_t>(agg_find_or_insert(A, key, h, P.error_flag));
+  }
+  __syncthreads();
+  const int per = A.n_accs + 1;   // accumulators + the seen word
+  for (int p = threadIdx.x; p < n * per; p += NT) {
+    const int g = p / per, j = p % per;
+    uint64_t* e = reinterpret_cast<uint64_t*>(H.entry[g]);
+    if (!e) continue;
+    const uint64_t* base = H.priv + ((size_t)g * H.pw) * NT;
+    if (j == A.n_accs) {
+      uint64_t seen = 0;
+      for (int t = 0; t < NT; ++t) seen |= base[t];
+      if (seen) atomicOr(reinterpret_cast<unsigned long long*>(e + 1), (unsigned long long)seen);
+      continue;
+    }
+    const AccDesc& d = A.accs[j];
+    uint64_t w0 = acc_identity(d.op, 0), w1 = acc_identity(d.op, 1);
+    const bool wide = acc_words_of(d.op) == 2;
+    for (int t = 0; t < NT; ++t) {
+      uint64_t v0 = base[(size_t)(1 + d.word) * NT + t];
+      uint64_t v1 = wide ? base[(size_t)(2 + d.word) * NT + t] : 0;
+      acc_combine_words(d.op, w0, w1, v0, v1);
+    }
+    uint64_t* w = e + 2 + A.key_words + d.word;
+    switch (d.op) {
+      case ACC_SUM_I64: case ACC_COUNT: if (w0) atomicAdd(reinterpret_cast<unsigned long long*>(w), (unsigned long long)w0); break;
+      case ACC_SUM_I128: atomic_add_i128(w, (i128)(((u128)w1 << 64) | w0)); break;
+      case ACC_SUM_F64: atomicAdd(reinterpret_cast<double*>(w), __longlong_as_double((long long)w0)); break;
+      case ACC_MIN_I32: case ACC_MIN_I64: atomicMin(reinterpret_cast<long long*>(w), (long long)w0); break;
+      case ACC_MAX_I32: case ACC_MAX_I64: atomicMax(reinterpret_cast<long long*>(w), (long long)w0); break;
+      case ACC_MIN_I128: atomic_minmax_i128(w, (i128)(((u128)w1 << 64) | w0), true); break;
+      case ACC_MAX_I128: atomic_minmax_i128(w, (i128)(((u128)w1 << 64) | w0), false); break;
+      case ACC_MIN_F64: atomic_minmax_f64(w, __longlong_as_double((long long)w0), true); break;
+      case ACC_MAX_F64: atomic_minmax_f64(w, __longlong_as_double((long long)w0), false); break;
+      default: break;
+    }
+  }
+}
+
+// ================================================================================================
+// store / compact sinks
+// ================================================================================================
+__device__ __forceinline__ void store_value(const OutputCol& o, const TileCtx& c, int r, int64_t pos) {
+  const uint8_t* p = c.arena + eff(c, o.slot) + r * o.stride;
+  uint8_t* dst = o.data + pos * o.width;
+  // (slot stride, output width): 16->16 copy, 8->16 sign-extend (narrow decimal), 8->8, 4->4, 4->1/2 truncate, 8->4
+  if (o.width == 16) {
+    if (o.stride >= 16) *reinterpret_cast<ulonglong2*>(dst) = *reinterpret_cast<const ulonglong2*>(p);
+    else { int64_t v = lds<int64_t>(p); ulonglong2 w; w.x = (unsigned long long)v; w.y = (unsigned long long)(v >> 63); *reinterpret_cast<ulonglong2*>(dst) = w; }
+  } else if (o.width == 8) {
+    *reinterpret_cast<uint64_t*>(dst) = lds<uint64_t>(p);
+  } else if (o.width == 4) {
+    *reinterpret_cast<uint32_t*>(dst) = lds<uint32_t>(p);
+  } else if (o.width == 2) {
+    *reinterpret_cast<uint16_t*>(dst) = (uint16_t)lds<uint32_t>(p);
+  } else {
+    *dst = *p;
+  }
+}
+
+template <int RPT>
+__device__ __forceinline__ void sink_store(const PipelineParams& P, const TileCtx& c) {
+  const int lane = threadIdx.x & 31;
+  for (int j = 0; j < P.n_out; ++j) {
+    const OutputCol& o = P.out[j];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const int r = threadIdx.x + k * NT;
+      const bool in = r < c.nrows;
+      if (o.width) { if (in) store_value(o, c, r, c.row0 + r); }
+      else {   // boolean column -> bitmap word per 32 rows
+        const uint32_t bits = __ballot_sync(0xFFFFFFFFu, in && c.arena[eff(c, o.slot) + r]);
+        if (lane == 0 && (r - lane) < c.nrows) reinterpret_cast<uint32_t*>(o.data)[(c.row0 + r) >> 5] = bits;
+      }
+      if (o.valid_slot != NO_SLOT) {
+        const uint32_t vb = __ballot_sync(0xFFFFFFFFu, in && c.arena[eff(c, o.valid_slot) + r]);
+        if (lane == 0 && (r - lane) < c.nrows) reinterpret_cast<uint32_t*>(o.valid_bytes)[(c.row0 + r) >> 5] = vb;
+      }
+    }
+  }
+}
+
+// look-back word: bits 63..62 = 0 invalid / 1 tile aggregate / 2 inclusive prefix
+template <int RPT>
+__device__ __forceinline__ void sink_compact(const PipelineParams& P, const TileCtx& c, Smem* sm, int tile) {
+  const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, P.mask_slot);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool keep[RPT]; uint32_t before[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    keep[k] = r < c.nrows && (pact == nullptr || pact[r]);
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, keep[k]);
+    before[k] = __popc(b & ((1u << lane) - 1));
+    if (lane == 0) sm->warp_sums[k * (NT / 32) + warp] = __popc(b);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // exclusive scan of the RPT * 8 (<= 32) warp totals, in row order
+    const int n = RPT * (NT / 32);
+    uint32_t v = lane < n ? sm->warp_sums[lane] : 0, incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    if (lane < n) sm->warp_sums[lane] = incl - v;
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (lane == 0) {
+      unsigned long long excl = 0;
+      if (tile > 0) {
+        st_release_u64(P.tile_status + tile, (1ull << 62) | total);
+        int t = tile - 1;
+        for (;;) {
+          unsigned long long s = ld_acquire_u64(P.tile_status + t);
+          const unsigned long long flag = s >> 62;
+          if (flag == 0) continue;
+          excl += s & ((1ull << 62) - 1);
+          if (flag == 2 || t == 0) break;
+          --t;
+        }
+      }
+      st_release_u64(P.tile_status + tile, (2ull << 62) | (excl + total));
+      sm->tile_base = excl;
+      if ((int64_t)(tile + 1) * P.tile_rows >= P.n_rows) *P.out_count = excl + total;
+    }
+  }
+  __syncthreads();
+  const unsigned long long base = sm->tile_base;
+  for (int j = 0; j < P.n_out; ++j) {
+    const OutputCol& o = P.out[j];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      if (!keep[k]) continue;
+      const int r = threadIdx.x + k * NT;
+      const int64_t pos = (int64_t)(base + sm->warp_sums[k * (NT / 32) + warp] + before[k]);
+      if (o.width) store_value(o, c, r, pos);
+      else o.data[pos] = c.arena[eff(c, o.slot) + r];                  // boolean column as bytes (packed later)
+      if (o.valid_slot != NO_SLOT) o.valid_bytes[pos] = c.arena[eff(c, o.valid_slot) + r];
+    }
+  }
+}
+
+// ================================================================================================
+// join build sink / partition sink
+// ================================================================================================
+template <int RPT>
+__device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildParams& B, const TileCtx& c) {
+  const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, P.mask_slot);
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    if (!(r < c.nrows && (pact == nullptr || pact[r]))) continue;
+    KeyRegs key; bool has_null;
+    uint64_t h = pack_key<MAX_KEYS>(B.keys, B.n_keys, 0, c, r, key, &has_null);
+    if (has_null) continue;           // NULL keys never match (NullEqualsNothing)
+    const unsigned long long tag = h | 1ull;
+    const long long row = B.row_base + c.row0 + r;
+    uint64_t idx = (h >> 1) & B.capacity_mask;
+    for (uint64_t probes = 0; probes <= B.capacity_mask; ++probes) {
+      unsigned long long* slot = reinterpret_cast<unsigned long long*>(B.table + idx * 16);
+      unsigned long long old = atomicCAS(slot, 0ull, tag);
+      if (old == 0ull) { reinterpret_cast<long long*>(slot)[1] = row; break; }
+      if (old == tag) atomicOr(B.dup_flag, 1u);   // same hash: duplicate key (or full 64-bit collision)
+      idx = (idx + 1) & B.capacity_mask;
+    }
+  }
+}
+
+template <int RPT>
+__device__ __forceinline__ void sink_partition(const PipelineParams& P, const PartitionParams& Q, const TileCtx& c) {
+  const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, P.mask_slot);
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    if (!(r < c.nrows && (pact == nullptr || pact[r]))) continue;
+    // hash of the key columns exactly as oracle/ops.py::hash_partition_ids: h = mix64(h ^ colhash)
+    uint64_t h = 0;
+    for (int i = 0; i < Q.n_keys; ++i) {
+      const KeyDesc& d = Q.keys[i];
+      const uint8_t* p = c.arena + eff(c, d.slot) + r * d.stride;
+      uint64_t ch;
+      const bool isnull = d.valid_slot != NO_SLOT && c.arena[eff(c, d.valid_slot) + r] == 0;
+      if (isnull) ch = 0x6E756C6C6E756C6Cull;
+      else if (d.width == 16) {
+        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+        if (d.is_view) {
+          // length-seeded chain over 8-byte little-endian words of the string bytes
+          const uint32_t len = (uint32_t)v.x;
+          const uint8_t* s = view_ptr(v, p);
+          uint64_t x = len;
+          for (uint32_t o = 0; o < len; o += 8) {
+            uint64_t w = 0;
+            for (uint32_t b = 0; b < 8 && o + b < len; ++b) w |= (uint64_t)s[o + b] << (8 * b);
+            x = mix64(x ^ w);
+          }
+          ch = mix64(x);
+        } else ch = mix64(v.x ^ mix64(v.y));
+      } else if (d.width == 8) ch = mix64(lds<uint64_t>(p));
+      else if (d.width == 4) ch = mix64((uint64_t)(int64_t)lds<int32_t>(p));
+      else ch = mix64((uint64_t)*p);
+      h = mix64(h ^ ch);
+    }
+    const uint32_t pid = (uint32_t)(h % (uint64_t)Q.n_parts);
+    if (Q.pass == 0) {
+      atomicAdd(Q.part_counts + pid, 1ull);
+    } else {
+      const unsigned long long pos = Q.part_offsets[pid] + atomicAdd(Q.part_counts + pid, 1ull);
+      for (int j = 0; j < P.n_out; ++j) {
+        const OutputCol& o = P.out[j];
+        if (o.width) store_value(o, c, r, (int64_t)pos);
+        else o.data[pos] = c.arena[eff(c, o.slot) + r];
+        if (o.valid_slot != NO_SLOT) o.valid_bytes[pos] = c.arena[eff(c, o.valid_slot) + r];
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// the kernel
+// ================================================================================================
+template <int RPT>
+__global__ void __launch_bounds__(NT) pipeline_kernel(const __grid_constant__ PipelineParams P, const PipelineAux* __restrict__ aux,
+                                                      int n_stages, uint32_t stage_bytes) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  Smem* sm = reinterpret_cast<Smem*>(smem_raw);
+  VmInst* prog = reinterpret_cast<VmInst*>(smem_raw + SMEM_HDR);
+  uint8_t* arena = smem_raw + SMEM_HDR + ((P.n_inst * (int)sizeof(VmInst) + 127) & ~127);
+  const int tile_rows = RPT * NT;
+  const int64_t n_tiles = (P.n_rows + tile_rows - 1) / tile_rows;
+  const bool dynamic = P.sink == SINK_COMPACT;
+
+  for (int i = threadIdx.x; i < P.n_inst * (int)(sizeof(VmInst) / 8); i += NT)
+    reinterpret_cast<uint64_t*>(prog)[i] = reinterpret_cast<const uint64_t*>(P.prog)[i];
+  if (threadIdx.x == 0) {
+    mbar_init(&sm->full[0], 1);
+    mbar_init(&sm->full[1], 1);
+    fence_barrier_init();
+    sm->hot_n = 0;
+    sm->tile[0] = dynamic ? (int)atomicAdd(P.ticket, 1u) : (int)blockIdx.x;
+  }
+  if (P.sink == SINK_AGG) hot_init(aux->agg, arena);
+  __syncthreads();
+
+  uint32_t tma_bytes = 0;
+  for (int i = 0; i < P.n_inputs; ++i) tma_bytes += tile_bytes_of(P.in[i], tile_rows);
+
+  auto issue = [&](int64_t tile, int stage) {      // returns via side effects; uniform across the CTA
+    const int64_t row0 = tile * tile_rows;
+    const int nrows = (int)min((int64_t)tile_rows, P.n_rows - row0);
+    const uint32_t soff = (uint32_t)stage * stage_bytes;
+    if (P.use_tma && nrows == tile_rows) {
+      if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&sm->full[stage], tma_bytes);
+        for (int i = 0; i < P.n_inputs; ++i) {
+          const InputCol& in = P.in[i];
+          const uint32_t bytes = tile_bytes_of(in, tile_rows);
+          const uint8_t* src = in.data + (in.width ? (int64_t)in.width * row0 : (row0 >> 3));
+          tma_load_1d(arena + (in.slot & 0x7FFFFFFFu) + ((in.slot >> 31) ? soff : 0u), src, bytes, &sm->full[stage]);
+        }
+      }
+    } else {
+      load_tile_generic(P, arena, soff, row0, nrows);
+    }
+  };
+
+  int64_t cur = sm->tile[0];
+  uint32_t parity[2] = {0, 0};
+  int it = 0;
+  if (cur < n_tiles) issue(cur, 0);
+  for (;; ++it) {
+    if (cur >= n_tiles) break;
+    const int s = (n_stages == 2) ? (it & 1) : 0;
+    if (threadIdx.x == 0) sm->tile[(it + 1) & 1] = dynamic ? (int)atomicAdd(P.ticket, 1u) : (int)(cur + gridDim.x);
+    __syncthreads();                                          // (A) publishes next tile id, orders generic loads
+    const int64_t nxt = sm->tile[(it + 1) & 1];
+    if (n_stages == 2 && nxt < n_tiles) issue(nxt, s ^ 1);    // prefetch while this tile is computed
+    TileCtx c;
+    c.arena = arena; c.stage_off = (uint32_t)s * stage_bytes; c.row0 = cur * tile_rows;
+    c.nrows = (int)min((int64_t)tile_rows, P.n_rows - c.row0);
+    if (P.use_tma && c.nrows == tile_rows) { mbar_wait(&sm->full[s], parity[s]); parity[s] ^= 1; }
+
+    vm_exec<RPT>(prog, P.n_inst, c, P, aux);
+    switch (P.sink) {
+      case SINK_STORE: sink_store<RPT>(P, c); break;
+      case SINK_COMPACT: sink_compact<RPT>(P, c, sm, (int)cur); break;
+      case SINK_AGG: sink_agg<RPT>(P, aux->agg, c, sm); break;
+      case SINK_BUILD: sink_build<RPT>(P, aux->build, c); break;
+      case SINK_PARTITION: sink_partition<RPT>(P, aux->part, c); break;
+    }
+    __syncthreads();                                          // (B) stage s and scratch are free again
+    if (n_stages == 1 && nxt < n_tiles) { issue(nxt, 0); }
+    cur = nxt;
+  }
+  if (P.sink == SINK_AGG) hot_flush(P, aux->agg, arena, sm);
+}
+
+// ================================================================================================
+// helper kernels
+// ================================================================================================
+// grow: move every READY entry of `old` into the (larger, empty) table of `A`
+__global__ void agg_rehash_kernel(AggParams A, const uint8_t* old_table, const uint32_t* old_state, uint64_t old_capacity, uint32_t* err) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_capacity; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (old_state[i] != ST_READY) continue;
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(old_table) + i * A.entry_words;
+    KeyRegs key;
+    for (int w = 0; w < A.key_words; ++w) key.w[w] = src[2 + w];
+    uint64_t* e = agg_find_or_insert(A, key, hash_packed_key(A, key), err);
+    if (!e) continue;
+    e[1] = src[1];
+    for (int w = 0; w < A.acc_words; ++w) e[2 + A.key_words + w] = src[2 + A.key_words + w];
+  }
+}
+
+__global__ void agg_extract_kernel(AggParams A, AggExtractParams X, unsigned long long* cursor, uint32_t* err) {
+  const uint64_t cap = A.capacity_mask + 1;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t* e = reinterpret_cast<const uint64_t*>(A.table) + i * A.entry_words;
+    if (A.state[i] != ST_READY) continue;
+    const unsigned long long pos = atomicAdd(cursor, 1ull);
+    const uint64_t seen = e[1];
+    const uint64_t* kw = e + 2;
+    const uint64_t* aw = e + 2 + A.key_words;
+    for (int cidx = 0; cidx < X.n_cols; ++cidx) {
+      const AggOutCol& o = X.cols[cidx];
+      uint8_t* dst = o.data + pos * o.width;
+      bool valid = true;
+      if (o.kind == 0) {
+        if (A.has_null_word) valid = !((kw[0] >> o.a) & 1);
+        const uint64_t* s = kw + o.key_word;
+        if (o.width == 16) {
+          reinterpret_cast<uint64_t*>(dst)[0] = s[0];
+          reinterpret_cast<uint64_t*>(dst)[1] = o.src_words == 2 ? s[1] : (uint64_t)((int64_t)s[0] >> 63);
+        }
+        else if (o.width == 8) *reinterpret_cast<uint64_t*>(dst) = s[0];
+        else if (o.width == 4) *reinterpret_cast<uint32_t*>(dst) = (uint32_t)s[0];
+        else *dst = (uint8_t)s[0];
+      } else if (o.kind == 1) {
+        const AccDesc& d = A.accs[o.a];
+        if (d.track_seen) valid = (seen >> o.a) & 1;
+        const uint64_t* s = aw + d.word;
+        if (o.width == 16) {
+          uint64_t lo = s[0], hi = o.src_words == 2 ? s[1] : (uint64_t)((int64_t)s[0] >> 63);
+          reinterpret_cast<uint64_t*>(dst)[0] = valid ? lo : 0; reinterpret_cast<uint64_t*>(dst)[1] = valid ? hi : 0;
+        } else if (o.width == 8) *reinterpret_cast<uint64_t*>(dst) = valid ? s[0] : 0;
+        else if (o.width == 4) *reinterpret_cast<uint32_t*>(dst) = valid ? (uint32_t)s[0] : 0;
+        else if (o.width == 2) *reinterpret_cast<uint16_t*>(dst) = valid ? (uint16_t)s[0] : 0;
+        else *dst = valid ? (uint8_t)s[0] : 0;
+      } else {
+        const AccDesc& ds = A.accs[o.a];
+        const uint64_t cnt = aw[A.accs[o.b].word];
+        valid = cnt != 0 && (!ds.track_seen || ((seen >> o.a) & 1));
+        if (o.is_float) {
+          double sum = __longlong_as_double((long long)aw[ds.word]);
+          *reinterpret_cast<double*>(dst) = valid ? sum / (double)cnt : 0.0;
+        } else {
+          // DecimalAverager: (sum * 10^(s_out - s_in)) / count, truncating toward zero
+          i128 sum = acc_words_of(ds.op) == 2 ? (i128)(((u128)aw[ds.word + 1] << 64) | aw[ds.word]) : (i128)(int64_t)aw[ds.word];
+          i128 mul = (i128)(((u128)o.scale_mul_hi << 64) | o.scale_mul_lo);
+          i128 q = 0;
+          if (valid) q = (sum * mul) / (i128)cnt;
+          reinterpret_cast<uint64_t*>(dst)[0] = (uint64_t)(u128)q; reinterpret_cast<uint64_t*>(dst)[1] = (uint64_t)((u128)q >> 64);
+        }
+      }
+      if (o.nullable && o.valid_bytes) o.valid_bytes[pos] = valid ? 1 : 0;
+    }
+  }
+}
+
+// bytes (one per row) -> Arrow bitmap
+__global__ void pack_bytes_kernel(const uint8_t* __restrict__ bytes, uint32_t* __restrict__ bits, int64_t n, unsigned long long* null_count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_round = (n + 31) & ~31ll;
+  unsigned long long nulls = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool v = i < n && bytes[i] != 0;
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, v);
+    if (lane == 0) { bits[i >> 5] = b; }
+    if (i < n && !v) ++nulls;
+  }
+  if (null_count && nulls) atomicAdd(null_count, nulls);
+}
+
+// Arrow bitmap -> bytes (used when a nullable / boolean column must be row-addressable, e.g. join payloads)
+__global__ void unpack_bits_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ bytes, int64_t n, int64_t bit_offset) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i + bit_offset;
+    bytes[i] = (bits[b >> 3] >> (b & 7)) & 1;
+  }
+}
+
+// Utf8View import: turn (buffer_index, offset) of long views into absolute device pointers.
+__global__ void resolve_views_kernel(ulonglong2* views, int64_t n, const uint64_t* __restrict__ buffer_bases) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    ulonglong2 v = views[i];
+    if ((uint32_t)v.x > 12) {
+      const uint32_t buf = (uint32_t)v.y, off = (uint32_t)(v.y >> 32);
+      v.y = buffer_bases[buf] + off;
+      views[i] = v;
+    }
+  }
+}
+// Utf8 (offsets + bytes) -> resolved views
+__global__ void utf8_to_views_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ bytes, ulonglong2* views, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t o = offsets[i];
+    const uint32_t len = (uint32_t)(offsets[i + 1] - o);
+    const uint8_t* s = bytes + o;
+    ulonglong2 v; v.x = len; v.y = 0;
+    if (len <= 12) {
+      uint64_t a = 0, b = 0;
+      for (uint32_t k = 0; k < len && k < 4; ++k) a |= (uint64_t)s[k] << (8 * k);
+      for (uint32_t k = 4; k < len; ++k) b |= (uint64_t)s[k] << (8 * (k - 4));
+      v.x |= a << 32; v.y = b;
+    } else {
+      uint64_t a = 0;
+      for (uint32_t k = 0; k < 4; ++k) a |= (uint64_t)s[k] << (8 * k);
+      v.x |= a << 32; v.y = reinterpret_cast<uint64_t>(s);
+    }
+    views[i] = v;
+  }
+}
+// Export: lengths of long strings (0 for inline) -> exclusive scan on host side is avoided by a
+// single-block scan for small outputs or the two-pass below for large ones.
+__global__ void view_long_lengths_kernel(const ulonglong2* __restrict__ views, int64_t n, uint32_t* __restrict__ lens, int all) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t len = (uint32_t)views[i].x;
+    lens[i] = (all || len > 12) ? len : 0;
+  }
+}
+// copy long-string bytes into a compact heap at offs[i] and rewrite views to (buffer 0, offset)
+__global__ void views_to_arrow_kernel(ulonglong2* views, int64_t n, const uint64_t* __restrict__ offs, uint8_t* heap) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    ulonglong2 v = views[i];
+    const uint32_t len = (uint32_t)v.x;
+    if (len > 12) {
+      const uint8_t* s = reinterpret_cast<const uint8_t*>(v.y);
+      uint8_t* d = heap + offs[i];
+      for (uint32_t k = 0; k < len; ++k) d[k] = s[k];
+      v.y = (uint64_t)0 | (offs[i] << 32);
+      views[i] = v;
+    }
+  }
+}
+// views -> Utf8 (offsets int32 + bytes)
+__global__ void views_to_utf8_kernel(const ulonglong2* __restrict__ views, int64_t n, const uint64_t* __restrict__ offs, int32_t* out_offsets, uint8_t* heap) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* vp = reinterpret_cast<const uint8_t*>(views + i);
+    ulonglong2 v = views[i];
+    const uint32_t len = (uint32_t)v.x;
+    const uint8_t* s = len <= 12 ? vp + 4 : reinterpret_cast<const uint8_t*>(v.y);
+    uint8_t* d = heap + offs[i];
+    for (uint32_t k = 0; k < len; ++k) d[k] = s[k];
+    out_offsets[i] = (int32_t)offs[i];
+    if (i == n - 1) out_offsets[n] = (int32_t)(offs[i] + len);
+  }
+}
+
+// exclusive scan of u32 -> u64, single kernel, one CTA walking the array (outputs are small/medium;
+// large inputs use chunked partial sums: pass 1 per-block totals, pass 2 applies block offsets)
+__global__ void scan_block_totals_kernel(const uint32_t* __restrict__ in, int64_t n, uint64_t* __restrict__ block_totals, int64_t per_block) {
+  __shared__ unsigned long long ws[32];
+  const int64_t b0 = blockIdx.x * per_block, b1 = min(n, b0 + per_block);
+  unsigned long long s = 0;
+  for (int64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) s += in[i];
+  for (int d = 16; d; d >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, d);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned long long t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += ws[w]; block_totals[blockIdx.x] = t; }
+}
+__global__ void scan_apply_kernel(const uint32_t* __restrict__ in, int64_t n, const uint64_t* __restrict__ block_offsets, uint64_t* __restrict__ out, int64_t per_block) {
+  // one warp per block-chunk walks sequentially in 32-wide steps (chunks are sized so this is cheap)
+  const int64_t b0 = blockIdx.x * per_block, b1 = min(n, b0 + per_block);
+  const int lane = threadIdx.x;
+  unsigned long long run = block_offsets[blockIdx.x];
+  for (int64_t i = b0; i < b1; i += 32) {
+    const int64_t idx = i + lane;
+    const unsigned long long v = idx < b1 ? in[idx] : 0;
+    unsigned long long incl = v;
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    if (idx < b1) out[idx] = run + incl - v;
+    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+  }
+}
+
+// ================================================================================================
+// host-callable launchers (C++ linkage inside libsailgpu)
+// ================================================================================================
+cudaError_t launch_pipeline(const PipelineParams& P, const PipelineAux* aux_dev, int rpt, int n_stages, uint32_t stage_bytes,
+                            size_t smem_bytes, int grid, cudaStream_t stream) {
+  void (*k)(const PipelineParams, const PipelineAux*, int, uint32_t) = nullptr;
+  switch (rpt) {
+    case 1: k = pipeline_kernel<1>; break;
+    case 2: k = pipeline_kernel<2>; break;
+    default: k = pipeline_kernel<4>; break;
+  }
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return e;
+  k<<<grid, NT, smem_bytes, stream>>>(P, aux_dev, n_stages, stage_bytes);
+  return cudaGetLastError();
+}
+
+int pipeline_max_ctas_per_sm(int rpt, size_t smem_bytes) {
+  void (*k)(const PipelineParams, const PipelineAux*, int, uint32_t) =
+      rpt == 1 ? pipeline_kernel<1> : rpt == 2 ? pipeline_kernel<2> : pipeline_kernel<4>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, NT, smem_bytes) != cudaSuccess) return 0;
+  return n;
+}
+
+cudaError_t launch_agg_rehash(const AggParams& A, const uint8_t* old_table, const uint32_t* old_state, uint64_t old_capacity, uint32_t* err, cudaStream_t s) {
+  int grid = (int)std::min<uint64_t>((old_capacity + 255) / 256, 148 * 8);
+  agg_rehash_kernel<<<grid, 256, 0, s>>>(A, old_table, old_state, old_capacity, err);
+  return cudaGetLastError();
+}
+cudaError_t launch_agg_extract(const AggParams& A, const AggExtractParams& X, unsigned long long* cursor, uint32_t* err, cudaStream_t s) {
+  const uint64_t cap = A.capacity_mask + 1;
+  int grid = (int)std::min<uint64_t>((cap + 255) / 256, 148 * 8);
+  agg_extract_kernel<<<grid, 256, 0, s>>>(A, X, cursor, err);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_bytes(const uint8_t* bytes, uint32_t* bits, int64_t n, unsigned long long* null_count, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  pack_bytes_kernel<<<grid, 256, 0, s>>>(bytes, bits, n, null_count);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack_bits(const uint8_t* bits, uint8_t* bytes, int64_t n, int64_t bit_offset, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  unpack_bits_kernel<<<grid, 256, 0, s>>>(bits, bytes, n, bit_offset);
+  return cudaGetLastError();
+}
+cudaError_t launch_resolve_views(void* views, int64_t n, const uint64_t* bases, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  resolve_views_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<ulonglong2*>(views), n, bases);
+  return cudaGetLastError();
+}
+cudaError_t launch_utf8_to_views(const int32_t* offsets, const uint8_t* bytes, void* views, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  utf8_to_views_kernel<<<grid, 256, 0, s>>>(offsets, bytes, reinterpret_cast<ulonglong2*>(views), n);
+  return cudaGetLastError();
+}
+__global__ void scan_totals_kernel(uint64_t* t, int64_t nb) {
+  const int lane = threadIdx.x; unsigned long long run = 0;
+  for (int64_t i = 0; i < nb; i += 32) {
+    const int64_t idx = i + lane; const unsigned long long v = idx < nb ? t[idx] : 0; unsigned long long incl = v;
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += x; }
+    if (idx < nb) t[idx] = run + incl - v;
+    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+  }
+  if (lane == 0) t[nb] = run;     // grand total after the offsets
+}
+// exclusive scan of u32 lengths into u64 offsets; block_scratch[nblocks] receives the grand total
+cudaError_t launch_exclusive_scan_u32(const uint32_t* in, int64_t n, uint64_t* out, uint64_t* block_scratch /* >= 1025 u64 */, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const int64_t nblocks = std::min<int64_t>(1024, (n + 4095) / 4096);
+  const int64_t per_block = (n + nblocks - 1) / nblocks;
+  scan_block_totals_kernel<<<(int)nblocks, 256, 0, s>>>(in, n, block_scratch, per_block);
+  scan_totals_kernel<<<1, 32, 0, s>>>(block_scratch, nblocks);
+  scan_apply_kernel<<<(int)nblocks, 32, 0, s>>>(in, n, block_scratch, out, per_block);
+  return cudaGetLastError();
+}
+cudaError_t launch_view_lengths(const void* views, int64_t n, uint32_t* lens, int all, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  view_long_lengths_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const ulonglong2*>(views), n, lens, all);
+  return cudaGetLastError();
+}
+cudaError_t launch_views_to_arrow(void* views, int64_t n, const uint64_t* offs, uint8_t* heap, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  views_to_arrow_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<ulonglong2*>(views), n, offs, heap);
+  return cudaGetLastError();
+}
+cudaError_t launch_views_to_utf8(const void* views, int64_t n, const uint64_t* offs, int32_t* out_offsets, uint8_t* heap, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  views_to_utf8_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const ulonglong2*>(views), n, offs, out_offsets, heap);
+  return cudaGetLastError();
+}
+
+}  // namespace sg

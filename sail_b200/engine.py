@@ -1,0 +1,334 @@
+"""Host-side mirror of the reference's operator interface over the libsailgpu C ABI.
+
+In Sail the callers are Rust: `ExecutionPlan::execute(partition, ctx) -> SendableRecordBatchStream`
+(shape: crates/sail-execution/src/plan/shuffle_write.rs:146-206) and the stream's `poll_next`.
+The Rust toolchain is absent from this image, so this module plays that role for tests and the
+bench: `GpuExec` <-> a DataFusion `ExecutionPlan` node, `push/finish/pull` <-> what the shim's
+`poll_next` does with each child batch (INTEGRATION.md has the Rust side).  Everything below goes
+through `include/sailgpu.h` entry points with Arrow C Data Interface structs -- no torch types.
+
+There is no CPU fallback: importing works anywhere (so symbol/ABI tests run on CPU), but creating a
+`Context` without a B200 raises `GpuUnavailable`.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+
+import pyarrow as pa
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libsailgpu.so")
+
+
+class ArrowSchemaC(ctypes.Structure):
+    _fields_ = [("format", ctypes.c_char_p), ("name", ctypes.c_char_p), ("metadata", ctypes.c_char_p),
+                ("flags", ctypes.c_int64), ("n_children", ctypes.c_int64), ("children", ctypes.c_void_p),
+                ("dictionary", ctypes.c_void_p), ("release", ctypes.c_void_p), ("private_data", ctypes.c_void_p)]
+
+
+class ArrowArrayC(ctypes.Structure):
+    _fields_ = [("length", ctypes.c_int64), ("null_count", ctypes.c_int64), ("offset", ctypes.c_int64),
+                ("n_buffers", ctypes.c_int64), ("n_children", ctypes.c_int64), ("buffers", ctypes.c_void_p),
+                ("children", ctypes.c_void_p), ("dictionary", ctypes.c_void_p), ("release", ctypes.c_void_p),
+                ("private_data", ctypes.c_void_p)]
+
+
+class ArrowDeviceArrayC(ctypes.Structure):
+    _fields_ = [("array", ArrowArrayC), ("device_id", ctypes.c_int64), ("device_type", ctypes.c_int32),
+                ("sync_event", ctypes.c_void_p), ("reserved", ctypes.c_int64 * 3)]
+
+
+class SailGpuError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"[sailgpu {code}] {message}")
+        self.code = code
+
+
+class GpuUnavailable(SailGpuError):
+    pass
+
+
+ERR_NO_DEVICE = 5
+_lib = None
+
+
+def lib():
+    """Loads libsailgpu.so (built in-tree by sail_b200/build.py).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SailGpuError(-1, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        L.sailgpu_version.restype = ctypes.c_uint32
+        L.sailgpu_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
+        L.sailgpu_ctx_destroy.argtypes = [vp]
+        L.sailgpu_ctx_destroy.restype = None
+        L.sailgpu_ctx_last_error.argtypes = [vp]
+        L.sailgpu_ctx_last_error.restype = ctypes.c_char_p
+        L.sailgpu_op_create.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), i32, i32,
+                                        ctypes.POINTER(vp), vp]
+        L.sailgpu_op_push.argtypes = [vp, i32, vp]
+        L.sailgpu_op_push_device.argtypes = [vp, i32, vp]
+        L.sailgpu_op_finish_input.argtypes = [vp, i32]
+        L.sailgpu_op_pull.argtypes = [vp, vp, ctypes.POINTER(i32)]
+        L.sailgpu_op_pull_device.argtypes = [vp, vp, ctypes.POINTER(i32)]
+        L.sailgpu_op_pull_partition.argtypes = [vp, i32, vp, ctypes.POINTER(i32)]
+        L.sailgpu_op_metrics.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
+        L.sailgpu_op_metrics.restype = i64
+        L.sailgpu_last_error.argtypes = [vp]
+        L.sailgpu_last_error.restype = ctypes.c_char_p
+        L.sailgpu_op_destroy.argtypes = [vp]
+        L.sailgpu_op_destroy.restype = None
+        L.sailgpu_host_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+        L.sailgpu_host_free.argtypes = [vp, vp]
+        L.sailgpu_host_free.restype = None
+        L.sailgpu_comm_unique_id.argtypes = [ctypes.c_char_p]
+        L.sailgpu_ctx_comm_init.argtypes = [vp, ctypes.c_char_p, i32, i32]
+        L.sailgpu_exchange.argtypes = [vp, vp, vp, i32, vp]
+        _lib = L
+    return _lib
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        rc = lib().sailgpu_ctx_create(device, ctypes.byref(self._h))
+        if rc != 0:
+            msg = lib().sailgpu_ctx_last_error(None).decode()
+            raise (GpuUnavailable if rc == ERR_NO_DEVICE else SailGpuError)(rc, msg)
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().sailgpu_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        rc = lib().sailgpu_ctx_comm_init(self._h, unique_id, rank, world)
+        if rc != 0:
+            raise SailGpuError(rc, lib().sailgpu_ctx_last_error(None).decode())
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def comm_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    rc = lib().sailgpu_comm_unique_id(buf)
+    if rc != 0:
+        raise SailGpuError(rc, "sailgpu_comm_unique_id failed")
+    return buf.raw
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx
+
+
+class DeviceBatch:
+    """An Arrow C Device array (ARROW_DEVICE_CUDA) resident in HBM.  Owns the C struct until it is
+    pushed into an operator (push takes ownership) or dropped."""
+
+    def __init__(self, schema: pa.Schema):
+        self.schema = schema
+        self.c = ArrowDeviceArrayC()
+        self._live = False
+
+    @property
+    def num_rows(self) -> int:
+        return self.c.array.length
+
+    def borrow(self) -> "DeviceBatch":
+        """A second handle on the same HBM buffers whose release is a no-op: lets a resident batch be
+        pushed into many operators (each push consumes only the borrowed handle)."""
+        b = DeviceBatch(self.schema)
+        ctypes.memmove(ctypes.addressof(b.c), ctypes.addressof(self.c), ctypes.sizeof(ArrowDeviceArrayC))
+        b.c.array.release = ctypes.cast(_NOOP_RELEASE, ctypes.c_void_p).value
+        b.c.array.private_data = None
+        b._live = True
+        b._owner = self          # keep the buffers alive
+        return b
+
+    def release(self):
+        if getattr(self, "_owner", None) is not None:
+            self._live = False
+            return
+        if self._live and self.c.array.release:
+            fn = ctypes.CFUNCTYPE(None, ctypes.c_void_p)(self.c.array.release)
+            fn(ctypes.addressof(self.c.array))
+        self._live = False
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+@ctypes.CFUNCTYPE(None, ctypes.c_void_p)
+def _NOOP_RELEASE(ptr):
+    a = ArrowArrayC.from_address(ptr)
+    a.release = None
+
+
+def _export_schema(schema: pa.Schema) -> ArrowSchemaC:
+    c = ArrowSchemaC()
+    schema._export_to_c(ctypes.addressof(c))
+    return c
+
+
+def _release_schema(c: ArrowSchemaC):
+    if c.release:
+        ctypes.CFUNCTYPE(None, ctypes.c_void_p)(c.release)(ctypes.addressof(c))
+
+
+class GpuExec:
+    """One GPU operator instance (the analogue of a DataFusion ExecutionPlan node + its stream).
+
+    spec: operator spec dict (see include/sailgpu.h); inputs: list of pyarrow.Schema.
+    """
+
+    def __init__(self, spec: dict, inputs: list, ctx: Context | None = None, partition: int = 0):
+        self.ctx = ctx or default_context()
+        self.spec = spec
+        self.inputs = list(inputs)
+        text = json.dumps(spec).encode()
+        cs = [_export_schema(s) for s in inputs]
+        arr = (ctypes.c_void_p * len(cs))(*[ctypes.addressof(c) for c in cs])
+        out_schema = ArrowSchemaC()
+        self._h = ctypes.c_void_p()
+        rc = lib().sailgpu_op_create(self.ctx._h, text, len(text), arr, len(cs), partition, ctypes.byref(self._h),
+                                     ctypes.addressof(out_schema))
+        for c in cs:
+            _release_schema(c)
+        if rc != 0:
+            raise SailGpuError(rc, lib().sailgpu_ctx_last_error(None).decode())
+        self.schema = pa.Schema._import_from_c(ctypes.addressof(out_schema))
+
+    def name(self) -> str:
+        return {"filter": "GpuFilterExec", "projection": "GpuProjectionExec", "aggregate": "GpuAggregateExec",
+                "hash_join": "GpuHashJoinExec", "sort": "GpuSortExec", "repartition": "GpuRepartitionExec",
+                "pipeline": "GpuPipelineExec"}.get(self.spec.get("op"), "GpuExec")
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SailGpuError(rc, lib().sailgpu_last_error(self._h).decode())
+
+    def push(self, batch, input_idx: int = 0):
+        """batch: pyarrow RecordBatch/Table (host) or DeviceBatch (HBM)."""
+        if isinstance(batch, DeviceBatch):
+            if not batch._live:
+                raise SailGpuError(6, "device batch was already consumed")
+            self._check(lib().sailgpu_op_push_device(self._h, input_idx, ctypes.addressof(batch.c)))
+            batch._live = False
+            return
+        if isinstance(batch, pa.Table):
+            batch = batch.combine_chunks()
+            batches = batch.to_batches()
+            if not batches:
+                batches = [pa.RecordBatch.from_arrays([pa.array([], type=f.type) for f in batch.schema], schema=batch.schema)]
+            for b in batches:
+                self.push(b, input_idx)
+            return
+        c = ArrowArrayC()
+        batch._export_to_c(ctypes.addressof(c))
+        self._check(lib().sailgpu_op_push(self._h, input_idx, ctypes.addressof(c)))
+
+    def finish(self, input_idx: int = 0):
+        self._check(lib().sailgpu_op_finish_input(self._h, input_idx))
+
+    def pull(self):
+        """-> (RecordBatch, has_more)"""
+        c = ArrowArrayC()
+        more = ctypes.c_int32(0)
+        self._check(lib().sailgpu_op_pull(self._h, ctypes.addressof(c), ctypes.byref(more)))
+        sc = _export_schema(self.schema)
+        batch = pa.RecordBatch._import_from_c(ctypes.addressof(c), ctypes.addressof(sc))
+        return batch, bool(more.value)
+
+    def pull_device(self, partition: int | None = None):
+        """-> (DeviceBatch, has_more)"""
+        d = DeviceBatch(self.schema)
+        more = ctypes.c_int32(0)
+        if partition is None:
+            self._check(lib().sailgpu_op_pull_device(self._h, ctypes.addressof(d.c), ctypes.byref(more)))
+        else:
+            self._check(lib().sailgpu_op_pull_partition(self._h, partition, ctypes.addressof(d.c), ctypes.byref(more)))
+        d._live = True
+        return d, bool(more.value)
+
+    def metrics(self) -> dict:
+        buf = ctypes.create_string_buffer(2048)
+        lib().sailgpu_op_metrics(self._h, buf, 2048)
+        return json.loads(buf.value.decode())
+
+    def collect(self) -> pa.Table:
+        out = []
+        while True:
+            b, more = self.pull()
+            if b.num_rows or not more:
+                out.append(b)
+            if not more:
+                break
+        return pa.Table.from_batches(out, schema=self.schema)
+
+    def collect_device(self) -> list:
+        out = []
+        while True:
+            d, more = self.pull_device()
+            if d.num_rows or not more:
+                out.append(d)
+            if not more:
+                break
+        return out
+
+    def close(self):
+        if self._h:
+            lib().sailgpu_op_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_op(spec: dict, *tables, ctx: Context | None = None) -> pa.Table:
+    """Execute one operator over whole tables through the C ABI (host buffers in, host buffers out)."""
+    op = GpuExec(spec, [t.schema for t in tables], ctx)
+    try:
+        for i, t in enumerate(tables):
+            op.push(t, i)
+            op.finish(i)
+        return op.collect()
+    finally:
+        op.close()
+
+
+def to_device(table: pa.Table, ctx: Context | None = None) -> DeviceBatch:
+    """Upload a table once; the returned DeviceBatch is HBM-resident Arrow (used by the bench's
+    'inputs already resident in HBM' leg)."""
+    spec = {"op": "projection", "exprs": [{"expr": {"col": i}, "name": n} for i, n in enumerate(table.schema.names)]}
+    op = GpuExec(spec, [table.schema], ctx)
+    try:
+        op.push(table)
+        op.finish()
+        parts = op.collect_device()
+        assert len(parts) == 1, "to_device expects a single-chunk table"
+        d = parts[0]
+        d.schema = table.schema
+        return d
+    finally:
+        op.close()
