@@ -70,6 +70,23 @@ Val PipelineCompiler::compile_bin(const ExprPtr& e) {
   const std::string& op = e->op;
   const ExprPtr& le = e->args[0];
   const ExprPtr& re = e->args[1];
+  if (is_cmp(op) && le->type.is_string()) {
+    // literal longer than 12 bytes: dedicated op with the bytes in device memory
+    const ExprPtr* lit = (re->kind == Expr::Lit && !re->lit_null) ? &re : (le->kind == Expr::Lit && !le->lit_null) ? &le : nullptr;
+    if (lit && (*lit)->lit_s.size() > 12) {
+      Val x = ensure_slot(compile(lit == &re ? le : re));
+      Val out = temp(K_B);
+      const std::string& s = (*lit)->lit_s;
+      uint32_t prefix = 0; memcpy(&prefix, s.data(), 4);
+      VmInst I{}; I.op = OP_STR_EQ_LONG; I.aux = op == "!=" ? 1 : 0; I.dst = (uint32_t)out.slot; I.a = (uint32_t)x.slot; I.b = I.c = NO_SLOT;
+      I.sa = (uint8_t)x.stride; I.imm0 = (uint64_t)s.size() | ((uint64_t)prefix << 32);
+      literal_fixups_.push_back({(int)prog_.size(), (int)literals_.size()});
+      literals_.push_back(s);
+      prog_.push_back(I);
+      out.vslot = x.vslot;
+      return out;
+    }
+  }
   Val l = compile(le), r = compile(re);
   if (op == "and" || op == "or") {
     // Kleene logic: t = definitely true, f = definitely false
@@ -91,23 +108,8 @@ Val PipelineCompiler::compile_bin(const ExprPtr& e) {
   if (is_cmp(op)) {
     const int base = op == "=" ? OP_EQ : op == "!=" ? OP_NE : op == "<" ? OP_LT : op == "<=" ? OP_LE : op == ">" ? OP_GT : OP_GE;
     if (le->type.is_string()) {
-      // long literal (> 12 bytes): dedicated op with the bytes in device memory
-      const ExprPtr* lit = re->kind == Expr::Lit ? &re : le->kind == Expr::Lit ? &le : nullptr;
-      if (lit && (*lit)->lit_s.size() > 12) {
-        const Val& colv = lit == &re ? l : r;
-        Val x = ensure_slot(colv);
-        Val out = temp(K_B);
-        const std::string& s = (*lit)->lit_s;
-        uint32_t prefix = 0; memcpy(&prefix, s.data(), 4);
-        VmInst I{}; I.op = OP_STR_EQ_LONG; I.aux = base == OP_NE ? 1 : 0; I.dst = (uint32_t)out.slot; I.a = (uint32_t)x.slot; I.b = I.c = NO_SLOT;
-        I.sa = (uint8_t)x.stride; I.imm0 = (uint64_t)s.size() | ((uint64_t)prefix << 32);
-        literal_fixups_.push_back({(int)prog_.size(), (int)literals_.size()});
-        literals_.push_back(s);
-        prog_.push_back(I);
-        d = out;
-      } else {
-        d = emit2(base, K_V16, K_B, l, r);
-      }
+      d = emit2(base, K_V16, K_B, l, r);
+
     } else {
       SG_CHECK(l.kind == r.kind, SAILGPU_ERR_UNSUPPORTED, "comparison operands lowered to different kinds");
       d = emit2(base, l.kind, K_B, l, r);

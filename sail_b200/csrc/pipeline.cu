@@ -674,36 +674,63 @@ enum : uint32_t { ST_EMPTY = 0, ST_LOCKED = 1, ST_READY = 2 };
 __host__ __device__ inline uint64_t acc_identity(int op, int word_in_acc);
 __host__ __device__ inline int acc_words_of(int op);
 
+// state word: 0 = empty, else (tag30 << 2) | {1 = being written, 2 = ready}.  Carrying the tag in the
+// state lets a thread skip a slot that is being written for a different key without waiting on it.
 __device__ __forceinline__ uint64_t* agg_find_or_insert(const AggParams& A, const KeyRegs& key, uint64_t h, uint32_t* err) {
-  const uint32_t tag = (uint32_t)(h >> 32);
+  const uint32_t tag = (uint32_t)(h >> 34) << 2;
   uint64_t idx = h & A.capacity_mask;
   uint64_t probes = 0;
+  uint32_t spins = 0;
   while (probes <= A.capacity_mask) {
     uint64_t* e = reinterpret_cast<uint64_t*>(A.table) + idx * A.entry_words;
     uint32_t* st = A.state + idx;
     uint32_t s = ld_acquire_u32(st);
     if (s == ST_EMPTY) {
-      s = atomicCAS(st, ST_EMPTY, ST_LOCKED);
+      s = atomicCAS(st, ST_EMPTY, tag | ST_LOCKED);
       if (s == ST_EMPTY) {
-        e[0] = tag;
+        e[0] = h;
         e[1] = 0;                                                   // seen
         for (int w = 0; w < A.key_words; ++w) e[2 + w] = key.w[w];
         for (int j = 0; j < A.n_accs; ++j)
           for (int w = 0; w < acc_words_of(A.accs[j].op); ++w)
             e[2 + A.key_words + A.accs[j].word + w] = acc_identity(A.accs[j].op, w);
         __threadfence();
-        st_release_u32(st, ST_READY);
+        st_release_u32(st, tag | ST_READY);
         atomicAdd(A.n_groups, 1ull);
         return e;
       }
     }
-    if (s == ST_LOCKED) continue;     // another thread is publishing this slot: look again
-    if ((uint32_t)e[0] == tag && key_words_equal(A.keys, A.n_keys, A.has_null_word, e + 2, key)) return e;
+    if ((s & ~3u) == tag) {
+      if ((s & 3u) == ST_LOCKED) {          // same tag, still being published: look again (bounded)
+        if (++spins > (1u << 24)) { atomicOr(err, ERR_TABLE_FULL); return nullptr; }
+        __nanosleep(32);
+        continue;
+      }
+      if (e[0] == h && key_words_equal(A.keys, A.n_keys, A.has_null_word, e + 2, key)) return e;
+    }
     idx = (idx + 1) & A.capacity_mask;
     ++probes;
   }
   atomicOr(err, ERR_TABLE_FULL);
   return nullptr;
+}
+
+// Warp-cooperative front end: lanes of one warp that carry the same key hash elect a leader
+// (__match_any_sync); only leaders touch the table, followers receive the entry pointer by shuffle.
+// Removes same-warp contention on a slot that is being published.  All 32 lanes must call.
+__device__ __forceinline__ uint64_t* agg_find_or_insert_warp(const AggParams& A, const KeyRegs& key, uint64_t h, bool need, uint32_t* err) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long probe = need ? h : (0xFFFFFFFF00000000ull | lane);   // idle lanes match nobody useful
+  const unsigned peers = __match_any_sync(0xFFFFFFFFu, probe);
+  const int leader = __ffs(peers) - 1;
+  uint64_t* e = nullptr;
+  if (need && (int)lane == leader) e = agg_find_or_insert(A, key, h, err);
+  unsigned long long p = __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(e), leader);
+  uint64_t* got = reinterpret_cast<uint64_t*>(p);
+  // same hash but different key (64-bit collision inside one warp): fall back to an own lookup
+  if (need && (int)lane != leader && got && !key_words_equal(A.keys, A.n_keys, A.has_null_word, got + 2, key))
+    got = agg_find_or_insert(A, key, h, err);
+  return need ? got : nullptr;
 }
 
 // hash of an already packed key (same value pack_key() returns for the row it was packed from)
@@ -910,12 +937,14 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
       gid[k] = -1;
     }
   }
-  // phase C: accumulate
+  // phase C: accumulate.  Hot rows update thread-private accumulators; cold rows go to the global
+  // table, one warp-cooperative lookup per row slot (every lane of the warp takes part).
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
-    if (!live[k]) continue;
     const int r = threadIdx.x + k * NT;
-    if (gid[k] >= 0) {
+    const bool hot = live[k] && gid[k] >= 0;
+    const bool cold = live[k] && gid[k] < 0;
+    if (hot) {
       uint64_t* base = H.priv + ((size_t)gid[k] * H.pw) * NT + threadIdx.x;
       uint64_t seen = 0;
       for (int j = 0; j < A.n_accs; ++j) {
@@ -936,11 +965,12 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
         if (d.track_seen) seen |= 1ull << j;
       }
       if (seen) base[0] |= seen;
-    } else {
-      KeyRegs key; bool hn;
-      uint64_t h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
-      uint64_t* e = agg_find_or_insert(A, key, h, P.error_flag);
-      if (e) {
+    }
+    if (__any_sync(0xFFFFFFFFu, cold)) {
+      KeyRegs key; bool hn; uint64_t h = 0;
+      if (cold) h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
+      uint64_t* e = agg_find_or_insert_warp(A, key, h, cold, P.error_flag);
+      if (cold && e) {
         for (int j = 0; j < A.n_accs; ++j) acc_global(e, A, j, load_acc_value(A.accs[j], c, r));
       }
     }
@@ -1080,10 +1110,11 @@ __device__ __forceinline__ void sink_compact(const PipelineParams& P, const Tile
       if (tile > 0) {
         st_release_u64(P.tile_status + tile, (1ull << 62) | total);
         int t = tile - 1;
+        uint32_t spins = 0;
         for (;;) {
           unsigned long long s = ld_acquire_u64(P.tile_status + t);
           const unsigned long long flag = s >> 62;
-          if (flag == 0) continue;
+          if (flag == 0) { if (++spins > (1u << 26)) __trap(); continue; }
           excl += s & ((1ull << 62) - 1);
           if (flag == 2 || t == 0) break;
           --t;
@@ -1269,7 +1300,7 @@ __global__ void __launch_bounds__(NT) pipeline_kernel(const __grid_constant__ Pi
 // grow: move every READY entry of `old` into the (larger, empty) table of `A`
 __global__ void agg_rehash_kernel(AggParams A, const uint8_t* old_table, const uint32_t* old_state, uint64_t old_capacity, uint32_t* err) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_capacity; i += (uint64_t)gridDim.x * blockDim.x) {
-    if (old_state[i] != ST_READY) continue;
+    if ((old_state[i] & 3u) != ST_READY) continue;
     const uint64_t* src = reinterpret_cast<const uint64_t*>(old_table) + i * A.entry_words;
     KeyRegs key;
     for (int w = 0; w < A.key_words; ++w) key.w[w] = src[2 + w];
@@ -1284,7 +1315,7 @@ __global__ void agg_extract_kernel(AggParams A, AggExtractParams X, unsigned lon
   const uint64_t cap = A.capacity_mask + 1;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t* e = reinterpret_cast<const uint64_t*>(A.table) + i * A.entry_words;
-    if (A.state[i] != ST_READY) continue;
+    if ((A.state[i] & 3u) != ST_READY) continue;
     const unsigned long long pos = atomicAdd(cursor, 1ull);
     const uint64_t seen = e[1];
     const uint64_t* kw = e + 2;
