@@ -138,6 +138,11 @@ SAILGPU_API void sailgpu_ctx_destroy(sailgpu_ctx* ctx);
 /* last error message of a failed ctx-level call (thread-local copy, valid until next call) */
 SAILGPU_API const char* sailgpu_ctx_last_error(const sailgpu_ctx* ctx);
 
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is ordered on, so callers can
+ * bracket work with their own CUDA events; and a full synchronisation of that stream. */
+SAILGPU_API void* sailgpu_ctx_stream(sailgpu_ctx* ctx);
+SAILGPU_API int32_t sailgpu_ctx_synchronize(sailgpu_ctx* ctx);
+
 /* NCCL communicator for the hash-repartition exchange (one rank per GPU/process).
  * unique_id: 128 bytes obtained from sailgpu_comm_unique_id on rank 0 and distributed out of band
  * (the Rust shim sends it in the RunTask message; tests use torch.distributed's store). */

@@ -15,8 +15,11 @@ struct sailgpu_op {
   std::vector<bool> input_finished;
 };
 
+namespace sg { std::atomic<bool> g_exiting{false}; }
+
 namespace {
 thread_local std::string g_ctx_error;
+void mark_exiting() { sg::g_exiting.store(true); }
 
 template <typename F>
 int32_t guard(std::string* err, F&& f) {
@@ -46,6 +49,8 @@ SAILGPU_API int32_t sailgpu_ctx_create(int32_t device, sailgpu_ctx** out) {
     if (e != cudaSuccess || n == 0)
       fail(SAILGPU_ERR_NO_DEVICE, std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); libsailgpu has no CPU fallback");
     SG_CHECK(device >= 0 && device < n, SAILGPU_ERR_INVALID, "device ordinal out of range");
+    static const int hooked = std::atexit(mark_exiting);
+    (void)hooked;
     auto c = std::make_unique<sailgpu_ctx>();
     c->ctx.device = device;
     SG_CUDA(cudaSetDevice(device));
@@ -66,6 +71,7 @@ SAILGPU_API int32_t sailgpu_ctx_create(int32_t device, sailgpu_ctx** out) {
 
 SAILGPU_API void sailgpu_ctx_destroy(sailgpu_ctx* c) {
   if (!c) return;
+  if (sg::g_exiting.load()) return;
   cudaSetDevice(c->ctx.device);
   if (c->ctx.stream) { cudaStreamSynchronize(c->ctx.stream); cudaStreamDestroy(c->ctx.stream); }
   if (c->ctx.copy_stream) cudaStreamDestroy(c->ctx.copy_stream);
@@ -73,6 +79,15 @@ SAILGPU_API void sailgpu_ctx_destroy(sailgpu_ctx* c) {
 }
 
 SAILGPU_API const char* sailgpu_ctx_last_error(const sailgpu_ctx*) { return g_ctx_error.c_str(); }
+
+SAILGPU_API void* sailgpu_ctx_stream(sailgpu_ctx* c) { return c ? (void*)c->ctx.stream : nullptr; }
+SAILGPU_API int32_t sailgpu_ctx_synchronize(sailgpu_ctx* c) {
+  return guard(&g_ctx_error, [&] {
+    SG_CHECK(c != nullptr, SAILGPU_ERR_INVALID, "null context");
+    set_device(c->ctx);
+    SG_CUDA(cudaStreamSynchronize(c->ctx.stream));
+  });
+}
 
 SAILGPU_API int32_t sailgpu_op_create(sailgpu_ctx* c, const char* spec_json, size_t spec_len, const struct ArrowSchema* const* input_schemas,
                           int32_t n_inputs, int32_t partition, sailgpu_op** out, struct ArrowSchema* out_schema) {
@@ -149,17 +164,20 @@ SAILGPU_API int32_t sailgpu_op_pull_partition(sailgpu_op* h, int32_t part, struc
 
 SAILGPU_API int64_t sailgpu_op_metrics(sailgpu_op* h, char* json_buf, size_t cap) {
   if (!h) return -1;
+  cudaSetDevice(h->owner->ctx.device);
   const Metrics& m = h->op->m;
   char tmp[1024];
   int n = snprintf(tmp, sizeof(tmp),
                    "{\"output_rows\":%llu,\"output_batches\":%llu,\"input_rows\":%llu,\"input_batches\":%llu,"
                    "\"elapsed_compute\":%llu,\"build_input_rows\":%llu,\"build_input_batches\":%llu,\"build_time\":%llu,"
-                   "\"join_time\":%llu,\"gpu.kernel_launches\":%llu,\"gpu.h2d_bytes\":%llu,\"gpu.d2h_bytes\":%llu}",
+                   "\"join_time\":%llu,\"gpu.kernel_launches\":%llu,\"gpu.h2d_bytes\":%llu,\"gpu.d2h_bytes\":%llu,"
+                   "\"gpu.pipeline_launches\":%llu,\"gpu.pipeline_kernel_ns\":%llu}",
                    (unsigned long long)m.output_rows, (unsigned long long)m.output_batches, (unsigned long long)m.input_rows,
                    (unsigned long long)m.input_batches, (unsigned long long)m.elapsed_compute_ns, (unsigned long long)m.build_input_rows,
                    (unsigned long long)m.build_input_batches, (unsigned long long)m.build_time_ns, (unsigned long long)m.join_time_ns,
                    (unsigned long long)m.kernel_launches, (unsigned long long)h->owner->ctx.h2d_bytes.load(),
-                   (unsigned long long)h->owner->ctx.d2h_bytes.load());
+                   (unsigned long long)h->owner->ctx.d2h_bytes.load(), (unsigned long long)h->op->m.pipeline_launches,
+                   (unsigned long long)h->op->pipeline_kernel_ns());
   if (json_buf && cap) { size_t k = std::min<size_t>((size_t)n, cap - 1); memcpy(json_buf, tmp, k); json_buf[k] = 0; }
   return n + 1;
 }
@@ -168,6 +186,7 @@ SAILGPU_API const char* sailgpu_last_error(const sailgpu_op* h) { return h ? h->
 
 SAILGPU_API void sailgpu_op_destroy(sailgpu_op* h) {
   if (!h) return;
+  if (sg::g_exiting.load()) return;
   cudaSetDevice(h->owner->ctx.device);
   cudaStreamSynchronize(h->owner->ctx.stream);
   delete h;

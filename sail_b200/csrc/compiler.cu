@@ -313,7 +313,7 @@ void PipelineCompiler::finish_aggregate(CompiledPipeline& out, const StageSpec& 
     AccDesc d{}; d.op = (uint8_t)op; d.vkind = (uint8_t)vkind; d.stride = (uint8_t)stride;
     d.value_slot = vslot >= 0 ? (uint32_t)vslot : NO_SLOT; d.valid_slot = valid >= 0 ? (uint32_t)valid : NO_SLOT;
     d.track_seen = (op != ACC_COUNT && (valid >= 0 || A.n_keys == 0)) ? 1 : 0;
-    d.word = (uint32_t)words;
+    d.word = (uint16_t)words;
     words += (op == ACC_SUM_I128 || op == ACC_MIN_I128 || op == ACC_MAX_I128) ? 2 : 1;
     A.accs[A.n_accs] = d;
     dedup[key] = A.n_accs;
@@ -388,6 +388,40 @@ void PipelineCompiler::finish_aggregate(CompiledPipeline& out, const StageSpec& 
   }
   A.acc_words = words;
   A.entry_words = (uint32_t)(2 + A.key_words + A.acc_words);
+  // thread-private layout: [seen?][one word per accumulator; two for 128-bit min/max]
+  bool any_seen = false;
+  for (int j = 0; j < A.n_accs; ++j) any_seen |= A.accs[j].track_seen != 0;
+  A.priv_seen = any_seen ? 1 : 0;
+  int pw = A.priv_seen;
+  for (int j = 0; j < A.n_accs; ++j) {
+    A.accs[j].pword = (uint16_t)pw;
+    pw += (A.accs[j].op == ACC_MIN_I128 || A.accs[j].op == ACC_MAX_I128) ? 2 : 1;
+  }
+  A.priv_words = pw;
+  // integer fast path: every accumulator is a count or an integer/decimal sum without validity-dependent
+  // NULL results, and few enough to live in registers
+  {
+    bool ok = A.n_accs <= REG_ACCS && getenv("SAILGPU_NO_REGPATH") == nullptr;
+    for (int j = 0; j < A.n_accs; ++j) {
+      const int op = A.accs[j].op;
+      ok &= (op == ACC_COUNT || op == ACC_SUM_I64 || op == ACC_SUM_I128) && !A.accs[j].track_seen;
+      ok &= A.accs[j].vkind != K_F64;
+    }
+    A.reg_path = ok ? 1 : 0;
+  }
+  // word-wise key loading plan
+  {
+    int w = A.has_null_word;
+    for (int i = 0; i < A.n_keys; ++i) {
+      const KeyDesc& k = A.keys[i];
+      const int nw = k.width == 16 ? 2 : 1;
+      for (int q = 0; q < nw; ++q) {
+        KeyWord kwd{}; kwd.slot = k.slot; kwd.valid_slot = k.valid_slot; kwd.stride = k.stride; kwd.key_index = (uint8_t)i;
+        kwd.width = (uint8_t)(k.width == 16 ? 8 : k.width); kwd.byte_off = (uint8_t)(q * 8);
+        A.kwords[w++] = kwd;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -397,9 +431,11 @@ static int env_int(const char* name, int dflt) { const char* v = getenv(name); r
 
 void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted) {
   const size_t budget = ctx->max_smem;
-  const size_t fixed = 256 + ((prog_.size() * sizeof(VmInst) + 127) & ~(size_t)127);
+  const size_t fixed = 256;
+  SG_CHECK(prog_.size() <= (size_t)MAX_INST, SAILGPU_ERR_UNSUPPORTED, "fused pipeline needs more than " + std::to_string(MAX_INST) + " VM instructions");
   const AggParams& A = out.agg;
-  const size_t per_group = out.sink == SINK_AGG ? (size_t)NT * (1 + A.acc_words) * 8 + (size_t)A.key_words * 8 + 8 + 8 : 0;
+  // per hot group: key words + fingerprint + entry pointer + one accumulator block per warp
+  const size_t per_group = out.sink == SINK_AGG ? (size_t)A.key_words * 8 + 16 + (size_t)(NT / 32) * (1 + 2 * A.n_accs) * 8 : 0;
   auto layout = [&](int rpt, int stages, uint32_t* temps, uint32_t* stage) {
     const uint32_t tile = (uint32_t)rpt * NT;
     uint32_t t = 0, s = 0;
@@ -411,7 +447,7 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
     return fixed + *temps + (size_t)stages * s;
   };
   const int force_rpt = env_int("SAILGPU_RPT", 0), force_stages = env_int("SAILGPU_STAGES", 0), force_hot = env_int("SAILGPU_HOT", -1);
-  const int cands[][2] = {{2, 2}, {4, 2}, {1, 2}, {2, 1}, {4, 1}, {1, 1}};
+  const int cands[][2] = {{2, 1}, {1, 2}, {2, 2}, {1, 1}, {4, 1}, {4, 2}};   // measured order on B200 (scripts/sweep_q1.py)
   int best_rpt = 0, best_stages = 0, best_hot = 0;
   if (hot_wanted > 0 && force_hot >= 0) hot_wanted = force_hot;
   for (int pass = 0; pass < 2 && !best_rpt; ++pass) {
@@ -463,6 +499,7 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
   if (out.sink == SINK_AGG) {
     AggParams& AA = out.agg;
     for (int i = 0; i < AA.n_keys; ++i) { AA.keys[i].slot = off(AA.keys[i].slot); AA.keys[i].valid_slot = off(AA.keys[i].valid_slot); }
+    for (int w = AA.has_null_word; w < AA.key_words; ++w) { AA.kwords[w].slot = off(AA.kwords[w].slot); AA.kwords[w].valid_slot = off(AA.kwords[w].valid_slot); }
     for (int j = 0; j < AA.n_accs; ++j) { AA.accs[j].value_slot = off(AA.accs[j].value_slot); AA.accs[j].valid_slot = off(AA.accs[j].valid_slot); }
     AA.hot_groups = best_hot;
     AA.hot_smem_off = temps;

@@ -34,6 +34,9 @@ struct Ctx {
   std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};
 };
 
+// set by an atexit hook: CUDA may already be torn down when late destructors run at process exit
+extern std::atomic<bool> g_exiting;
+
 // A reference-counted HBM allocation (stream-ordered pool) or a borrowed foreign pointer.
 struct DevBuf {
   void* ptr = nullptr;
@@ -41,6 +44,7 @@ struct DevBuf {
   Ctx* ctx = nullptr;
   std::function<void()> on_release;   // borrowed buffers: drop the producer's reference
   ~DevBuf() {
+    if (g_exiting.load()) return;
     if (on_release) on_release();
     else if (ptr && ctx) cudaFreeAsync(ptr, ctx->stream);
   }

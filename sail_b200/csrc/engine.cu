@@ -106,9 +106,11 @@ void check_device_error(Ctx* ctx, uint32_t* dev_flag) {
 // launching one compiled pipeline over one batch
 // ------------------------------------------------------------------------------------------------
 struct DevProgram {
-  BufPtr prog, literals, aux;
+  BufPtr literals;
   std::vector<uint64_t> literal_ptrs;
 };
+
+static bool timing_enabled() { static const bool on = getenv("SAILGPU_TIMING") != nullptr; return on; }
 
 struct PipelineRunner {
   Ctx* ctx;
@@ -155,7 +157,7 @@ struct PipelineRunner {
     return cp;
   }
 
-  DevProgram& program_for(const std::shared_ptr<CompiledPipeline>& cp, const PipelineAux* aux_host) {
+  DevProgram& program_for(const std::shared_ptr<CompiledPipeline>& cp) {
     auto it = programs.find(cp.get());
     if (it == programs.end()) {
       DevProgram dp;
@@ -169,17 +171,13 @@ struct PipelineRunner {
         dp.literal_ptrs.push_back(reinterpret_cast<uint64_t>(dp.literals->ptr) + off);
         off += (s.size() + 15) & ~(size_t)15;
       }
-      SG_CUDA(cudaMemcpyAsync(dp.literals->ptr, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
-      std::vector<VmInst> prog = cp->prog;
-      for (auto& fx : cp->literal_fixups) prog[(size_t)fx.first].imm1 = dp.literal_ptrs[(size_t)fx.second];
-      dp.prog = dev_alloc(ctx, prog.size() * sizeof(VmInst) + 64);
-      SG_CUDA(cudaMemcpyAsync(dp.prog->ptr, prog.data(), prog.size() * sizeof(VmInst), cudaMemcpyHostToDevice, ctx->stream));
-      dp.aux = dev_alloc(ctx, sizeof(PipelineAux));
-      SG_CUDA(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
-      cp->prog = prog;                                // keep patched copy (GATHER pointers are patched per launch)
+      if (!cp->literals.empty()) {
+        SG_CUDA(cudaMemcpyAsync(dp.literals->ptr, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+        SG_CUDA(cudaStreamSynchronize(ctx->stream));   // host blob goes out of scope
+      }
+      for (auto& fx : cp->literal_fixups) cp->prog[(size_t)fx.first].imm1 = dp.literal_ptrs[(size_t)fx.second];
       it = programs.emplace(cp.get(), std::move(dp)).first;
     }
-    if (aux_host) SG_CUDA(cudaMemcpyAsync(it->second.aux->ptr, aux_host, sizeof(PipelineAux), cudaMemcpyHostToDevice, ctx->stream));
     return it->second;
   }
 
@@ -211,15 +209,54 @@ struct PipelineRunner {
     P.use_tma = tma ? 1 : 0;
   }
 
+  static uint32_t rs(uint32_t off, uint32_t add) { return off == NO_SLOT ? NO_SLOT : (off & 0x7FFFFFFFu) + ((off >> 31) ? add : 0u); }
+  static void rs_key(KeyDesc& k, uint32_t add) { k.slot = rs(k.slot, add); k.valid_slot = rs(k.valid_slot, add); }
+
+  // Builds the kernel argument block: program, descriptors and parameters resolved for both stages.
   void launch(PipelineParams& P, const std::shared_ptr<CompiledPipeline>& cp, const PipelineAux* aux_host, Metrics& m) {
-    DevProgram& dp = program_for(cp, aux_host);
-    P.prog = static_cast<const VmInst*>(dp.prog->ptr);
+    program_for(cp);
     const int64_t n_tiles = (P.n_rows + P.tile_rows - 1) / P.tile_rows;
     if (n_tiles == 0) return;
+    P.prog = nullptr;
+    auto K = std::make_unique<KernelArgs>();
+    memset(K.get(), 0, sizeof(KernelArgs));
+    for (int st = 0; st < 2; ++st) {
+      const uint32_t add = (uint32_t)st * cp->stage_bytes;
+      PipelineParams& Q = K->P[st];
+      Q = P;
+      Q.mask_slot = rs(P.mask_slot, add);
+      for (int i = 0; i < Q.n_inputs; ++i) Q.in[i].slot = rs(P.in[i].slot, add);
+      for (int j = 0; j < Q.n_out; ++j) { Q.out[j].slot = rs(P.out[j].slot, add); Q.out[j].valid_slot = rs(P.out[j].valid_slot, add); }
+      for (size_t i = 0; i < cp->prog.size(); ++i) {
+        VmInst I = cp->prog[i];
+        I.dst = rs(I.dst, add); I.a = rs(I.a, add); I.b = rs(I.b, add); I.c = rs(I.c, add);
+        K->prog[st][i] = I;
+      }
+      if (aux_host) {
+        PipelineAux& A = K->aux[st];
+        A = *aux_host;
+        for (int i = 0; i < A.agg.n_keys; ++i) rs_key(A.agg.keys[i], add);
+        for (int w = 0; w < A.agg.key_words; ++w) { A.agg.kwords[w].slot = rs(A.agg.kwords[w].slot, add); A.agg.kwords[w].valid_slot = rs(A.agg.kwords[w].valid_slot, add); }
+        for (int j = 0; j < A.agg.n_accs; ++j) { A.agg.accs[j].value_slot = rs(A.agg.accs[j].value_slot, add); A.agg.accs[j].valid_slot = rs(A.agg.accs[j].valid_slot, add); }
+        for (int i = 0; i < A.build.n_keys; ++i) rs_key(A.build.keys[i], add);
+        for (int i = 0; i < A.part.n_keys; ++i) rs_key(A.part.keys[i], add);
+        A.part.pid_slot = rs(A.part.pid_slot, add);
+        for (int q = 0; q < MAX_PROBES; ++q) {
+          for (int i = 0; i < A.probe[q].n_keys; ++i) rs_key(A.probe[q].keys[i], add);
+          A.probe[q].rowid_slot = rs(A.probe[q].rowid_slot, add);
+          A.probe[q].match_slot = rs(A.probe[q].match_slot, add);
+        }
+      }
+    }
     int per_sm = std::max(1, (int)(ctx->max_smem / (cp->smem_bytes + 1024)));
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * per_sm);
-    SG_CUDA(launch_pipeline(P, static_cast<const PipelineAux*>(dp.aux->ptr), cp->rpt, cp->n_stages, cp->stage_bytes, cp->smem_bytes, grid, ctx->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool timed = timing_enabled();
+    if (timed) { SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1)); SG_CUDA(cudaEventRecord(e0, ctx->stream)); }
+    SG_CUDA(launch_pipeline(*K, cp->rpt, cp->n_stages, cp->smem_bytes, grid, ctx->stream));
+    if (timed) { SG_CUDA(cudaEventRecord(e1, ctx->stream)); m.pending.emplace_back(e0, e1); }
     m.kernel_launches++;
+    m.pipeline_launches++;
   }
 };
 

@@ -15,6 +15,8 @@ struct Metrics {
   uint64_t input_rows = 0, input_batches = 0, output_rows = 0, output_batches = 0;
   uint64_t elapsed_compute_ns = 0, kernel_launches = 0;
   uint64_t build_input_rows = 0, build_input_batches = 0, build_time_ns = 0, join_time_ns = 0;
+  uint64_t pipeline_launches = 0, pipeline_kernel_ns = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;   // CUDA events bracketing each pipeline-kernel launch
 };
 
 struct Op {
@@ -24,7 +26,18 @@ struct Op {
   std::string last_error;
   std::string kind;
   Metrics m;
-  virtual ~Op() {}
+  virtual ~Op() { if (!g_exiting.load()) for (auto& p : m.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
+  // device time spent inside pipeline_kernel launches (resolves the pending event pairs; synchronises them)
+  uint64_t pipeline_kernel_ns() {
+    for (auto& p : m.pending) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(p.second) == cudaSuccess && cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess)
+        m.pipeline_kernel_ns += (uint64_t)((double)ms * 1e6);
+      cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+    }
+    m.pending.clear();
+    return m.pipeline_kernel_ns;
+  }
   virtual void push(int input, const BatchPtr& b) = 0;
   virtual void finish(int input) = 0;
   // returns has_more; *out == nullptr when nothing is ready yet

@@ -23,8 +23,7 @@ struct AggExtractParams {
   AggOutCol cols[MAX_KEYS + 2 * MAX_ACCS];
 };
 
-cudaError_t launch_pipeline(const PipelineParams& P, const PipelineAux* aux_dev, int rpt, int n_stages, uint32_t stage_bytes,
-                            size_t smem_bytes, int grid, cudaStream_t stream);
+cudaError_t launch_pipeline(const KernelArgs& K, int rpt, int n_stages, size_t smem_bytes, int grid, cudaStream_t stream);
 int pipeline_max_ctas_per_sm(int rpt, size_t smem_bytes);
 cudaError_t launch_agg_rehash(const AggParams& A, const uint8_t* old_table, const uint32_t* old_state, uint64_t old_capacity, uint32_t* err, cudaStream_t s);
 cudaError_t launch_agg_extract(const AggParams& A, const AggExtractParams& X, unsigned long long* cursor, uint32_t* err, cudaStream_t s);

@@ -32,9 +32,8 @@ struct TileCtx {
   int nrows;               // valid rows of this tile
   int64_t row0;
 };
-__device__ __forceinline__ uint32_t eff(const TileCtx& c, uint32_t off) {
-  return (off & 0x7FFFFFFFu) + ((off >> 31) ? c.stage_off : 0u);
-}
+// offsets arrive pre-resolved per stage (KernelArgs): nothing to compute on the device
+__device__ __forceinline__ uint32_t eff(const TileCtx&, uint32_t off) { return off; }
 
 // ================================================================================================
 // tile VM
@@ -66,33 +65,48 @@ struct CmpLe { template <typename T> static __device__ __forceinline__ bool f(T 
 struct CmpGt { template <typename T> static __device__ __forceinline__ bool f(T a, T b) { return a > b; } };
 struct CmpGe { template <typename T> static __device__ __forceinline__ bool f(T a, T b) { return a >= b; } };
 
-template <int RPT, typename T, typename F>
-__device__ __forceinline__ void vm_bin(const VmInst& I, const TileCtx& c) {
+// Operands of all RPT rows are loaded first, then computed, then stored: shared-memory loads of
+// different rows may alias the stores as far as the compiler knows, so interleaving them would
+// serialise the rows; batching exposes RPT independent dependency chains per instruction.
+template <int RPT, typename T, bool IA, bool IB>
+__device__ __forceinline__ void vm_load2(const VmInst& I, const TileCtx& c, T (&a)[RPT], T (&b)[RPT]) {
   const T imm = ImmOf<T>::get(I);
-  const uint8_t* pa = c.arena + eff(c, I.a);
-  const uint8_t* pb = c.arena + eff(c, I.b);
-  uint8_t* pd = c.arena + eff(c, I.dst);
+  const uint8_t* pa = c.arena + eff(c, I.a) + threadIdx.x * I.sa;
+  const uint8_t* pb = c.arena + eff(c, I.b) + threadIdx.x * I.sb;
+  const int sa = I.sa * NT, sb = I.sb * NT;
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
-    const int r = threadIdx.x + k * NT;
-    T a = (I.flags & F_IMM_A) ? imm : lds<T>(pa + r * I.sa);
-    T b = (I.flags & F_IMM_B) ? imm : lds<T>(pb + r * I.sb);
-    sts<T>(pd + r * (int)sizeof(T), F::template f<T>(a, b));
+    a[k] = IA ? imm : lds<T>(pa + k * sa);
+    b[k] = IB ? imm : lds<T>(pb + k * sb);
   }
+}
+template <int RPT, typename T, typename F, bool IA, bool IB>
+__device__ __forceinline__ void vm_bin_i(const VmInst& I, const TileCtx& c) {
+  T a[RPT], b[RPT];
+  vm_load2<RPT, T, IA, IB>(I, c, a, b);
+  uint8_t* pd = c.arena + eff(c, I.dst) + threadIdx.x * (int)sizeof(T);
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) sts<T>(pd + k * NT * (int)sizeof(T), F::template f<T>(a[k], b[k]));
+}
+template <int RPT, typename T, typename F>
+__device__ __forceinline__ void vm_bin(const VmInst& I, const TileCtx& c) {
+  if (I.flags & F_IMM_B) vm_bin_i<RPT, T, F, false, true>(I, c);
+  else if (I.flags & F_IMM_A) vm_bin_i<RPT, T, F, true, false>(I, c);
+  else vm_bin_i<RPT, T, F, false, false>(I, c);
+}
+template <int RPT, typename T, typename F, bool IA, bool IB>
+__device__ __forceinline__ void vm_cmp_i(const VmInst& I, const TileCtx& c) {
+  T a[RPT], b[RPT];
+  vm_load2<RPT, T, IA, IB>(I, c, a, b);
+  uint8_t* pd = c.arena + eff(c, I.dst) + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) pd[k * NT] = F::template f<T>(a[k], b[k]) ? 1 : 0;
 }
 template <int RPT, typename T, typename F>
 __device__ __forceinline__ void vm_cmp(const VmInst& I, const TileCtx& c) {
-  const T imm = ImmOf<T>::get(I);
-  const uint8_t* pa = c.arena + eff(c, I.a);
-  const uint8_t* pb = c.arena + eff(c, I.b);
-  uint8_t* pd = c.arena + eff(c, I.dst);
-#pragma unroll
-  for (int k = 0; k < RPT; ++k) {
-    const int r = threadIdx.x + k * NT;
-    T a = (I.flags & F_IMM_A) ? imm : lds<T>(pa + r * I.sa);
-    T b = (I.flags & F_IMM_B) ? imm : lds<T>(pb + r * I.sb);
-    pd[r] = F::template f<T>(a, b) ? 1 : 0;
-  }
+  if (I.flags & F_IMM_B) vm_cmp_i<RPT, T, F, false, true>(I, c);
+  else if (I.flags & F_IMM_A) vm_cmp_i<RPT, T, F, true, false>(I, c);
+  else vm_cmp_i<RPT, T, F, false, false>(I, c);
 }
 template <int RPT, typename F>
 __device__ __forceinline__ void vm_bin_kind(const VmInst& I, int kind, const TileCtx& c) {
@@ -118,7 +132,7 @@ __device__ __forceinline__ void vm_cmp_kind(const VmInst& I, int kind, const Til
 
 // views: equality only (ordering comparisons on strings are rejected by the compiler)
 template <int RPT>
-__device__ __forceinline__ void vm_view_eq(const VmInst& I, const TileCtx& c, bool negate) {
+__device__ __noinline__ void vm_view_eq(const VmInst& I, const TileCtx& c, bool negate) {
   const uint8_t* pa = c.arena + eff(c, I.a);
   const uint8_t* pb = c.arena + eff(c, I.b);
   uint8_t* pd = c.arena + eff(c, I.dst);
@@ -136,7 +150,7 @@ __device__ __forceinline__ void vm_view_eq(const VmInst& I, const TileCtx& c, bo
 template <typename T> __device__ __forceinline__ T trunc_div(T a, T b) { return a / b; }
 
 template <int RPT, typename T, bool REM>
-__device__ __forceinline__ void vm_div(const VmInst& I, const TileCtx& c, uint32_t* err) {
+__device__ __noinline__ void vm_div(const VmInst& I, const TileCtx& c, uint32_t* err) {
   const T imm = ImmOf<T>::get(I);
   const uint8_t* pa = c.arena + eff(c, I.a);
   const uint8_t* pb = c.arena + eff(c, I.b);
@@ -158,7 +172,7 @@ __device__ __forceinline__ void vm_div(const VmInst& I, const TileCtx& c, uint32
   }
 }
 template <int RPT>
-__device__ __forceinline__ void vm_div_f64(const VmInst& I, const TileCtx& c, bool rem) {
+__device__ __noinline__ void vm_div_f64(const VmInst& I, const TileCtx& c, bool rem) {
   const double imm = ImmOf<double>::get(I);
   const uint8_t* pa = c.arena + eff(c, I.a);
   const uint8_t* pb = c.arena + eff(c, I.b);
@@ -174,7 +188,7 @@ __device__ __forceinline__ void vm_div_f64(const VmInst& I, const TileCtx& c, bo
 
 // decimal rescale down: round half away from zero (arrow `rescale_decimal`)
 template <int RPT, typename T>
-__device__ __forceinline__ void vm_divround(const VmInst& I, const TileCtx& c) {
+__device__ __noinline__ void vm_divround(const VmInst& I, const TileCtx& c) {
   const T d = ImmOf<T>::get(I);
   const uint8_t* pa = c.arena + eff(c, I.a);
   uint8_t* pd = c.arena + eff(c, I.dst);
@@ -191,7 +205,7 @@ __device__ __forceinline__ void vm_divround(const VmInst& I, const TileCtx& c) {
 
 
 template <int RPT>
-__device__ __forceinline__ void vm_cvt(const VmInst& I, int dkind, const TileCtx& c) {
+__device__ __noinline__ void vm_cvt(const VmInst& I, int dkind, const TileCtx& c) {
   const uint8_t* pa = c.arena + eff(c, I.a);
   uint8_t* pd = c.arena + eff(c, I.dst);
 #pragma unroll
@@ -238,7 +252,7 @@ __device__ __forceinline__ void vm_select(const VmInst& I, const TileCtx& c) {
   }
 }
 template <int RPT>
-__device__ __forceinline__ void vm_select_v16(const VmInst& I, const TileCtx& c) {
+__device__ __noinline__ void vm_select_v16(const VmInst& I, const TileCtx& c) {
   const uint8_t* pa = c.arena + eff(c, I.a);
   const uint8_t* pb = c.arena + eff(c, I.b);
   const uint8_t* pc = c.arena + eff(c, I.c);
@@ -442,7 +456,7 @@ __device__ __noinline__ void vm_probe(const ProbeParams& P, const TileCtx& c, ui
 }
 
 template <int RPT>
-__device__ __forceinline__ void vm_gather(const VmInst& I, const TileCtx& c) {
+__device__ __noinline__ void vm_gather(const VmInst& I, const TileCtx& c) {
   const uint8_t* prow = c.arena + eff(c, I.a);
   uint8_t* pd = c.arena + eff(c, I.dst);
   const uint8_t* src = reinterpret_cast<const uint8_t*>(I.imm1);
@@ -469,7 +483,7 @@ template <int RPT>
 __device__ __forceinline__ void vm_exec(const VmInst* prog, int n_inst, const TileCtx& c, const PipelineParams& P,
                                         const PipelineAux* aux) {
   for (int pc = 0; pc < n_inst; ++pc) {
-    const VmInst I = prog[pc];
+    const VmInst& I = prog[pc];      // stays in shared memory: fields are read with uniform LDS
     const int base = I.op & 0xFF, kind = I.op >> 8;
     switch (base) {
       case OP_UNPACK_BITS: {
@@ -537,38 +551,39 @@ __device__ __forceinline__ void vm_exec(const VmInst* prog, int n_inst, const Ti
         break;
       }
       case OP_MULW: {
-        const int64_t imm = (int64_t)I.imm0;
-        const uint8_t* pa = c.arena + eff(c, I.a);
-        const uint8_t* pb = c.arena + eff(c, I.b);
-        uint8_t* pd = c.arena + eff(c, I.dst);
+        int64_t a[RPT], b[RPT];
+        if (I.flags & F_IMM_B) vm_load2<RPT, int64_t, false, true>(I, c, a, b);
+        else if (I.flags & F_IMM_A) vm_load2<RPT, int64_t, true, false>(I, c, a, b);
+        else vm_load2<RPT, int64_t, false, false>(I, c, a, b);
+        uint8_t* pd = c.arena + eff(c, I.dst) + threadIdx.x * 16;
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          const int r = threadIdx.x + k * NT;
-          int64_t a = (I.flags & F_IMM_A) ? imm : lds<int64_t>(pa + r * I.sa);
-          int64_t b = (I.flags & F_IMM_B) ? imm : lds<int64_t>(pb + r * I.sb);
           ulonglong2 w;
-          w.x = (unsigned long long)a * (unsigned long long)b;
-          w.y = (unsigned long long)__mul64hi((long long)a, (long long)b);
-          *reinterpret_cast<ulonglong2*>(pd + r * 16) = w;
+          w.x = (unsigned long long)a[k] * (unsigned long long)b[k];
+          w.y = (unsigned long long)__mul64hi((long long)a[k], (long long)b[k]);
+          *reinterpret_cast<ulonglong2*>(pd + k * NT * 16) = w;
         }
         break;
       }
       case OP_MUL128_64: {
         const int64_t imm = (int64_t)I.imm0;
-        const uint8_t* pa = c.arena + eff(c, I.a);
-        const uint8_t* pb = c.arena + eff(c, I.b);
-        uint8_t* pd = c.arena + eff(c, I.dst);
+        const uint8_t* pa = c.arena + eff(c, I.a) + threadIdx.x * I.sa;
+        const uint8_t* pb = c.arena + eff(c, I.b) + threadIdx.x * I.sb;
+        uint8_t* pd = c.arena + eff(c, I.dst) + threadIdx.x * 16;
+        ulonglong2 a[RPT]; int64_t b[RPT];
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          const int r = threadIdx.x + k * NT;
-          ulonglong2 a = *reinterpret_cast<const ulonglong2*>(pa + r * I.sa);
-          int64_t b = (I.flags & F_IMM_B) ? imm : lds<int64_t>(pb + r * I.sb);
+          a[k] = *reinterpret_cast<const ulonglong2*>(pa + k * NT * I.sa);
+          b[k] = (I.flags & F_IMM_B) ? imm : lds<int64_t>(pb + k * NT * I.sb);
+        }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
           // (ahi:alo) * sext(b)  mod 2^128
-          unsigned long long ub = (unsigned long long)b;
+          const unsigned long long ub = (unsigned long long)b[k];
           ulonglong2 w;
-          w.x = a.x * ub;
-          w.y = __umul64hi(a.x, ub) + a.y * ub - (b < 0 ? a.x : 0ull);
-          *reinterpret_cast<ulonglong2*>(pd + r * 16) = w;
+          w.x = a[k].x * ub;
+          w.y = __umul64hi(a[k].x, ub) + a[k].y * ub - (b[k] < 0 ? a[k].x : 0ull);
+          *reinterpret_cast<ulonglong2*>(pd + k * NT * 16) = w;
         }
         break;
       }
@@ -647,10 +662,10 @@ __device__ __forceinline__ uint32_t tile_bytes_of(const InputCol& in, int tile_r
 }
 
 // cooperative copy (partial / unaligned tiles): zero-fills rows >= nrows
-__device__ __forceinline__ void load_tile_generic(const PipelineParams& P, uint8_t* arena, uint32_t stage_off, int64_t row0, int nrows) {
+__device__ __forceinline__ void load_tile_generic(const PipelineParams& P, uint8_t* arena, int64_t row0, int nrows) {
   for (int i = 0; i < P.n_inputs; ++i) {
     const InputCol& in = P.in[i];
-    uint8_t* dst = arena + (in.slot & 0x7FFFFFFFu) + ((in.slot >> 31) ? stage_off : 0u);
+    uint8_t* dst = arena + in.slot;
     const uint32_t total = tile_bytes_of(in, P.tile_rows);
     const uint32_t valid = in.width ? (uint32_t)in.width * nrows : (uint32_t)((nrows + 7) >> 3);
     const uint8_t* src = in.data + (in.width ? (int64_t)in.width * row0 : (row0 >> 3));
@@ -849,49 +864,112 @@ __device__ __forceinline__ void acc_combine_words(int op, uint64_t& w0, uint64_t
   }
 }
 
-// Hot-path scratch in shared memory (offsets relative to arena + A.hot_smem_off):
-//   u32  tags[G]            (padded to 8 bytes)
-//   u64  keys[G][key_words]
-//   u64  entry[G]           (global entry pointers, filled at flush)
-//   u64  priv[(G * pw + w) * NT + tid]   pw = 1 + acc_words  (word 0 = seen mask)
+// Hot path for low-cardinality grouping (TPC-H Q1: 4 groups).  Scratch in shared memory, at
+// arena + A.hot_smem_off:
+//   u64 keys[G][key_words]     CTA-local dictionary of the first G distinct keys seen
+//   u64 fps[G]                 key fingerprints (cheap multiply-add mix) for the lookup
+//   u64 entry[G]               global table entries (resolved lazily / at flush)
+//   u64 wacc[(warp*G + g) * (1 + 2*n_accs)]   per-WARP accumulators: [seen][acc0 lo,hi][acc1 lo,hi]...
+// Every row finds its group id by fingerprint; then, accumulator by accumulator and group by
+// group, the warp reduces its rows with shuffles and lane 0 folds the warp total into wacc.  No
+// atomics, no per-thread state, ~G*n_accs*30 instructions per warp-tile regardless of tile size.
+constexpr int NWARPS = NT / 32;
 struct HotView {
-  uint32_t* tags; uint64_t* keys; uint64_t* entry; uint64_t* priv; int G; int pw;
+  uint64_t* keys; uint64_t* fps; uint64_t* entry; uint64_t* wacc; int G; int aw;
 };
 __device__ __forceinline__ HotView hot_view(const AggParams& A, uint8_t* arena) {
-  HotView h; h.G = A.hot_groups; h.pw = 1 + A.acc_words;
+  HotView h; h.G = A.hot_groups; h.aw = 1 + 2 * A.n_accs;
   uint8_t* p = arena + A.hot_smem_off;
-  h.tags = reinterpret_cast<uint32_t*>(p); p += ((h.G * 4 + 7) & ~7);
   h.keys = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * A.key_words * 8;
+  h.fps = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * 8;
   h.entry = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * 8;
-  h.priv = reinterpret_cast<uint64_t*>(p);
+  h.wacc = reinterpret_cast<uint64_t*>(p);
   return h;
 }
 
-__device__ __forceinline__ int hot_lookup(const AggParams& A, const HotView& H, int hot_n, const KeyRegs& key, uint64_t h) {
-  const uint32_t tag = (uint32_t)(h >> 32);
-  for (int g = 0; g < hot_n; ++g)
-    if (H.tags[g] == tag && key_words_equal(A.keys, A.n_keys, A.has_null_word, H.keys + (size_t)g * A.key_words, key)) return g;
+// packed key of row r as 8-byte words held in registers (static indexing) + its fingerprint
+__device__ __forceinline__ uint64_t pack_words(const AggParams& A, const TileCtx& c, int r, uint64_t (&kw)[MAX_KEY_WORDS]) {
+  uint64_t nullmask = 0;
+  uint64_t fp = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+  for (int w = 0; w < MAX_KEY_WORDS; ++w) {
+    kw[w] = 0;
+    if (w < A.key_words && !(A.has_null_word && w == 0)) {
+      const KeyWord& d = A.kwords[w];
+      const uint8_t* p = c.arena + d.slot + r * d.stride + d.byte_off;
+      uint64_t v = d.width == 8 ? lds<uint64_t>(p) : d.width == 4 ? (uint64_t)lds<uint32_t>(p) : (uint64_t)*p;
+      if (d.valid_slot != NO_SLOT && c.arena[d.valid_slot + r] == 0) { v = 0; nullmask |= 1ull << d.key_index; }
+      kw[w] = v;
+      fp = (fp ^ v) * 0xD6E8FEB86659FD93ull;
+    }
+  }
+  if (A.has_null_word) { kw[0] = nullmask; fp = (fp ^ nullmask) * 0xD6E8FEB86659FD93ull; }
+  return fp;
+}
+
+__device__ __forceinline__ int hot_lookup(const AggParams& A, const HotView& H, int hot_n, const uint64_t (&kw)[MAX_KEY_WORDS], uint64_t fp) {
+  for (int g = 0; g < hot_n; ++g) {
+    if (H.fps[g] != fp) continue;
+    const uint64_t* hk = H.keys + g * A.key_words;
+    bool eq = true;
+#pragma unroll
+    for (int w = 0; w < MAX_KEY_WORDS; ++w)
+      if (w < A.key_words) eq &= hk[w] == kw[w];
+    if (eq) return g;
+  }
   return -1;
+}
+
+__device__ __noinline__ uint64_t* hot_entry(const PipelineParams& P, const AggParams& A, const HotView& H, int g) {
+  uint64_t* e = reinterpret_cast<uint64_t*>(H.entry[g]);
+  if (e) return e;
+  KeyRegs key;
+  for (int w = 0; w < MAX_KEY_WORDS; ++w) key.w[w] = w < A.key_words ? H.keys[g * A.key_words + w] : 0;
+  e = agg_find_or_insert(A, key, hash_packed_key(A, key), P.error_flag);
+  H.entry[g] = reinterpret_cast<uint64_t>(e);     // benign race: every writer stores the same pointer
+  return e;
+}
+
+__device__ __forceinline__ int64_t warp_sum_i64(int64_t v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  return v;
+}
+
+// values whose magnitude is below 2^55 may be summed 128 at a time in 64 bits without overflow
+__device__ __forceinline__ bool fits55(i128 v) {
+  const int64_t lo = (int64_t)v;
+  return (i128)lo == v && ((uint64_t)(lo + (1ll << 55)) >> 56) == 0;
 }
 
 template <int RPT>
 __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParams& A, const TileCtx& c, Smem* sm) {
-  const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, P.mask_slot);
+  const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + P.mask_slot;
   HotView H = hot_view(A, c.arena);
-  int8_t gid[RPT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int gid[RPT];
   bool live[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    live[k] = r < c.nrows && (pact == nullptr || pact[r]);
+    gid[k] = -1;
+  }
   if (A.hot_groups > 0) {
     // phase A: look every live row up in the CTA-local dictionary
     bool miss = false;
+    const int hot_n0 = sm->hot_n;
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-      const int r = threadIdx.x + k * NT;
-      live[k] = r < c.nrows && (pact == nullptr || pact[r]);
-      gid[k] = -1;
       if (live[k]) {
-        KeyRegs key; bool hn;
-        uint64_t h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
-        gid[k] = (int8_t)hot_lookup(A, H, sm->hot_n, key, h);
+        uint64_t kw[MAX_KEY_WORDS];
+        const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
+        gid[k] = hot_lookup(A, H, hot_n0, kw, fp);
         miss |= gid[k] < 0;
       }
     }
@@ -905,12 +983,12 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
       if (want && sm->elect == (int)threadIdx.x) {
         for (int k = 0; k < RPT; ++k) {
           if (live[k] && gid[k] < 0) {
-            const int r = threadIdx.x + k * NT;
-            KeyRegs key; bool hn;
-            uint64_t h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
+            uint64_t kw[MAX_KEY_WORDS];
+            const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
             const int g = sm->hot_n;
-            for (int w = 0; w < A.key_words; ++w) H.keys[(size_t)g * A.key_words + w] = key.w[w];
-            H.tags[g] = (uint32_t)(h >> 32);
+            for (int w = 0; w < MAX_KEY_WORDS; ++w) if (w < A.key_words) H.keys[g * A.key_words + w] = kw[w];
+            H.fps[g] = fp;
+            H.entry[g] = 0;
             sm->hot_n = g + 1;
             break;
           }
@@ -918,55 +996,261 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
       }
       __syncthreads();
       miss = false;
+      const int hot_n1 = sm->hot_n;
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         if (live[k] && gid[k] < 0) {
-          const int r = threadIdx.x + k * NT;
-          KeyRegs key; bool hn;
-          uint64_t h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
-          gid[k] = (int8_t)hot_lookup(A, H, sm->hot_n, key, h);
+          uint64_t kw[MAX_KEY_WORDS];
+          const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
+          gid[k] = hot_lookup(A, H, hot_n1, kw, fp);
           miss |= gid[k] < 0;
         }
       }
     }
-  } else {
+    // phase C: accumulator by accumulator, group by group: thread-local partial -> warp reduce -> lane 0
+    const int hot_n = sm->hot_n;
+    bool anyhot = false;
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-      const int r = threadIdx.x + k * NT;
-      live[k] = r < c.nrows && (pact == nullptr || pact[r]);
-      gid[k] = -1;
+    for (int k = 0; k < RPT; ++k) anyhot |= live[k] && gid[k] >= 0;
+    if (__any_sync(0xFFFFFFFFu, anyhot)) {
+      for (int j = 0; j < A.n_accs; ++j) {
+        const AccDesc& d = A.accs[j];
+        i128 vi[RPT]; double vf[RPT]; bool ok[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          vi[k] = 0; vf[k] = 0.0; ok[k] = false;
+          if (live[k] && gid[k] >= 0) {
+            const int r = threadIdx.x + k * NT;
+            ok[k] = d.valid_slot == NO_SLOT || c.arena[d.valid_slot + r] != 0;
+            if (d.value_slot != NO_SLOT) {
+              const uint8_t* p = c.arena + d.value_slot + r * d.stride;
+              switch (d.vkind) {
+                case K_I32: vi[k] = lds<int32_t>(p); break;
+                case K_I64: vi[k] = lds<int64_t>(p); break;
+                case K_I128: vi[k] = lds<i128>(p); break;
+                case K_F64: vf[k] = lds<double>(p); break;
+                default: vi[k] = *p;
+              }
+            }
+            if (d.op == ACC_SUM_I128 && ok[k] && !fits55(vi[k])) {   // rare: exact value straight to the table
+              uint64_t* e = hot_entry(P, A, H, gid[k]);
+              if (e) { atomic_add_i128(e + 2 + A.key_words + d.word, vi[k]); if (d.track_seen) atomicOr(reinterpret_cast<unsigned long long*>(e + 1), 1ull << j); }
+              ok[k] = false;
+            }
+          }
+        }
+        for (int g = 0; g < hot_n; ++g) {
+          uint64_t* wa = H.wacc + ((size_t)(warp * H.G + g)) * H.aw;
+          uint64_t* slot = wa + 1 + 2 * j;
+          bool any = false;
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) any |= ok[k] && gid[k] == g;
+          const unsigned members = __ballot_sync(0xFFFFFFFFu, any);
+          if (members == 0) continue;
+          switch (d.op) {
+            case ACC_COUNT: {
+              int cnt = 0;
+#pragma unroll
+              for (int k = 0; k < RPT; ++k) cnt += (ok[k] && gid[k] == g) ? 1 : 0;
+              cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+              if (lane == 0) slot[0] += (uint64_t)cnt;
+              break;
+            }
+            case ACC_SUM_I64: case ACC_SUM_I128: {
+              int64_t part = 0;
+#pragma unroll
+              for (int k = 0; k < RPT; ++k) part += (ok[k] && gid[k] == g) ? (int64_t)vi[k] : 0;
+              part = warp_sum_i64(part);
+              if (lane == 0) {
+                if (d.op == ACC_SUM_I64) slot[0] += (uint64_t)part;
+                else { const uint64_t lo = slot[0] + (uint64_t)part; slot[1] += (uint64_t)(part >> 63) + (lo < slot[0] ? 1ull : 0ull); slot[0] = lo; }
+              }
+              break;
+            }
+            case ACC_SUM_F64: {
+              double part = 0.0;
+#pragma unroll
+              for (int k = 0; k < RPT; ++k) part += (ok[k] && gid[k] == g) ? vf[k] : 0.0;
+              part = warp_sum_f64(part);
+              if (lane == 0) slot[0] = (uint64_t)__double_as_longlong(__longlong_as_double((long long)slot[0]) + part);
+              break;
+            }
+            default: {   // min / max: serial over member lanes through lane 0 (rarely hot)
+              uint64_t w0 = acc_identity(d.op, 0), w1 = acc_identity(d.op, 1);
+#pragma unroll
+              for (int k = 0; k < RPT; ++k) {
+                if (ok[k] && gid[k] == g) {
+                  const bool isf = d.op == ACC_MIN_F64 || d.op == ACC_MAX_F64;
+                  const uint64_t v0 = isf ? (uint64_t)__double_as_longlong(vf[k]) : (uint64_t)(u128)vi[k];
+                  const uint64_t v1 = isf ? 0 : (uint64_t)((u128)vi[k] >> 64);
+                  acc_combine_words(d.op, w0, w1, v0, v1);
+                }
+              }
+#pragma unroll
+              for (int dlt = 16; dlt; dlt >>= 1) {
+                const uint64_t o0 = __shfl_xor_sync(0xFFFFFFFFu, w0, dlt), o1 = __shfl_xor_sync(0xFFFFFFFFu, w1, dlt);
+                acc_combine_words(d.op, w0, w1, o0, o1);
+              }
+              if (lane == 0) { uint64_t a0 = slot[0], a1 = slot[1]; acc_combine_words(d.op, a0, a1, w0, w1); slot[0] = a0; slot[1] = a1; }
+            }
+          }
+          if (d.track_seen && lane == 0) wa[0] |= 1ull << j;
+        }
+      }
     }
   }
-  // phase C: accumulate.  Hot rows update thread-private accumulators; cold rows go to the global
-  // table, one warp-cooperative lookup per row slot (every lane of the warp takes part).
+  // cold rows (dictionary full): global table, one warp-cooperative lookup per row slot
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const bool cold = live[k] && gid[k] < 0;
+    if (__any_sync(0xFFFFFFFFu, cold)) {
+      const int r = threadIdx.x + k * NT;
+      KeyRegs key; bool hn; uint64_t h = 0;
+      if (cold) h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
+      uint64_t* e = agg_find_or_insert_warp(A, key, h, cold, P.error_flag);
+      if (cold && e) {
+        for (int j = 0; j < A.n_accs; ++j) acc_global(e, A, j, load_acc_value(A.accs[j], c, r));
+      }
+    }
+  }
+}
+
+// ---- integer fast path: register-resident partials -------------------------------------------------
+// racc[g][j]: this thread's running 64-bit partial of accumulator j for hot group g.  Values are
+// admitted only below 2^55 in magnitude and the partials are spilled to the CTA accumulators (shared
+// memory atomics, once per REG_FLUSH rows) so they can never overflow.
+constexpr int REG_FLUSH = 96;
+struct RegAcc { int64_t v[REG_GROUPS][REG_ACCS]; int rows; };
+
+__device__ __forceinline__ void reg_flush(const AggParams& A, const HotView& H, RegAcc& R, int hot_n) {
+  // CTA accumulators live in warp 0's wacc blocks: slot (g, j) = {lo, hi} with carry through atomics
+#pragma unroll
+  for (int g = 0; g < REG_GROUPS; ++g) {
+    if (g < hot_n) {
+      uint64_t* wa = H.wacc + (size_t)g * H.aw;
+#pragma unroll
+      for (int j = 0; j < REG_ACCS; ++j) {
+        if (j < A.n_accs) {
+          const int64_t part = R.v[g][j];
+          if (part != 0) {
+            unsigned long long* lo = reinterpret_cast<unsigned long long*>(wa + 1 + 2 * j);
+            const unsigned long long old = atomicAdd(lo, (unsigned long long)part);
+            const unsigned long long carry = (old + (unsigned long long)part) < old ? 1ull : 0ull;
+            const unsigned long long hi = (unsigned long long)(part >> 63) + carry;
+            if (hi) atomicAdd(lo + 1, hi);
+          }
+          R.v[g][j] = 0;
+        }
+      }
+    }
+  }
+  R.rows = 0;
+}
+
+template <int RPT>
+__device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggParams& A, const TileCtx& c, Smem* sm, RegAcc& R) {
+  const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + P.mask_slot;
+  HotView H = hot_view(A, c.arena);
+  int gid[RPT];
+  bool live[RPT];
+  bool miss = false;
+  const int hot_n0 = sm->hot_n;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    live[k] = r < c.nrows && (pact == nullptr || pact[r]);
+    gid[k] = -1;
+    if (live[k]) {
+      uint64_t kw[MAX_KEY_WORDS];
+      const uint64_t fp = pack_words(A, c, r, kw);
+      gid[k] = hot_lookup(A, H, hot_n0, kw, fp);
+      miss |= gid[k] < 0;
+    }
+  }
+  // dictionary growth (only while fewer than REG_GROUPS groups are known): same protocol as sink_agg
+  if (hot_n0 < REG_GROUPS) {
+    while (__syncthreads_or(miss && sm->hot_n < REG_GROUPS)) {
+      if (threadIdx.x == 0) sm->elect = NT;
+      __syncthreads();
+      const bool want = miss && sm->hot_n < REG_GROUPS;
+      if (want) atomicMin(&sm->elect, (int)threadIdx.x);
+      __syncthreads();
+      if (want && sm->elect == (int)threadIdx.x) {
+        for (int k = 0; k < RPT; ++k) {
+          if (live[k] && gid[k] < 0) {
+            uint64_t kw[MAX_KEY_WORDS];
+            const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
+            const int g = sm->hot_n;
+            for (int w = 0; w < MAX_KEY_WORDS; ++w) if (w < A.key_words) H.keys[g * A.key_words + w] = kw[w];
+            H.fps[g] = fp;
+            H.entry[g] = 0;
+            sm->hot_n = g + 1;
+            break;
+          }
+        }
+      }
+      __syncthreads();
+      miss = false;
+      const int hot_n1 = sm->hot_n;
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        if (live[k] && gid[k] < 0) {
+          uint64_t kw[MAX_KEY_WORDS];
+          const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
+          gid[k] = hot_lookup(A, H, hot_n1, kw, fp);
+          miss |= gid[k] < 0;
+        }
+      }
+    }
+  }
+  // accumulate: values first (RPT x n_accs loads), then predicated adds into the register partials
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     const int r = threadIdx.x + k * NT;
     const bool hot = live[k] && gid[k] >= 0;
-    const bool cold = live[k] && gid[k] < 0;
     if (hot) {
-      uint64_t* base = H.priv + ((size_t)gid[k] * H.pw) * NT + threadIdx.x;
-      uint64_t seen = 0;
-      for (int j = 0; j < A.n_accs; ++j) {
-        const AccDesc& d = A.accs[j];
-        AccVal v = load_acc_value(d, c, r);
-        if (!v.valid) continue;
-        uint64_t* w0p = base + (size_t)(1 + d.word) * NT;
-        uint64_t w0 = *w0p, w1 = 0;
-        const bool wide = acc_words_of(d.op) == 2;
-        if (wide) w1 = w0p[NT];
-        uint64_t v0, v1 = 0;
-        if (d.op == ACC_COUNT) v0 = 1;
-        else if (d.op == ACC_SUM_F64 || d.op == ACC_MIN_F64 || d.op == ACC_MAX_F64) v0 = (uint64_t)__double_as_longlong(v.f);
-        else { v0 = (uint64_t)(u128)v.i; v1 = (uint64_t)((u128)v.i >> 64); }
-        acc_combine_words(d.op, w0, w1, v0, v1);
-        *w0p = w0;
-        if (wide) w0p[NT] = w1;
-        if (d.track_seen) seen |= 1ull << j;
+      int64_t val[REG_ACCS];
+#pragma unroll
+      for (int j = 0; j < REG_ACCS; ++j) {
+        val[j] = 0;
+        if (j < A.n_accs) {
+          const AccDesc& d = A.accs[j];
+          bool ok = d.valid_slot == NO_SLOT || c.arena[d.valid_slot + r] != 0;
+          if (d.op == ACC_COUNT) val[j] = ok ? 1 : 0;
+          else if (ok) {
+            const uint8_t* p = c.arena + d.value_slot + r * d.stride;
+            if (d.vkind == K_I128) {
+              const i128 x = lds<i128>(p);
+              if (fits55(x)) val[j] = (int64_t)x;
+              else {                                  // rare: exact value straight to the table entry
+                uint64_t* e = hot_entry(P, A, H, gid[k]);
+                if (e) atomic_add_i128(e + 2 + A.key_words + d.word, x);
+              }
+            } else {
+              const int64_t x = d.vkind == K_I64 ? lds<int64_t>(p) : d.vkind == K_I32 ? (int64_t)lds<int32_t>(p) : (int64_t)*p;
+              if (d.op == ACC_SUM_I64 || fits55((i128)x)) val[j] = x;
+              else { uint64_t* e = hot_entry(P, A, H, gid[k]); if (e) atomic_add_i128(e + 2 + A.key_words + d.word, (i128)x); }
+            }
+          }
+        }
       }
-      if (seen) base[0] |= seen;
+#pragma unroll
+      for (int g = 0; g < REG_GROUPS; ++g) {
+        const bool mine = gid[k] == g;
+#pragma unroll
+        for (int j = 0; j < REG_ACCS; ++j)
+          if (j < A.n_accs) R.v[g][j] += mine ? val[j] : 0;
+      }
     }
+  }
+  R.rows += RPT;
+  if (R.rows >= REG_FLUSH) reg_flush(A, H, R, sm->hot_n);
+  // rows of groups beyond the register set: global table
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const bool cold = live[k] && gid[k] < 0;
     if (__any_sync(0xFFFFFFFFu, cold)) {
+      const int r = threadIdx.x + k * NT;
       KeyRegs key; bool hn; uint64_t h = 0;
       if (cold) h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
       uint64_t* e = agg_find_or_insert_warp(A, key, h, cold, P.error_flag);
@@ -980,60 +1264,50 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
 __device__ __forceinline__ void hot_init(const AggParams& A, uint8_t* arena) {
   if (A.hot_groups <= 0) return;
   HotView H = hot_view(A, arena);
-  for (int g = 0; g < H.G; ++g) {
-    H.priv[((size_t)g * H.pw) * NT + threadIdx.x] = 0;   // seen
-    for (int j = 0; j < A.n_accs; ++j) {
-      const AccDesc& d = A.accs[j];
-      for (int w = 0; w < acc_words_of(d.op); ++w)
-        H.priv[((size_t)g * H.pw + 1 + d.word + w) * NT + threadIdx.x] = acc_identity(d.op, w);
-    }
+  for (int i = threadIdx.x; i < NWARPS * H.G; i += NT) {
+    uint64_t* wa = H.wacc + (size_t)i * H.aw;
+    wa[0] = 0;
+    for (int j = 0; j < A.n_accs; ++j) { wa[1 + 2 * j] = acc_identity(A.accs[j].op, 0); wa[2 + 2 * j] = acc_identity(A.accs[j].op, 1); }
   }
 }
 
-// end of kernel: fold the NT thread-private copies of every hot group into the global table
+// end of kernel: fold the per-warp accumulators of every hot group into the global table
 __device__ __forceinline__ void hot_flush(const PipelineParams& P, const AggParams& A, uint8_t* arena, Smem* sm) {
   if (A.hot_groups <= 0) return;
   __syncthreads();
   HotView H = hot_view(A, arena);
   const int n = sm->hot_n;
-  for (int g = threadIdx.x; g < n; g += NT) {
-    KeyRegs key;
-    for (int w = 0; w < A.key_words; ++w) key.w[w] = H.keys[(size_t)g * A.key_words + w];
-    const uint64_t h = hash_packed_key(A, key);
-    H.entry[g] = reinterpret_cast<uint64_t>(agg_find_or_insert(A, key, h, P.error_flag));
-  }
+  for (int g = threadIdx.x; g < n; g += NT) hot_entry(P, A, H, g);
   __syncthreads();
   const int per = A.n_accs + 1;   // accumulators + the seen word
   for (int p = threadIdx.x; p < n * per; p += NT) {
     const int g = p / per, j = p % per;
     uint64_t* e = reinterpret_cast<uint64_t*>(H.entry[g]);
     if (!e) continue;
-    const uint64_t* base = H.priv + ((size_t)g * H.pw) * NT;
     if (j == A.n_accs) {
       uint64_t seen = 0;
-      for (int t = 0; t < NT; ++t) seen |= base[t];
+      for (int w = 0; w < NWARPS; ++w) seen |= H.wacc[((size_t)(w * H.G + g)) * H.aw];
       if (seen) atomicOr(reinterpret_cast<unsigned long long*>(e + 1), (unsigned long long)seen);
       continue;
     }
     const AccDesc& d = A.accs[j];
     uint64_t w0 = acc_identity(d.op, 0), w1 = acc_identity(d.op, 1);
-    const bool wide = acc_words_of(d.op) == 2;
-    for (int t = 0; t < NT; ++t) {
-      uint64_t v0 = base[(size_t)(1 + d.word) * NT + t];
-      uint64_t v1 = wide ? base[(size_t)(2 + d.word) * NT + t] : 0;
-      acc_combine_words(d.op, w0, w1, v0, v1);
+    if (d.op == ACC_SUM_I128) { w0 = 0; w1 = 0; }
+    for (int w = 0; w < NWARPS; ++w) {
+      const uint64_t* slot = H.wacc + ((size_t)(w * H.G + g)) * H.aw + 1 + 2 * j;
+      acc_combine_words(d.op, w0, w1, slot[0], slot[1]);
     }
-    uint64_t* w = e + 2 + A.key_words + d.word;
+    uint64_t* dst = e + 2 + A.key_words + d.word;
     switch (d.op) {
-      case ACC_SUM_I64: case ACC_COUNT: if (w0) atomicAdd(reinterpret_cast<unsigned long long*>(w), (unsigned long long)w0); break;
-      case ACC_SUM_I128: atomic_add_i128(w, (i128)(((u128)w1 << 64) | w0)); break;
-      case ACC_SUM_F64: atomicAdd(reinterpret_cast<double*>(w), __longlong_as_double((long long)w0)); break;
-      case ACC_MIN_I32: case ACC_MIN_I64: atomicMin(reinterpret_cast<long long*>(w), (long long)w0); break;
-      case ACC_MAX_I32: case ACC_MAX_I64: atomicMax(reinterpret_cast<long long*>(w), (long long)w0); break;
-      case ACC_MIN_I128: atomic_minmax_i128(w, (i128)(((u128)w1 << 64) | w0), true); break;
-      case ACC_MAX_I128: atomic_minmax_i128(w, (i128)(((u128)w1 << 64) | w0), false); break;
-      case ACC_MIN_F64: atomic_minmax_f64(w, __longlong_as_double((long long)w0), true); break;
-      case ACC_MAX_F64: atomic_minmax_f64(w, __longlong_as_double((long long)w0), false); break;
+      case ACC_SUM_I64: case ACC_COUNT: if (w0) atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)w0); break;
+      case ACC_SUM_I128: atomic_add_i128(dst, (i128)(((u128)w1 << 64) | w0)); break;
+      case ACC_SUM_F64: atomicAdd(reinterpret_cast<double*>(dst), __longlong_as_double((long long)w0)); break;
+      case ACC_MIN_I32: case ACC_MIN_I64: atomicMin(reinterpret_cast<long long*>(dst), (long long)w0); break;
+      case ACC_MAX_I32: case ACC_MAX_I64: atomicMax(reinterpret_cast<long long*>(dst), (long long)w0); break;
+      case ACC_MIN_I128: atomic_minmax_i128(dst, (i128)(((u128)w1 << 64) | w0), true); break;
+      case ACC_MAX_I128: atomic_minmax_i128(dst, (i128)(((u128)w1 << 64) | w0), false); break;
+      case ACC_MIN_F64: atomic_minmax_f64(dst, __longlong_as_double((long long)w0), true); break;
+      case ACC_MAX_F64: atomic_minmax_f64(dst, __longlong_as_double((long long)w0), false); break;
       default: break;
     }
   }
@@ -1218,35 +1492,32 @@ __device__ __forceinline__ void sink_partition(const PipelineParams& P, const Pa
 // the kernel
 // ================================================================================================
 template <int RPT>
-__global__ void __launch_bounds__(NT) pipeline_kernel(const __grid_constant__ PipelineParams P, const PipelineAux* __restrict__ aux,
-                                                      int n_stages, uint32_t stage_bytes) {
+__global__ void __launch_bounds__(NT, 2) pipeline_kernel(const __grid_constant__ KernelArgs K, int n_stages) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem* sm = reinterpret_cast<Smem*>(smem_raw);
-  VmInst* prog = reinterpret_cast<VmInst*>(smem_raw + SMEM_HDR);
-  uint8_t* arena = smem_raw + SMEM_HDR + ((P.n_inst * (int)sizeof(VmInst) + 127) & ~127);
+  uint8_t* arena = smem_raw + SMEM_HDR;
+  const PipelineParams& P0 = K.P[0];
   const int tile_rows = RPT * NT;
-  const int64_t n_tiles = (P.n_rows + tile_rows - 1) / tile_rows;
-  const bool dynamic = P.sink == SINK_COMPACT;
+  const int64_t n_tiles = (P0.n_rows + tile_rows - 1) / tile_rows;
+  const bool dynamic = P0.sink == SINK_COMPACT;
 
-  for (int i = threadIdx.x; i < P.n_inst * (int)(sizeof(VmInst) / 8); i += NT)
-    reinterpret_cast<uint64_t*>(prog)[i] = reinterpret_cast<const uint64_t*>(P.prog)[i];
   if (threadIdx.x == 0) {
     mbar_init(&sm->full[0], 1);
     mbar_init(&sm->full[1], 1);
     fence_barrier_init();
     sm->hot_n = 0;
-    sm->tile[0] = dynamic ? (int)atomicAdd(P.ticket, 1u) : (int)blockIdx.x;
+    sm->tile[0] = dynamic ? (int)atomicAdd(P0.ticket, 1u) : (int)blockIdx.x;
   }
-  if (P.sink == SINK_AGG) hot_init(aux->agg, arena);
+  if (P0.sink == SINK_AGG) hot_init(K.aux[0].agg, arena);
   __syncthreads();
 
   uint32_t tma_bytes = 0;
-  for (int i = 0; i < P.n_inputs; ++i) tma_bytes += tile_bytes_of(P.in[i], tile_rows);
+  for (int i = 0; i < P0.n_inputs; ++i) tma_bytes += tile_bytes_of(P0.in[i], tile_rows);
 
-  auto issue = [&](int64_t tile, int stage) {      // returns via side effects; uniform across the CTA
+  auto issue = [&](int64_t tile, int stage) {      // uniform across the CTA
+    const PipelineParams& P = K.P[stage];
     const int64_t row0 = tile * tile_rows;
     const int nrows = (int)min((int64_t)tile_rows, P.n_rows - row0);
-    const uint32_t soff = (uint32_t)stage * stage_bytes;
     if (P.use_tma && nrows == tile_rows) {
       if (threadIdx.x == 0) {
         fence_proxy_async();
@@ -1255,14 +1526,20 @@ __global__ void __launch_bounds__(NT) pipeline_kernel(const __grid_constant__ Pi
           const InputCol& in = P.in[i];
           const uint32_t bytes = tile_bytes_of(in, tile_rows);
           const uint8_t* src = in.data + (in.width ? (int64_t)in.width * row0 : (row0 >> 3));
-          tma_load_1d(arena + (in.slot & 0x7FFFFFFFu) + ((in.slot >> 31) ? soff : 0u), src, bytes, &sm->full[stage]);
+          tma_load_1d(arena + in.slot, src, bytes, &sm->full[stage]);
         }
       }
     } else {
-      load_tile_generic(P, arena, soff, row0, nrows);
+      load_tile_generic(P, arena, row0, nrows);
     }
   };
 
+  RegAcc R;
+#pragma unroll
+  for (int g = 0; g < REG_GROUPS; ++g)
+#pragma unroll
+    for (int j = 0; j < REG_ACCS; ++j) R.v[g][j] = 0;
+  R.rows = 0;
   int64_t cur = sm->tile[0];
   uint32_t parity[2] = {0, 0};
   int it = 0;
@@ -1270,20 +1547,24 @@ __global__ void __launch_bounds__(NT) pipeline_kernel(const __grid_constant__ Pi
   for (;; ++it) {
     if (cur >= n_tiles) break;
     const int s = (n_stages == 2) ? (it & 1) : 0;
+    const PipelineParams& P = K.P[s];
+    const PipelineAux* aux = &K.aux[s];
     if (threadIdx.x == 0) sm->tile[(it + 1) & 1] = dynamic ? (int)atomicAdd(P.ticket, 1u) : (int)(cur + gridDim.x);
     __syncthreads();                                          // (A) publishes next tile id, orders generic loads
     const int64_t nxt = sm->tile[(it + 1) & 1];
     if (n_stages == 2 && nxt < n_tiles) issue(nxt, s ^ 1);    // prefetch while this tile is computed
     TileCtx c;
-    c.arena = arena; c.stage_off = (uint32_t)s * stage_bytes; c.row0 = cur * tile_rows;
+    c.arena = arena; c.stage_off = 0; c.row0 = cur * tile_rows;
     c.nrows = (int)min((int64_t)tile_rows, P.n_rows - c.row0);
     if (P.use_tma && c.nrows == tile_rows) { mbar_wait(&sm->full[s], parity[s]); parity[s] ^= 1; }
 
-    vm_exec<RPT>(prog, P.n_inst, c, P, aux);
+    vm_exec<RPT>(K.prog[s], P.n_inst, c, P, aux);
     switch (P.sink) {
       case SINK_STORE: sink_store<RPT>(P, c); break;
       case SINK_COMPACT: sink_compact<RPT>(P, c, sm, (int)cur); break;
-      case SINK_AGG: sink_agg<RPT>(P, aux->agg, c, sm); break;
+      case SINK_AGG:
+        if (aux->agg.reg_path) sink_agg_reg<RPT>(P, aux->agg, c, sm, R); else sink_agg<RPT>(P, aux->agg, c, sm);
+        break;
       case SINK_BUILD: sink_build<RPT>(P, aux->build, c); break;
       case SINK_PARTITION: sink_partition<RPT>(P, aux->part, c); break;
     }
@@ -1291,7 +1572,10 @@ __global__ void __launch_bounds__(NT) pipeline_kernel(const __grid_constant__ Pi
     if (n_stages == 1 && nxt < n_tiles) { issue(nxt, 0); }
     cur = nxt;
   }
-  if (P.sink == SINK_AGG) hot_flush(P, aux->agg, arena, sm);
+  if (P0.sink == SINK_AGG) {
+    if (K.aux[0].agg.reg_path) { HotView H = hot_view(K.aux[0].agg, arena); reg_flush(K.aux[0].agg, H, R, sm->hot_n); }
+    hot_flush(P0, K.aux[0].agg, arena, sm);
+  }
 }
 
 // ================================================================================================
@@ -1485,9 +1769,8 @@ __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, int64_t n, co
 // ================================================================================================
 // host-callable launchers (C++ linkage inside libsailgpu)
 // ================================================================================================
-cudaError_t launch_pipeline(const PipelineParams& P, const PipelineAux* aux_dev, int rpt, int n_stages, uint32_t stage_bytes,
-                            size_t smem_bytes, int grid, cudaStream_t stream) {
-  void (*k)(const PipelineParams, const PipelineAux*, int, uint32_t) = nullptr;
+cudaError_t launch_pipeline(const KernelArgs& K, int rpt, int n_stages, size_t smem_bytes, int grid, cudaStream_t stream) {
+  void (*k)(const KernelArgs, int) = nullptr;
   switch (rpt) {
     case 1: k = pipeline_kernel<1>; break;
     case 2: k = pipeline_kernel<2>; break;
@@ -1495,13 +1778,12 @@ cudaError_t launch_pipeline(const PipelineParams& P, const PipelineAux* aux_dev,
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return e;
-  k<<<grid, NT, smem_bytes, stream>>>(P, aux_dev, n_stages, stage_bytes);
+  k<<<grid, NT, smem_bytes, stream>>>(K, n_stages);
   return cudaGetLastError();
 }
 
 int pipeline_max_ctas_per_sm(int rpt, size_t smem_bytes) {
-  void (*k)(const PipelineParams, const PipelineAux*, int, uint32_t) =
-      rpt == 1 ? pipeline_kernel<1> : rpt == 2 ? pipeline_kernel<2> : pipeline_kernel<4>;
+  void (*k)(const KernelArgs, int) = rpt == 1 ? pipeline_kernel<1> : rpt == 2 ? pipeline_kernel<2> : pipeline_kernel<4>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, NT, smem_bytes) != cudaSuccess) return 0;

@@ -24,6 +24,8 @@ constexpr int MAX_KEYS = 6;
 constexpr int MAX_KEY_WORDS = 8;   // 64 bytes of packed key
 constexpr int MAX_ACCS = 16;
 constexpr int MAX_PROBES = 4;
+constexpr int REG_GROUPS = 4;      // hot groups held in registers by the integer fast path
+constexpr int REG_ACCS = 8;        // accumulators held in registers per group
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
 enum VmKind : uint8_t { K_B = 0, K_I32 = 1, K_I64 = 2, K_F64 = 3, K_I128 = 4, K_V16 = 5 };
@@ -99,7 +101,19 @@ struct AccDesc {
   uint8_t track_seen;      // set bit `index` of the row's seen word when a value is accumulated
   uint32_t value_slot;     // NO_SLOT for count(*)
   uint32_t valid_slot;     // NO_SLOT => never null
-  uint32_t word;           // first 8-byte word of this accumulator inside the accumulator block
+  uint16_t word;           // first 8-byte word of this accumulator inside a global table entry
+  uint16_t pword;          // first word inside the thread-private (shared memory) block: sums are kept
+                           // as 64-bit partials there and spilled to the table entry on overflow
+};
+
+// One 8-byte word of the packed group key: where it is loaded from (static indexing => registers).
+struct KeyWord {
+  uint32_t slot;
+  uint32_t valid_slot;     // NO_SLOT => never null
+  uint8_t width;           // bytes to load: 1, 4 or 8
+  uint8_t stride;
+  uint8_t byte_off;        // 0 or 8: low / high half of a 16-byte element
+  uint8_t key_index;
 };
 
 struct KeyDesc {
@@ -121,7 +135,13 @@ struct AggParams {
   int32_t has_null_word;
   int32_t hot_groups;      // thread-private slots per CTA (0 disables the hot path)
   KeyDesc keys[MAX_KEYS];
+  KeyWord kwords[MAX_KEY_WORDS];
   AccDesc accs[MAX_ACCS];
+  int32_t priv_words;      // (unused by the kernels; kept for layout stability)
+  int32_t priv_seen;
+  int32_t reg_path;        // all accumulators are integer sums/counts: per-thread REGISTER partials for the first
+                           // REG_GROUPS hot groups (no shuffles, no shared-memory traffic per row)
+  int32_t pad_;
   uint8_t* table;          // capacity * entry_bytes
   uint32_t* state;         // capacity
   uint64_t capacity_mask;  // capacity - 1 (power of two)
@@ -192,6 +212,16 @@ struct PipelineAux {
   BuildParams build;
   PartitionParams part;
   ProbeParams probe[MAX_PROBES];
+};
+
+// Everything uniform across the grid travels as ONE kernel parameter (constant bank: uniform loads,
+// no per-thread cost), pre-resolved on the host for each of the two input stages so the device never
+// computes stage-relative offsets.
+constexpr int MAX_INST = 64;
+struct KernelArgs {
+  PipelineParams P[2];
+  PipelineAux aux[2];
+  VmInst prog[2][MAX_INST];
 };
 
 enum : uint32_t { ERR_DIV_ZERO = 1, ERR_OVERFLOW = 2, ERR_TABLE_FULL = 4, ERR_UNSUPPORTED = 8 };

@@ -15,6 +15,7 @@ from __future__ import annotations
 import ctypes
 import json
 import os
+import sys
 
 import pyarrow as pa
 
@@ -68,6 +69,9 @@ def lib():
         L.sailgpu_ctx_destroy.restype = None
         L.sailgpu_ctx_last_error.argtypes = [vp]
         L.sailgpu_ctx_last_error.restype = ctypes.c_char_p
+        L.sailgpu_ctx_stream.argtypes = [vp]
+        L.sailgpu_ctx_stream.restype = vp
+        L.sailgpu_ctx_synchronize.argtypes = [vp]
         L.sailgpu_op_create.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), i32, i32,
                                         ctypes.POINTER(vp), vp]
         L.sailgpu_op_push.argtypes = [vp, i32, vp]
@@ -106,6 +110,15 @@ class Context:
             lib().sailgpu_ctx_destroy(self._h)
             self._h = ctypes.c_void_p()
 
+    def stream(self) -> int:
+        """cudaStream_t of this context as an integer (wrap with torch.cuda.ExternalStream to record events)"""
+        return int(lib().sailgpu_ctx_stream(self._h) or 0)
+
+    def synchronize(self):
+        rc = lib().sailgpu_ctx_synchronize(self._h)
+        if rc != 0:
+            raise SailGpuError(rc, lib().sailgpu_ctx_last_error(None).decode())
+
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         rc = lib().sailgpu_ctx_comm_init(self._h, unique_id, rank, world)
         if rc != 0:
@@ -113,7 +126,8 @@ class Context:
 
     def __del__(self):
         try:
-            self.close()
+            if not sys.is_finalizing():
+                self.close()
         except Exception:
             pass
 
@@ -171,7 +185,8 @@ class DeviceBatch:
 
     def __del__(self):
         try:
-            self.release()
+            if not sys.is_finalizing():
+                self.release()
         except Exception:
             pass
 
@@ -300,7 +315,8 @@ class GpuExec:
 
     def __del__(self):
         try:
-            self.close()
+            if not sys.is_finalizing():
+                self.close()
         except Exception:
             pass
 

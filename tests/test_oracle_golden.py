@@ -23,3 +23,25 @@ def test_tpch_golden(q, strings, golden):
     want = golden[q]
     assert got.schema.names == want["columns"]
     assert render.rows(got) == want["rows"]
+
+
+def test_c_pipelines_match_golden_and_python_oracle(golden):
+    """oracle/cpipelines.c (the CPU-baseline port) against the golden Q1/Q6 snapshot and ops.py."""
+    from datagen import tpch
+    from oracle import cpipelines
+    li = tpch.lineitem(0.001)
+    rows = cpipelines.q1(li, plans.days("1998-09-24"), threads=3)
+    want = golden["q1"]["rows"]
+    assert len(rows) == len(want)
+
+    def dec(v, s):
+        sign = "-" if v < 0 else ""
+        v = abs(v)
+        return f"{sign}{v // 10**s}.{v % 10**s:0{s}d}"
+    for r, w in zip(rows, want):
+        rf, ls, sq, sp, sdp, sc, sd, cnt = r
+        got = [rf, ls, dec(sq, 2), dec(sp, 2), dec(sdp, 4), dec(sc, 6),
+               dec(sq * 10**4 // cnt, 6), dec(sp * 10**4 // cnt, 6), dec(sd * 10**4 // cnt, 6), str(cnt)]
+        assert got == w
+    n, s = cpipelines.q6(li, plans.days("1994-01-01"), plans.days("1995-01-01"), threads=2)
+    assert dec(s, 4) == golden["q6"]["rows"][0][0]
