@@ -866,7 +866,8 @@ def col_hash64(c: Col) -> np.ndarray:
     if is_decimal(c.type):
         lo = np.array([int(v) & 0xFFFFFFFFFFFFFFFF for v in c.data], dtype=np.uint64)
         hi = np.array([(int(v) >> 64) & 0xFFFFFFFFFFFFFFFF for v in c.data], dtype=np.uint64)
-        h = mix64(lo ^ mix64(hi))
+        # <=18-digit decimals are keyed on their low 64 bits (they fit), wider ones on all 128
+        h = mix64(lo) if dec_ps(c.type)[0] <= 18 else mix64(lo ^ mix64(hi))
     elif is_string(c.type):
         out = np.zeros(n, dtype=np.uint64)
         for i, v in enumerate(c.data):

@@ -147,6 +147,12 @@ class PipelineCompiler {
     prog_.push_back(I);
     return d;
   }
+  Val not_val(const Val& v) { return b_not(v); }
+  Val and_val(const Val& a, const Val& b) { return b_and(a, b); }
+  Val materialize(const Val& v) { return ensure_slot(v); }
+  static ExprPtr placeholder(int id, const DataType& t, bool nullable) {
+    auto e = std::make_shared<Expr>(); e->kind = Expr::Col; e->col = 100000 + id; e->type = t; e->nullable = nullable; return e;
+  }
   void and_mask(const Val& b) { mask_ = (mask_.slot < 0 && !mask_.is_imm) ? b : b_and(mask_, b); has_filter_ = true; }
   void bind_value(const ExprPtr& placeholder, const Val& v) { cse_[placeholder->key()] = v; }
 

@@ -432,7 +432,7 @@ __device__ __noinline__ void vm_probe(const ProbeParams& P, const TileCtx& c, ui
             int w = 0;
             for (int i = 0; i < P.n_keys && eq; ++i) {
               const KeyDesc& d = P.keys[i];
-              const uint8_t* bp = P.build_keys[i] + cand * d.width;
+              const uint8_t* bp = P.build_keys[i] + cand * P.build_stride[i];
               if (d.width == 16) {
                 ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bp);
                 if (d.is_view) { ulonglong2 pv; pv.x = key.w[w]; pv.y = key.w[w + 1]; eq = view_equal(bv, pv); }

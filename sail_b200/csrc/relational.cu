@@ -1,0 +1,298 @@
+// relational.cu -- kernels behind HashJoinExec (multi-match path), SortExec/TopK and row gathers.
+//
+//   * join_count / join_emit : duplicate-key build sides (HashJoinExec general case): per probe row
+//     walk the open-addressing run, count then emit (build row, probe row) pairs.  The unique-key
+//     fast path never comes here: it runs inside the tile pipeline (OP_PROBE, pipeline.cu).
+//   * sort_encode + radix passes : SortExec.  Rows are encoded into order-preserving fixed-width keys
+//     (arrow-row style: null byte, sign-flipped big-endian integers, IEEE total order, padded strings
+//     + length) and sorted by a stable LSD radix sort on 8-bit digits whose per-warp ranking uses
+//     __match_any_sync / ballots ("radix sort via warp shuffles", BASELINE.json north_star).
+//   * gather_rows : `take` of fixed-width / view columns by row index.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "dev_util.cuh"
+#include "kernels.hpp"
+#include "relational.hpp"
+
+namespace sg {
+
+// ------------------------------------------------------------------------------------------------
+// raw-column key hashing: must equal pack_key() in pipeline.cu (the build sink hashes VM slots)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool col_is_null(const RawKeyCol& k, int64_t row) {
+  return k.validity_bits && !((k.validity_bits[row >> 3] >> (row & 7)) & 1);
+}
+__device__ __forceinline__ uint64_t raw_key_hash(const RawKeyCol* keys, int n_keys, int64_t row, bool* has_null) {
+  uint64_t h = 0x243F6A8885A308D3ull;
+  *has_null = false;
+  for (int i = 0; i < n_keys; ++i) {
+    const RawKeyCol& k = keys[i];
+    if (col_is_null(k, row)) { *has_null = true; return 0; }
+    const uint8_t* p = k.data + row * k.width;
+    if (k.width == 16) {
+      ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+      h = mix64(h ^ (k.is_view ? view_hash(v) : mix64(v.x ^ mix64(v.y))));
+    } else {
+      uint64_t v = k.width == 8 ? *reinterpret_cast<const uint64_t*>(p) : k.width == 4 ? (uint64_t)*reinterpret_cast<const uint32_t*>(p) : (uint64_t)*p;
+      h = mix64(h ^ v);
+    }
+  }
+  return h;
+}
+__device__ __forceinline__ bool raw_keys_equal(const RawKeyCol* a, int64_t ra, const RawKeyCol* b, int64_t rb, int n_keys) {
+  for (int i = 0; i < n_keys; ++i) {
+    const uint8_t* pa = a[i].data + ra * a[i].width;
+    const uint8_t* pb = b[i].data + rb * b[i].width;
+    if (a[i].width == 16) {
+      ulonglong2 x = *reinterpret_cast<const ulonglong2*>(pa), y = *reinterpret_cast<const ulonglong2*>(pb);
+      if (a[i].is_view ? !view_equal(x, y) : (x.x != y.x || x.y != y.y)) return false;
+    } else if (a[i].width == 8) { if (*reinterpret_cast<const uint64_t*>(pa) != *reinterpret_cast<const uint64_t*>(pb)) return false; }
+    else if (a[i].width == 4) { if (*reinterpret_cast<const uint32_t*>(pa) != *reinterpret_cast<const uint32_t*>(pb)) return false; }
+    else if (*pa != *pb) return false;
+  }
+  return true;
+}
+
+// pass 0: counts[i] = number of build rows matching probe row i.  pass 1: write pairs at offs[i].
+__global__ void join_multi_kernel(JoinMultiParams P) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.n_probe; i += (int64_t)gridDim.x * blockDim.x) {
+    bool has_null;
+    const uint64_t h = raw_key_hash(P.probe_keys, P.n_keys, i, &has_null);
+    uint32_t n = 0;
+    uint64_t out = P.pass == 1 ? P.offsets[i] : 0;
+    if (!has_null) {
+      const uint64_t tag = h | 1ull;
+      uint64_t idx = (h >> 1) & P.capacity_mask;
+      for (;;) {
+        const ulonglong2 s = *reinterpret_cast<const ulonglong2*>(P.table + idx * 16);
+        if (s.x == 0) break;
+        if (s.x == tag && raw_keys_equal(P.build_keys, (int64_t)s.y, P.probe_keys, i, P.n_keys)) {
+          if (P.pass == 1) { P.out_build[out] = (int64_t)s.y; P.out_probe[out] = i; ++out; }
+          if (P.pass >= 1 && P.visited) P.visited[s.y] = 1;     // pass 2 = mark only (semi / anti joins emitting build rows)
+          ++n;
+        }
+        idx = (idx + 1) & P.capacity_mask;
+      }
+    }
+    if (P.pass == 0) {
+      P.counts[i] = (P.emit_unmatched_probe && n == 0) ? 1u : n;
+    } else if (P.pass == 1 && P.emit_unmatched_probe && n == 0) {
+      P.out_build[out] = -1; P.out_probe[out] = i;
+    }
+  }
+}
+
+cudaError_t launch_join_multi(const JoinMultiParams& P, cudaStream_t s) {
+  if (P.n_probe == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((P.n_probe + 255) / 256, 148 * 16);
+  join_multi_kernel<<<grid, 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather (take)
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int64_t* __restrict__ idx, int64_t n, int width) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx[i];
+    if (width == 16) { ulonglong2 v; v.x = 0; v.y = 0; if (r >= 0) v = *reinterpret_cast<const ulonglong2*>(src + r * 16); *reinterpret_cast<ulonglong2*>(dst + i * 16) = v; }
+    else if (width == 8) *reinterpret_cast<uint64_t*>(dst + i * 8) = r >= 0 ? *reinterpret_cast<const uint64_t*>(src + r * 8) : 0;
+    else if (width == 4) *reinterpret_cast<uint32_t*>(dst + i * 4) = r >= 0 ? *reinterpret_cast<const uint32_t*>(src + r * 4) : 0;
+    else if (width == 2) *reinterpret_cast<uint16_t*>(dst + i * 2) = r >= 0 ? *reinterpret_cast<const uint16_t*>(src + r * 2) : 0;
+    else dst[i] = r >= 0 ? src[r] : 0;
+  }
+}
+cudaError_t launch_gather_rows(const uint8_t* src, uint8_t* dst, const int64_t* idx, int64_t n, int width, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  gather_rows_kernel<<<grid, 256, 0, s>>>(src, dst, idx, n, width);
+  return cudaGetLastError();
+}
+// bit column gathered into bytes: out[i] = bit(src, idx[i]) (0 when idx < 0 or src == null -> `dflt`)
+__global__ void gather_bits_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ out, const int64_t* __restrict__ idx, int64_t n, int dflt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx[i];
+    out[i] = r < 0 ? 0 : (bits ? (bits[r >> 3] >> (r & 7)) & 1 : dflt);
+  }
+}
+cudaError_t launch_gather_bits(const uint8_t* bits, uint8_t* out, const int64_t* idx, int64_t n, int dflt, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  gather_bits_kernel<<<grid, 256, 0, s>>>(bits, out, idx, n, dflt);
+  return cudaGetLastError();
+}
+__global__ void iota_kernel(int64_t* out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = i;
+}
+__global__ void widen_u32_kernel(const uint32_t* in, int64_t* out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// sort: key encoding
+// ------------------------------------------------------------------------------------------------
+__global__ void max_view_len_kernel(const ulonglong2* views, int64_t n, unsigned int* out) {
+  unsigned int m = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, (unsigned int)views[i].x);
+  for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, d));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+cudaError_t launch_max_view_len(const void* views, int64_t n, unsigned int* out, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  max_view_len_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const ulonglong2*>(views), n, out);
+  return cudaGetLastError();
+}
+
+__global__ void sort_encode_kernel(SortEncodeParams P) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t* out = P.keys + i * P.key_bytes;
+    for (int k = 0; k < P.n_keys; ++k) {
+      const SortKeyCol& c = P.cols[k];
+      uint8_t* o = out + c.out_off;
+      const bool isnull = c.validity_bits && !((c.validity_bits[i >> 3] >> (i & 7)) & 1);
+      *o++ = isnull ? (c.nulls_first ? 0x00 : 0xFF) : (c.nulls_first ? 0x01 : 0x00);
+      const uint8_t inv = c.asc ? 0x00 : 0xFF;
+      const int w = c.enc_bytes;
+      if (isnull) { for (int b = 0; b < w; ++b) o[b] = 0; continue; }
+      switch (c.kind) {
+        case SORT_INT: {      // signed integer of c.width bytes -> big endian, sign bit flipped
+          const uint8_t* p = c.data + i * c.width;
+          for (int b = 0; b < c.width; ++b) o[b] = p[c.width - 1 - b] ^ inv;
+          o[0] ^= 0x80;
+          break;
+        }
+        case SORT_UINT: {
+          const uint8_t* p = c.data + i * c.width;
+          for (int b = 0; b < c.width; ++b) o[b] = p[c.width - 1 - b] ^ inv;
+          break;
+        }
+        case SORT_F64: {      // IEEE-754 total order
+          uint64_t v = *reinterpret_cast<const uint64_t*>(c.data + i * 8);
+          v = (v >> 63) ? ~v : (v | 0x8000000000000000ull);
+          for (int b = 0; b < 8; ++b) o[b] = (uint8_t)(v >> (56 - 8 * b)) ^ inv;
+          break;
+        }
+        case SORT_BOOL: {
+          const uint8_t v = (c.data[i >> 3] >> (i & 7)) & 1;
+          o[0] = v ^ inv;
+          break;
+        }
+        default: {            // SORT_VIEW: bytes padded with zeros to c.str_len, then 4-byte big-endian length
+          const uint8_t* vp = c.data + i * 16;
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(vp);
+          const uint32_t len = (uint32_t)v.x;
+          const uint8_t* s = view_ptr(v, vp);
+          for (int b = 0; b < c.str_len; ++b) o[b] = ((uint32_t)b < len ? s[b] : 0) ^ inv;
+          for (int b = 0; b < 4; ++b) o[c.str_len + b] = (uint8_t)(len >> (24 - 8 * b)) ^ inv;
+        }
+      }
+    }
+  }
+}
+cudaError_t launch_sort_encode(const SortEncodeParams& P, cudaStream_t s) {
+  if (P.n == 0) return cudaSuccess;
+  int grid = (int)std::min<int64_t>((P.n + 255) / 256, 148 * 8);
+  sort_encode_kernel<<<grid, 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// sort: stable LSD radix passes over row indices (u32), 8-bit digits
+// Each warp owns a contiguous chunk of RADIX_CHUNK elements.
+// ------------------------------------------------------------------------------------------------
+constexpr int RADIX_CHUNK = 2048;
+
+__global__ void radix_hist_kernel(const uint8_t* __restrict__ keys, int key_bytes, int digit, const uint32_t* __restrict__ idx, int64_t n,
+                                  uint32_t* __restrict__ hist /* [256][n_chunks] */, int64_t n_chunks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (chunk >= n_chunks) return;
+  __shared__ uint32_t sh[8][256];
+  uint32_t* h = sh[(threadIdx.x >> 5)];
+  for (int b = lane; b < 256; b += 32) h[b] = 0;
+  __syncwarp();
+  const int64_t b0 = chunk * RADIX_CHUNK, b1 = min(n, b0 + RADIX_CHUNK);
+  for (int64_t i = b0 + lane; i < b1; i += 32) atomicAdd(&h[keys[(int64_t)idx[i] * key_bytes + digit]], 1u);
+  __syncwarp();
+  for (int b = lane; b < 256; b += 32) hist[(int64_t)b * n_chunks + chunk] = h[b];
+}
+
+__global__ void radix_scatter_kernel(const uint8_t* __restrict__ keys, int key_bytes, int digit, const uint32_t* __restrict__ idx_in,
+                                     uint32_t* __restrict__ idx_out, int64_t n, const uint64_t* __restrict__ offs /* scanned hist */, int64_t n_chunks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (chunk >= n_chunks) return;
+  __shared__ uint64_t sh[8][256];
+  uint64_t* base = sh[(threadIdx.x >> 5)];
+  for (int b = lane; b < 256; b += 32) base[b] = offs[(int64_t)b * n_chunks + chunk];
+  __syncwarp();
+  const int64_t b0 = chunk * RADIX_CHUNK, b1 = min(n, b0 + RADIX_CHUNK);
+  for (int64_t g = b0; g < b1; g += 32) {
+    const int64_t i = g + lane;
+    const bool in = i < b1;
+    const uint32_t row = in ? idx_in[i] : 0;
+    const uint32_t d = in ? keys[(int64_t)row * key_bytes + digit] : 0x100u + lane;   // idle lanes match nobody
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+    const int rank = __popc(peers & ((1u << lane) - 1));
+    uint64_t pos = 0;
+    if (in) pos = base[d] + rank;
+    __syncwarp();
+    if (in && rank == __popc(peers) - 1) base[d] += __popc(peers);   // last peer advances the cursor
+    __syncwarp();
+    if (in) idx_out[pos] = row;
+  }
+}
+
+__global__ void iota_u32_kernel(uint32_t* out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint32_t)i;
+}
+
+// Sorts row indices by the encoded keys.  `idx_a` receives the final order.  scratch: idx_b [n] u32,
+// hist [256*n_chunks] u32, offs [256*n_chunks] u64, scan scratch [1026] u64.
+cudaError_t radix_sort_indices(const uint8_t* keys, int key_bytes, int64_t n, uint32_t* idx_a, uint32_t* idx_b, uint32_t* hist, uint64_t* offs,
+                               uint64_t* scan_scratch, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const int64_t n_chunks = (n + RADIX_CHUNK - 1) / RADIX_CHUNK;
+  const int blocks = (int)((n_chunks + 7) / 8);
+  iota_u32_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(idx_a, n);
+  uint32_t* in = idx_a; uint32_t* out = idx_b;
+  for (int digit = key_bytes - 1; digit >= 0; --digit) {
+    radix_hist_kernel<<<blocks, 256, 0, s>>>(keys, key_bytes, digit, in, n, hist, n_chunks);
+    cudaError_t e = launch_exclusive_scan_u32(hist, 256 * n_chunks, offs, scan_scratch, s);
+    if (e != cudaSuccess) return e;
+    radix_scatter_kernel<<<blocks, 256, 0, s>>>(keys, key_bytes, digit, in, out, n, offs, n_chunks);
+    std::swap(in, out);
+  }
+  if (in != idx_a) { cudaError_t e = cudaMemcpyAsync(idx_a, in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s); if (e != cudaSuccess) return e; }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_iota(int64_t* out, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  iota_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(out, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_widen_u32(const uint32_t* in, int64_t* out, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  widen_u32_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+// rebases resolved views by a constant delta (exchange: received heap segment vs sender heap)
+__global__ void rebase_views_kernel(ulonglong2* views, int64_t n, uint64_t heap_base) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    ulonglong2 v = views[i];
+    if ((uint32_t)v.x > 12) { v.y = heap_base + (v.y >> 32); views[i] = v; }   // Arrow view: offset in the high half
+  }
+}
+cudaError_t launch_rebase_views(void* views, int64_t n, uint64_t heap_base, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  rebase_views_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(reinterpret_cast<ulonglong2*>(views), n, heap_base);
+  return cudaGetLastError();
+}
+
+}  // namespace sg

@@ -1,0 +1,62 @@
+// relational.hpp -- parameter blocks and launchers of relational.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vm.h"
+
+namespace sg {
+
+struct RawKeyCol {
+  const uint8_t* data;
+  const uint8_t* validity_bits;   // Arrow bitmap or null
+  int32_t width;                  // 1, 4, 8, 16
+  int32_t is_view;
+};
+
+struct JoinMultiParams {
+  int64_t n_probe;
+  int32_t n_keys;
+  int32_t pass;                   // 0 count, 1 emit
+  int32_t emit_unmatched_probe;   // right-outer: a probe row without match yields (-1, row)
+  int32_t pad;
+  RawKeyCol probe_keys[MAX_KEYS];
+  RawKeyCol build_keys[MAX_KEYS];
+  const uint8_t* table;
+  uint64_t capacity_mask;
+  uint32_t* counts;
+  const uint64_t* offsets;
+  int64_t* out_build;
+  int64_t* out_probe;
+  uint8_t* visited;
+};
+
+enum SortKind : int32_t { SORT_INT = 0, SORT_UINT = 1, SORT_F64 = 2, SORT_BOOL = 3, SORT_VIEW = 4 };
+struct SortKeyCol {
+  const uint8_t* data;
+  const uint8_t* validity_bits;
+  int32_t kind, width;
+  int32_t asc, nulls_first;
+  int32_t out_off;                // offset of this key inside the encoded row
+  int32_t enc_bytes;              // value bytes after the null byte
+  int32_t str_len;                // SORT_VIEW: padded string bytes (max length in the column)
+  int32_t pad;
+};
+struct SortEncodeParams {
+  int64_t n;
+  int32_t n_keys, key_bytes;
+  uint8_t* keys;
+  SortKeyCol cols[8];
+};
+
+cudaError_t launch_join_multi(const JoinMultiParams& P, cudaStream_t s);
+cudaError_t launch_gather_bits(const uint8_t* bits, uint8_t* out, const int64_t* idx, int64_t n, int dflt, cudaStream_t s);
+cudaError_t launch_max_view_len(const void* views, int64_t n, unsigned int* out, cudaStream_t s);
+cudaError_t launch_sort_encode(const SortEncodeParams& P, cudaStream_t s);
+cudaError_t radix_sort_indices(const uint8_t* keys, int key_bytes, int64_t n, uint32_t* idx_a, uint32_t* idx_b, uint32_t* hist, uint64_t* offs,
+                               uint64_t* scan_scratch, cudaStream_t s);
+cudaError_t launch_iota(int64_t* out, int64_t n, cudaStream_t s);
+cudaError_t launch_widen_u32(const uint32_t* in, int64_t* out, int64_t n, cudaStream_t s);
+cudaError_t launch_rebase_views(void* views, int64_t n, uint64_t heap_base, cudaStream_t s);
+
+}  // namespace sg

@@ -160,6 +160,7 @@ struct ProbeParams {
   int32_t join_kind;       // 0 inner (filter + row id), 1 semi (filter), 2 anti (inverse filter), 3 left-outer (row id or -1)
   KeyDesc keys[MAX_KEYS];  // probe-side key slots
   const uint8_t* build_keys[MAX_KEYS];   // build-side key columns (for equality verification)
+  uint8_t build_stride[MAX_KEYS];        // their element stride (16 for a <=18-digit decimal compared on its low 8 bytes)
   uint32_t rowid_slot;     // I64 slot receiving the matching build row id
   uint32_t match_slot;     // B slot receiving "matched"
   uint8_t* visited;        // build-side visited bitmap bytes (left/semi/anti emitting build rows) or null

@@ -333,6 +333,28 @@ def run_op(spec: dict, *tables, ctx: Context | None = None) -> pa.Table:
         op.close()
 
 
+def exchange(send: list, schema: pa.Schema, ctx: Context | None = None) -> DeviceBatch:
+    """All-to-all over NCCL/NVLink: send[p] (DeviceBatch) goes to rank p; returns what this rank received.
+    Replaces the body of shuffle_write/shuffle_read for Partitioning::Hash
+    (crates/sail-execution/src/plan/shuffle_write.rs:209-267, shuffle_read.rs:107-117)."""
+    ctx = ctx or default_context()
+    n = len(send)
+    arr = (ArrowDeviceArrayC * n)()
+    for i, d in enumerate(send):
+        if not d._live:
+            raise SailGpuError(6, "device batch was already consumed")
+        ctypes.memmove(ctypes.addressof(arr[i]), ctypes.addressof(d.c), ctypes.sizeof(ArrowDeviceArrayC))
+        d._live = False
+    out = DeviceBatch(schema)
+    sc = _export_schema(schema)
+    rc = lib().sailgpu_exchange(ctx._h, ctypes.addressof(sc), ctypes.addressof(arr), n, ctypes.addressof(out.c))
+    _release_schema(sc)
+    if rc != 0:
+        raise SailGpuError(rc, "sailgpu_exchange failed")
+    out._live = True
+    return out
+
+
 def to_device(table: pa.Table, ctx: Context | None = None) -> DeviceBatch:
     """Upload a table once; the returned DeviceBatch is HBM-resident Arrow (used by the bench's
     'inputs already resident in HBM' leg)."""

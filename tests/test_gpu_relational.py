@@ -1,0 +1,148 @@
+"""GPU parity for HashJoinExec, SortExec/TopK, hash RepartitionExec and whole TPC-H plans
+(Q1,Q3,Q4,Q5,Q6,Q12) through the C ABI, against the oracle and the reference's golden snapshots."""
+import decimal
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from oracle import render
+from sail_b200 import plans
+from tests.util import assert_same, gpu_op, oracle_op
+
+pytestmark = pytest.mark.gpu
+
+
+def left_table(n, seed, dups, nulls):
+    rng = np.random.default_rng(seed)
+    k = rng.integers(0, max(1, n // (3 if dups else 1)), n).astype(np.int64) if dups else rng.permutation(np.arange(n, dtype=np.int64) * 3)
+    k2 = (k % 7).astype(np.int32)
+    return pa.table({
+        "lk": pa.array(k, mask=(rng.random(n) < 0.05) if nulls else None),
+        "lk2": pa.array(k2),
+        "lv": pa.array([decimal.Decimal(int(x)) / 100 for x in rng.integers(0, 10**6, n)], type=pa.decimal128(15, 2)),
+        "ls": pa.array([["red", "green", "a long colour name indeed", "blue"][i] for i in rng.integers(0, 4, n)], type=pa.string_view(),
+                       mask=(rng.random(n) < 0.1) if nulls else None),
+    })
+
+
+def right_table(n, seed, key_range, nulls):
+    rng = np.random.default_rng(seed)
+    k = (rng.integers(0, max(1, key_range), n) * 3).astype(np.int64)
+    return pa.table({
+        "rk": pa.array(k, mask=(rng.random(n) < 0.05) if nulls else None),
+        "rk2": pa.array((k // 3 % 7).astype(np.int32)),
+        "rd": pa.array(rng.integers(8000, 9000, n).astype(np.int32), type=pa.int32()).cast(pa.date32()),
+        "rf": pa.array(rng.normal(size=n)),
+    })
+
+
+@pytest.mark.parametrize("jt", ["inner", "left", "right", "left_semi", "left_anti", "right_semi", "right_anti"])
+@pytest.mark.parametrize("nulls", [False, True])
+@pytest.mark.parametrize("nl,nr", [(0, 10), (10, 0), (50, 500), (3000, 20000)])
+def test_hash_join_unique_build(jt, nulls, nl, nr):
+    l, r = left_table(nl, 1, False, nulls), right_table(nr, 2, max(nl, 1) * 2, nulls)
+    spec = {"op": "hash_join", "join_type": jt, "on": [[0, 0]], "filter": None, "projection": None}
+    if jt == "right" and nl == 0:
+        pytest.skip("right outer with empty build: documented as unsupported")
+    assert_same(gpu_op(spec, l, r), oracle_op(spec, l, r), float_cols={7})
+
+
+@pytest.mark.parametrize("jt", ["inner", "left", "right", "left_semi", "right_semi", "right_anti"])
+def test_hash_join_duplicate_build_keys(jt):
+    l = pa.table({"lk": pa.array(np.array([1, 1, 2, 3, 3, 3, 9], dtype=np.int64)), "lv": pa.array(np.arange(7, dtype=np.int64))})
+    r = pa.table({"rk": pa.array(np.array([3, 1, 5, 3, 2, 7], dtype=np.int64)), "rv": pa.array(np.arange(6, dtype=np.int64) * 10)})
+    spec = {"op": "hash_join", "join_type": jt, "on": [[0, 0]], "filter": None, "projection": None}
+    assert_same(gpu_op(spec, l, r), oracle_op(spec, l, r))
+    rng = np.random.default_rng(7)
+    l = left_table(2000, 3, True, False)
+    r = right_table(9000, 4, 700, False)
+    l = l.set_column(0, "lk", pa.array((np.asarray(l["lk"]) * 3).astype(np.int64)))
+    assert_same(gpu_op(spec, l, r), oracle_op(spec, l, r), float_cols={7})
+
+
+def test_hash_join_two_keys_projection_and_filter():
+    l, r = left_table(1500, 5, False, False), right_table(8000, 6, 1500, False)
+    spec = {"op": "hash_join", "join_type": "inner", "on": [[0, 0], [1, 1]], "filter": None, "projection": [2, 3, 6]}
+    assert_same(gpu_op(spec, l, r), oracle_op(spec, l, r))
+    spec = {"op": "hash_join", "join_type": "inner", "on": [[0, 0]],
+            "filter": plans.binop(">", {"col": 2}, plans.dec(300000, 15, 2)), "projection": [0, 2, 6]}
+    assert_same(gpu_op(spec, l, r), oracle_op(spec, l, r))
+
+
+def test_hash_join_string_keys():
+    names = ["UNITED KINGDOM", "UNITED STATES", "PERU", "CHINA", "SAUDI ARABIA", "MOZAMBIQUE"]
+    l = pa.table({"n": pa.array(names, type=pa.string_view()), "id": pa.array(np.arange(6, dtype=np.int64))})
+    rng = np.random.default_rng(3)
+    r = pa.table({"n": pa.array([names[i] if i < 6 else "ATLANTIS" for i in rng.integers(0, 8, 4000)], type=pa.string_view()),
+                  "v": pa.array(rng.integers(0, 100, 4000).astype(np.int64))})
+    spec = {"op": "hash_join", "join_type": "inner", "on": [[0, 0]], "filter": None, "projection": [1, 2, 3]}
+    assert_same(gpu_op(spec, l, r), oracle_op(spec, l, r))
+
+
+@pytest.mark.parametrize("n", [0, 1, 100, 5000, 70000])
+@pytest.mark.parametrize("fetch", [None, 10])
+def test_sort(n, fetch):
+    rng = np.random.default_rng(n)
+    t = pa.table({
+        "a": pa.array(rng.integers(-50, 50, n).astype(np.int64), mask=rng.random(n) < 0.1),
+        "d": pa.array([decimal.Decimal(int(x)) / 100 for x in rng.integers(-10**6, 10**6, n)], type=pa.decimal128(15, 2)),
+        "s": pa.array([["x", "xy", "", "a rather long string to sort", "b"][i] for i in rng.integers(0, 5, n)], type=pa.string_view()),
+        "f": pa.array(rng.normal(size=n)),
+        "u": pa.array(np.arange(n, dtype=np.int64)),
+    })
+    keys = [{"expr": {"col": 0}, "asc": False, "nulls_first": False}, {"expr": {"col": 2}, "asc": True, "nulls_first": True},
+            {"expr": {"col": 1}, "asc": False, "nulls_first": False}, {"expr": {"col": 4}, "asc": True, "nulls_first": True}]
+    spec = {"op": "sort", "keys": keys, "fetch": fetch}
+    assert_same(gpu_op(spec, t), oracle_op(spec, t), ordered=True, float_cols={3})
+    spec = {"op": "sort", "keys": [{"expr": {"col": 3}, "asc": True, "nulls_first": True}], "fetch": fetch}
+    assert_same(gpu_op(spec, t), oracle_op(spec, t), ordered=True, float_cols={3})
+
+
+@pytest.mark.parametrize("n_parts", [1, 2, 8])
+def test_hash_repartition(n_parts):
+    from sail_b200 import engine
+    l = left_table(20000, 11, True, True)
+    spec = {"op": "repartition", "scheme": "hash", "exprs": [{"col": 0}, {"col": 3}], "n": n_parts}
+    want = oracle_op(spec, l)
+    op = engine.GpuExec(spec, [l.schema])
+    op.push(l)
+    op.finish()
+    total = 0
+    for p in range(n_parts):
+        parts = []
+        while True:
+            d, more = op.pull_device(partition=p)
+            if d.num_rows:
+                # bring it to the host through an identity projection
+                ident = engine.GpuExec({"op": "projection", "exprs": [{"expr": {"col": i}, "name": nm} for i, nm in enumerate(l.schema.names)]}, [l.schema])
+                ident.push(d); ident.finish()
+                parts.append(ident.collect())
+                ident.close()
+            if not more:
+                break
+        got = pa.concat_tables(parts) if parts else l.slice(0, 0)
+        assert_same(got, want[p])        # same rows in the same partition (order inside a partition is free)
+        total += got.num_rows
+    assert total == l.num_rows           # every row delivered exactly once
+    op.close()
+
+
+@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q12"])
+def test_tpch_golden_on_gpu(q, golden):
+    """whole plans through the C ABI on dbgen SF0.001 == the reference's own snapshot"""
+    from datagen import tpch
+    tables = tpch.tables(0.001)
+    got = plans.execute(plans.TPCH[q](), tables, gpu_op)
+    assert got.schema.names == golden[q]["columns"]
+    assert render.rows(got) == golden[q]["rows"]
+
+
+@pytest.mark.parametrize("q", ["q3", "q4", "q5", "q12"])
+def test_tpch_sf01_vs_oracle(q):
+    from datagen import tpch
+    tables = tpch.tables(0.1)
+    plan = plans.TPCH[q]()
+    got = plans.execute(plan, tables, gpu_op)
+    want = plans.execute(plan, tables, oracle_op)
+    assert_same(got, want, ordered=(q != "q3"))   # Q3's top-10 may tie on (revenue, date): compare as sets
