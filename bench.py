@@ -132,10 +132,41 @@ def pin_table(ctx, table):
     return pa.table(arrays, names=table.schema.names), keep, total
 
 
+def run_query_dist(backend, specs, inputs, in_schema, host_chunks=None):
+    """world > 1: fused partial on the shard -> hash repartition + NCCL all-to-all -> final on the owner ->
+    gather to rank 0 -> sort there.  Returns (result table on rank 0, launches, kernel ns, kernel launches)."""
+    from sail_b200 import dist as sdist
+    from sail_b200 import engine
+    fused, final, sort = specs
+    op1 = engine.GpuExec(fused, [in_schema], backend.ctx)
+    if host_chunks is None:
+        for d in inputs:
+            op1.push(d.borrow())
+    else:
+        for b in host_chunks:
+            op1.push(b)
+    op1.finish()
+    parts = op1.collect_device()
+    m1 = op1.metrics()
+    pschema = op1.schema
+    op1.close()
+    for p in parts:
+        p.schema = pschema
+    backend.launches = 0
+    mine = sdist.exchange_by_key(backend, parts, pschema, [0, 1])
+    fin = backend.run(final, mine)
+    root = sdist.gather_to_root(backend, fin, fin[0].schema)
+    out = backend.run(sort, root)
+    table = backend.to_host(out)
+    return table, m1["gpu.kernel_launches"] + backend.launches, m1["gpu.pipeline_kernel_ns"], m1["gpu.pipeline_launches"]
+
+
 def run_query(ctx, specs, inputs, in_schema, host_chunks=None):
     """One Q1 execution.  inputs: list of DeviceBatch (resident leg) or None with host_chunks (e2e leg).
     Returns (result table, #kernel launches, pipeline kernel ns, pipeline launches)."""
     from sail_b200 import engine
+    if DIST_BACKEND is not None:
+        return run_query_dist(DIST_BACKEND, specs, inputs, in_schema, host_chunks)
     fused, final, sort = specs
     op1 = engine.GpuExec(fused, [in_schema], ctx)
     if host_chunks is None:
@@ -169,6 +200,7 @@ def run_query(ctx, specs, inputs, in_schema, host_chunks=None):
 
 
 SORT_ON_GPU = True
+DIST_BACKEND = None
 
 
 def check_result(table, want_rows):
@@ -240,8 +272,14 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from sail_b200 import engine
-    global SORT_ON_GPU
+    global SORT_ON_GPU, DIST_BACKEND
     ctx = engine.Context(local)
+    if world > 1:
+        from sail_b200 import dist as sdist
+        uid = [engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+        DIST_BACKEND = sdist.GpuBackend(ctx, rank, world)
     table = gen_shard(args.sf, rank, world).combine_chunks()
     n_rows = table.num_rows
     specs = q1_specs()
@@ -322,7 +360,8 @@ def main():
             "config": {"workload": f"TPC-H Q1 SF{args.sf:g} per GPU, 1 partition per GPU, Arrow batches resident in HBM",
                        "rows_per_gpu": n_rows, "strings": "Utf8View", "l2": "inputs (6 GB) larger than L2; no flush",
                        "plan": "GpuPipelineExec[Filter+Projection+Aggregate(Partial)] -> GpuAggregateExec(FinalPartitioned)"
-                               + (" -> GpuSortExec" if SORT_ON_GPU else "")},
+                               + (" -> GpuRepartitionExec(Hash) -> NCCL all-to-all" if world > 1 else "")
+                               + (" -> GpuSortExec" if SORT_ON_GPU else ""), "parallelism": f"{world} rank(s), lineitem sharded by order range"},
             "e2e": None if e2e_value is None else {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                                                     "ms_per_step": ms_e / e2e_steps, "host_batches": len(chunks)},
             "gpu_launches": launches,
