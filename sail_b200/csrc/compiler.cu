@@ -403,9 +403,10 @@ void PipelineCompiler::finish_aggregate(CompiledPipeline& out, const StageSpec& 
   {
     bool ok = A.n_accs <= REG_ACCS && getenv("SAILGPU_NO_REGPATH") == nullptr;
     for (int j = 0; j < A.n_accs; ++j) {
-      const int op = A.accs[j].op;
-      ok &= (op == ACC_COUNT || op == ACC_SUM_I64 || op == ACC_SUM_I128) && !A.accs[j].track_seen;
-      ok &= A.accs[j].vkind != K_F64;
+      const AccDesc& d = A.accs[j];
+      ok &= (d.op == ACC_COUNT || d.op == ACC_SUM_I64 || d.op == ACC_SUM_I128) && !d.track_seen && d.valid_slot == NO_SLOT;
+      ok &= d.op == ACC_COUNT || d.vkind == K_I64 || d.vkind == K_I128;
+      ok &= !(d.op == ACC_SUM_I64 && d.vkind != K_I64);
     }
     A.reg_path = ok ? 1 : 0;
   }
@@ -435,7 +436,8 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
   SG_CHECK(prog_.size() <= (size_t)MAX_INST, SAILGPU_ERR_UNSUPPORTED, "fused pipeline needs more than " + std::to_string(MAX_INST) + " VM instructions");
   const AggParams& A = out.agg;
   // per hot group: key words + fingerprint + entry pointer + one accumulator block per warp
-  const size_t per_group = out.sink == SINK_AGG ? (size_t)A.key_words * 8 + 16 + (size_t)(NT / 32) * (1 + 2 * A.n_accs) * 8 : 0;
+  const size_t per_group = out.sink == SINK_AGG ? (size_t)HOT_KEY_WORDS * 8 + 16 + (size_t)(NT / 32) * (1 + 2 * A.n_accs) * 8 : 0;
+  if (out.sink == SINK_AGG && A.key_words > HOT_KEY_WORDS) hot_wanted = 0;
   auto layout = [&](int rpt, int stages, uint32_t* temps, uint32_t* stage) {
     const uint32_t tile = (uint32_t)rpt * NT;
     uint32_t t = 0, s = 0;
@@ -501,6 +503,10 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
     for (int i = 0; i < AA.n_keys; ++i) { AA.keys[i].slot = off(AA.keys[i].slot); AA.keys[i].valid_slot = off(AA.keys[i].valid_slot); }
     for (int w = AA.has_null_word; w < AA.key_words; ++w) { AA.kwords[w].slot = off(AA.kwords[w].slot); AA.kwords[w].valid_slot = off(AA.kwords[w].valid_slot); }
     for (int j = 0; j < AA.n_accs; ++j) { AA.accs[j].value_slot = off(AA.accs[j].value_slot); AA.accs[j].valid_slot = off(AA.accs[j].valid_slot); }
+    for (int j = 0; j < AA.n_accs && j < REG_ACCS; ++j) {
+      AA.rload[j].slot = AA.accs[j].value_slot; AA.rload[j].stride = AA.accs[j].stride;
+      AA.rload[j].mode = (uint8_t)(AA.accs[j].op == ACC_COUNT ? 0 : AA.accs[j].vkind == K_I64 ? 1 : 2);
+    }
     AA.hot_groups = best_hot;
     AA.hot_smem_off = temps;
   }

@@ -880,7 +880,7 @@ struct HotView {
 __device__ __forceinline__ HotView hot_view(const AggParams& A, uint8_t* arena) {
   HotView h; h.G = A.hot_groups; h.aw = 1 + 2 * A.n_accs;
   uint8_t* p = arena + A.hot_smem_off;
-  h.keys = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * A.key_words * 8;
+  h.keys = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * HOT_KEY_WORDS * 8;
   h.fps = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * 8;
   h.entry = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * 8;
   h.wacc = reinterpret_cast<uint64_t*>(p);
@@ -888,11 +888,11 @@ __device__ __forceinline__ HotView hot_view(const AggParams& A, uint8_t* arena) 
 }
 
 // packed key of row r as 8-byte words held in registers (static indexing) + its fingerprint
-__device__ __forceinline__ uint64_t pack_words(const AggParams& A, const TileCtx& c, int r, uint64_t (&kw)[MAX_KEY_WORDS]) {
+__device__ __forceinline__ uint64_t pack_words(const AggParams& A, const TileCtx& c, int r, uint64_t (&kw)[HOT_KEY_WORDS]) {
   uint64_t nullmask = 0;
   uint64_t fp = 0x9E3779B97F4A7C15ull;
 #pragma unroll
-  for (int w = 0; w < MAX_KEY_WORDS; ++w) {
+  for (int w = 0; w < HOT_KEY_WORDS; ++w) {
     kw[w] = 0;
     if (w < A.key_words && !(A.has_null_word && w == 0)) {
       const KeyWord& d = A.kwords[w];
@@ -900,22 +900,19 @@ __device__ __forceinline__ uint64_t pack_words(const AggParams& A, const TileCtx
       uint64_t v = d.width == 8 ? lds<uint64_t>(p) : d.width == 4 ? (uint64_t)lds<uint32_t>(p) : (uint64_t)*p;
       if (d.valid_slot != NO_SLOT && c.arena[d.valid_slot + r] == 0) { v = 0; nullmask |= 1ull << d.key_index; }
       kw[w] = v;
-      fp = (fp ^ v) * 0xD6E8FEB86659FD93ull;
+      fp = ((fp << 9) | (fp >> 55)) ^ v;        // only a fast reject: every candidate is verified word by word
     }
   }
-  if (A.has_null_word) { kw[0] = nullmask; fp = (fp ^ nullmask) * 0xD6E8FEB86659FD93ull; }
+  if (A.has_null_word) { kw[0] = nullmask; fp = ((fp << 9) | (fp >> 55)) ^ nullmask; }
   return fp;
 }
 
-__device__ __forceinline__ int hot_lookup(const AggParams& A, const HotView& H, int hot_n, const uint64_t (&kw)[MAX_KEY_WORDS], uint64_t fp) {
+// dictionary entries are stored padded to HOT_KEY_WORDS words, so the verify is 4 unconditional compares
+__device__ __forceinline__ int hot_lookup(const AggParams& A, const HotView& H, int hot_n, const uint64_t (&kw)[HOT_KEY_WORDS], uint64_t fp) {
   for (int g = 0; g < hot_n; ++g) {
     if (H.fps[g] != fp) continue;
-    const uint64_t* hk = H.keys + g * A.key_words;
-    bool eq = true;
-#pragma unroll
-    for (int w = 0; w < MAX_KEY_WORDS; ++w)
-      if (w < A.key_words) eq &= hk[w] == kw[w];
-    if (eq) return g;
+    const uint64_t* hk = H.keys + g * HOT_KEY_WORDS;
+    if (hk[0] == kw[0] && hk[1] == kw[1] && hk[2] == kw[2] && hk[3] == kw[3]) return g;
   }
   return -1;
 }
@@ -924,7 +921,7 @@ __device__ __noinline__ uint64_t* hot_entry(const PipelineParams& P, const AggPa
   uint64_t* e = reinterpret_cast<uint64_t*>(H.entry[g]);
   if (e) return e;
   KeyRegs key;
-  for (int w = 0; w < MAX_KEY_WORDS; ++w) key.w[w] = w < A.key_words ? H.keys[g * A.key_words + w] : 0;
+  for (int w = 0; w < MAX_KEY_WORDS; ++w) key.w[w] = (w < A.key_words && w < HOT_KEY_WORDS) ? H.keys[g * HOT_KEY_WORDS + w] : 0;
   e = agg_find_or_insert(A, key, hash_packed_key(A, key), P.error_flag);
   H.entry[g] = reinterpret_cast<uint64_t>(e);     // benign race: every writer stores the same pointer
   return e;
@@ -947,6 +944,23 @@ __device__ __forceinline__ bool fits55(i128 v) {
   return (i128)lo == v && ((uint64_t)(lo + (1ll << 55)) >> 56) == 0;
 }
 
+// rows whose group is not in the CTA-local dictionary: global table, one warp-cooperative lookup per row slot
+template <int RPT>
+__device__ __noinline__ void agg_cold_rows(const PipelineParams& P, const AggParams& A, const TileCtx& c, const int (&gid)[RPT], const bool (&live)[RPT]) {
+  for (int k = 0; k < RPT; ++k) {
+    const bool cold = live[k] && gid[k] < 0;
+    if (__any_sync(0xFFFFFFFFu, cold)) {
+      const int r = threadIdx.x + k * NT;
+      KeyRegs key; bool hn; uint64_t h = 0;
+      if (cold) h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
+      uint64_t* e = agg_find_or_insert_warp(A, key, h, cold, P.error_flag);
+      if (cold && e) {
+        for (int j = 0; j < A.n_accs; ++j) acc_global(e, A, j, load_acc_value(A.accs[j], c, r));
+      }
+    }
+  }
+}
+
 template <int RPT>
 __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParams& A, const TileCtx& c, Smem* sm) {
   const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + P.mask_slot;
@@ -967,7 +981,7 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       if (live[k]) {
-        uint64_t kw[MAX_KEY_WORDS];
+        uint64_t kw[HOT_KEY_WORDS];
         const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
         gid[k] = hot_lookup(A, H, hot_n0, kw, fp);
         miss |= gid[k] < 0;
@@ -983,10 +997,10 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
       if (want && sm->elect == (int)threadIdx.x) {
         for (int k = 0; k < RPT; ++k) {
           if (live[k] && gid[k] < 0) {
-            uint64_t kw[MAX_KEY_WORDS];
+            uint64_t kw[HOT_KEY_WORDS];
             const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
             const int g = sm->hot_n;
-            for (int w = 0; w < MAX_KEY_WORDS; ++w) if (w < A.key_words) H.keys[g * A.key_words + w] = kw[w];
+            for (int w = 0; w < HOT_KEY_WORDS; ++w) H.keys[g * HOT_KEY_WORDS + w] = kw[w];
             H.fps[g] = fp;
             H.entry[g] = 0;
             sm->hot_n = g + 1;
@@ -1000,7 +1014,7 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         if (live[k] && gid[k] < 0) {
-          uint64_t kw[MAX_KEY_WORDS];
+          uint64_t kw[HOT_KEY_WORDS];
           const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
           gid[k] = hot_lookup(A, H, hot_n1, kw, fp);
           miss |= gid[k] < 0;
@@ -1099,19 +1113,11 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
       }
     }
   }
-  // cold rows (dictionary full): global table, one warp-cooperative lookup per row slot
+  {
+    bool anycold = false;
 #pragma unroll
-  for (int k = 0; k < RPT; ++k) {
-    const bool cold = live[k] && gid[k] < 0;
-    if (__any_sync(0xFFFFFFFFu, cold)) {
-      const int r = threadIdx.x + k * NT;
-      KeyRegs key; bool hn; uint64_t h = 0;
-      if (cold) h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
-      uint64_t* e = agg_find_or_insert_warp(A, key, h, cold, P.error_flag);
-      if (cold && e) {
-        for (int j = 0; j < A.n_accs; ++j) acc_global(e, A, j, load_acc_value(A.accs[j], c, r));
-      }
-    }
+    for (int k = 0; k < RPT; ++k) anycold |= live[k] && gid[k] < 0;
+    if (__syncthreads_or(anycold)) agg_cold_rows<RPT>(P, A, c, gid, live);
   }
 }
 
@@ -1119,7 +1125,7 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
 // racc[g][j]: this thread's running 64-bit partial of accumulator j for hot group g.  Values are
 // admitted only below 2^55 in magnitude and the partials are spilled to the CTA accumulators (shared
 // memory atomics, once per REG_FLUSH rows) so they can never overflow.
-constexpr int REG_FLUSH = 96;
+constexpr int REG_FLUSH = 224;    // 224 + RPT values below 2^55 cannot overflow 64 bits
 struct RegAcc { int64_t v[REG_GROUPS][REG_ACCS]; int rows; };
 
 __device__ __forceinline__ void reg_flush(const AggParams& A, const HotView& H, RegAcc& R, int hot_n) {
@@ -1161,7 +1167,7 @@ __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggP
     live[k] = r < c.nrows && (pact == nullptr || pact[r]);
     gid[k] = -1;
     if (live[k]) {
-      uint64_t kw[MAX_KEY_WORDS];
+      uint64_t kw[HOT_KEY_WORDS];
       const uint64_t fp = pack_words(A, c, r, kw);
       gid[k] = hot_lookup(A, H, hot_n0, kw, fp);
       miss |= gid[k] < 0;
@@ -1178,10 +1184,10 @@ __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggP
       if (want && sm->elect == (int)threadIdx.x) {
         for (int k = 0; k < RPT; ++k) {
           if (live[k] && gid[k] < 0) {
-            uint64_t kw[MAX_KEY_WORDS];
+            uint64_t kw[HOT_KEY_WORDS];
             const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
             const int g = sm->hot_n;
-            for (int w = 0; w < MAX_KEY_WORDS; ++w) if (w < A.key_words) H.keys[g * A.key_words + w] = kw[w];
+            for (int w = 0; w < HOT_KEY_WORDS; ++w) H.keys[g * HOT_KEY_WORDS + w] = kw[w];
             H.fps[g] = fp;
             H.entry[g] = 0;
             sm->hot_n = g + 1;
@@ -1195,7 +1201,7 @@ __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggP
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         if (live[k] && gid[k] < 0) {
-          uint64_t kw[MAX_KEY_WORDS];
+          uint64_t kw[HOT_KEY_WORDS];
           const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
           gid[k] = hot_lookup(A, H, hot_n1, kw, fp);
           miss |= gid[k] < 0;
@@ -1214,50 +1220,46 @@ __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggP
       for (int j = 0; j < REG_ACCS; ++j) {
         val[j] = 0;
         if (j < A.n_accs) {
-          const AccDesc& d = A.accs[j];
-          bool ok = d.valid_slot == NO_SLOT || c.arena[d.valid_slot + r] != 0;
-          if (d.op == ACC_COUNT) val[j] = ok ? 1 : 0;
-          else if (ok) {
-            const uint8_t* p = c.arena + d.value_slot + r * d.stride;
-            if (d.vkind == K_I128) {
-              const i128 x = lds<i128>(p);
-              if (fits55(x)) val[j] = (int64_t)x;
-              else {                                  // rare: exact value straight to the table entry
-                uint64_t* e = hot_entry(P, A, H, gid[k]);
-                if (e) atomic_add_i128(e + 2 + A.key_words + d.word, x);
-              }
-            } else {
-              const int64_t x = d.vkind == K_I64 ? lds<int64_t>(p) : d.vkind == K_I32 ? (int64_t)lds<int32_t>(p) : (int64_t)*p;
-              if (d.op == ACC_SUM_I64 || fits55((i128)x)) val[j] = x;
-              else { uint64_t* e = hot_entry(P, A, H, gid[k]); if (e) atomic_add_i128(e + 2 + A.key_words + d.word, (i128)x); }
+          const AggParams::RegLoad& L = A.rload[j];          // constant bank, static index
+          if (L.mode == 0) val[j] = 1;
+          else {
+            const uint8_t* p = c.arena + L.slot + r * L.stride;
+            i128 x;
+            if (L.mode == 1) x = (i128)lds<int64_t>(p); else x = lds<i128>(p);
+            if (fits55(x)) val[j] = (int64_t)x;
+            else {                                            // rare: exact value straight to the table entry
+              uint64_t* e = hot_entry(P, A, H, gid[k]);
+              if (e) atomic_add_i128(e + 2 + A.key_words + A.accs[j].word, x);
             }
           }
         }
       }
+      switch (gid[k]) {            // only this row's group is touched (divergent, but 4x fewer adds than predication)
+        case 0:
 #pragma unroll
-      for (int g = 0; g < REG_GROUPS; ++g) {
-        const bool mine = gid[k] == g;
+          for (int j = 0; j < REG_ACCS; ++j) R.v[0][j] += val[j];
+          break;
+        case 1:
 #pragma unroll
-        for (int j = 0; j < REG_ACCS; ++j)
-          if (j < A.n_accs) R.v[g][j] += mine ? val[j] : 0;
+          for (int j = 0; j < REG_ACCS; ++j) R.v[1][j] += val[j];
+          break;
+        case 2:
+#pragma unroll
+          for (int j = 0; j < REG_ACCS; ++j) R.v[2][j] += val[j];
+          break;
+        default:
+#pragma unroll
+          for (int j = 0; j < REG_ACCS; ++j) R.v[3][j] += val[j];
       }
     }
   }
   R.rows += RPT;
   if (R.rows >= REG_FLUSH) reg_flush(A, H, R, sm->hot_n);
-  // rows of groups beyond the register set: global table
+  {
+    bool anycold = false;
 #pragma unroll
-  for (int k = 0; k < RPT; ++k) {
-    const bool cold = live[k] && gid[k] < 0;
-    if (__any_sync(0xFFFFFFFFu, cold)) {
-      const int r = threadIdx.x + k * NT;
-      KeyRegs key; bool hn; uint64_t h = 0;
-      if (cold) h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, r, key, &hn);
-      uint64_t* e = agg_find_or_insert_warp(A, key, h, cold, P.error_flag);
-      if (cold && e) {
-        for (int j = 0; j < A.n_accs; ++j) acc_global(e, A, j, load_acc_value(A.accs[j], c, r));
-      }
-    }
+    for (int k = 0; k < RPT; ++k) anycold |= live[k] && gid[k] < 0;
+    if (__syncthreads_or(anycold)) agg_cold_rows<RPT>(P, A, c, gid, live);
   }
 }
 

@@ -25,7 +25,8 @@ constexpr int MAX_KEY_WORDS = 8;   // 64 bytes of packed key
 constexpr int MAX_ACCS = 16;
 constexpr int MAX_PROBES = 4;
 constexpr int REG_GROUPS = 4;      // hot groups held in registers by the integer fast path
-constexpr int REG_ACCS = 8;        // accumulators held in registers per group
+constexpr int REG_ACCS = 6;        // accumulators held in registers per group
+constexpr int HOT_KEY_WORDS = 4;   // group keys wider than 32 bytes skip the hot paths (global table only)
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
 enum VmKind : uint8_t { K_B = 0, K_I32 = 1, K_I64 = 2, K_F64 = 3, K_I128 = 4, K_V16 = 5 };
@@ -142,6 +143,8 @@ struct AggParams {
   int32_t reg_path;        // all accumulators are integer sums/counts: per-thread REGISTER partials for the first
                            // REG_GROUPS hot groups (no shuffles, no shared-memory traffic per row)
   int32_t pad_;
+  // register fast path load plan: mode 0 = constant 1 (count(*)), 1 = i64 slot, 2 = i128 slot
+  struct RegLoad { uint32_t slot; uint16_t stride; uint8_t mode; uint8_t pad; } rload[REG_ACCS];
   uint8_t* table;          // capacity * entry_bytes
   uint32_t* state;         // capacity
   uint64_t capacity_mask;  // capacity - 1 (power of two)
