@@ -38,7 +38,7 @@ FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sf", type=float, default=10.0, help="scale factor PER GPU (weak scaling)")
@@ -62,23 +62,37 @@ def gen_shard(sf_per_gpu: float, rank: int, world: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, every 2 ms; nvidia-smi as fallback)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
-        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+        self.index, self.sm, self.bits, self.stop_flag, self.thread, self.max_mhz = index, [], 0, False, None, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
 
     def _run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.sm.append(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+                    self.bits |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    time.sleep(0.002)
+                else:
+                    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.sm.append(int(out[0]))
+                    self.max_mhz = int(out[1])
+                    self.bits |= int(out[2].strip(), 16)
             except Exception:
-                pass
-            time.sleep(0.1)
+                time.sleep(0.01)
 
     def start(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -88,13 +102,11 @@ class ClockSampler:
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=6)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": [n for n, b in self.REASONS.items() if self.bits & b],
+                "samples": len(sm)}
 
 
 def q1_specs():
@@ -168,35 +180,20 @@ def run_query(ctx, specs, inputs, in_schema, host_chunks=None):
     if DIST_BACKEND is not None:
         return run_query_dist(DIST_BACKEND, specs, inputs, in_schema, host_chunks)
     fused, final, sort = specs
-    op1 = engine.GpuExec(fused, [in_schema], ctx)
+    # one GPU island: fused partial -> final -> sort handed over inside the library (HBM), result pulled to the host
+    chain = {"op": "chain", "ops": [fused, final] + ([sort] if SORT_ON_GPU else [])}
+    op = engine.GpuExec(chain, [in_schema], ctx)
     if host_chunks is None:
         for d in inputs:
-            op1.push(d.borrow())
+            op.push(d.borrow())
     else:
         for b in host_chunks:
-            op1.push(b)
-    op1.finish()
-    parts = op1.collect_device()
-    op2 = engine.GpuExec(final, [op1.schema], ctx)
-    for p in parts:
-        op2.push(p)
-    op2.finish()
-    if SORT_ON_GPU:
-        mids = op2.collect_device()
-        op3 = engine.GpuExec(sort, [op2.schema], ctx)
-        for p in mids:
-            op3.push(p)
-        op3.finish()
-        out = op3.collect()
-        ops = [op1, op2, op3]
-    else:
-        out = op2.collect()
-        ops = [op1, op2]
-    launches = sum(o.metrics()["gpu.kernel_launches"] for o in ops)
-    m1 = op1.metrics()
-    for o in ops:
-        o.close()
-    return out, launches, m1["gpu.pipeline_kernel_ns"], m1["gpu.pipeline_launches"]
+            op.push(b)
+    op.finish()
+    out = op.collect()
+    mm = op.metrics()
+    op.close()
+    return out, mm["gpu.kernel_launches"], mm["gpu.pipeline_kernel_ns"], mm["gpu.pipeline_launches"]
 
 
 SORT_ON_GPU = True
@@ -359,9 +356,9 @@ def main():
             "dtype": "i128 (Decimal128) / i64", "data": "synthetic (dbgen-exact TPC-H lineitem)",
             "config": {"workload": f"TPC-H Q1 SF{args.sf:g} per GPU, 1 partition per GPU, Arrow batches resident in HBM",
                        "rows_per_gpu": n_rows, "strings": "Utf8View", "l2": "inputs (6 GB) larger than L2; no flush",
-                       "plan": "GpuPipelineExec[Filter+Projection+Aggregate(Partial)] -> GpuAggregateExec(FinalPartitioned)"
+                       "plan": "GpuChainExec{GpuPipelineExec[Filter+Projection+Aggregate(Partial)] -> GpuAggregateExec(FinalPartitioned)"
                                + (" -> GpuRepartitionExec(Hash) -> NCCL all-to-all" if world > 1 else "")
-                               + (" -> GpuSortExec" if SORT_ON_GPU else ""), "parallelism": f"{world} rank(s), lineitem sharded by order range"},
+                               + (" -> GpuSortExec" if SORT_ON_GPU else "") + "}", "parallelism": f"{world} rank(s), lineitem sharded by order range"},
             "e2e": None if e2e_value is None else {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                                                     "ms_per_step": ms_e / e2e_steps, "host_batches": len(chunks)},
             "gpu_launches": launches,

@@ -43,6 +43,8 @@
  *   {"op":"repartition","scheme":"hash","exprs":[E],"n":N}
  *   {"op":"pipeline","stages":[spec,...]}  (fused chain of filter/projection ending in at most one
  *                                           aggregate: one kernel, one pass over HBM)
+ *   {"op":"chain","ops":[spec,...]}        (consecutive single-input operators run as one GPU island:
+ *                                           batches move between them inside the library, in HBM)
  * Expressions E: {"col":i} {"lit":v,"type":"T"} {"op":"+|-|*|/|%|=|!=|<|<=|>|>=|and|or","l":E,"r":E}
  *   {"not":E} {"neg":E} {"is_null":E} {"is_not_null":E} {"cast":E,"to":"T"}
  *   {"case":[[E,E],...],"else":E|null} {"in":E,"set":[lit,...],"negated":b}

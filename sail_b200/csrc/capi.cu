@@ -1,7 +1,7 @@
 // capi.cu -- the extern "C" surface declared in include/sailgpu.h.
 #include <cstdio>
 
-#include "engine.hpp"
+#include "runner.hpp"
 
 using namespace sg;
 
@@ -125,7 +125,8 @@ SAILGPU_API int32_t sailgpu_op_push_device(sailgpu_op* h, int32_t input_idx, str
     SG_CHECK(!h->input_finished[(size_t)input_idx], SAILGPU_ERR_STATE, "push after finish_input");
     SG_CHECK(batch && batch->array.release, SAILGPU_ERR_INVALID, "batch is null or released");
     BatchPtr b = take_internal_batch(batch);
-    if (!b) b = import_device_batch(&h->owner->ctx, h->op->in_schemas[(size_t)input_idx], batch);
+    if (!b) { Trace t(&h->owner->ctx, "import_device_batch"); b = import_device_batch(&h->owner->ctx, h->op->in_schemas[(size_t)input_idx], batch); }
+    Trace t2(&h->owner->ctx, "op.push");
     h->op->push(input_idx, b);
   });
 }
@@ -137,6 +138,7 @@ SAILGPU_API int32_t sailgpu_op_finish_input(sailgpu_op* h, int32_t input_idx) {
     SG_CHECK(input_idx >= 0 && input_idx < (int)h->op->in_schemas.size(), SAILGPU_ERR_INVALID, "input index out of range");
     if (h->input_finished[(size_t)input_idx]) return;
     h->input_finished[(size_t)input_idx] = true;
+    Trace t(&h->owner->ctx, "op.finish");
     h->op->finish(input_idx);
   });
 }
@@ -147,7 +149,9 @@ static int32_t pull_common(sailgpu_op* h, int part, struct ArrowArray* host_out,
     set_device(h->owner->ctx);
     SG_CHECK(has_more && (host_out || dev_out), SAILGPU_ERR_INVALID, "null argument");
     BatchPtr b;
-    const bool more = part >= 0 ? h->op->pull_partition(part, &b) : h->op->pull(&b);
+    bool more;
+    { Trace t(&h->owner->ctx, "op.pull"); more = part >= 0 ? h->op->pull_partition(part, &b) : h->op->pull(&b); }
+    Trace t2(&h->owner->ctx, "export");
     *has_more = more ? 1 : 0;
     if (!b) b = empty_batch(&h->owner->ctx, h->op->out_schema);
     if (host_out) export_host_batch(&h->owner->ctx, h->op->out_schema, b, host_out);

@@ -155,7 +155,8 @@ DevColumn import_column(Ctx* ctx, const Field& f, const ArrowArray* a, bool on_d
     case TypeId::Utf8View: {
       const uint8_t* views = static_cast<const uint8_t*>(a->buffers[1]) + a->offset * 16;
       const int64_t n_data = a->n_buffers - 3;   // validity, views, data..., sizes
-      c.data = upload(ctx, views, (size_t)a->length * 16, kind, stream);
+      // views without data buffers are all inline (<= 12 bytes): a device batch can be used in place
+      c.data = (on_device && n_data <= 0) ? borrow(views, (size_t)a->length * 16) : upload(ctx, views, (size_t)a->length * 16, kind, stream);
       if (n_data > 0) {
         std::vector<int64_t> sizes((size_t)n_data);
         const int64_t* size_buf = static_cast<const int64_t*>(a->buffers[a->n_buffers - 1]);
@@ -311,7 +312,8 @@ void export_column(Ctx* ctx, const Field& f, const DevColumn& c, ArrowArray* out
       p->buffers.push_back(emit(s.heap, (size_t)s.heap_bytes));
     } else {
       p->buffers.push_back(emit(s.views_or_offsets, (size_t)n * 16));
-      p->buffers.push_back(emit(s.heap, (size_t)s.heap_bytes));
+      const bool has_heap = s.heap_bytes > 0;          // all-inline columns carry no variadic data buffer
+      if (has_heap) p->buffers.push_back(emit(s.heap, (size_t)s.heap_bytes));
       // variadic buffer sizes (host array in both modes: tiny)
       int64_t* sizes = static_cast<int64_t*>(malloc(8));
       sizes[0] = s.heap_bytes;

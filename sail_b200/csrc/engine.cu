@@ -100,7 +100,7 @@ void check_device_error(Ctx* ctx, uint32_t* dev_flag) {
 // PipelineOp
 // ------------------------------------------------------------------------------------------------
 struct AggTable {
-  BufPtr table, state;
+  BufPtr table, state, occ;
   uint64_t capacity = 0;
   uint64_t rows_bound = 0;     // upper bound on the number of groups (rows fed so far)
 };
@@ -168,6 +168,7 @@ struct PipelineOp : Op {
   void fill_table(AggParams& A) {
     A.table = static_cast<uint8_t*>(tab.table->ptr);
     A.state = static_cast<uint32_t*>(tab.state->ptr);
+    A.occ = static_cast<uint32_t*>(tab.occ->ptr);
     A.capacity_mask = tab.capacity - 1;
     A.n_groups = run.scal.n_groups();
   }
@@ -190,17 +191,19 @@ struct PipelineOp : Op {
     tab.capacity = need;
     tab.table = dev_alloc(ctx, (size_t)need * A0.entry_words * 8);
     tab.state = dev_alloc_zero(ctx, (size_t)need * 4);
+    tab.occ = dev_alloc(ctx, (size_t)need * 4);
     if (old.capacity && groups) {
       AggParams A = A0;
       fill_table(A);
       SG_CUDA(cudaMemsetAsync(run.scal.n_groups(), 0, 8, ctx->stream));
-      SG_CUDA(launch_agg_rehash(A, static_cast<const uint8_t*>(old.table->ptr), static_cast<const uint32_t*>(old.state->ptr), old.capacity, run.scal.error(), ctx->stream));
+      SG_CUDA(launch_agg_rehash(A, static_cast<const uint8_t*>(old.table->ptr), static_cast<const uint32_t*>(old.occ->ptr), groups, run.scal.error(), ctx->stream));
       m.kernel_launches++;
     }
     tab.rows_bound = groups + rows;
   }
 
   void push_agg(const BatchPtr& b) {
+    Trace tr(ctx, "agg.push");
     auto cp = run.compiled_for(*b);
     if (!agg_cp) agg_cp = cp;
     SG_CHECK(cp->agg.entry_words == agg_cp->agg.entry_words && cp->agg.key_words == agg_cp->agg.key_words, SAILGPU_ERR_UNSUPPORTED,
@@ -218,7 +221,8 @@ struct PipelineOp : Op {
           SG_CHECK(chunk > 0, SAILGPU_ERR_UNSUPPORTED, "aggregate exceeds 2^26 groups");
         }
       }
-      ensure_capacity(*cp, (uint64_t)chunk);
+      { Trace t2(ctx, "agg.ensure_capacity"); ensure_capacity(*cp, (uint64_t)chunk); }
+      Trace t3(ctx, "agg.launch");
       PipelineParams P;
       run.prepare(P, *cp, *b, done, chunk);
       PipelineAux aux;
@@ -231,6 +235,7 @@ struct PipelineOp : Op {
   }
 
   BatchPtr extract_agg() {
+    Trace tr(ctx, "agg.extract");
     std::shared_ptr<CompiledPipeline> cp = agg_cp;
     if (!cp) {   // no input at all: compile against an all-valid signature to learn the output layout
       DevBatch dummy;
@@ -270,8 +275,7 @@ struct PipelineOp : Op {
     if (!synth && rows > 0) {
       AggParams A = A0;
       fill_table(A);
-      SG_CUDA(cudaMemsetAsync(run.scal.cursor(), 0, 8, ctx->stream));
-      SG_CUDA(launch_agg_extract(A, X, run.scal.cursor(), run.scal.error(), ctx->stream));
+      SG_CUDA(launch_agg_extract(A, X, groups, run.scal.error(), ctx->stream));
       m.kernel_launches++;
     } else if (synth) {
       // counts are 0 (valid); every other aggregate is NULL -> validity bytes stay 0, count columns get no validity
@@ -305,6 +309,7 @@ struct PipelineOp : Op {
 std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_sort_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
+std::unique_ptr<Op> make_chain_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 
 std::unique_ptr<Op> make_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs, int partition) {
   (void)partition;
@@ -312,6 +317,7 @@ std::unique_ptr<Op> make_op(Ctx* ctx, const Json& spec, const std::vector<Schema
   if (kind == "hash_join") return make_join_op(ctx, spec, inputs);
   if (kind == "sort") return make_sort_op(ctx, spec, inputs);
   if (kind == "repartition") return make_repartition_op(ctx, spec, inputs);
+  if (kind == "chain") return make_chain_op(ctx, spec, inputs);
   SG_CHECK(inputs.size() == 1, SAILGPU_ERR_INVALID, "operator '" + kind + "' takes exactly one input");
   auto op = std::make_unique<PipelineOp>();
   op->ctx = ctx; op->kind = kind; op->in_schemas = inputs;

@@ -25,8 +25,8 @@ struct AggExtractParams {
 
 cudaError_t launch_pipeline(const KernelArgs& K, int rpt, int n_stages, size_t smem_bytes, int grid, cudaStream_t stream);
 int pipeline_max_ctas_per_sm(int rpt, size_t smem_bytes);
-cudaError_t launch_agg_rehash(const AggParams& A, const uint8_t* old_table, const uint32_t* old_state, uint64_t old_capacity, uint32_t* err, cudaStream_t s);
-cudaError_t launch_agg_extract(const AggParams& A, const AggExtractParams& X, unsigned long long* cursor, uint32_t* err, cudaStream_t s);
+cudaError_t launch_agg_rehash(const AggParams& A, const uint8_t* old_table, const uint32_t* old_occ, uint64_t old_groups, uint32_t* err, cudaStream_t s);
+cudaError_t launch_agg_extract(const AggParams& A, const AggExtractParams& X, uint64_t n_groups, uint32_t* err, cudaStream_t s);
 cudaError_t launch_pack_bytes(const uint8_t* bytes, uint32_t* bits, int64_t n, unsigned long long* null_count, cudaStream_t s);
 cudaError_t launch_unpack_bits(const uint8_t* bits, uint8_t* bytes, int64_t n, int64_t bit_offset, cudaStream_t s);
 cudaError_t launch_resolve_views(void* views, int64_t n, const uint64_t* bases, cudaStream_t s);

@@ -651,6 +651,75 @@ std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::v
   return op;
 }
 
+
+// ================================================================================================
+// A linear chain of GPU operators executed as one island: batches move between the stages as HBM
+// batches inside the library (no Arrow export/import, no host round trip between stages).  This is
+// what the rewrite pass emits for consecutive replaced nodes, e.g. Q1's
+//   pipeline[Filter+Projection+Aggregate(Partial)] -> Aggregate(FinalPartitioned) -> Sort.
+// ================================================================================================
+struct ChainOp : Op {
+  std::vector<std::unique_ptr<Op>> ops;
+  bool finished = false;
+  void pump(size_t from) {
+    for (size_t i = from; i + 1 < ops.size(); ++i) {
+      for (;;) {
+        BatchPtr b;
+        const bool more = ops[i]->pull(&b);
+        if (b && b->rows >= 0 && (b->rows > 0 || !more)) ops[i + 1]->push(0, b);
+        if (!b || !more) break;
+      }
+    }
+  }
+  void push(int input, const BatchPtr& b) override {
+    SG_CHECK(input == 0, SAILGPU_ERR_INVALID, "chain has one input");
+    m.input_rows += (uint64_t)b->rows; m.input_batches++;
+    ops[0]->push(0, b);
+    pump(0);
+  }
+  void finish(int) override {
+    for (size_t i = 0; i < ops.size(); ++i) {
+      ops[i]->finish(0);
+      if (i + 1 < ops.size()) {
+        for (;;) {
+          BatchPtr b;
+          const bool more = ops[i]->pull(&b);
+          if (b && (b->rows > 0 || !more)) ops[i + 1]->push(0, b);
+          if (!more) break;
+        }
+      }
+    }
+    finished = true;
+    // gpu.pipeline_* of a chain describe its FIRST stage (the pass over the input batches: the dominant kernel);
+    // every stage counts towards gpu.kernel_launches
+    for (auto& o : ops) m.kernel_launches += o->m.kernel_launches;
+    m.pipeline_launches += ops[0]->m.pipeline_launches;
+    for (auto& p : ops[0]->m.pending) m.pending.push_back(p);
+    ops[0]->m.pending.clear();
+    m.pipeline_kernel_ns += ops[0]->m.pipeline_kernel_ns;
+  }
+  bool pull(BatchPtr* out) override {
+    const bool more = ops.back()->pull(out);
+    if (*out) { m.output_rows += (uint64_t)(*out)->rows; m.output_batches++; }
+    return more;
+  }
+};
+
+std::unique_ptr<Op> make_chain_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs) {
+  SG_CHECK(inputs.size() == 1, SAILGPU_ERR_INVALID, "chain takes one input");
+  auto op = std::make_unique<ChainOp>();
+  op->ctx = ctx; op->kind = "chain"; op->in_schemas = inputs;
+  Schema cur = inputs[0];
+  for (auto& s : spec.at("ops").a) {
+    SG_CHECK(s.at("op").as_str() != "hash_join" && s.at("op").as_str() != "repartition", SAILGPU_ERR_UNSUPPORTED, "chain stages must be single-input, single-output operators");
+    op->ops.push_back(make_op(ctx, s, {cur}, 0));
+    cur = op->ops.back()->out_schema;
+  }
+  SG_CHECK(!op->ops.empty(), SAILGPU_ERR_INVALID, "empty chain");
+  op->out_schema = cur;
+  return op;
+}
+
 }  // namespace sg
 
 // ================================================================================================

@@ -711,7 +711,7 @@ __device__ __forceinline__ uint64_t* agg_find_or_insert(const AggParams& A, cons
             e[2 + A.key_words + A.accs[j].word + w] = acc_identity(A.accs[j].op, w);
         __threadfence();
         st_release_u32(st, tag | ST_READY);
-        atomicAdd(A.n_groups, 1ull);
+        A.occ[atomicAdd(A.n_groups, 1ull)] = (uint32_t)idx;
         return e;
       }
     }
@@ -1584,10 +1584,9 @@ __global__ void __launch_bounds__(NT, 2) pipeline_kernel(const __grid_constant__
 // helper kernels
 // ================================================================================================
 // grow: move every READY entry of `old` into the (larger, empty) table of `A`
-__global__ void agg_rehash_kernel(AggParams A, const uint8_t* old_table, const uint32_t* old_state, uint64_t old_capacity, uint32_t* err) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_capacity; i += (uint64_t)gridDim.x * blockDim.x) {
-    if ((old_state[i] & 3u) != ST_READY) continue;
-    const uint64_t* src = reinterpret_cast<const uint64_t*>(old_table) + i * A.entry_words;
+__global__ void agg_rehash_kernel(AggParams A, const uint8_t* old_table, const uint32_t* old_occ, uint64_t old_groups, uint32_t* err) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_groups; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(old_table) + (uint64_t)old_occ[i] * A.entry_words;
     KeyRegs key;
     for (int w = 0; w < A.key_words; ++w) key.w[w] = src[2 + w];
     uint64_t* e = agg_find_or_insert(A, key, hash_packed_key(A, key), err);
@@ -1597,12 +1596,10 @@ __global__ void agg_rehash_kernel(AggParams A, const uint8_t* old_table, const u
   }
 }
 
-__global__ void agg_extract_kernel(AggParams A, AggExtractParams X, unsigned long long* cursor, uint32_t* err) {
-  const uint64_t cap = A.capacity_mask + 1;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t* e = reinterpret_cast<const uint64_t*>(A.table) + i * A.entry_words;
-    if ((A.state[i] & 3u) != ST_READY) continue;
-    const unsigned long long pos = atomicAdd(cursor, 1ull);
+__global__ void agg_extract_kernel(AggParams A, AggExtractParams X, uint64_t n_groups, uint32_t* err) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_groups; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t* e = reinterpret_cast<const uint64_t*>(A.table) + (uint64_t)A.occ[i] * A.entry_words;
+    const unsigned long long pos = i;
     const uint64_t seen = e[1];
     const uint64_t* kw = e + 2;
     const uint64_t* aw = e + 2 + A.key_words;
@@ -1792,15 +1789,16 @@ int pipeline_max_ctas_per_sm(int rpt, size_t smem_bytes) {
   return n;
 }
 
-cudaError_t launch_agg_rehash(const AggParams& A, const uint8_t* old_table, const uint32_t* old_state, uint64_t old_capacity, uint32_t* err, cudaStream_t s) {
-  int grid = (int)std::min<uint64_t>((old_capacity + 255) / 256, 148 * 8);
-  agg_rehash_kernel<<<grid, 256, 0, s>>>(A, old_table, old_state, old_capacity, err);
+cudaError_t launch_agg_rehash(const AggParams& A, const uint8_t* old_table, const uint32_t* old_occ, uint64_t old_groups, uint32_t* err, cudaStream_t s) {
+  if (old_groups == 0) return cudaSuccess;
+  int grid = (int)std::min<uint64_t>((old_groups + 255) / 256, 148 * 8);
+  agg_rehash_kernel<<<grid, 256, 0, s>>>(A, old_table, old_occ, old_groups, err);
   return cudaGetLastError();
 }
-cudaError_t launch_agg_extract(const AggParams& A, const AggExtractParams& X, unsigned long long* cursor, uint32_t* err, cudaStream_t s) {
-  const uint64_t cap = A.capacity_mask + 1;
-  int grid = (int)std::min<uint64_t>((cap + 255) / 256, 148 * 8);
-  agg_extract_kernel<<<grid, 256, 0, s>>>(A, X, cursor, err);
+cudaError_t launch_agg_extract(const AggParams& A, const AggExtractParams& X, uint64_t n_groups, uint32_t* err, cudaStream_t s) {
+  if (n_groups == 0) return cudaSuccess;
+  int grid = (int)std::min<uint64_t>((n_groups + 255) / 256, 148 * 8);
+  agg_extract_kernel<<<grid, 256, 0, s>>>(A, X, n_groups, err);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_bytes(const uint8_t* bytes, uint32_t* bits, int64_t n, unsigned long long* null_count, cudaStream_t s) {

@@ -251,11 +251,27 @@ __global__ void iota_u32_kernel(uint32_t* out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint32_t)i;
 }
 
+// n <= 1024: one CTA ranks every row against every other (stable: ties broken by input position)
+__global__ void small_sort_kernel(const uint8_t* __restrict__ keys, int key_bytes, int n, uint32_t* __restrict__ idx_out) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* ki = keys + (int64_t)i * key_bytes;
+  int rank = 0;
+  for (int j = 0; j < n; ++j) {
+    const uint8_t* kj = keys + (int64_t)j * key_bytes;
+    int c = 0;
+    for (int b = 0; b < key_bytes && c == 0; ++b) c = (int)kj[b] - (int)ki[b];
+    rank += (c < 0 || (c == 0 && j < i)) ? 1 : 0;
+  }
+  idx_out[rank] = (uint32_t)i;
+}
+
 // Sorts row indices by the encoded keys.  `idx_a` receives the final order.  scratch: idx_b [n] u32,
 // hist [256*n_chunks] u32, offs [256*n_chunks] u64, scan scratch [1026] u64.
 cudaError_t radix_sort_indices(const uint8_t* keys, int key_bytes, int64_t n, uint32_t* idx_a, uint32_t* idx_b, uint32_t* hist, uint64_t* offs,
                                uint64_t* scan_scratch, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
+  if (n <= 1024) { small_sort_kernel<<<1, 1024, 0, s>>>(keys, key_bytes, (int)n, idx_a); return cudaGetLastError(); }
   const int64_t n_chunks = (n + RADIX_CHUNK - 1) / RADIX_CHUNK;
   const int blocks = (int)((n_chunks + 7) / 8);
   iota_u32_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(idx_a, n);

@@ -9,6 +9,13 @@ namespace sg {
 inline uint64_t now_ns() {
   return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+// SAILGPU_TRACE=1: synchronising phase timer printed to stderr (diagnostics only)
+struct Trace {
+  Ctx* ctx; const char* what; uint64_t t0; bool on;
+  Trace(Ctx* c, const char* w) : ctx(c), what(w), on(getenv("SAILGPU_TRACE") != nullptr) { if (on) { cudaStreamSynchronize(ctx->stream); t0 = now_ns(); } }
+  ~Trace() { if (on) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[sailgpu trace] %-28s %8.3f ms\n", what, (now_ns() - t0) / 1e6); } }
+};
+
 inline uint64_t next_pow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
 
 // ------------------------------------------------------------------------------------------------

@@ -147,6 +147,7 @@ struct AggParams {
   struct RegLoad { uint32_t slot; uint16_t stride; uint8_t mode; uint8_t pad; } rload[REG_ACCS];
   uint8_t* table;          // capacity * entry_bytes
   uint32_t* state;         // capacity
+  uint32_t* occ;           // slot index of the i-th inserted group (i < *n_groups): extraction walks this, not the table
   uint64_t capacity_mask;  // capacity - 1 (power of two)
   uint32_t entry_words;    // 2 + key_words + acc_words   (8-byte words)
   uint32_t hot_smem_off;   // arena offset of the hot-path scratch

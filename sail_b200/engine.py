@@ -234,7 +234,7 @@ class GpuExec:
     def name(self) -> str:
         return {"filter": "GpuFilterExec", "projection": "GpuProjectionExec", "aggregate": "GpuAggregateExec",
                 "hash_join": "GpuHashJoinExec", "sort": "GpuSortExec", "repartition": "GpuRepartitionExec",
-                "pipeline": "GpuPipelineExec"}.get(self.spec.get("op"), "GpuExec")
+                "pipeline": "GpuPipelineExec", "chain": "GpuChainExec"}.get(self.spec.get("op"), "GpuExec")
 
     def _check(self, rc):
         if rc != 0:

@@ -146,3 +146,23 @@ def test_tpch_sf01_vs_oracle(q):
     got = plans.execute(plan, tables, gpu_op)
     want = plans.execute(plan, tables, oracle_op)
     assert_same(got, want, ordered=(q != "q3"))   # Q3's top-10 may tie on (revenue, date): compare as sets
+
+
+def test_chain_operator_matches_separate_operators():
+    """{"op":"chain"}: the GPU island hand-off inside the library gives the same result as separate operators"""
+    from datagen import tpch
+    from sail_b200 import engine
+    li = tpch.lineitem(0.01)
+    sort_node = plans.q1()
+    final = sort_node.inputs[0]
+    partial = final.inputs[0]
+    stages, n = [], partial
+    while n.spec["op"] != "scan":
+        stages.append(n.spec)
+        n = n.inputs[0]
+    fused = {"op": "pipeline", "stages": stages[::-1]}
+    chain = {"op": "chain", "ops": [fused, final.spec, sort_node.spec]}
+    t = li.select(n.spec["columns"])
+    got = engine.run_op(chain, t)
+    want = plans.execute(sort_node, {"lineitem": li}, oracle_op)
+    assert_same(got, want, ordered=True)
