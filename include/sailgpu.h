@@ -157,6 +157,13 @@ SAILGPU_API int32_t sailgpu_op_create(sailgpu_ctx* ctx, const char* spec_json, s
                           const struct ArrowSchema* const* input_schemas, int32_t n_inputs,
                           int32_t partition, sailgpu_op** out, struct ArrowSchema* out_schema);
 
+/* Plan-time validation for the rewrite pass (LocalJobRunner::execute, job_runner.rs:63): parses the spec, runs the
+ * same type inference as sailgpu_op_create and fills *out_schema, or returns SAILGPU_ERR_UNSUPPORTED / _INVALID with a
+ * message in err_buf.  No device is touched, so the decision "GPU node or keep the DataFusion node" is made while
+ * planning, never as a silent run-time fallback. */
+SAILGPU_API int32_t sailgpu_spec_validate(const char* spec_json, size_t spec_len, const struct ArrowSchema* const* input_schemas,
+                                          int32_t n_inputs, struct ArrowSchema* out_schema, char* err_buf, size_t err_cap);
+
 /* Hand one input batch (struct array, host memory) to the operator.  Takes ownership: the library
  * calls batch->release when it no longer needs the host buffers (after the H2D copy). */
 SAILGPU_API int32_t sailgpu_op_push(sailgpu_op* op, int32_t input_idx, struct ArrowArray* batch);

@@ -106,6 +106,23 @@ SAILGPU_API int32_t sailgpu_op_create(sailgpu_ctx* c, const char* spec_json, siz
   });
 }
 
+// Plan-time check used by the rewrite pass: parses the spec, runs type inference and reports the output schema or
+// why the operator cannot run on the GPU.  Touches no device: works on a machine without a GPU.
+SAILGPU_API int32_t sailgpu_spec_validate(const char* spec_json, size_t spec_len, const struct ArrowSchema* const* input_schemas,
+                                          int32_t n_inputs, struct ArrowSchema* out_schema, char* err_buf, size_t err_cap) {
+  std::string err;
+  const int32_t rc = guard(&err, [&] {
+    SG_CHECK(spec_json && out_schema, SAILGPU_ERR_INVALID, "null argument");
+    Json spec = JsonParser(spec_json, spec_len).parse();
+    std::vector<Schema> ins;
+    for (int i = 0; i < n_inputs; ++i) ins.push_back(schema_from_arrow(input_schemas[i]));
+    std::unique_ptr<Op> op = make_op(nullptr, spec, ins, 0);
+    schema_to_arrow(op->out_schema, out_schema);
+  });
+  if (rc != 0 && err_buf && err_cap) { const size_t k = std::min(err.size(), err_cap - 1); memcpy(err_buf, err.data(), k); err_buf[k] = 0; }
+  return rc;
+}
+
 SAILGPU_API int32_t sailgpu_op_push(sailgpu_op* h, int32_t input_idx, struct ArrowArray* batch) {
   if (!h) return SAILGPU_ERR_INVALID;
   return guard(&h->last_error, [&] {

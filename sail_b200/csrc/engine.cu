@@ -159,6 +159,7 @@ struct PipelineOp : Op {
   static constexpr uint64_t MAX_CAPACITY = 1ull << 27;
 
   uint64_t read_n_groups() {
+    run.ensure_scratch();
     unsigned long long g = 0;
     SG_CUDA(cudaMemcpyAsync(&g, run.scal.n_groups(), 8, cudaMemcpyDeviceToHost, ctx->stream));
     SG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -243,6 +244,7 @@ struct PipelineOp : Op {
       cp = run.compiled_for(dummy);
     }
     const AggParams& A0 = cp->agg;
+    run.ensure_scratch();
     uint64_t groups = 0;
     if (tab.capacity) { check_device_error(ctx, run.scal.error()); groups = read_n_groups(); }
     const bool synth = A0.n_keys == 0 && groups == 0;   // global aggregate over zero rows: one row of NULLs / zero counts

@@ -39,10 +39,8 @@ struct PipelineRunner {
   std::function<void(PipelineCompiler&, CompiledPipeline&)> custom_sink;   // build / partition sinks
   std::function<void(PipelineCompiler&, CompiledPipeline&)> pre_stages;    // probe ops injected before the stages
 
-  void init(Ctx* c, const Schema& in) {
-    ctx = c; in_schema = in;
-    scal.buf = dev_alloc_zero(ctx, 256);
-  }
+  void init(Ctx* c, const Schema& in) { ctx = c; in_schema = in; }   // no device work: specs can be validated without a GPU
+  void ensure_scratch() { if (!scal.buf) scal.buf = dev_alloc_zero(ctx, 256); }
 
   std::shared_ptr<CompiledPipeline> compiled_for(const DevBatch& b) {
     std::vector<bool> sig;
@@ -99,6 +97,7 @@ struct PipelineRunner {
 
   // fills inputs + common fields; caller fills sink buffers; then launch()
   void prepare(PipelineParams& P, const CompiledPipeline& cp, const DevBatch& b, int64_t row0, int64_t nrows) {
+    ensure_scratch();
     memset(&P, 0, sizeof(P));
     P.n_rows = nrows;
     P.tile_rows = cp.rpt * NT;

@@ -74,6 +74,7 @@ def lib():
         L.sailgpu_ctx_synchronize.argtypes = [vp]
         L.sailgpu_op_create.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), i32, i32,
                                         ctypes.POINTER(vp), vp]
+        L.sailgpu_spec_validate.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), i32, vp, ctypes.c_char_p, ctypes.c_size_t]
         L.sailgpu_op_push.argtypes = [vp, i32, vp]
         L.sailgpu_op_push_device.argtypes = [vp, i32, vp]
         L.sailgpu_op_finish_input.argtypes = [vp, i32]
@@ -319,6 +320,21 @@ class GpuExec:
                 self.close()
         except Exception:
             pass
+
+
+def validate(spec: dict, inputs: list) -> pa.Schema:
+    """Plan-time check (no GPU needed): output schema of `spec` over the input schemas, or SailGpuError."""
+    text = json.dumps(spec).encode()
+    cs = [_export_schema(s) for s in inputs]
+    arr = (ctypes.c_void_p * len(cs))(*[ctypes.addressof(c) for c in cs])
+    out = ArrowSchemaC()
+    err = ctypes.create_string_buffer(1024)
+    rc = lib().sailgpu_spec_validate(text, len(text), arr, len(cs), ctypes.addressof(out), err, 1024)
+    for c in cs:
+        _release_schema(c)
+    if rc != 0:
+        raise SailGpuError(rc, err.value.decode())
+    return pa.Schema._import_from_c(ctypes.addressof(out))
 
 
 def run_op(spec: dict, *tables, ctx: Context | None = None) -> pa.Table:

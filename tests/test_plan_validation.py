@@ -1,0 +1,64 @@
+"""CPU tests of the host side of libsailgpu (no GPU): spec parsing, DataFusion/arrow type inference and
+error reporting through `sailgpu_spec_validate`, checked against the oracle's result types on every node of the
+TPC-H plans whose results are pinned by the reference's golden snapshots."""
+import pyarrow as pa
+import pytest
+
+from sail_b200 import engine, plans
+from tests.util import oracle_op
+
+
+def walk(node, tables, fn):
+    if node.spec["op"] == "scan":
+        return tables[node.spec["table"]].select(node.spec["columns"])
+    ins = [walk(c, tables, fn) for c in node.inputs]
+    out = oracle_op(node.spec, *ins)
+    fn(node, ins, out)
+    return out
+
+
+@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q12"])
+def test_output_schema_of_every_plan_node_matches_the_oracle(q, tpch_tiny):
+    seen = []
+
+    def check(node, ins, out):
+        got = engine.validate(node.spec, [t.schema for t in ins])
+        assert got.names == out.schema.names, (node.spec["op"], got.names, out.schema.names)
+        assert [str(f.type) for f in got] == [str(f.type) for f in out.schema], (node.spec, got, out.schema)
+        seen.append(node.spec["op"])
+
+    walk(plans.TPCH[q](), tpch_tiny, check)
+    assert seen
+
+
+def test_decimal_type_rules():
+    s = pa.schema([("a", pa.decimal128(15, 2)), ("b", pa.decimal128(16, 2)), ("i", pa.int32())])
+    def ty(e):
+        return str(engine.validate({"op": "projection", "exprs": [{"expr": e, "name": "x"}]}, [s]).field(0).type)
+    A, B, I = {"col": 0}, {"col": 1}, {"col": 2}
+    assert ty(plans.binop("*", A, B)) == "decimal128(32, 4)"        # arrow-arith: p1+p2+1, s1+s2
+    assert ty(plans.binop("+", A, B)) == "decimal128(17, 2)"
+    assert ty(plans.binop("-", plans.dec(1, 10, 0), A)) == "decimal128(16, 2)"   # Int32(1) coerced to Decimal128(10,0)
+    assert ty(plans.binop("/", A, B)) == "decimal128(21, 6)"        # scale s1+4, precision p1-s1+s2+scale
+    assert ty(plans.binop("+", A, I)) == "decimal128(16, 2)"
+    agg = {"op": "aggregate", "mode": "single", "group_by": [], "aggs": [{"fn": "sum", "args": [A], "name": "s"}, {"fn": "avg", "args": [A], "name": "a"},
+                                                                          {"fn": "count", "args": [], "name": "c"}, {"fn": "avg", "args": [I], "name": "ai"}]}
+    out = engine.validate(agg, [s])
+    assert [str(f.type) for f in out] == ["decimal128(25, 2)", "decimal128(19, 6)", "int64", "double"]
+
+
+def test_unsupported_and_invalid_specs_are_rejected_at_plan_time():
+    s = pa.schema([("a", pa.int64()), ("s", pa.string_view())])
+    with pytest.raises(engine.SailGpuError) as e:
+        engine.validate({"op": "projection", "exprs": [{"expr": {"fn": "regexp_replace", "args": [{"col": 1}]}, "name": "x"}]}, [s])
+    assert e.value.code == 2 and "regexp_replace" in str(e.value)
+    with pytest.raises(engine.SailGpuError) as e:
+        engine.validate({"op": "filter", "predicate": {"col": 7}, "projection": None}, [s])
+    assert e.value.code == 1
+    with pytest.raises(engine.SailGpuError) as e:
+        engine.validate({"op": "repartition", "scheme": "round_robin_row", "exprs": [], "n": 4}, [s])
+    assert e.value.code == 2            # only Partitioning::Hash runs on the GPU
+    with pytest.raises(engine.SailGpuError):
+        engine.validate({"op": "hash_join", "join_type": "full", "on": [[0, 0]]}, [s, s])
+    with pytest.raises(engine.SailGpuError):
+        engine.validate({"op": "nonsense"}, [s])
