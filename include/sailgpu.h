@@ -131,6 +131,10 @@ enum {
   SAILGPU_ERR_STATE = 6         /* call sequence violation (push after finish, ...) -> DataFusionError::Internal */
 };
 
+/* Release callback for a borrowed copy of an ArrowArray struct (shares the producer's buffers, owns nothing): lets one
+ * HBM-resident batch be pushed into several operators. */
+SAILGPU_API void sailgpu_borrowed_release(struct ArrowArray* array);
+
 /* library / ABI version: major<<16 | minor */
 SAILGPU_API uint32_t sailgpu_version(void);
 

@@ -39,6 +39,9 @@ void set_device(const Ctx& c) { SG_CUDA(cudaSetDevice(c.device)); }
 
 extern "C" {
 
+// release callback for a borrowed (non-owning) copy of an Arrow array struct: marks it released, frees nothing
+SAILGPU_API void sailgpu_borrowed_release(struct ArrowArray* a) { if (a) a->release = nullptr; }
+
 SAILGPU_API uint32_t sailgpu_version(void) { return (0u << 16) | 1u; }
 
 SAILGPU_API int32_t sailgpu_ctx_create(int32_t device, sailgpu_ctx** out) {

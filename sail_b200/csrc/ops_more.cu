@@ -25,7 +25,7 @@ struct JoinOp : Op {
   std::vector<BatchPtr> bparts;
   BatchPtr build;
   bool build_done = false, probe_done = false, tail_done = false;
-  BufPtr table, dupflag, visited;
+  BufPtr table, dupflag, visited, next;
   uint64_t capacity = 0;
   bool dup = false;
   std::vector<BufPtr> build_valid_bytes, build_bool_bytes;
@@ -87,6 +87,7 @@ struct JoinOp : Op {
     capacity = next_pow2(std::max<uint64_t>(16, 2 * (uint64_t)n));
     table = dev_alloc_zero(ctx, (size_t)capacity * 16);
     dupflag = dev_alloc_zero(ctx, 16);
+    next = dev_alloc(ctx, (size_t)n * 8 + 16);
     if (needs_visited()) visited = dev_alloc_zero(ctx, (size_t)n + 16);
     for (auto& c : build->cols) {
       BufPtr vb, bb;
@@ -108,6 +109,12 @@ struct JoinOp : Op {
     for (size_t i = 0; i < cp->keys.size(); ++i) aux.build.keys[i] = cp->keys[i];
     aux.build.row_base = 0;
     aux.build.dup_flag = static_cast<uint32_t*>(dupflag->ptr);
+    aux.build.next = static_cast<int64_t*>(next->ptr);
+    for (size_t i = 0; i < lkeys.size(); ++i) {
+      const DataType& kt = bs[(size_t)lkeys[i]].type;
+      aux.build.key_cols[i] = static_cast<const uint8_t*>(build->cols[(size_t)lkeys[i]].data->ptr);
+      aux.build.key_stride[i] = (uint8_t)(kt.is_string() ? 16 : kt.arrow_width());
+    }
     brun.launch(P, cp, &aux, m);
     uint32_t d = 0;
     SG_CUDA(cudaMemcpyAsync(&d, dupflag->ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -290,6 +297,7 @@ struct JoinOp : Op {
     fill_raw(J.probe_keys, *b, rkeys, ps);
     J.table = static_cast<const uint8_t*>(table->ptr); J.capacity_mask = capacity - 1;
     J.visited = static_cast<uint8_t*>(visited->ptr);
+    J.next = static_cast<const int64_t*>(next->ptr);
     J.pass = 2;
     SG_CUDA(launch_join_multi(J, ctx->stream));
     m.kernel_launches++;
@@ -303,6 +311,7 @@ struct JoinOp : Op {
     fill_raw(J.probe_keys, *b, rkeys, ps);
     J.table = static_cast<const uint8_t*>(table->ptr); J.capacity_mask = capacity - 1;
     J.emit_unmatched_probe = jt == "right" ? 1 : 0;
+    J.next = static_cast<const int64_t*>(next->ptr);
     BufPtr counts = dev_alloc(ctx, (size_t)n * 4), offs = dev_alloc(ctx, (size_t)n * 8), scratch = dev_alloc(ctx, 1026 * 8);
     J.counts = static_cast<uint32_t*>(counts->ptr); J.pass = 0;
     SG_CUDA(launch_join_multi(J, ctx->stream));

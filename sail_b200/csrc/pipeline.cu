@@ -1420,6 +1420,28 @@ __device__ __forceinline__ void sink_compact(const PipelineParams& P, const Tile
 // ================================================================================================
 // join build sink / partition sink
 // ================================================================================================
+// does build row `cand` carry the key packed in `key`?
+__device__ __forceinline__ bool build_row_has_key(const KeyDesc* keys, const uint8_t* const* cols, const uint8_t* strides, int n_keys,
+                                                  int64_t cand, const KeyRegs& key) {
+  int w = 0;
+  for (int i = 0; i < n_keys; ++i) {
+    const KeyDesc& d = keys[i];
+    const uint8_t* bp = cols[i] + cand * strides[i];
+    if (d.width == 16) {
+      ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(bp);
+      if (d.is_view) { ulonglong2 pv; pv.x = key.w[w]; pv.y = key.w[w + 1]; if (!view_equal(bv, pv)) return false; }
+      else if (bv.x != key.w[w] || bv.y != key.w[w + 1]) return false;
+      w += 2;
+    } else {
+      if (load_key_word(bp, d.width) != key.w[w]) return false;
+      w += 1;
+    }
+  }
+  return true;
+}
+
+// HashJoinExec build: one slot {hash tag, head row} per DISTINCT key; rows with an equal key are pushed on the
+// slot's chain (next[]) with a 128-bit CAS, so heavy duplicate keys stay O(1) per row.
 template <int RPT>
 __device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildParams& B, const TileCtx& c) {
   const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, P.mask_slot);
@@ -1428,15 +1450,32 @@ __device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildP
     if (!(r < c.nrows && (pact == nullptr || pact[r]))) continue;
     KeyRegs key; bool has_null;
     uint64_t h = pack_key<MAX_KEYS>(B.keys, B.n_keys, 0, c, r, key, &has_null);
+    const long long row = B.row_base + c.row0 + r;
+    B.next[row] = -1;
     if (has_null) continue;           // NULL keys never match (NullEqualsNothing)
     const unsigned long long tag = h | 1ull;
-    const long long row = B.row_base + c.row0 + r;
     uint64_t idx = (h >> 1) & B.capacity_mask;
     for (uint64_t probes = 0; probes <= B.capacity_mask; ++probes) {
-      unsigned long long* slot = reinterpret_cast<unsigned long long*>(B.table + idx * 16);
-      unsigned long long old = atomicCAS(slot, 0ull, tag);
-      if (old == 0ull) { reinterpret_cast<long long*>(slot)[1] = row; break; }
-      if (old == tag) atomicOr(B.dup_flag, 1u);   // same hash: duplicate key (or full 64-bit collision)
+      uint8_t* slot = B.table + idx * 16;
+      ulonglong2 s;
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(s.x), "=l"(s.y) : "l"(slot) : "memory");
+      if (s.x == 0ull) {
+        const u128 prev = atomic_cas_128(slot, (u128)0, ((u128)(unsigned long long)row << 64) | tag);
+        if (prev == 0) break;                                   // claimed an empty slot
+        s.x = (unsigned long long)prev; s.y = (unsigned long long)(prev >> 64);
+      }
+      if (s.x == tag && build_row_has_key(B.keys, B.key_cols, B.key_stride, B.n_keys, (int64_t)s.y, key)) {
+        atomicOr(B.dup_flag, 1u);                               // same key: push this row on the chain
+        for (;;) {
+          B.next[row] = (long long)s.y;
+          __threadfence();
+          const u128 want = ((u128)s.y << 64) | s.x;
+          const u128 prev = atomic_cas_128(slot, want, ((u128)(unsigned long long)row << 64) | tag);
+          if (prev == want) break;
+          s.x = (unsigned long long)prev; s.y = (unsigned long long)(prev >> 64);
+        }
+        break;
+      }
       idx = (idx + 1) & B.capacity_mask;
     }
   }

@@ -70,9 +70,12 @@ __global__ void join_multi_kernel(JoinMultiParams P) {
         const ulonglong2 s = *reinterpret_cast<const ulonglong2*>(P.table + idx * 16);
         if (s.x == 0) break;
         if (s.x == tag && raw_keys_equal(P.build_keys, (int64_t)s.y, P.probe_keys, i, P.n_keys)) {
-          if (P.pass == 1) { P.out_build[out] = (int64_t)s.y; P.out_probe[out] = i; ++out; }
-          if (P.pass >= 1 && P.visited) P.visited[s.y] = 1;     // pass 2 = mark only (semi / anti joins emitting build rows)
-          ++n;
+          for (int64_t b = (int64_t)s.y; b >= 0; b = P.next[b]) {      // every build row with this key
+            if (P.pass == 1) { P.out_build[out] = b; P.out_probe[out] = i; ++out; }
+            if (P.pass >= 1 && P.visited) P.visited[b] = 1;            // pass 2 = mark only (semi / anti joins emitting build rows)
+            ++n;
+          }
+          break;                                                        // one slot per distinct key
         }
         idx = (idx + 1) & P.capacity_mask;
       }

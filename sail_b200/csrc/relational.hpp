@@ -29,6 +29,7 @@ struct JoinMultiParams {
   int64_t* out_build;
   int64_t* out_probe;
   uint8_t* visited;
+  const int64_t* next;            // duplicate-key chains built by the build sink
 };
 
 enum SortKind : int32_t { SORT_INT = 0, SORT_UINT = 1, SORT_F64 = 2, SORT_BOOL = 3, SORT_VIEW = 4 };

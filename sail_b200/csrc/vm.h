@@ -177,7 +177,9 @@ struct BuildParams {
   KeyDesc keys[MAX_KEYS];
   int64_t row_base;        // global row id of row 0 of this launch
   uint32_t* dup_flag;
-  int64_t* next;           // chain array (row -> next row with the same slot) for duplicate keys
+  int64_t* next;           // next[row] = next build row with the same key (-1 ends the chain): duplicates cost O(1)
+  const uint8_t* key_cols[MAX_KEYS];   // build key columns (to tell "same key" from "same hash" while inserting)
+  uint8_t key_stride[MAX_KEYS];
 };
 
 struct PartitionParams {

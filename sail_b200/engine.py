@@ -169,7 +169,7 @@ class DeviceBatch:
         pushed into many operators (each push consumes only the borrowed handle)."""
         b = DeviceBatch(self.schema)
         ctypes.memmove(ctypes.addressof(b.c), ctypes.addressof(self.c), ctypes.sizeof(ArrowDeviceArrayC))
-        b.c.array.release = ctypes.cast(_NOOP_RELEASE, ctypes.c_void_p).value
+        b.c.array.release = ctypes.cast(lib().sailgpu_borrowed_release, ctypes.c_void_p).value   # C callback: safe at interpreter exit
         b.c.array.private_data = None
         b._live = True
         b._owner = self          # keep the buffers alive

@@ -148,6 +148,40 @@ def execute(node: Node, tables: dict, run_op):
     return run_op(node.spec, *ins)
 
 
+def execute_gpu(node: Node, dev_tables: dict, ctx=None, stats: dict | None = None):
+    """Runs the plan through libsailgpu with every intermediate batch staying in HBM (device hand-off between
+    operators).  dev_tables: {table: (DeviceBatch, schema names)} resident inputs; returns a list of DeviceBatch.
+    stats (optional) collects per-operator metrics keyed by a running node number."""
+    from . import engine
+    if node.spec["op"] == "scan":
+        dev, names = dev_tables[node.spec["table"]]
+        idx = [names.index(c) for c in node.spec["columns"]]
+        spec = {"op": "projection", "exprs": [{"expr": {"col": i}, "name": names[i]} for i in idx]}
+        op = engine.GpuExec(spec, [dev.schema], ctx)
+        op.push(dev.borrow())
+        op.finish()
+        out = op.collect_device()
+        for d in out:
+            d.schema = op.schema
+        op.close()
+        return out
+    ins = [execute_gpu(c, dev_tables, ctx, stats) for c in node.inputs]
+    op = engine.GpuExec(node.spec, [i[0].schema for i in ins], ctx)
+    for k, batches in enumerate(ins):
+        for b in batches:
+            op.push(b, k)
+        op.finish(k)
+    out = op.collect_device()
+    for d in out:
+        d.schema = op.schema
+    if stats is not None:
+        m = op.metrics()
+        stats[f"{len(stats):02d} {op.name()}"] = {"in": m["input_rows"] + m.get("build_input_rows", 0), "out": m["output_rows"],
+                                               "launches": m["gpu.kernel_launches"]}
+    op.close()
+    return out
+
+
 # ---- TPC-H ------------------------------------------------------------------------------------------
 ONE = dec(1, 10, 0)     # `Int32(1)` coerced by DataFusion to Decimal128(10,0): test_tpch.plan.yaml:15
 D152 = "Decimal128(15,2)"

