@@ -256,6 +256,10 @@ def e2e_leg(args, ctx, specs, table, stream, world, total_rows):
 def main():
     args = parse_args()
     rank, world, local = dist_env()
+    # libraries (NCCL, torchrun) may print to stdout: keep fd 1 for the ONE JSON line only
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if world > 1 and args.gpus != world:
         args.gpus = world
     if args.impl == "reference":

@@ -800,6 +800,7 @@ SAILGPU_API int32_t sailgpu_exchange(sailgpu_ctx* c, const struct ArrowSchema* s
     Schema schema = schema_from_arrow(schema_c);
     std::vector<BatchPtr> parts;
     for (int p = 0; p < n; ++p) {
+      if (send[p].array.release == nullptr) { parts.push_back(empty_batch(ctx, schema)); continue; }   // nothing for rank p
       BatchPtr b = take_internal_batch(&send[p]);
       if (!b) b = import_device_batch(ctx, schema, &send[p]);
       parts.push_back(b);
@@ -816,36 +817,52 @@ SAILGPU_API int32_t sailgpu_exchange(sailgpu_ctx* c, const struct ArrowSchema* s
       // strings travel as Arrow views + compact heap: convert through the export path per destination
       struct SendCol { BufPtr data, validity_bytes, heap; int64_t heap_bytes = 0; };
       std::vector<std::vector<SendCol>> sc((size_t)W, std::vector<SendCol>(ncols));
+      (void)0;
+      // pass 1: launch the length scans of every (destination, string column) without synchronising
+      struct Pending { int p; size_t ci; BufPtr offs, scratch; int64_t nblocks; };
+      std::vector<Pending> pend;
+      BufPtr totals = dev_alloc_zero(ctx, (size_t)W * ncols * 8 + 8);
       for (int p = 0; p < W; ++p) {
         mine[(size_t)p * rec] = parts[(size_t)p]->rows;
         for (size_t ci = 0; ci < ncols; ++ci) {
           const DevColumn& col = parts[(size_t)p]->cols[ci];
-          SendCol& s = sc[(size_t)p][ci];
+          SendCol& sd = sc[(size_t)p][ci];
           const int64_t k = col.length;
           if (schema[ci].type.is_string() && k > 0) {
             BufPtr lens = dev_alloc(ctx, (size_t)k * 4), offs = dev_alloc(ctx, (size_t)k * 8), scratch = dev_alloc(ctx, 1026 * 8);
             SG_CUDA(launch_view_lengths(col.data->ptr, k, static_cast<uint32_t*>(lens->ptr), 0, ctx->stream));
             SG_CUDA(launch_exclusive_scan_u32(static_cast<uint32_t*>(lens->ptr), k, static_cast<uint64_t*>(offs->ptr), static_cast<uint64_t*>(scratch->ptr), ctx->stream));
             const int64_t nblocks = std::min<int64_t>(1024, (k + 4095) / 4096);
-            uint64_t total = 0;
-            SG_CUDA(cudaMemcpyAsync(&total, static_cast<uint64_t*>(scratch->ptr) + nblocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            SG_CUDA(cudaStreamSynchronize(ctx->stream));
-            s.heap_bytes = (int64_t)total;
-            s.heap = dev_alloc(ctx, (size_t)total);
-            s.data = dev_alloc(ctx, (size_t)k * 16);
-            SG_CUDA(cudaMemcpyAsync(s.data->ptr, col.data->ptr, (size_t)k * 16, cudaMemcpyDeviceToDevice, ctx->stream));
-            SG_CUDA(launch_views_to_arrow(s.data->ptr, k, static_cast<uint64_t*>(offs->ptr), static_cast<uint8_t*>(s.heap->ptr), ctx->stream));
-            mine[(size_t)p * rec + 1 + ci] = s.heap_bytes;
+            SG_CUDA(cudaMemcpyAsync(static_cast<uint64_t*>(totals->ptr) + (size_t)p * ncols + ci, static_cast<uint64_t*>(scratch->ptr) + nblocks, 8,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+            pend.push_back({p, ci, offs, scratch, nblocks});
           } else if (schema[ci].type.id == TypeId::Bool && k > 0) {
-            s.data = dev_alloc(ctx, (size_t)k);     // booleans travel as bytes
-            SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.data->ptr), static_cast<uint8_t*>(s.data->ptr), k, 0, ctx->stream));
-          } else s.data = col.data;
+            sd.data = dev_alloc(ctx, (size_t)k);     // booleans travel as bytes
+            SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.data->ptr), static_cast<uint8_t*>(sd.data->ptr), k, 0, ctx->stream));
+          } else sd.data = col.data;
           if (k > 0) {                              // validity always travels as bytes (1 = valid)
-            s.validity_bytes = dev_alloc(ctx, (size_t)k);
-            if (col.validity) SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.validity->ptr), static_cast<uint8_t*>(s.validity_bytes->ptr), k, 0, ctx->stream));
-            else SG_CUDA(cudaMemsetAsync(s.validity_bytes->ptr, 1, (size_t)k, ctx->stream));
+            sd.validity_bytes = dev_alloc(ctx, (size_t)k);
+            if (col.validity) SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.validity->ptr), static_cast<uint8_t*>(sd.validity_bytes->ptr), k, 0, ctx->stream));
+            else SG_CUDA(cudaMemsetAsync(sd.validity_bytes->ptr, 1, (size_t)k, ctx->stream));
           }
         }
+      }
+      // one synchronisation for all heap sizes, then pass 2: compact heaps + Arrow-conformant views
+      std::vector<uint64_t> htot((size_t)W * ncols, 0);
+      if (!pend.empty()) {
+        SG_CUDA(cudaMemcpyAsync(htot.data(), totals->ptr, htot.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SG_CUDA(cudaStreamSynchronize(ctx->stream));
+      }
+      for (auto& q : pend) {
+        const DevColumn& col = parts[(size_t)q.p]->cols[q.ci];
+        SendCol& sd = sc[(size_t)q.p][q.ci];
+        const int64_t k = col.length;
+        sd.heap_bytes = (int64_t)htot[(size_t)q.p * ncols + q.ci];
+        sd.heap = dev_alloc(ctx, (size_t)sd.heap_bytes);
+        sd.data = dev_alloc(ctx, (size_t)k * 16);
+        SG_CUDA(cudaMemcpyAsync(sd.data->ptr, col.data->ptr, (size_t)k * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+        SG_CUDA(launch_views_to_arrow(sd.data->ptr, k, static_cast<uint64_t*>(q.offs->ptr), static_cast<uint8_t*>(sd.heap->ptr), ctx->stream));
+        mine[(size_t)q.p * rec + 1 + q.ci] = sd.heap_bytes;
       }
       BufPtr dmine = dev_alloc(ctx, mine.size() * 8), dall = dev_alloc(ctx, mine.size() * 8 * (size_t)W);
       SG_CUDA(cudaMemcpyAsync(dmine->ptr, mine.data(), mine.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -894,6 +911,7 @@ SAILGPU_API int32_t sailgpu_exchange(sailgpu_ctx* c, const struct ArrowSchema* s
       }
       NCCL_CALL(g_nccl.GroupEnd());
       // 3. post-process: rebase string views per source segment, pack byte columns
+      BufPtr nullctrs = dev_alloc_zero(ctx, ncols * 8 + 8);
       for (size_t ci = 0; ci < ncols; ++ci) {
         DevColumn& col = out->cols[ci];
         if (schema[ci].type.is_string())
@@ -906,15 +924,16 @@ SAILGPU_API int32_t sailgpu_exchange(sailgpu_ctx* c, const struct ArrowSchema* s
           col.data = dev_alloc_zero(ctx, (size_t)((total_rows + 31) / 32 * 4));
           SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(bbytes[ci]->ptr), static_cast<uint32_t*>(col.data->ptr), total_rows, nullptr, ctx->stream));
         }
-        BufPtr nullctr = dev_alloc_zero(ctx, 16);
         col.validity = dev_alloc_zero(ctx, (size_t)((total_rows + 31) / 32 * 4));
         SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(vbytes[ci]->ptr), static_cast<uint32_t*>(col.validity->ptr), total_rows,
-                                  static_cast<unsigned long long*>(nullctr->ptr), ctx->stream));
-        unsigned long long nulls = 0;
-        SG_CUDA(cudaMemcpyAsync(&nulls, nullctr->ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        SG_CUDA(cudaStreamSynchronize(ctx->stream));
-        col.null_count = (int64_t)nulls;
-        if (nulls == 0) col.validity = nullptr;
+                                  static_cast<unsigned long long*>(nullctrs->ptr) + ci, ctx->stream));
+      }
+      std::vector<unsigned long long> nulls(ncols, 0);
+      SG_CUDA(cudaMemcpyAsync(nulls.data(), nullctrs->ptr, ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      SG_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (size_t ci = 0; ci < ncols; ++ci) {
+        out->cols[ci].null_count = (int64_t)nulls[ci];
+        if (nulls[ci] == 0) out->cols[ci].validity = nullptr;
       }
       SG_CUDA(cudaStreamSynchronize(ctx->stream));
     }

@@ -111,12 +111,14 @@ class GpuBackend:
         return [self._single(seg, schema) for seg in parts]
 
     def _single(self, seg, schema):
+        if not seg:
+            return None
         if len(seg) == 1:
             seg[0].schema = schema
             return seg[0]
         ident = {"op": "projection", "exprs": [{"expr": {"col": i}, "name": n} for i, n in enumerate(schema.names)]}
         if not seg:
-            return self.empty(schema)
+            return None
         # several batches for one destination: concatenate them on the device (SortExec collects its whole input;
         # row order inside an exchange segment is free)
         op = self.engine.GpuExec({"op": "sort", "keys": [{"expr": {"col": 0}}], "fetch": None}, [schema], self.ctx)
@@ -129,7 +131,7 @@ class GpuBackend:
         return out[0]
 
     def empty(self, schema: pa.Schema):
-        return self.engine.to_device(schema.empty_table(), self.ctx)
+        return None                      # sailgpu_exchange treats a released / absent batch as empty
 
     def exchange(self, parts: list, schema: pa.Schema):
         return [self.engine.exchange(parts, schema, self.ctx)]

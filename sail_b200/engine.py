@@ -357,6 +357,8 @@ def exchange(send: list, schema: pa.Schema, ctx: Context | None = None) -> Devic
     n = len(send)
     arr = (ArrowDeviceArrayC * n)()
     for i, d in enumerate(send):
+        if d is None:
+            continue                      # zeroed struct (release == NULL): nothing for rank i
         if not d._live:
             raise SailGpuError(6, "device batch was already consumed")
         ctypes.memmove(ctypes.addressof(arr[i]), ctypes.addressof(d.c), ctypes.sizeof(ArrowDeviceArrayC))
