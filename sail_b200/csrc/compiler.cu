@@ -320,7 +320,7 @@ void PipelineCompiler::finish_aggregate(CompiledPipeline& out, const StageSpec& 
     return A.n_accs++;
   };
   auto sum_acc = [&](const Val& x, const DataType& t) -> int {
-    if (t.is_decimal()) return add_acc(ACC_SUM_I128, &x);
+    if (t.is_decimal()) { const int j = add_acc(ACC_SUM_I128, &x); if (t.precision <= 16 && j < MAX_ACCS) small_acc_[j] = true; return j; }
     if (t.is_float()) { Val f = convert(x, K_F64); f.vslot = x.vslot; return add_acc(ACC_SUM_F64, &f); }
     Val w = convert(x, K_I64); w.vslot = x.vslot;
     return add_acc(ACC_SUM_I64, &w);
@@ -436,7 +436,7 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
   SG_CHECK(prog_.size() <= (size_t)MAX_INST, SAILGPU_ERR_UNSUPPORTED, "fused pipeline needs more than " + std::to_string(MAX_INST) + " VM instructions");
   const AggParams& A = out.agg;
   // per hot group: key words + fingerprint + entry pointer + one accumulator block per warp
-  const size_t per_group = out.sink == SINK_AGG ? (size_t)HOT_KEY_WORDS * 8 + 16 + (size_t)(NT / 32) * (1 + 2 * A.n_accs) * 8 : 0;
+  const size_t per_group = out.sink == SINK_AGG ? (size_t)HOT_KEY_WORDS * 8 + 16 + 32 + (size_t)(NT / 32) * (1 + 2 * A.n_accs) * 8 : 0;
   if (out.sink == SINK_AGG && A.key_words > HOT_KEY_WORDS) hot_wanted = 0;
   auto layout = [&](int rpt, int stages, uint32_t* temps, uint32_t* stage) {
     const uint32_t tile = (uint32_t)rpt * NT;
@@ -505,7 +505,12 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
     for (int j = 0; j < AA.n_accs; ++j) { AA.accs[j].value_slot = off(AA.accs[j].value_slot); AA.accs[j].valid_slot = off(AA.accs[j].valid_slot); }
     for (int j = 0; j < AA.n_accs && j < REG_ACCS; ++j) {
       AA.rload[j].slot = AA.accs[j].value_slot; AA.rload[j].stride = AA.accs[j].stride;
-      AA.rload[j].mode = (uint8_t)(AA.accs[j].op == ACC_COUNT ? 0 : AA.accs[j].vkind == K_I64 ? 1 : 2);
+      AA.rload[j].mode = (uint8_t)(AA.accs[j].op == ACC_COUNT ? 0 : AA.accs[j].vkind == K_I64 ? (small_acc_[j] ? 3 : 1) : 2);
+    }
+    {
+      bool simple = true;
+      for (int w = 0; w < AA.key_words; ++w) simple &= !AA.has_null_word && AA.kwords[w].width == 8 && AA.kwords[w].valid_slot == NO_SLOT;
+      AA.kw_simple = simple ? 1 : 0;
     }
     AA.hot_groups = best_hot;
     AA.hot_smem_off = temps;

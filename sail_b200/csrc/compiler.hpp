@@ -178,6 +178,7 @@ class PipelineCompiler {
   std::vector<std::string> literals_;
   std::vector<std::pair<int, int>> literal_fixups_;
   std::vector<int> probe_slot_refs_;
+  bool small_acc_[MAX_ACCS] = {};      // accumulator input is statically below 2^55 (decimal precision <= 16)
   std::vector<OutputCol> outs_;
   std::vector<DataType> out_types_;
 

@@ -875,11 +875,12 @@ __device__ __forceinline__ void acc_combine_words(int op, uint64_t& w0, uint64_t
 // atomics, no per-thread state, ~G*n_accs*30 instructions per warp-tile regardless of tile size.
 constexpr int NWARPS = NT / 32;
 struct HotView {
-  uint64_t* keys; uint64_t* fps; uint64_t* entry; uint64_t* wacc; int G; int aw;
+  uint32_t* fp32; uint64_t* keys; uint64_t* fps; uint64_t* entry; uint64_t* wacc; int G; int aw;
 };
 __device__ __forceinline__ HotView hot_view(const AggParams& A, uint8_t* arena) {
   HotView h; h.G = A.hot_groups; h.aw = 1 + 2 * A.n_accs;
   uint8_t* p = arena + A.hot_smem_off;
+  h.fp32 = reinterpret_cast<uint32_t*>(p); p += 32;                    // 8 x u32 fingerprints (register path: one LDS.128)
   h.keys = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * HOT_KEY_WORDS * 8;
   h.fps = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * 8;
   h.entry = reinterpret_cast<uint64_t*>(p); p += (size_t)h.G * 8;
@@ -1153,6 +1154,37 @@ __device__ __forceinline__ void reg_flush(const AggParams& A, const HotView& H, 
   R.rows = 0;
 }
 
+// register path key handling: every key word is a plain 8-byte load (views, int64, decimals) unless the plan has
+// narrow or nullable keys, in which case the general packer runs; fingerprints are 32 bits so that the four
+// dictionary fingerprints arrive in one LDS.128
+__device__ __forceinline__ uint32_t fold32(uint64_t v) { return (uint32_t)v ^ (uint32_t)(v >> 32); }
+__device__ __forceinline__ uint32_t reg_pack(const AggParams& A, const TileCtx& c, int r, uint64_t (&kw)[HOT_KEY_WORDS]) {
+  if (A.kw_simple) {
+#pragma unroll
+    for (int w = 0; w < HOT_KEY_WORDS; ++w)
+      kw[w] = w < A.key_words ? lds<uint64_t>(c.arena + A.kwords[w].slot + r * A.kwords[w].stride + A.kwords[w].byte_off) : 0ull;
+  } else {
+    pack_words(A, c, r, kw);
+  }
+  uint32_t fp = fold32(kw[0]);
+  fp = __funnelshift_l(fp, fp, 7) ^ fold32(kw[1]);
+  fp = __funnelshift_l(fp, fp, 7) ^ fold32(kw[2]);
+  fp = __funnelshift_l(fp, fp, 7) ^ fold32(kw[3]);
+  return fp;
+}
+__device__ __forceinline__ bool reg_verify(const HotView& H, int g, const uint64_t (&kw)[HOT_KEY_WORDS]) {
+  const ulonglong2* hk = reinterpret_cast<const ulonglong2*>(H.keys + g * HOT_KEY_WORDS);
+  const ulonglong2 a = hk[0], b = hk[1];
+  return a.x == kw[0] && a.y == kw[1] && b.x == kw[2] && b.y == kw[3];
+}
+__device__ __forceinline__ int reg_lookup(const HotView& H, int hot_n, const uint4& f4, const uint64_t (&kw)[HOT_KEY_WORDS], uint32_t fp) {
+  if (hot_n > 0 && f4.x == fp && reg_verify(H, 0, kw)) return 0;
+  if (hot_n > 1 && f4.y == fp && reg_verify(H, 1, kw)) return 1;
+  if (hot_n > 2 && f4.z == fp && reg_verify(H, 2, kw)) return 2;
+  if (hot_n > 3 && f4.w == fp && reg_verify(H, 3, kw)) return 3;
+  return -1;
+}
+
 template <int RPT>
 __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggParams& A, const TileCtx& c, Smem* sm, RegAcc& R) {
   const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + P.mask_slot;
@@ -1161,6 +1193,7 @@ __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggP
   bool live[RPT];
   bool miss = false;
   const int hot_n0 = sm->hot_n;
+  const uint4 f4 = *reinterpret_cast<const uint4*>(H.fp32);
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     const int r = threadIdx.x + k * NT;
@@ -1168,8 +1201,8 @@ __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggP
     gid[k] = -1;
     if (live[k]) {
       uint64_t kw[HOT_KEY_WORDS];
-      const uint64_t fp = pack_words(A, c, r, kw);
-      gid[k] = hot_lookup(A, H, hot_n0, kw, fp);
+      const uint32_t fp = reg_pack(A, c, r, kw);
+      gid[k] = reg_lookup(H, hot_n0, f4, kw, fp);
       miss |= gid[k] < 0;
     }
   }
@@ -1185,10 +1218,10 @@ __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggP
         for (int k = 0; k < RPT; ++k) {
           if (live[k] && gid[k] < 0) {
             uint64_t kw[HOT_KEY_WORDS];
-            const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
+            const uint32_t fp = reg_pack(A, c, threadIdx.x + k * NT, kw);
             const int g = sm->hot_n;
             for (int w = 0; w < HOT_KEY_WORDS; ++w) H.keys[g * HOT_KEY_WORDS + w] = kw[w];
-            H.fps[g] = fp;
+            H.fp32[g] = fp;
             H.entry[g] = 0;
             sm->hot_n = g + 1;
             break;
@@ -1202,8 +1235,9 @@ __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggP
       for (int k = 0; k < RPT; ++k) {
         if (live[k] && gid[k] < 0) {
           uint64_t kw[HOT_KEY_WORDS];
-          const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
-          gid[k] = hot_lookup(A, H, hot_n1, kw, fp);
+          const uint32_t fp = reg_pack(A, c, threadIdx.x + k * NT, kw);
+          const uint4 g4 = *reinterpret_cast<const uint4*>(H.fp32);
+          gid[k] = reg_lookup(H, hot_n1, g4, kw, fp);
           miss |= gid[k] < 0;
         }
       }
@@ -1224,6 +1258,7 @@ __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggP
           if (L.mode == 0) val[j] = 1;
           else {
             const uint8_t* p = c.arena + L.slot + r * L.stride;
+            if (L.mode == 3) { val[j] = lds<int64_t>(p); continue; }         // statically below 2^55: no check
             i128 x;
             if (L.mode == 1) x = (i128)lds<int64_t>(p); else x = lds<i128>(p);
             if (fits55(x)) val[j] = (int64_t)x;
@@ -1532,8 +1567,8 @@ __device__ __forceinline__ void sink_partition(const PipelineParams& P, const Pa
 // ================================================================================================
 // the kernel
 // ================================================================================================
-template <int RPT>
-__global__ void __launch_bounds__(NT, 2) pipeline_kernel(const __grid_constant__ KernelArgs K, int n_stages) {
+template <int RPT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constant__ KernelArgs K, int n_stages) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem* sm = reinterpret_cast<Smem*>(smem_raw);
   uint8_t* arena = smem_raw + SMEM_HDR;
@@ -1807,21 +1842,23 @@ __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, int64_t n, co
 // ================================================================================================
 // host-callable launchers (C++ linkage inside libsailgpu)
 // ================================================================================================
-cudaError_t launch_pipeline(const KernelArgs& K, int rpt, int n_stages, size_t smem_bytes, int grid, cudaStream_t stream) {
-  void (*k)(const KernelArgs, int) = nullptr;
-  switch (rpt) {
-    case 1: k = pipeline_kernel<1>; break;
-    case 2: k = pipeline_kernel<2>; break;
-    default: k = pipeline_kernel<4>; break;
-  }
+typedef void (*PipelineFn)(const KernelArgs, int);
+// register budget variants: MINB = resident CTAs per SM the compiler must allow (2 -> 128 regs, 3 -> 80, 4 -> 64)
+static PipelineFn pick_kernel(int rpt, int minb) {
+  if (minb >= 4) return rpt == 1 ? pipeline_kernel<1, 4> : rpt == 2 ? pipeline_kernel<2, 4> : pipeline_kernel<4, 2>;
+  if (minb == 3) return rpt == 1 ? pipeline_kernel<1, 3> : rpt == 2 ? pipeline_kernel<2, 3> : pipeline_kernel<4, 2>;
+  return rpt == 1 ? pipeline_kernel<1, 2> : rpt == 2 ? pipeline_kernel<2, 2> : pipeline_kernel<4, 2>;
+}
+cudaError_t launch_pipeline(const KernelArgs& K, int rpt, int n_stages, size_t smem_bytes, int grid, int minb, cudaStream_t stream) {
+  PipelineFn k = pick_kernel(rpt, minb);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return e;
   k<<<grid, NT, smem_bytes, stream>>>(K, n_stages);
   return cudaGetLastError();
 }
 
-int pipeline_max_ctas_per_sm(int rpt, size_t smem_bytes) {
-  void (*k)(const KernelArgs, int) = rpt == 1 ? pipeline_kernel<1> : rpt == 2 ? pipeline_kernel<2> : pipeline_kernel<4>;
+int pipeline_max_ctas_per_sm(int rpt, int minb, size_t smem_bytes) {
+  PipelineFn k = pick_kernel(rpt, minb);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, NT, smem_bytes) != cudaSuccess) return 0;

@@ -164,12 +164,16 @@ struct PipelineRunner {
         }
       }
     }
-    int per_sm = std::max(1, (int)(ctx->max_smem / (cp->smem_bytes + 1024)));
+    // resident CTAs per SM: what shared memory allows, then the matching register-budget variant of the kernel
+    const int by_smem = std::max(1, (int)(ctx->max_smem / (cp->smem_bytes + 1024)));
+    const char* fm = getenv("SAILGPU_MINB");
+    const int minb = fm && *fm ? atoi(fm) : std::min(by_smem, cp->sink == SINK_AGG ? 2 : 3);
+    const int per_sm = std::max(1, std::min(by_smem, pipeline_max_ctas_per_sm(cp->rpt, minb, cp->smem_bytes)));
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * per_sm);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool timed = timing_enabled();
     if (timed) { SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1)); SG_CUDA(cudaEventRecord(e0, ctx->stream)); }
-    SG_CUDA(launch_pipeline(*K, cp->rpt, cp->n_stages, cp->smem_bytes, grid, ctx->stream));
+    SG_CUDA(launch_pipeline(*K, cp->rpt, cp->n_stages, cp->smem_bytes, grid, minb, ctx->stream));
     if (timed) { SG_CUDA(cudaEventRecord(e1, ctx->stream)); m.pending.emplace_back(e0, e1); }
     m.kernel_launches++;
     m.pipeline_launches++;

@@ -142,8 +142,8 @@ struct AggParams {
   int32_t priv_seen;
   int32_t reg_path;        // all accumulators are integer sums/counts: per-thread REGISTER partials for the first
                            // REG_GROUPS hot groups (no shuffles, no shared-memory traffic per row)
-  int32_t pad_;
-  // register fast path load plan: mode 0 = constant 1 (count(*)), 1 = i64 slot, 2 = i128 slot
+  int32_t kw_simple;       // every packed key word is a plain 8-byte load of a never-null column
+  // register fast path load plan: mode 0 = constant 1 (count(*)), 1 = i64 slot, 2 = i128 slot, 3 = i64 slot known < 2^55
   struct RegLoad { uint32_t slot; uint16_t stride; uint8_t mode; uint8_t pad; } rload[REG_ACCS];
   uint8_t* table;          // capacity * entry_bytes
   uint32_t* state;         // capacity

@@ -18,9 +18,9 @@ def main():
     bench.SORT_ON_GPU = False
     dev = engine.to_device(table, ctx)
     n = table.num_rows
-    configs = [dict()] + [dict(SAILGPU_RPT=str(r), SAILGPU_STAGES=str(st)) for r in (1, 2, 4) for st in (1, 2)]
+    configs = [dict(), dict(SAILGPU_RPT="1", SAILGPU_STAGES="2"), dict(SAILGPU_RPT="4", SAILGPU_STAGES="1")]
     for cfg in configs:
-        for k in ("SAILGPU_RPT", "SAILGPU_STAGES", "SAILGPU_HOT", "SAILGPU_NO_TMA"):
+        for k in ("SAILGPU_RPT", "SAILGPU_STAGES", "SAILGPU_HOT", "SAILGPU_NO_TMA", "SAILGPU_MINB"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         try:
