@@ -76,9 +76,11 @@ SAILGPU_API void sailgpu_ctx_destroy(sailgpu_ctx* c) {
   if (!c) return;
   if (sg::g_exiting.load()) return;
   cudaSetDevice(c->ctx.device);
-  if (c->ctx.stream) { cudaStreamSynchronize(c->ctx.stream); cudaStreamDestroy(c->ctx.stream); }
-  if (c->ctx.copy_stream) cudaStreamDestroy(c->ctx.copy_stream);
-  delete c;
+  // Batches handed out through pull_device may outlive the context: the (tiny) Ctx block is intentionally never freed,
+  // it is only marked dead so that late buffer releases use cudaFree instead of the destroyed stream.
+  c->ctx.dead.store(true);
+  if (c->ctx.stream) { cudaStreamSynchronize(c->ctx.stream); cudaStreamDestroy(c->ctx.stream); c->ctx.stream = nullptr; }
+  if (c->ctx.copy_stream) { cudaStreamDestroy(c->ctx.copy_stream); c->ctx.copy_stream = nullptr; }
 }
 
 SAILGPU_API const char* sailgpu_ctx_last_error(const sailgpu_ctx*) { return g_ctx_error.c_str(); }

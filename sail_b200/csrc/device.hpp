@@ -30,6 +30,7 @@ struct Ctx {
   std::string last_error;
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  std::atomic<bool> dead{false};     // context destroyed; buffers that outlive it fall back to cudaFree
   // metrics shared by all ops of the context
   std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};
 };
@@ -46,7 +47,7 @@ struct DevBuf {
   ~DevBuf() {
     if (g_exiting.load()) return;
     if (on_release) on_release();
-    else if (ptr && ctx) cudaFreeAsync(ptr, ctx->stream);
+    else if (ptr && ctx) { if (ctx->dead.load()) cudaFree(ptr); else cudaFreeAsync(ptr, ctx->stream); }
   }
 };
 using BufPtr = std::shared_ptr<DevBuf>;

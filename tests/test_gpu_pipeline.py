@@ -152,3 +152,42 @@ def test_divide_by_zero_is_an_error():
     with pytest.raises(engine.SailGpuError) as e:
         gpu_op(spec, t)
     assert "ivide by zero" in str(e.value)
+
+
+def test_aggregate_many_groups_multi_batch_growth():
+    """streams 16 batches into one AggregateExec: the global table grows (rehash) several times, most rows take the
+    cold (global-table) path, keys include long strings"""
+    from sail_b200 import engine
+    rng = np.random.default_rng(42)
+    n_batches, n = 16, 40000
+    words = [f"key-{i:06d}-{'x' * (i % 17)}" for i in range(3000)]
+    batches = []
+    for b in range(n_batches):
+        k = rng.integers(0, 20000 * (b + 1), n).astype(np.int64)          # key domain keeps widening -> growth
+        s = [words[i] for i in rng.integers(0, len(words), n)]
+        v = [decimal.Decimal(int(x)) / 100 for x in rng.integers(-10**7, 10**7, n)]
+        batches.append(pa.table({"k": pa.array(k), "s": pa.array(s, type=pa.string_view()), "v": pa.array(v, type=pa.decimal128(15, 2))}))
+    whole = pa.concat_tables(batches)
+    for keys in (["k"], ["s"], ["k", "s"]):
+        spec = {"op": "aggregate", "mode": "single", "group_by": [{"expr": {"col": whole.schema.names.index(c)}, "name": c} for c in keys],
+                "aggs": [{"fn": "sum", "args": [{"col": 2}], "name": "sv"}, {"fn": "count", "args": [], "name": "c"},
+                         {"fn": "max", "args": [{"col": 2}], "name": "mx"}, {"fn": "avg", "args": [{"col": 2}], "name": "av"}]}
+        op = engine.GpuExec(spec, [whole.schema])
+        for t in batches:
+            op.push(t)
+        op.finish()
+        got = op.collect()
+        op.close()
+        assert_same(got, oracle_op(spec, whole))
+
+
+def test_filter_streams_many_batches_in_order():
+    from sail_b200 import engine
+    t = make_table(30000, seed=9, nulls=True)
+    spec = {"op": "filter", "predicate": resolve(plans.binop("<", C("b"), plans.lit(20, "Int32")), t), "projection": [0, 1, 4]}
+    op = engine.GpuExec(spec, [t.schema])
+    for o in range(0, t.num_rows, 777):          # ragged batch sizes
+        op.push(t.slice(o, 777))
+    op.finish()
+    assert_same(op.collect(), oracle_op(spec, t), ordered=True)
+    op.close()

@@ -166,3 +166,43 @@ def test_chain_operator_matches_separate_operators():
     got = engine.run_op(chain, t)
     want = plans.execute(sort_node, {"lineitem": li}, oracle_op)
     assert_same(got, want, ordered=True)
+
+
+def test_large_sort_properties():
+    """size-independent properties at a size the oracle cannot sort quickly: output is sorted on the keys and is a
+    permutation of the input (order-insensitive checksums per column)"""
+    n = 3_000_000
+    rng = np.random.default_rng(5)
+    t = pa.table({"a": pa.array(rng.integers(-10**9, 10**9, n).astype(np.int64)), "b": pa.array(rng.integers(0, 1000, n).astype(np.int32)),
+                  "c": pa.array(rng.integers(0, 2**62, n).astype(np.int64))})
+    spec = {"op": "sort", "keys": [{"expr": {"col": 1}, "asc": False, "nulls_first": False}, {"expr": {"col": 0}, "asc": True, "nulls_first": True}], "fetch": None}
+    got = gpu_op(spec, t)
+    assert got.num_rows == n
+    a, b, c = (np.asarray(got[x]) for x in "abc")
+    assert np.all(np.diff(b.astype(np.int64)) <= 0)
+    same_b = np.diff(b) == 0
+    assert np.all(np.diff(a)[same_b] >= 0)
+    for col in "abc":
+        x, y = np.asarray(t[col]).astype(np.uint64), np.asarray(got[col]).astype(np.uint64)
+        assert x.sum() == y.sum() and np.bitwise_xor.reduce(x) == np.bitwise_xor.reduce(y)
+
+
+def test_join_then_aggregate_row_count_properties_sf1():
+    """Q3's join pipeline at SF1 (7.6 M scanned rows): every output group key exists in orders and the revenue total equals
+    the sum over the qualifying lineitems computed independently with numpy"""
+    from datagen import tpch
+    sf = 1.0
+    raw = tpch.gen_orders_lineitem_numpy(sf, ["o_orderkey", "o_custkey", "o_orderdate"], ["l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"])
+    cust = tpch.customer(sf)
+    tables = {"lineitem": tpch.lineitem(sf, ["l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"]),
+              "orders": tpch.orders(sf, ["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"]), "customer": cust}
+    plan = plans.q3().inputs[0].inputs[0]           # the FinalPartitioned aggregate, before projection + top-10
+    got = plans.execute(plan, tables, gpu_op)
+    cutoff = plans.days("1995-03-15")
+    building = set(np.asarray(cust["c_custkey"])[np.asarray(cust["c_mktsegment"].to_pylist()) == "BUILDING"].tolist())
+    okeys = raw["o_orderkey"][(raw["o_orderdate"] < cutoff) & np.isin(raw["o_custkey"], list(building))]
+    sel = (raw["l_shipdate"] > cutoff) & np.isin(raw["l_orderkey"], okeys)
+    want_total = int(np.sum(raw["l_extendedprice"][sel].astype(object) * (100 - raw["l_discount"][sel]).astype(object)))
+    got_total = sum(int(decimal.Decimal(v).scaleb(4)) for v in got["revenue"].to_pylist())
+    assert got_total == want_total
+    assert got.num_rows == len(np.unique(raw["l_orderkey"][sel]))
