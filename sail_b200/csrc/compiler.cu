@@ -446,15 +446,22 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
       if (sl.is_input) s += (b + 127) & ~127u; else t += (b + 15) & ~15u;
     }
     *temps = (t + 127) & ~127u; *stage = s;
-    return fixed + *temps + (size_t)stages * s;
+    return fixed + *temps + ((out.extra_scratch + 127) & ~127u) + (size_t)stages * s;
   };
   const int force_rpt = env_int("SAILGPU_RPT", 0), force_stages = env_int("SAILGPU_STAGES", 0), force_hot = env_int("SAILGPU_HOT", -1);
-  const int cands[][2] = {{2, 1}, {1, 2}, {2, 2}, {1, 1}, {4, 1}, {4, 2}};   // measured order on B200 (scripts/sweep_q1.py)
+  // (rows per thread, input stages) in measured order of preference on B200 (scripts/sweep_q1.py, scripts/bench_ops.py):
+  // aggregation wants 2 CTAs/SM of 512-row tiles; plain projection streams best with big double-buffered tiles;
+  // compaction / join / partition sinks prefer big single-stage tiles and more resident CTAs
+  static const int C_AGG[][2] = {{2, 1}, {1, 2}, {2, 2}, {1, 1}, {4, 1}, {4, 2}};
+  static const int C_STORE[][2] = {{4, 2}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
+  static const int C_OTHER[][2] = {{4, 1}, {4, 2}, {2, 1}, {2, 2}, {1, 2}, {1, 1}};
+  const int (*cands)[2] = out.sink == SINK_AGG ? C_AGG : out.sink == SINK_STORE ? C_STORE : C_OTHER;
   int best_rpt = 0, best_stages = 0, best_hot = 0;
   if (hot_wanted > 0 && force_hot >= 0) hot_wanted = force_hot;
   for (int pass = 0; pass < 2 && !best_rpt; ++pass) {
     // pass 0: demand the wanted number of hot groups (min 4 when grouping); pass 1: whatever fits
-    for (auto& c : cands) {
+    for (int ci = 0; ci < 6; ++ci) {
+      const int* c = cands[ci];
       if (force_rpt && c[0] != force_rpt) continue;
       if (force_stages && c[1] != force_stages) continue;
       uint32_t t, s;
@@ -473,7 +480,8 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
   layout(best_rpt, best_stages, &temps, &stage);
   const uint32_t tile = (uint32_t)best_rpt * NT;
   out.temps_bytes = temps; out.stage_bytes = stage;
-  out.hot_bytes = (uint32_t)((best_hot * per_group + 127) & ~(size_t)127);
+  out.hot_bytes = (uint32_t)((best_hot * per_group + 127) & ~(size_t)127) + ((out.extra_scratch + 127) & ~127u);
+  out.scratch_off = temps;
   // assign offsets
   uint32_t t_off = 0, s_off = temps + out.hot_bytes;
   for (auto& sl : slots_) {

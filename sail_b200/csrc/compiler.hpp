@@ -63,6 +63,8 @@ struct CompiledPipeline {
   uint32_t temps_bytes = 0, stage_bytes = 0, hot_bytes = 0, arena_bytes = 0;
   size_t smem_bytes = 0;
   int n_probes = 0;
+  uint32_t extra_scratch = 0;        // sink scratch bytes requested by the operator (partition counters)
+  uint32_t scratch_off = 0;          // its arena offset (set by finalize)
 };
 
 class PipelineCompiler {

@@ -576,6 +576,7 @@ struct RepartitionOp : Op {
     aux.part.part_counts = static_cast<unsigned long long*>(counts->ptr);
     aux.part.part_offsets = static_cast<const int64_t*>(offsets->ptr);
     aux.part.pid_slot = NO_SLOT;
+    aux.part.smem_off = cp->scratch_off;
     // pass 0: histogram
     PipelineParams P;
     run.prepare(P, *cp, *b, 0, n);
@@ -656,7 +657,10 @@ std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::v
   op->ready.resize((size_t)op->n_parts);
   op->run.init(ctx, inputs[0]);
   auto* raw = op.get();
-  op->run.custom_sink = [raw](PipelineCompiler& pc, CompiledPipeline& cp) { pc.finish_partition(cp, raw->exprs); };
+  op->run.custom_sink = [raw](PipelineCompiler& pc, CompiledPipeline& cp) {
+    pc.finish_partition(cp, raw->exprs);
+    cp.extra_scratch = (uint32_t)(raw->n_parts * 16 + 16);      // u32 cnt[n] + u64 base[n] per CTA
+  };
   return op;
 }
 

@@ -1416,21 +1416,32 @@ __device__ __forceinline__ void sink_compact(const PipelineParams& P, const Tile
     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
     if (lane < n) sm->warp_sums[lane] = incl - v;
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    if (lane == 0) {
-      unsigned long long excl = 0;
-      if (tile > 0) {
-        st_release_u64(P.tile_status + tile, (1ull << 62) | total);
-        int t = tile - 1;
-        uint32_t spins = 0;
-        for (;;) {
-          unsigned long long s = ld_acquire_u64(P.tile_status + t);
-          const unsigned long long flag = s >> 62;
-          if (flag == 0) { if (++spins > (1u << 26)) __trap(); continue; }
-          excl += s & ((1ull << 62) - 1);
-          if (flag == 2 || t == 0) break;
-          --t;
-        }
+    // decoupled look-back, one warp wide: 32 predecessor tiles are inspected per step; the walk stops at the
+    // closest tile that already published an inclusive prefix (flag 2) and adds the aggregates (flag 1) in between
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      if (lane == 0) st_release_u64(P.tile_status + tile, (1ull << 62) | total);
+      int hi = tile - 1;                       // newest tile not yet accounted for
+      uint32_t spins = 0;
+      for (;;) {
+        const int t = hi - lane;
+        unsigned long long sw = t >= 0 ? ld_acquire_u64(P.tile_status + t) : (2ull << 62);   // before tile 0: prefix 0
+        const unsigned flag = (unsigned)(sw >> 62);
+        const unsigned ready = __ballot_sync(0xFFFFFFFFu, flag != 0);
+        const unsigned prefix = __ballot_sync(0xFFFFFFFFu, flag == 2);
+        // usable window: lanes 0..first_prefix (inclusive) if all of them are ready
+        const int first_prefix = prefix ? __ffs(prefix) - 1 : 32;
+        const unsigned need = first_prefix >= 31 ? 0xFFFFFFFFu : ((2u << first_prefix) - 1);
+        if ((ready & need) != need) { if (++spins > (1u << 24)) __trap(); continue; }      // somebody in the window is not published yet
+        unsigned long long v = (lane <= first_prefix) ? (sw & ((1ull << 62) - 1)) : 0ull;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        excl += v;
+        if (first_prefix < 32) break;          // reached a published prefix
+        hi -= 32;
       }
+    }
+    if (lane == 0) {
       st_release_u64(P.tile_status + tile, (2ull << 62) | (excl + total));
       sm->tile_base = excl;
       if ((int64_t)(tile + 1) * P.tile_rows >= P.n_rows) *P.out_count = excl + total;
@@ -1516,50 +1527,83 @@ __device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildP
   }
 }
 
+// hash of the partition key columns of row r exactly as oracle/ops.py::hash_partition_ids: h = mix64(h ^ colhash)
+__device__ __forceinline__ uint32_t partition_of(const PartitionParams& Q, const TileCtx& c, int r) {
+  uint64_t h = 0;
+  for (int i = 0; i < Q.n_keys; ++i) {
+    const KeyDesc& d = Q.keys[i];
+    const uint8_t* p = c.arena + eff(c, d.slot) + r * d.stride;
+    uint64_t ch;
+    const bool isnull = d.valid_slot != NO_SLOT && c.arena[eff(c, d.valid_slot) + r] == 0;
+    if (isnull) ch = 0x6E756C6C6E756C6Cull;
+    else if (d.width == 16) {
+      ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+      if (d.is_view) {
+        // length-seeded chain over 8-byte little-endian words of the string bytes
+        const uint32_t len = (uint32_t)v.x;
+        const uint8_t* s = view_ptr(v, p);
+        uint64_t x = len;
+        for (uint32_t o = 0; o < len; o += 8) {
+          uint64_t w = 0;
+          for (uint32_t b = 0; b < 8 && o + b < len; ++b) w |= (uint64_t)s[o + b] << (8 * b);
+          x = mix64(x ^ w);
+        }
+        ch = mix64(x);
+      } else ch = mix64(v.x ^ mix64(v.y));
+    } else if (d.width == 8) ch = mix64(lds<uint64_t>(p));
+    else if (d.width == 4) ch = mix64((uint64_t)(int64_t)lds<int32_t>(p));
+    else ch = mix64((uint64_t)*p);
+    h = mix64(h ^ ch);
+  }
+  return (uint32_t)(h % (uint64_t)Q.n_parts);
+}
+
+// RepartitionExec Hash: per tile, rows are counted per partition in shared memory (warp-aggregated:
+// __match_any_sync elects one lane per distinct partition id in the warp), the CTA reserves one contiguous range per
+// non-empty partition with a single global atomic, and every row scatters to base[pid] + its rank.
+// pass 0 only accumulates the global histogram.
 template <int RPT>
 __device__ __forceinline__ void sink_partition(const PipelineParams& P, const PartitionParams& Q, const TileCtx& c) {
   const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, P.mask_slot);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(c.arena + Q.smem_off);
+  unsigned long long* base = reinterpret_cast<unsigned long long*>(c.arena + Q.smem_off + (((size_t)Q.n_parts * 4 + 7) & ~(size_t)7));
+  const int lane = threadIdx.x & 31;
+  for (int p = threadIdx.x; p < Q.n_parts; p += NT) cnt[p] = 0;
+  __syncthreads();
+  uint32_t pid[RPT], rank[RPT];
+  bool live[RPT];
+#pragma unroll
   for (int k = 0; k < RPT; ++k) {
     const int r = threadIdx.x + k * NT;
-    if (!(r < c.nrows && (pact == nullptr || pact[r]))) continue;
-    // hash of the key columns exactly as oracle/ops.py::hash_partition_ids: h = mix64(h ^ colhash)
-    uint64_t h = 0;
-    for (int i = 0; i < Q.n_keys; ++i) {
-      const KeyDesc& d = Q.keys[i];
-      const uint8_t* p = c.arena + eff(c, d.slot) + r * d.stride;
-      uint64_t ch;
-      const bool isnull = d.valid_slot != NO_SLOT && c.arena[eff(c, d.valid_slot) + r] == 0;
-      if (isnull) ch = 0x6E756C6C6E756C6Cull;
-      else if (d.width == 16) {
-        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
-        if (d.is_view) {
-          // length-seeded chain over 8-byte little-endian words of the string bytes
-          const uint32_t len = (uint32_t)v.x;
-          const uint8_t* s = view_ptr(v, p);
-          uint64_t x = len;
-          for (uint32_t o = 0; o < len; o += 8) {
-            uint64_t w = 0;
-            for (uint32_t b = 0; b < 8 && o + b < len; ++b) w |= (uint64_t)s[o + b] << (8 * b);
-            x = mix64(x ^ w);
-          }
-          ch = mix64(x);
-        } else ch = mix64(v.x ^ mix64(v.y));
-      } else if (d.width == 8) ch = mix64(lds<uint64_t>(p));
-      else if (d.width == 4) ch = mix64((uint64_t)(int64_t)lds<int32_t>(p));
-      else ch = mix64((uint64_t)*p);
-      h = mix64(h ^ ch);
+    live[k] = r < c.nrows && (pact == nullptr || pact[r]);
+    pid[k] = live[k] ? partition_of(Q, c, r) : 0xFFFFFFFFu - lane;       // idle lanes match nobody
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, pid[k]);
+    const int leader = __ffs(peers) - 1;
+    uint32_t first = 0;
+    if (live[k] && lane == leader) first = atomicAdd(&cnt[pid[k]], (uint32_t)__popc(peers));
+    first = __shfl_sync(0xFFFFFFFFu, first, leader);
+    rank[k] = first + __popc(peers & ((1u << lane) - 1));
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < Q.n_parts; p += NT) {
+    const uint32_t n = cnt[p];
+    if (n) {
+      const unsigned long long at = atomicAdd(Q.part_counts + p, (unsigned long long)n);
+      if (Q.pass) base[p] = (unsigned long long)Q.part_offsets[p] + at;
     }
-    const uint32_t pid = (uint32_t)(h % (uint64_t)Q.n_parts);
-    if (Q.pass == 0) {
-      atomicAdd(Q.part_counts + pid, 1ull);
-    } else {
-      const unsigned long long pos = Q.part_offsets[pid] + atomicAdd(Q.part_counts + pid, 1ull);
-      for (int j = 0; j < P.n_out; ++j) {
-        const OutputCol& o = P.out[j];
-        if (o.width) store_value(o, c, r, (int64_t)pos);
-        else o.data[pos] = c.arena[eff(c, o.slot) + r];
-        if (o.valid_slot != NO_SLOT) o.valid_bytes[pos] = c.arena[eff(c, o.valid_slot) + r];
-      }
+  }
+  if (Q.pass == 0) { __syncthreads(); return; }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    if (!live[k]) continue;
+    const int r = threadIdx.x + k * NT;
+    const unsigned long long pos = base[pid[k]] + rank[k];
+    for (int j = 0; j < P.n_out; ++j) {
+      const OutputCol& o = P.out[j];
+      if (o.width) store_value(o, c, r, (int64_t)pos);
+      else o.data[pos] = c.arena[eff(c, o.slot) + r];
+      if (o.valid_slot != NO_SLOT) o.valid_bytes[pos] = c.arena[eff(c, o.valid_slot) + r];
     }
   }
 }

@@ -190,6 +190,7 @@ struct PartitionParams {
   int32_t pass;                      // 0 = histogram only, 1 = scatter using cursors
   const int64_t* part_offsets;       // [n_parts] exclusive offsets into the output columns
   uint32_t pid_slot;
+  uint32_t smem_off;                 // arena offset of the per-CTA scratch: u32 cnt[n_parts], u64 base[n_parts]
 };
 
 struct PipelineParams {

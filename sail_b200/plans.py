@@ -166,6 +166,10 @@ def execute_gpu(node: Node, dev_tables: dict, ctx=None, stats: dict | None = Non
         op.close()
         return out
     ins = [execute_gpu(c, dev_tables, ctx, stats) for c in node.inputs]
+    if stats is not None:
+        import time
+        (ctx or engine.default_context()).synchronize()
+        t0 = time.perf_counter()
     op = engine.GpuExec(node.spec, [i[0].schema for i in ins], ctx)
     for k, batches in enumerate(ins):
         for b in batches:
@@ -176,8 +180,9 @@ def execute_gpu(node: Node, dev_tables: dict, ctx=None, stats: dict | None = Non
         d.schema = op.schema
     if stats is not None:
         m = op.metrics()
+        (ctx or engine.default_context()).synchronize()
         stats[f"{len(stats):02d} {op.name()}"] = {"in": m["input_rows"] + m.get("build_input_rows", 0), "out": m["output_rows"],
-                                               "launches": m["gpu.kernel_launches"]}
+                                               "launches": m["gpu.kernel_launches"], "ms": round((time.perf_counter() - t0) * 1e3, 3)}
     op.close()
     return out
 
