@@ -1486,43 +1486,85 @@ __device__ __forceinline__ bool build_row_has_key(const KeyDesc* keys, const uin
   return true;
 }
 
+__device__ __forceinline__ ulonglong2 ld_slot(const uint8_t* slot) {
+  ulonglong2 s;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(s.x), "=l"(s.y) : "l"(slot) : "memory");
+  return s;
+}
+// push the pre-linked chain first..last (next[] already links first -> ... -> last) on the slot's stack
+__device__ __forceinline__ void chain_push(const BuildParams& B, uint8_t* slot, ulonglong2 s, unsigned long long tag, long long first, long long last) {
+  for (;;) {
+    B.next[last] = (long long)s.y;
+    __threadfence();
+    const u128 want = ((u128)s.y << 64) | s.x;
+    const u128 prev = atomic_cas_128(slot, want, ((u128)(unsigned long long)first << 64) | tag);
+    if (prev == want) return;
+    s.x = (unsigned long long)prev; s.y = (unsigned long long)(prev >> 64);
+  }
+}
+// insert one row; returns the slot it ended up in (nullptr when the table is full)
+__device__ __forceinline__ uint8_t* build_insert_one(const BuildParams& B, const KeyRegs& key, uint64_t h, long long row) {
+  const unsigned long long tag = h | 1ull;
+  uint64_t idx = (h >> 1) & B.capacity_mask;
+  for (uint64_t probes = 0; probes <= B.capacity_mask; ++probes) {
+    uint8_t* slot = B.table + idx * 16;
+    ulonglong2 s = ld_slot(slot);
+    if (s.x == 0ull) {
+      const u128 prev = atomic_cas_128(slot, (u128)0, ((u128)(unsigned long long)row << 64) | tag);
+      if (prev == 0) return slot;                               // claimed an empty slot (next[row] is already -1)
+      s.x = (unsigned long long)prev; s.y = (unsigned long long)(prev >> 64);
+    }
+    if (s.x == tag && build_row_has_key(B.keys, B.key_cols, B.key_stride, B.n_keys, (int64_t)s.y, key)) {
+      atomicOr(B.dup_flag, 1u);                                 // same key: push this row on the chain
+      chain_push(B, slot, s, tag, row, row);
+      return slot;
+    }
+    idx = (idx + 1) & B.capacity_mask;
+  }
+  return nullptr;
+}
+
 // HashJoinExec build: one slot {hash tag, head row} per DISTINCT key; rows with an equal key are pushed on the
-// slot's chain (next[]) with a 128-bit CAS, so heavy duplicate keys stay O(1) per row.
+// slot's chain (next[]) with a 128-bit CAS.  Lanes of a warp that carry the same key are linked to each other first
+// (__match_any_sync) and pushed with ONE CAS, so a build side with few distinct keys does not serialise on the slot.
 template <int RPT>
 __device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildParams& B, const TileCtx& c) {
   const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, P.mask_slot);
+  const int lane = threadIdx.x & 31;
   for (int k = 0; k < RPT; ++k) {
     const int r = threadIdx.x + k * NT;
-    if (!(r < c.nrows && (pact == nullptr || pact[r]))) continue;
-    KeyRegs key; bool has_null;
-    uint64_t h = pack_key<MAX_KEYS>(B.keys, B.n_keys, 0, c, r, key, &has_null);
+    const bool live = r < c.nrows && (pact == nullptr || pact[r]);
+    KeyRegs key; bool has_null = false; uint64_t h = 0;
     const long long row = B.row_base + c.row0 + r;
-    B.next[row] = -1;
-    if (has_null) continue;           // NULL keys never match (NullEqualsNothing)
+    if (live) { h = pack_key<MAX_KEYS>(B.keys, B.n_keys, 0, c, r, key, &has_null); B.next[row] = -1; }
+    const bool ins = live && !has_null;                         // NULL keys never match (NullEqualsNothing)
     const unsigned long long tag = h | 1ull;
-    uint64_t idx = (h >> 1) & B.capacity_mask;
-    for (uint64_t probes = 0; probes <= B.capacity_mask; ++probes) {
-      uint8_t* slot = B.table + idx * 16;
-      ulonglong2 s;
-      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(s.x), "=l"(s.y) : "l"(slot) : "memory");
-      if (s.x == 0ull) {
-        const u128 prev = atomic_cas_128(slot, (u128)0, ((u128)(unsigned long long)row << 64) | tag);
-        if (prev == 0) break;                                   // claimed an empty slot
-        s.x = (unsigned long long)prev; s.y = (unsigned long long)(prev >> 64);
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, ins ? tag : (0xFFFFFFFFFFFFFF00ull | (unsigned)lane) & ~1ull);
+    const int leader = __ffs(peers) - 1;
+    // step A: the leader of every distinct hash inserts its own row
+    uint8_t* slot = nullptr;
+    if (ins && lane == leader) slot = build_insert_one(B, key, h, row);
+    const unsigned long long slot_bits = __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(slot), leader);
+    const long long leader_row = __shfl_sync(0xFFFFFFFFu, row, leader);
+    slot = reinterpret_cast<uint8_t*>(slot_bits);
+    // step B: followers whose key really equals the leader's are linked in lane order and pushed once
+    const bool follower = ins && lane != leader && slot != nullptr;
+    const bool same = follower && build_row_has_key(B.keys, B.key_cols, B.key_stride, B.n_keys, (int64_t)leader_row, key);
+    const unsigned chain = __ballot_sync(0xFFFFFFFFu, same) & peers;
+    if (same) {
+      const unsigned above = chain & ~((2u << lane) - 1);       // verified peers in higher lanes
+      const int nxt = above ? __ffs(above) - 1 : -1;
+      const long long next_row = __shfl_sync(chain, row, nxt >= 0 ? nxt : lane);
+      if (nxt >= 0) B.next[row] = next_row;
+      const int first = __ffs(chain) - 1, last = 31 - __clz(chain);
+      const long long last_row = __shfl_sync(chain, row, last);
+      if (lane == first) {
+        atomicOr(B.dup_flag, 1u);
+        __threadfence();
+        chain_push(B, slot, ld_slot(slot), tag, row, last_row);
       }
-      if (s.x == tag && build_row_has_key(B.keys, B.key_cols, B.key_stride, B.n_keys, (int64_t)s.y, key)) {
-        atomicOr(B.dup_flag, 1u);                               // same key: push this row on the chain
-        for (;;) {
-          B.next[row] = (long long)s.y;
-          __threadfence();
-          const u128 want = ((u128)s.y << 64) | s.x;
-          const u128 prev = atomic_cas_128(slot, want, ((u128)(unsigned long long)row << 64) | tag);
-          if (prev == want) break;
-          s.x = (unsigned long long)prev; s.y = (unsigned long long)(prev >> 64);
-        }
-        break;
-      }
-      idx = (idx + 1) & B.capacity_mask;
+    } else if (follower) {
+      build_insert_one(B, key, h, row);                         // same hash, different key (64-bit collision)
     }
   }
 }
