@@ -1118,7 +1118,7 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
     bool anycold = false;
 #pragma unroll
     for (int k = 0; k < RPT; ++k) anycold |= live[k] && gid[k] < 0;
-    if (__syncthreads_or(anycold)) agg_cold_rows<RPT>(P, A, c, gid, live);
+    if (__any_sync(0xFFFFFFFFu, anycold)) agg_cold_rows<RPT>(P, A, c, gid, live);   // warp-level: no CTA barrier
   }
 }
 
@@ -1130,7 +1130,9 @@ constexpr int REG_FLUSH = 224;    // 224 + RPT values below 2^55 cannot overflow
 struct RegAcc { int64_t v[REG_GROUPS][REG_ACCS]; int rows; };
 
 __device__ __forceinline__ void reg_flush(const AggParams& A, const HotView& H, RegAcc& R, int hot_n) {
-  // CTA accumulators live in warp 0's wacc blocks: slot (g, j) = {lo, hi} with carry through atomics
+  // CTA accumulators live in warp 0's wacc blocks: slot (g, j) = {lo, hi}.  The 32 lanes of a warp are summed with
+  // shuffles first, so only one lane per warp touches the shared accumulators (8-way instead of 256-way contention).
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int g = 0; g < REG_GROUPS; ++g) {
     if (g < hot_n) {
@@ -1138,13 +1140,24 @@ __device__ __forceinline__ void reg_flush(const AggParams& A, const HotView& H, 
 #pragma unroll
       for (int j = 0; j < REG_ACCS; ++j) {
         if (j < A.n_accs) {
+          // |partial| < 2^63 per lane and the warp total may exceed 64 bits: reduce as 128-bit (lo, carry-aware hi)
           const int64_t part = R.v[g][j];
-          if (part != 0) {
-            unsigned long long* lo = reinterpret_cast<unsigned long long*>(wa + 1 + 2 * j);
-            const unsigned long long old = atomicAdd(lo, (unsigned long long)part);
-            const unsigned long long carry = (old + (unsigned long long)part) < old ? 1ull : 0ull;
-            const unsigned long long hi = (unsigned long long)(part >> 63) + carry;
-            if (hi) atomicAdd(lo + 1, hi);
+          unsigned long long lo = (unsigned long long)part;
+          long long hi = part >> 63;
+#pragma unroll
+          for (int d = 16; d; d >>= 1) {
+            const unsigned long long olo = __shfl_xor_sync(0xFFFFFFFFu, lo, d);
+            const long long ohi = __shfl_xor_sync(0xFFFFFFFFu, hi, d);
+            const unsigned long long s = lo + olo;
+            hi += ohi + (s < lo ? 1 : 0);
+            lo = s;
+          }
+          if (lane == 0 && (lo | (unsigned long long)hi)) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(wa + 1 + 2 * j);
+            const unsigned long long old = atomicAdd(dst, lo);
+            const unsigned long long carry = (old + lo) < old ? 1ull : 0ull;
+            const unsigned long long h2 = (unsigned long long)hi + carry;
+            if (h2) atomicAdd(dst + 1, h2);
           }
           R.v[g][j] = 0;
         }
@@ -1294,7 +1307,7 @@ __device__ __forceinline__ void sink_agg_reg(const PipelineParams& P, const AggP
     bool anycold = false;
 #pragma unroll
     for (int k = 0; k < RPT; ++k) anycold |= live[k] && gid[k] < 0;
-    if (__syncthreads_or(anycold)) agg_cold_rows<RPT>(P, A, c, gid, live);
+    if (__any_sync(0xFFFFFFFFu, anycold)) agg_cold_rows<RPT>(P, A, c, gid, live);   // warp-level: no CTA barrier
   }
 }
 
@@ -1676,7 +1689,9 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
   uint32_t tma_bytes = 0;
   for (int i = 0; i < P0.n_inputs; ++i) tma_bytes += tile_bytes_of(P0.in[i], tile_rows);
 
-  auto issue = [&](int64_t tile, int stage) {      // uniform across the CTA
+  // returns true when the tile was copied cooperatively (generic proxy): the caller then needs a CTA barrier before
+  // anybody reads it; TMA tiles are ordered by their mbarrier instead
+  auto issue = [&](int64_t tile, int stage) -> bool {      // uniform across the CTA
     const PipelineParams& P = K.P[stage];
     const int64_t row0 = tile * tile_rows;
     const int nrows = (int)min((int64_t)tile_rows, P.n_rows - row0);
@@ -1691,9 +1706,10 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
           tma_load_1d(arena + in.slot, src, bytes, &sm->full[stage]);
         }
       }
-    } else {
-      load_tile_generic(P, arena, row0, nrows);
+      return false;
     }
+    load_tile_generic(P, arena, row0, nrows);
+    return true;
   };
 
   RegAcc R;
@@ -1705,16 +1721,21 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
   int64_t cur = sm->tile[0];
   uint32_t parity[2] = {0, 0};
   int it = 0;
-  if (cur < n_tiles) issue(cur, 0);
+  if (cur < n_tiles && issue(cur, 0)) __syncthreads();
   for (;; ++it) {
     if (cur >= n_tiles) break;
     const int s = (n_stages == 2) ? (it & 1) : 0;
     const PipelineParams& P = K.P[s];
     const PipelineAux* aux = &K.aux[s];
-    if (threadIdx.x == 0) sm->tile[(it + 1) & 1] = dynamic ? (int)atomicAdd(P.ticket, 1u) : (int)(cur + gridDim.x);
-    __syncthreads();                                          // (A) publishes next tile id, orders generic loads
-    const int64_t nxt = sm->tile[(it + 1) & 1];
-    if (n_stages == 2 && nxt < n_tiles) issue(nxt, s ^ 1);    // prefetch while this tile is computed
+    int64_t nxt;
+    if (dynamic) {       // ticket order (decoupled look-back needs tiles to start in order): published through shared memory
+      if (threadIdx.x == 0) sm->tile[(it + 1) & 1] = (int)atomicAdd(P.ticket, 1u);
+      __syncthreads();
+      nxt = sm->tile[(it + 1) & 1];
+    } else {
+      nxt = cur + gridDim.x;                                  // static stride: no barrier needed
+    }
+    if (n_stages == 2 && nxt < n_tiles) issue(nxt, s ^ 1);    // prefetch while this tile is computed (consumed after barrier B)
     TileCtx c;
     c.arena = arena; c.stage_off = 0; c.row0 = cur * tile_rows;
     c.nrows = (int)min((int64_t)tile_rows, P.n_rows - c.row0);
@@ -1731,7 +1752,7 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
       case SINK_PARTITION: sink_partition<RPT>(P, aux->part, c); break;
     }
     __syncthreads();                                          // (B) stage s and scratch are free again
-    if (n_stages == 1 && nxt < n_tiles) { issue(nxt, 0); }
+    if (n_stages == 1 && nxt < n_tiles && issue(nxt, 0)) __syncthreads();
     cur = nxt;
   }
   if (P0.sink == SINK_AGG) {
