@@ -453,9 +453,12 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
   // aggregation wants 2 CTAs/SM of 512-row tiles; plain projection streams best with big double-buffered tiles;
   // compaction / join / partition sinks prefer big single-stage tiles and more resident CTAs
   static const int C_AGG[][2] = {{2, 1}, {1, 2}, {2, 2}, {1, 1}, {4, 1}, {4, 2}};
+  // high-cardinality aggregation is bound by the latency of the global table: small tiles, 4 CTAs/SM (64 registers)
+  static const int C_AGG_COLD[][2] = {{2, 1}, {2, 2}, {1, 2}, {1, 1}, {4, 1}, {4, 2}};
   static const int C_STORE[][2] = {{4, 2}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
   static const int C_OTHER[][2] = {{4, 1}, {4, 2}, {2, 1}, {2, 2}, {1, 2}, {1, 1}};
-  const int (*cands)[2] = out.sink == SINK_AGG ? C_AGG : out.sink == SINK_STORE ? C_STORE : C_OTHER;
+  if (out.sink == SINK_AGG && out.cold_variant) hot_wanted = 0;
+  const int (*cands)[2] = out.sink == SINK_AGG ? (out.cold_variant ? C_AGG_COLD : C_AGG) : out.sink == SINK_STORE ? C_STORE : C_OTHER;
   int best_rpt = 0, best_stages = 0, best_hot = 0;
   if (hot_wanted > 0 && force_hot >= 0) hot_wanted = force_hot;
   for (int pass = 0; pass < 2 && !best_rpt; ++pass) {
@@ -521,6 +524,7 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
       AA.kw_simple = simple ? 1 : 0;
     }
     AA.hot_groups = best_hot;
+    if (out.cold_variant) { AA.cold_only = 1; AA.reg_path = 0; }
     AA.hot_smem_off = temps;
   }
   for (ProbeParams* pp : probe_params) {

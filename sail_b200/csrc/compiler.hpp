@@ -62,6 +62,7 @@ struct CompiledPipeline {
   int rpt = 2, n_stages = 2;
   uint32_t temps_bytes = 0, stage_bytes = 0, hot_bytes = 0, arena_bytes = 0;
   size_t smem_bytes = 0;
+  bool cold_variant = false;         // SINK_AGG compiled for high cardinality (set before finalize)
   int n_probes = 0;
   uint32_t extra_scratch = 0;        // sink scratch bytes requested by the operator (partition counters)
   uint32_t scratch_off = 0;          // its arena offset (set by finalize)
@@ -111,6 +112,18 @@ class PipelineCompiler {
   // ---- sinks ------------------------------------------------------------------------------------
   void finish_store_or_compact(CompiledPipeline& out) {
     out.sink = has_filter_ ? SINK_COMPACT : SINK_STORE;
+    emit_outputs(out);
+  }
+  // first pass of the two-pass filter: the only output is the filter mask itself, as a non-null Bool column
+  void finish_mask_store(CompiledPipeline& out) {
+    DataType bt; bt.id = TypeId::Bool;
+    ExprPtr ph = placeholder(90000, bt, false);
+    Val mv = ensure_slot(mask_);
+    mv.vslot = -1;
+    bind_value(ph, mv);
+    bindings_ = {ph};
+    mask_ = Val{}; has_filter_ = false;
+    out.sink = SINK_STORE;
     emit_outputs(out);
   }
   void finish_partition(CompiledPipeline& out, const std::vector<ExprPtr>& key_exprs_over_stage) {

@@ -153,10 +153,67 @@ struct PipelineOp : Op {
     return !input_done;
   }
 
-  BatchPtr run_stream(const BatchPtr& b) { return run_streaming(run, ctx, b, m, nullptr, {}); }
+  // ---- two-pass filter ---------------------------------------------------------------------------
+  // An order-preserving single-pass compaction chains every tile to all earlier ones (decoupled look-back), and since a
+  // tile only knows its count after evaluating the predicate the chain runs at the pace of the slowest resident tile
+  // (profiles/: ~45 % of the FilterExec kernel's stall samples).  Large batches therefore take two passes: pass 1
+  // reads only the predicate's columns and stores the mask (1 bit / row); the per-tile popcounts are scanned; pass 2
+  // reads the projected columns + mask and stores every tile at its known offset, tiles in any order.
+  static constexpr int64_t TWO_PASS_MIN_ROWS = 1 << 18;
+  PipelineRunner mask_run, sel_run;
+  bool two_pass_ready = false;
+  void setup_two_pass() {
+    const Schema& in = run.in_schema;
+    mask_run.init(ctx, in);
+    StageSpec f; f.kind = StageSpec::Filter; f.predicate = run.stages[0].predicate;
+    mask_run.stages.push_back(f);
+    mask_run.custom_sink = [](PipelineCompiler& pc, CompiledPipeline& cp) { pc.finish_mask_store(cp); };
+    Schema in2 = in;
+    Field mf; mf.name = "__mask"; mf.type.id = TypeId::Bool; mf.nullable = false;
+    in2.push_back(mf);
+    sel_run.init(ctx, in2);
+    sel_run.stages = run.stages;
+    StageSpec& s0 = sel_run.stages[0];
+    auto me = std::make_shared<Expr>(); me->kind = Expr::Col; me->col = (int)in.size(); me->type.id = TypeId::Bool; me->nullable = false;
+    s0.predicate = me;
+    if (!s0.has_projection) { s0.has_projection = true; s0.projection.clear(); for (size_t i = 0; i < in.size(); ++i) s0.projection.push_back((int)i); }
+    two_pass_ready = true;
+  }
+  bool two_pass_applies(const BatchPtr& b) const {
+    const char* mn = getenv("SAILGPU_TWO_PASS_MIN");     // rows from which a filter runs in two passes (tests lower it; "off" disables)
+    if (mn && !strcmp(mn, "off")) return false;
+    const int64_t min_rows = mn && *mn ? atoll(mn) : TWO_PASS_MIN_ROWS;
+    return !has_agg && !run.stages.empty() && run.stages[0].kind == StageSpec::Filter && b->rows >= min_rows;
+  }
+  BatchPtr run_two_pass(const BatchPtr& b) {
+    if (!two_pass_ready) setup_two_pass();
+    BatchPtr mb = run_streaming(mask_run, ctx, b, m, nullptr, {});
+    auto b2 = std::make_shared<DevBatch>(*b);
+    b2->cols.push_back(mb->cols[0]);
+    auto cp2 = sel_run.compiled_for(*b2);
+    const int tile_rows = cp2->rpt * NT;
+    const int64_t n = b->rows, n_tiles = (n + tile_rows - 1) / tile_rows;
+    BufPtr counts = dev_alloc_zero(ctx, (size_t)(n_tiles + 1) * 4), offs = dev_alloc(ctx, (size_t)(n_tiles + 1) * 8), scratch = dev_alloc(ctx, 1026 * 8);
+    SG_CUDA(launch_tile_popcount(static_cast<const uint32_t*>(mb->cols[0].data->ptr), n, tile_rows, n_tiles, static_cast<uint32_t*>(counts->ptr), ctx->stream));
+    SG_CUDA(launch_exclusive_scan_u32(static_cast<const uint32_t*>(counts->ptr), n_tiles + 1, static_cast<uint64_t*>(offs->ptr), static_cast<uint64_t*>(scratch->ptr), ctx->stream));
+    unsigned long long total = 0;
+    SG_CUDA(cudaMemcpyAsync(&total, static_cast<const uint64_t*>(offs->ptr) + n_tiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    m.kernel_launches += 4;
+    return run_streaming(sel_run, ctx, b2, m, nullptr, {}, static_cast<const unsigned long long*>(offs->ptr), (int64_t)total);
+  }
+
+  BatchPtr run_stream(const BatchPtr& b) {
+    if (two_pass_applies(b)) return run_two_pass(b);
+    return run_streaming(run, ctx, b, m, nullptr, {});
+  }
 
   // ---- aggregate ------------------------------------------------------------------------------
   static constexpr uint64_t MAX_CAPACITY = 1ull << 27;
+  static int64_t card_probe_rows() { const char* v = getenv("SAILGPU_CARD_PROBE_ROWS"); return v && *v ? atoll(v) : (1 << 18); }   // tests lower it
+  static constexpr uint64_t CARD_MANY_GROUPS = 256;
+  bool card_known = false, use_cold = false;
+  int64_t rows_in_table = 0;
 
   uint64_t read_n_groups() {
     run.ensure_scratch();
@@ -205,7 +262,15 @@ struct PipelineOp : Op {
 
   void push_agg(const BatchPtr& b) {
     Trace tr(ctx, "agg.push");
-    auto cp = run.compiled_for(*b);
+    // Cardinality probe: the CTA dictionary / register fast path only pay for a handful of groups.  Once CARD_PROBE_ROWS
+    // rows went in, the group count is read back once; with many groups the rest of the input runs through the variant
+    // compiled for the global table alone (no dictionary, small tiles, 4 CTAs/SM).
+    const int64_t CARD_PROBE_ROWS = card_probe_rows();
+    if (!card_known && rows_in_table >= CARD_PROBE_ROWS && tab.capacity) {
+      use_cold = read_n_groups() > CARD_MANY_GROUPS && getenv("SAILGPU_NO_COLD") == nullptr;
+      card_known = true;
+    }
+    auto cp = run.compiled_for(*b, use_cold);
     if (!agg_cp) agg_cp = cp;
     SG_CHECK(cp->agg.entry_words == agg_cp->agg.entry_words && cp->agg.key_words == agg_cp->agg.key_words, SAILGPU_ERR_UNSUPPORTED,
              "aggregate input batches differ in which key columns carry validity buffers");
@@ -213,6 +278,15 @@ struct PipelineOp : Op {
     int64_t done = 0;
     while (done < n) {
       int64_t chunk = n - done;
+      if (!card_known && cp->agg.n_keys > 0) {
+        if (rows_in_table >= CARD_PROBE_ROWS) {
+          use_cold = read_n_groups() > CARD_MANY_GROUPS && getenv("SAILGPU_NO_COLD") == nullptr;
+          card_known = true;
+          if (use_cold) cp = run.compiled_for(*b, true);
+        } else if (chunk > 4 * CARD_PROBE_ROWS) {
+          chunk = CARD_PROBE_ROWS;                       // a big first batch: look at its head before committing
+        }
+      }
       if (cp->agg.n_keys > 0) {
         const int64_t max_chunk = (int64_t)(MAX_CAPACITY / 2) - (int64_t)std::min<uint64_t>(tab.rows_bound, MAX_CAPACITY / 4);
         if (chunk > max_chunk) {
@@ -232,6 +306,7 @@ struct PipelineOp : Op {
       fill_table(aux.agg);
       run.launch(P, cp, &aux, m);
       done += chunk;
+      rows_in_table += chunk;
     }
   }
 

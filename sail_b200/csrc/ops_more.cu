@@ -492,14 +492,20 @@ struct SortOp : Op {
     for (size_t k = 0; k < keys.size(); ++k) { E.cols[k].out_off = off; off += 1 + E.cols[k].enc_bytes; }
     E.key_bytes = off;
     BufPtr kb = dev_alloc(ctx, (size_t)n * off);
+    BufPtr bits = dev_alloc_zero(ctx, (size_t)off * 8);
     E.keys = static_cast<uint8_t*>(kb->ptr);
+    E.bits = static_cast<uint32_t*>(bits->ptr);
     SG_CUDA(launch_sort_encode(E, ctx->stream));
     const int64_t n_chunks = (n + 2047) / 2048;
-    BufPtr ia = dev_alloc(ctx, (size_t)n * 4), ib = dev_alloc(ctx, (size_t)n * 4), hist = dev_alloc(ctx, (size_t)n_chunks * 256 * 4),
-           offs = dev_alloc(ctx, (size_t)n_chunks * 256 * 8), scr = dev_alloc(ctx, 1026 * 8);
-    SG_CUDA(radix_sort_indices(E.keys, off, n, static_cast<uint32_t*>(ia->ptr), static_cast<uint32_t*>(ib->ptr), static_cast<uint32_t*>(hist->ptr),
-                               static_cast<uint64_t*>(offs->ptr), static_cast<uint64_t*>(scr->ptr), ctx->stream));
-    m.kernel_launches += (uint64_t)(3 * off + 2);
+    BufPtr ia = dev_alloc(ctx, (size_t)n * 4), ib = dev_alloc(ctx, (size_t)n * 4), ka = dev_alloc(ctx, (size_t)n * 8), kbuf = dev_alloc(ctx, (size_t)n * 8),
+           hist = dev_alloc(ctx, (size_t)n_chunks * 256 * 4), offs = dev_alloc(ctx, (size_t)n_chunks * 256 * 8), scr = dev_alloc(ctx, 1026 * 8);
+    RadixScratch S;
+    S.idx_a = static_cast<uint32_t*>(ia->ptr); S.idx_b = static_cast<uint32_t*>(ib->ptr);
+    S.kw_a = static_cast<uint64_t*>(ka->ptr); S.kw_b = static_cast<uint64_t*>(kbuf->ptr);
+    S.hist = static_cast<uint32_t*>(hist->ptr); S.offs = static_cast<uint64_t*>(offs->ptr); S.scan_scratch = static_cast<uint64_t*>(scr->ptr);
+    int sort_launches = 0;
+    SG_CUDA(radix_sort_indices(E.keys, off, n, S, E.bits, ctx->stream, &sort_launches));
+    m.kernel_launches += (uint64_t)(sort_launches + 2);
     const int64_t take = fetch >= 0 ? std::min<int64_t>(fetch, n) : n;
     BufPtr idx = dev_alloc(ctx, (size_t)take * 8);
     SG_CUDA(launch_widen_u32(static_cast<const uint32_t*>(ia->ptr), static_cast<int64_t*>(idx->ptr), take, ctx->stream));

@@ -407,8 +407,9 @@ __device__ __forceinline__ bool key_words_equal(const KeyDesc* keys, int n_keys,
 }
 
 // join table slot: { u64 tag (0 = empty; hash | 1), i64 row }
+// General lookup: any number / type of keys; the rows of a thread are resolved one after the other.
 template <int RPT>
-__device__ __noinline__ void vm_probe(const ProbeParams& P, const TileCtx& c, uint32_t mask_slot) {
+__device__ __noinline__ void vm_probe_general(const ProbeParams& P, const TileCtx& c, uint32_t mask_slot) {
   uint8_t* pm = c.arena + eff(c, P.match_slot);
   uint8_t* prow = c.arena + eff(c, P.rowid_slot);
   const uint8_t* pact = mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, mask_slot);
@@ -453,6 +454,66 @@ __device__ __noinline__ void vm_probe(const ProbeParams& P, const TileCtx& c, ui
     pm[r] = row >= 0 ? 1 : 0;
     sts<int64_t>(prow + r * 8, row);
   }
+}
+
+// One key of at most 8 bytes (the usual integer / date join key).  The lookup is latency bound (table slot, then the
+// build key of the candidate: two dependent random loads), so the RPT rows of a thread advance in lock step: all
+// first-slot loads are issued together, then all candidate key loads; only rows that collide continue probing.
+// Hash as pack_key(): mix64(seed ^ key word).
+template <int RPT>
+__device__ __noinline__ void vm_probe_narrow(const ProbeParams& P, const TileCtx& c, uint32_t mask_slot) {
+  uint8_t* pm = c.arena + eff(c, P.match_slot);
+  uint8_t* prow = c.arena + eff(c, P.rowid_slot);
+  const uint8_t* pact = mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, mask_slot);
+  const KeyDesc d = P.keys[0];
+  const uint8_t* pk = c.arena + eff(c, d.slot);
+  const uint8_t* pv = d.valid_slot == NO_SLOT ? nullptr : c.arena + eff(c, d.valid_slot);
+  const uint8_t* bcol = P.build_keys[0];
+  const int bstride = P.build_stride[0];
+  uint64_t key[RPT], tag[RPT], bkey[RPT];
+  ulonglong2 s[RPT];
+  bool act[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    act[k] = r < c.nrows && (pact == nullptr || pact[r]) && (pv == nullptr || pv[r]);     // NULL keys match nothing
+    key[k] = load_key_word(pk + r * d.stride, d.width);
+    const uint64_t h = mix64(0x243F6A8885A308D3ull ^ key[k]);
+    tag[k] = h | 1ull;
+    s[k].x = 0; s[k].y = 0;
+    if (act[k]) s[k] = *reinterpret_cast<const ulonglong2*>(P.table + ((h >> 1) & P.capacity_mask) * 16);
+  }
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    bkey[k] = 0;
+    if (s[k].x == tag[k]) bkey[k] = load_key_word(bcol + (int64_t)s[k].y * bstride, d.width);
+  }
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    int64_t row = -1;
+    if (s[k].x != 0) {
+      if (s[k].x == tag[k] && bkey[k] == key[k]) row = (int64_t)s[k].y;
+      else {                                                  // collision: ordinary linear probe from the next slot
+        uint64_t idx = (((tag[k] >> 1) & P.capacity_mask) + 1) & P.capacity_mask;
+        for (;;) {
+          const ulonglong2 cur = *reinterpret_cast<const ulonglong2*>(P.table + idx * 16);
+          if (cur.x == 0) break;
+          if (cur.x == tag[k] && load_key_word(bcol + (int64_t)cur.y * bstride, d.width) == key[k]) { row = (int64_t)cur.y; break; }
+          idx = (idx + 1) & P.capacity_mask;
+        }
+      }
+    }
+    if (row >= 0 && P.visited) P.visited[row] = 1;
+    pm[r] = row >= 0 ? 1 : 0;
+    sts<int64_t>(prow + r * 8, row);
+  }
+}
+
+template <int RPT>
+__device__ __forceinline__ void vm_probe(const ProbeParams& P, const TileCtx& c, uint32_t mask_slot) {
+  if (P.n_keys == 1 && P.keys[0].width != 16) vm_probe_narrow<RPT>(P, c, mask_slot);
+  else vm_probe_general<RPT>(P, c, mask_slot);
 }
 
 template <int RPT>
@@ -709,9 +770,18 @@ __device__ __forceinline__ uint64_t* agg_find_or_insert(const AggParams& A, cons
         for (int j = 0; j < A.n_accs; ++j)
           for (int w = 0; w < acc_words_of(A.accs[j].op); ++w)
             e[2 + A.key_words + A.accs[j].word + w] = acc_identity(A.accs[j].op, w);
-        __threadfence();
-        st_release_u32(st, tag | ST_READY);
-        A.occ[atomicAdd(A.n_groups, 1ull)] = (uint32_t)idx;
+        st_release_u32(st, tag | ST_READY);                         // release: the entry words above are visible first
+        {
+          // occupied-slot list: one counter for the whole table, so the increment is aggregated over the lanes
+          // that insert in the same step (same-address atomics serialise in one L2 slice)
+          const unsigned m = __activemask();
+          const unsigned lane = threadIdx.x & 31;
+          const int lead = __ffs(m) - 1;
+          unsigned long long base = 0;
+          if ((int)lane == lead) base = atomicAdd(A.n_groups, (unsigned long long)__popc(m));
+          base = __shfl_sync(m, base, lead);
+          A.occ[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)idx;
+        }
         return e;
       }
     }
@@ -946,8 +1016,22 @@ __device__ __forceinline__ bool fits55(i128 v) {
 }
 
 // rows whose group is not in the CTA-local dictionary: global table, one warp-cooperative lookup per row slot
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int RPT>
 __device__ __noinline__ void agg_cold_rows(const PipelineParams& P, const AggParams& A, const TileCtx& c, const int (&gid)[RPT], const bool (&live)[RPT]) {
+  // the table walk below is a chain of dependent global accesses per row: start the first state word and entry line of
+  // every row of this thread on their way first
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    if (live[k] && gid[k] < 0) {
+      KeyRegs key; bool hn;
+      const uint64_t h = pack_key<MAX_KEYS>(A.keys, A.n_keys, A.has_null_word, c, threadIdx.x + k * NT, key, &hn);
+      const uint64_t idx = h & A.capacity_mask;
+      prefetch_l2(A.state + idx);
+      prefetch_l2(reinterpret_cast<const uint64_t*>(A.table) + idx * A.entry_words);
+    }
+  }
   for (int k = 0; k < RPT; ++k) {
     const bool cold = live[k] && gid[k] < 0;
     if (__any_sync(0xFFFFFFFFu, cold)) {
@@ -960,6 +1044,21 @@ __device__ __noinline__ void agg_cold_rows(const PipelineParams& P, const AggPar
       }
     }
   }
+}
+
+// high-cardinality variant (AggParams::cold_only): no dictionary, every live row goes to the global table
+template <int RPT>
+__device__ __forceinline__ void sink_agg_cold(const PipelineParams& P, const AggParams& A, const TileCtx& c) {
+  const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + P.mask_slot;
+  int gid[RPT];
+  bool live[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = threadIdx.x + k * NT;
+    live[k] = r < c.nrows && (pact == nullptr || pact[r]);
+    gid[k] = -1;
+  }
+  agg_cold_rows<RPT>(P, A, c, gid, live);
 }
 
 template <int RPT>
@@ -1432,7 +1531,9 @@ __device__ __forceinline__ void sink_compact(const PipelineParams& P, const Tile
     // decoupled look-back, one warp wide: 32 predecessor tiles are inspected per step; the walk stops at the
     // closest tile that already published an inclusive prefix (flag 2) and adds the aggregates (flag 1) in between
     unsigned long long excl = 0;
-    if (tile > 0) {
+    if (P.tile_offsets) {
+      excl = P.tile_offsets[tile];             // two-pass filter: the mask pass already fixed every tile's position
+    } else if (tile > 0) {
       if (lane == 0) st_release_u64(P.tile_status + tile, (1ull << 62) | total);
       int hi = tile - 1;                       // newest tile not yet accounted for
       uint32_t spins = 0;
@@ -1455,9 +1556,11 @@ __device__ __forceinline__ void sink_compact(const PipelineParams& P, const Tile
       }
     }
     if (lane == 0) {
-      st_release_u64(P.tile_status + tile, (2ull << 62) | (excl + total));
       sm->tile_base = excl;
-      if ((int64_t)(tile + 1) * P.tile_rows >= P.n_rows) *P.out_count = excl + total;
+      if (!P.tile_offsets) {
+        st_release_u64(P.tile_status + tile, (2ull << 62) | (excl + total));
+        if ((int64_t)(tile + 1) * P.tile_rows >= P.n_rows) *P.out_count = excl + total;
+      }
     }
   }
   __syncthreads();
@@ -1674,7 +1777,7 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
   const PipelineParams& P0 = K.P[0];
   const int tile_rows = RPT * NT;
   const int64_t n_tiles = (P0.n_rows + tile_rows - 1) / tile_rows;
-  const bool dynamic = P0.sink == SINK_COMPACT;
+  const bool dynamic = P0.sink == SINK_COMPACT && P0.tile_offsets == nullptr;
 
   if (threadIdx.x == 0) {
     mbar_init(&sm->full[0], 1);
@@ -1746,7 +1849,9 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
       case SINK_STORE: sink_store<RPT>(P, c); break;
       case SINK_COMPACT: sink_compact<RPT>(P, c, sm, (int)cur); break;
       case SINK_AGG:
-        if (aux->agg.reg_path) sink_agg_reg<RPT>(P, aux->agg, c, sm, R); else sink_agg<RPT>(P, aux->agg, c, sm);
+        if (aux->agg.cold_only) sink_agg_cold<RPT>(P, aux->agg, c);
+        else if (aux->agg.reg_path) sink_agg_reg<RPT>(P, aux->agg, c, sm, R);
+        else sink_agg<RPT>(P, aux->agg, c, sm);
         break;
       case SINK_BUILD: sink_build<RPT>(P, aux->build, c); break;
       case SINK_PARTITION: sink_partition<RPT>(P, aux->part, c); break;
@@ -1970,6 +2075,36 @@ int pipeline_max_ctas_per_sm(int rpt, int minb, size_t smem_bytes) {
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, NT, smem_bytes) != cudaSuccess) return 0;
   return n;
+}
+
+// two-pass filter: rows kept per tile = popcount of the tile's slice of the packed mask (one warp per tile)
+__global__ void tile_popcount_kernel(const uint32_t* __restrict__ bits, int64_t n_rows, int tile_rows, int64_t n_tiles, uint32_t* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int words_per_tile = tile_rows >> 5;
+  const int64_t n_words = (n_rows + 31) >> 5;
+  for (int64_t t = warp; t < n_tiles; t += n_warps) {
+    uint32_t c = 0;
+    for (int w = lane; w < words_per_tile; w += 32) {
+      const int64_t g = t * words_per_tile + w;
+      if (g < n_words) {
+        uint32_t x = bits[g];
+        const int64_t rem = n_rows - (g << 5);
+        if (rem < 32) x &= (1u << rem) - 1;        // bits past the last row are not rows
+        c += __popc(x);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    if (lane == 0) counts[t] = c;
+  }
+}
+cudaError_t launch_tile_popcount(const uint32_t* bits, int64_t n_rows, int tile_rows, int64_t n_tiles, uint32_t* counts, cudaStream_t s) {
+  if (n_tiles == 0) return cudaSuccess;
+  const int grid = (int)std::min<int64_t>((n_tiles * 32 + 255) / 256, 148 * 8);
+  tile_popcount_kernel<<<grid, 256, 0, s>>>(bits, n_rows, tile_rows, n_tiles, counts);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_agg_rehash(const AggParams& A, const uint8_t* old_table, const uint32_t* old_occ, uint64_t old_groups, uint32_t* err, cudaStream_t s) {

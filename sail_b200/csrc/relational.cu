@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "dev_util.cuh"
 #include "kernels.hpp"
@@ -150,38 +151,48 @@ cudaError_t launch_max_view_len(const void* views, int64_t n, unsigned int* out,
   return cudaGetLastError();
 }
 
+// Encodes every row into `key_bytes` order-preserving bytes (memcmp order == sort order) and, on the way, records
+// per byte position which bits were ever set / ever clear (P.bits_or / P.bits_nand): a position where no bit was
+// both set and clear is constant over the input and its radix pass is skipped.
 __global__ void sort_encode_kernel(SortEncodeParams P) {
+  extern __shared__ uint32_t sh_bits[];            // [0, kb): or, [kb, 2kb): nand
+  const int kb = P.key_bytes;
+  for (int b = threadIdx.x; b < 2 * kb; b += blockDim.x) sh_bits[b] = 0;
+  __syncthreads();
+#define SG_PUT(pos, val)                                                                 \
+  do {                                                                                   \
+    const int p_ = (pos); const uint32_t v_ = (uint8_t)(val);                            \
+    out[p_] = (uint8_t)v_;                                                               \
+    if (v_ & ~sh_bits[p_]) atomicOr(&sh_bits[p_], v_);                                   \
+    if ((v_ ^ 0xFFu) & ~sh_bits[kb + p_]) atomicOr(&sh_bits[kb + p_], v_ ^ 0xFFu);       \
+  } while (0)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * blockDim.x) {
-    uint8_t* out = P.keys + i * P.key_bytes;
+    uint8_t* out = P.keys + i * kb;
     for (int k = 0; k < P.n_keys; ++k) {
       const SortKeyCol& c = P.cols[k];
-      uint8_t* o = out + c.out_off;
+      int o = c.out_off;
       const bool isnull = c.validity_bits && !((c.validity_bits[i >> 3] >> (i & 7)) & 1);
-      *o++ = isnull ? (c.nulls_first ? 0x00 : 0xFF) : (c.nulls_first ? 0x01 : 0x00);
+      SG_PUT(o, isnull ? (c.nulls_first ? 0x00 : 0xFF) : (c.nulls_first ? 0x01 : 0x00));
+      ++o;
       const uint8_t inv = c.asc ? 0x00 : 0xFF;
       const int w = c.enc_bytes;
-      if (isnull) { for (int b = 0; b < w; ++b) o[b] = 0; continue; }
+      if (isnull) { for (int b = 0; b < w; ++b) SG_PUT(o + b, 0); continue; }
       switch (c.kind) {
-        case SORT_INT: {      // signed integer of c.width bytes -> big endian, sign bit flipped
-          const uint8_t* p = c.data + i * c.width;
-          for (int b = 0; b < c.width; ++b) o[b] = p[c.width - 1 - b] ^ inv;
-          o[0] ^= 0x80;
-          break;
-        }
+        case SORT_INT:        // signed integer of c.width bytes -> big endian, sign bit flipped
         case SORT_UINT: {
           const uint8_t* p = c.data + i * c.width;
-          for (int b = 0; b < c.width; ++b) o[b] = p[c.width - 1 - b] ^ inv;
+          for (int b = 0; b < c.width; ++b) SG_PUT(o + b, p[c.width - 1 - b] ^ inv ^ ((b == 0 && c.kind == SORT_INT) ? 0x80 : 0x00));
           break;
         }
         case SORT_F64: {      // IEEE-754 total order
           uint64_t v = *reinterpret_cast<const uint64_t*>(c.data + i * 8);
           v = (v >> 63) ? ~v : (v | 0x8000000000000000ull);
-          for (int b = 0; b < 8; ++b) o[b] = (uint8_t)(v >> (56 - 8 * b)) ^ inv;
+          for (int b = 0; b < 8; ++b) SG_PUT(o + b, (uint8_t)(v >> (56 - 8 * b)) ^ inv);
           break;
         }
         case SORT_BOOL: {
           const uint8_t v = (c.data[i >> 3] >> (i & 7)) & 1;
-          o[0] = v ^ inv;
+          SG_PUT(o, v ^ inv);
           break;
         }
         default: {            // SORT_VIEW: bytes padded with zeros to c.str_len, then 4-byte big-endian length
@@ -189,28 +200,44 @@ __global__ void sort_encode_kernel(SortEncodeParams P) {
           const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(vp);
           const uint32_t len = (uint32_t)v.x;
           const uint8_t* s = view_ptr(v, vp);
-          for (int b = 0; b < c.str_len; ++b) o[b] = ((uint32_t)b < len ? s[b] : 0) ^ inv;
-          for (int b = 0; b < 4; ++b) o[c.str_len + b] = (uint8_t)(len >> (24 - 8 * b)) ^ inv;
+          for (int b = 0; b < c.str_len; ++b) SG_PUT(o + b, ((uint32_t)b < len ? s[b] : 0) ^ inv);
+          for (int b = 0; b < 4; ++b) SG_PUT(o + c.str_len + b, (uint8_t)(len >> (24 - 8 * b)) ^ inv);
         }
       }
     }
   }
+#undef SG_PUT
+  __syncthreads();
+  for (int b = threadIdx.x; b < 2 * kb; b += blockDim.x)
+    if (sh_bits[b]) atomicOr(P.bits + b, sh_bits[b]);
 }
 cudaError_t launch_sort_encode(const SortEncodeParams& P, cudaStream_t s) {
   if (P.n == 0) return cudaSuccess;
   int grid = (int)std::min<int64_t>((P.n + 255) / 256, 148 * 8);
-  sort_encode_kernel<<<grid, 256, 0, s>>>(P);
+  sort_encode_kernel<<<grid, 256, (size_t)P.key_bytes * 8, s>>>(P);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
-// sort: stable LSD radix passes over row indices (u32), 8-bit digits
-// Each warp owns a contiguous chunk of RADIX_CHUNK elements.
+// sort: stable LSD radix sort of (key word, row index) pairs, 8-bit digits.
+// The encoded key is consumed 8 bytes at a time from its least significant end: the 8 bytes of every row are
+// gathered once (in the current order) into a u64 that then travels with the row index through the passes of
+// that word, so a pass reads and writes only sequential / bucket-contiguous 12 B records.  Digits that are
+// constant over the input (see sort_encode_kernel) cost nothing.  Each warp owns RADIX_CHUNK consecutive records.
 // ------------------------------------------------------------------------------------------------
 constexpr int RADIX_CHUNK = 2048;
 
-__global__ void radix_hist_kernel(const uint8_t* __restrict__ keys, int key_bytes, int digit, const uint32_t* __restrict__ idx, int64_t n,
-                                  uint32_t* __restrict__ hist /* [256][n_chunks] */, int64_t n_chunks) {
+__global__ void radix_gather_word_kernel(const uint8_t* __restrict__ keys, int key_bytes, int lo, int nb, const uint32_t* __restrict__ idx, int64_t n,
+                                         uint64_t* __restrict__ kw) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* p = keys + (int64_t)(idx ? idx[i] : (uint32_t)i) * key_bytes + lo;
+    uint64_t v = 0;
+    for (int b = 0; b < nb; ++b) v = (v << 8) | p[b];
+    kw[i] = v;
+  }
+}
+
+__global__ void radix_hist_kernel(const uint64_t* __restrict__ kw, int shift, int64_t n, uint32_t* __restrict__ hist /* [256][n_chunks] */, int64_t n_chunks) {
   const int lane = threadIdx.x & 31;
   const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (chunk >= n_chunks) return;
@@ -219,13 +246,14 @@ __global__ void radix_hist_kernel(const uint8_t* __restrict__ keys, int key_byte
   for (int b = lane; b < 256; b += 32) h[b] = 0;
   __syncwarp();
   const int64_t b0 = chunk * RADIX_CHUNK, b1 = min(n, b0 + RADIX_CHUNK);
-  for (int64_t i = b0 + lane; i < b1; i += 32) atomicAdd(&h[keys[(int64_t)idx[i] * key_bytes + digit]], 1u);
+  for (int64_t i = b0 + lane; i < b1; i += 32) atomicAdd(&h[(kw[i] >> shift) & 255u], 1u);
   __syncwarp();
   for (int b = lane; b < 256; b += 32) hist[(int64_t)b * n_chunks + chunk] = h[b];
 }
 
-__global__ void radix_scatter_kernel(const uint8_t* __restrict__ keys, int key_bytes, int digit, const uint32_t* __restrict__ idx_in,
-                                     uint32_t* __restrict__ idx_out, int64_t n, const uint64_t* __restrict__ offs /* scanned hist */, int64_t n_chunks) {
+__global__ void radix_scatter_kernel(const uint64_t* __restrict__ kw_in, const uint32_t* __restrict__ idx_in, uint64_t* __restrict__ kw_out,
+                                     uint32_t* __restrict__ idx_out, int shift, int64_t n, const uint64_t* __restrict__ offs /* scanned hist */,
+                                     int64_t n_chunks) {
   const int lane = threadIdx.x & 31;
   const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (chunk >= n_chunks) return;
@@ -237,8 +265,9 @@ __global__ void radix_scatter_kernel(const uint8_t* __restrict__ keys, int key_b
   for (int64_t g = b0; g < b1; g += 32) {
     const int64_t i = g + lane;
     const bool in = i < b1;
-    const uint32_t row = in ? idx_in[i] : 0;
-    const uint32_t d = in ? keys[(int64_t)row * key_bytes + digit] : 0x100u + lane;   // idle lanes match nobody
+    const uint64_t w = in ? kw_in[i] : 0;
+    const uint32_t row = in ? (idx_in ? idx_in[i] : (uint32_t)i) : 0;
+    const uint32_t d = in ? (uint32_t)((w >> shift) & 255u) : 0x100u + lane;   // idle lanes match nobody
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
     const int rank = __popc(peers & ((1u << lane) - 1));
     uint64_t pos = 0;
@@ -246,7 +275,7 @@ __global__ void radix_scatter_kernel(const uint8_t* __restrict__ keys, int key_b
     __syncwarp();
     if (in && rank == __popc(peers) - 1) base[d] += __popc(peers);   // last peer advances the cursor
     __syncwarp();
-    if (in) idx_out[pos] = row;
+    if (in) { kw_out[pos] = w; idx_out[pos] = row; }
   }
 }
 
@@ -269,24 +298,49 @@ __global__ void small_sort_kernel(const uint8_t* __restrict__ keys, int key_byte
   idx_out[rank] = (uint32_t)i;
 }
 
-// Sorts row indices by the encoded keys.  `idx_a` receives the final order.  scratch: idx_b [n] u32,
-// hist [256*n_chunks] u32, offs [256*n_chunks] u64, scan scratch [1026] u64.
-cudaError_t radix_sort_indices(const uint8_t* keys, int key_bytes, int64_t n, uint32_t* idx_a, uint32_t* idx_b, uint32_t* hist, uint64_t* offs,
-                               uint64_t* scan_scratch, cudaStream_t s) {
+// Sorts row indices by the encoded keys; `S.idx_a` receives the final order.  `bits` = the [2 * key_bytes] words
+// sort_encode_kernel filled.  Synchronises the stream once (to read `bits`).  *launches counts the kernels issued.
+cudaError_t radix_sort_indices(const uint8_t* keys, int key_bytes, int64_t n, const RadixScratch& S, const uint32_t* bits, cudaStream_t s, int* launches) {
+  int nl = 0;
+  if (launches) *launches = 0;
   if (n == 0) return cudaSuccess;
-  if (n <= 1024) { small_sort_kernel<<<1, 1024, 0, s>>>(keys, key_bytes, (int)n, idx_a); return cudaGetLastError(); }
+  if (n <= 1024) { small_sort_kernel<<<1, 1024, 0, s>>>(keys, key_bytes, (int)n, S.idx_a); if (launches) *launches = 1; return cudaGetLastError(); }
+  std::vector<uint32_t> hb((size_t)key_bytes * 2);
+  cudaError_t e = cudaMemcpyAsync(hb.data(), bits, hb.size() * 4, cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return e;
+  auto trivial = [&](int d) { return (hb[(size_t)d] & hb[(size_t)key_bytes + d] & 0xFFu) == 0; };
   const int64_t n_chunks = (n + RADIX_CHUNK - 1) / RADIX_CHUNK;
   const int blocks = (int)((n_chunks + 7) / 8);
-  iota_u32_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(idx_a, n);
-  uint32_t* in = idx_a; uint32_t* out = idx_b;
-  for (int digit = key_bytes - 1; digit >= 0; --digit) {
-    radix_hist_kernel<<<blocks, 256, 0, s>>>(keys, key_bytes, digit, in, n, hist, n_chunks);
-    cudaError_t e = launch_exclusive_scan_u32(hist, 256 * n_chunks, offs, scan_scratch, s);
-    if (e != cudaSuccess) return e;
-    radix_scatter_kernel<<<blocks, 256, 0, s>>>(keys, key_bytes, digit, in, out, n, offs, n_chunks);
-    std::swap(in, out);
+  const int flat = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  const uint32_t* in_idx = nullptr;            // nullptr = identity order
+  uint32_t* out_idx = S.idx_a;
+  uint64_t* kw_in = S.kw_a; uint64_t* kw_out = S.kw_b;
+  for (int hi = key_bytes; hi > 0;) {
+    const int lo = std::max(0, hi - 8);
+    bool any = false;
+    for (int d = lo; d < hi; ++d) any |= !trivial(d);
+    if (any) {
+      radix_gather_word_kernel<<<flat, 256, 0, s>>>(keys, key_bytes, lo, hi - lo, in_idx, n, kw_in); ++nl;
+      for (int d = hi - 1; d >= lo; --d) {
+        if (trivial(d)) continue;
+        const int shift = 8 * (hi - 1 - d);
+        radix_hist_kernel<<<blocks, 256, 0, s>>>(kw_in, shift, n, S.hist, n_chunks);
+        e = launch_exclusive_scan_u32(S.hist, 256 * n_chunks, S.offs, S.scan_scratch, s);
+        if (e != cudaSuccess) return e;
+        radix_scatter_kernel<<<blocks, 256, 0, s>>>(kw_in, in_idx, kw_out, out_idx, shift, n, S.offs, n_chunks);
+        nl += 5;
+        std::swap(kw_in, kw_out);
+        in_idx = out_idx;
+        out_idx = (out_idx == S.idx_a) ? S.idx_b : S.idx_a;
+      }
+    }
+    hi = lo;
   }
-  if (in != idx_a) { cudaError_t e = cudaMemcpyAsync(idx_a, in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s); if (e != cudaSuccess) return e; }
+  if (in_idx == nullptr) { iota_u32_kernel<<<flat, 256, 0, s>>>(S.idx_a, n); ++nl; }
+  else if (in_idx != S.idx_a) { e = cudaMemcpyAsync(S.idx_a, in_idx, (size_t)n * 4, cudaMemcpyDeviceToDevice, s); if (e != cudaSuccess) return e; }
+  if (launches) *launches = nl;
   return cudaGetLastError();
 }
 

@@ -47,15 +47,22 @@ struct SortEncodeParams {
   int64_t n;
   int32_t n_keys, key_bytes;
   uint8_t* keys;
+  uint32_t* bits;                 // [2 * key_bytes], zeroed: per byte position the OR of the bytes, then the OR of their complements
   SortKeyCol cols[8];
+};
+struct RadixScratch {
+  uint32_t *idx_a, *idx_b;        // [n]
+  uint64_t *kw_a, *kw_b;          // [n]
+  uint32_t* hist;                 // [256 * ceil(n / 2048)]
+  uint64_t* offs;                 // [256 * ceil(n / 2048)]
+  uint64_t* scan_scratch;         // [1026]
 };
 
 cudaError_t launch_join_multi(const JoinMultiParams& P, cudaStream_t s);
 cudaError_t launch_gather_bits(const uint8_t* bits, uint8_t* out, const int64_t* idx, int64_t n, int dflt, cudaStream_t s);
 cudaError_t launch_max_view_len(const void* views, int64_t n, unsigned int* out, cudaStream_t s);
 cudaError_t launch_sort_encode(const SortEncodeParams& P, cudaStream_t s);
-cudaError_t radix_sort_indices(const uint8_t* keys, int key_bytes, int64_t n, uint32_t* idx_a, uint32_t* idx_b, uint32_t* hist, uint64_t* offs,
-                               uint64_t* scan_scratch, cudaStream_t s);
+cudaError_t radix_sort_indices(const uint8_t* keys, int key_bytes, int64_t n, const RadixScratch& S, const uint32_t* bits, cudaStream_t s, int* launches);
 cudaError_t launch_iota(int64_t* out, int64_t n, cudaStream_t s);
 cudaError_t launch_widen_u32(const uint32_t* in, int64_t* out, int64_t n, cudaStream_t s);
 cudaError_t launch_rebase_views(void* views, int64_t n, uint64_t heap_base, cudaStream_t s);

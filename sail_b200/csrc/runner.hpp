@@ -42,12 +42,15 @@ struct PipelineRunner {
   void init(Ctx* c, const Schema& in) { ctx = c; in_schema = in; }   // no device work: specs can be validated without a GPU
   void ensure_scratch() { if (!scal.buf) scal.buf = dev_alloc_zero(ctx, 256); }
 
-  std::shared_ptr<CompiledPipeline> compiled_for(const DevBatch& b) {
+  std::shared_ptr<CompiledPipeline> compiled_for(const DevBatch& b, bool cold_variant = false) {
     std::vector<bool> sig;
     for (auto& c : b.cols) sig.push_back((bool)c.validity);
-    auto it = cache.find(sig);
+    std::vector<bool> cache_key = sig;
+    cache_key.push_back(cold_variant);
+    auto it = cache.find(cache_key);
     if (it != cache.end()) return it->second;
     auto cp = std::make_shared<CompiledPipeline>();
+    cp->cold_variant = cold_variant;
     PipelineCompiler pc(in_schema, sig);
     if (pre_stages) pre_stages(pc, *cp);
     bool agg = false;
@@ -67,7 +70,7 @@ struct PipelineRunner {
     int hot = 0;
     if (agg) hot = cp->agg.n_keys == 0 ? 1 : hot_wanted;
     pc.finalize(*cp, ctx, hot);
-    cache[sig] = cp;
+    cache[cache_key] = cp;
     return cp;
   }
 
@@ -167,7 +170,7 @@ struct PipelineRunner {
     // resident CTAs per SM: what shared memory allows, then the matching register-budget variant of the kernel
     const int by_smem = std::max(1, (int)(ctx->max_smem / (cp->smem_bytes + 1024)));
     const char* fm = getenv("SAILGPU_MINB");
-    const int minb = fm && *fm ? atoi(fm) : std::min(by_smem, cp->sink == SINK_AGG ? 2 : 3);
+    const int minb = fm && *fm ? atoi(fm) : std::min(by_smem, cp->sink == SINK_AGG ? (cp->cold_variant ? 4 : 2) : 3);
     const int per_sm = std::max(1, std::min(by_smem, pipeline_max_ctas_per_sm(cp->rpt, minb, cp->smem_bytes)));
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * per_sm);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -182,7 +185,9 @@ struct PipelineRunner {
 
 
 // Runs a STORE / COMPACT pipeline over one batch and returns the output batch.
-inline BatchPtr run_streaming(PipelineRunner& run, Ctx* ctx, const BatchPtr& b, Metrics& m, const PipelineAux* aux_host, const std::vector<BufPtr>& extra_heaps) {
+// `tile_offsets` (with `known_out_rows`): COMPACT without look-back, every tile's output position precomputed (two-pass filter).
+inline BatchPtr run_streaming(PipelineRunner& run, Ctx* ctx, const BatchPtr& b, Metrics& m, const PipelineAux* aux_host, const std::vector<BufPtr>& extra_heaps,
+                              const unsigned long long* tile_offsets = nullptr, int64_t known_out_rows = -1) {
   auto cp = run.compiled_for(*b);
   auto out = std::make_shared<DevBatch>();
   const int64_t n = b->rows;
@@ -210,7 +215,9 @@ inline BatchPtr run_streaming(PipelineRunner& run, Ctx* ctx, const BatchPtr& b, 
     out->cols.push_back(c);
   }
   BufPtr status;
-  if (compact) {
+  if (compact && tile_offsets) {
+    P.tile_offsets = tile_offsets;
+  } else if (compact) {
     const int64_t n_tiles = (n + P.tile_rows - 1) / P.tile_rows;
     status = dev_alloc_zero(ctx, (size_t)(n_tiles + 1) * 8);
     P.tile_status = static_cast<unsigned long long*>(status->ptr);
@@ -221,8 +228,8 @@ inline BatchPtr run_streaming(PipelineRunner& run, Ctx* ctx, const BatchPtr& b, 
   run.launch(P, cp, aux_host, m);
   int64_t out_rows = n;
   if (compact) {
-    unsigned long long cnt = 0;
-    SG_CUDA(cudaMemcpyAsync(&cnt, run.scal.out_count(), 8, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long cnt = (unsigned long long)known_out_rows;
+    if (!tile_offsets) SG_CUDA(cudaMemcpyAsync(&cnt, run.scal.out_count(), 8, cudaMemcpyDeviceToHost, ctx->stream));
     check_device_error(ctx, run.scal.error());   // synchronises
     out_rows = (int64_t)cnt;
     for (int j = 0; j < P.n_out; ++j) {

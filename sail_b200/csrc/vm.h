@@ -152,6 +152,8 @@ struct AggParams {
   uint32_t entry_words;    // 2 + key_words + acc_words   (8-byte words)
   uint32_t hot_smem_off;   // arena offset of the hot-path scratch
   unsigned long long* n_groups;   // number of occupied entries
+  int32_t cold_only;       // high-cardinality variant: no CTA dictionary, every row goes straight to the global table
+  int32_t pad_cold;
 };
 
 // Join hash table (build side): open addressing on a 64-bit key hash.
@@ -210,6 +212,7 @@ struct PipelineParams {
   unsigned long long* tile_status;   // [n_tiles] decoupled look-back words
   unsigned int* ticket;              // dynamic tile counter
   unsigned long long* out_count;     // total rows kept
+  const unsigned long long* tile_offsets;   // COMPACT, two-pass filter: exclusive output offset of every tile (no look-back, static tile order)
   uint32_t* error_flag;              // bit 0 divide by zero, bit 1 overflow, bit 2 table full, bit 3 unsupported
   int32_t n_probes;
 };

@@ -72,6 +72,42 @@ def test_filter(n, nulls):
     assert_same(gpu_op(spec, t), oracle_op(spec, t), ordered=True)
 
 
+@pytest.mark.parametrize("n", [1, 300, 1024, 4097, 100003, 300007])
+@pytest.mark.parametrize("nulls", [False, True])
+def test_filter_two_pass(n, nulls, monkeypatch):
+    """Large batches filter in two passes (mask pass, scan of the per-tile popcounts, store pass at known offsets);
+    the threshold is lowered so that the small and ragged sizes take that path too."""
+    monkeypatch.setenv("SAILGPU_TWO_PASS_MIN", "1")
+    t = make_table(n, seed=n + 5, nulls=nulls)
+    pred = plans.and_(plans.binop(">=", C("a"), plans.lit(-500, "Int64")),
+                      plans.or_(plans.binop("<", C("d"), plans.dec(12345, 15, 2)), plans.binop("=", C("s"), plans.string("gamma"))))
+    spec = {"op": "filter", "predicate": resolve(pred, t), "projection": [0, 2, 4, 5]}
+    assert_same(gpu_op(spec, t), oracle_op(spec, t), ordered=True)
+    # nothing / everything passes, no projection list
+    spec = {"op": "filter", "predicate": resolve(plans.binop(">", C("a"), plans.lit(10**6, "Int64")), t), "projection": None}
+    assert_same(gpu_op(spec, t), oracle_op(spec, t), ordered=True)
+    spec = {"op": "filter", "predicate": resolve(plans.binop("<", C("b"), plans.lit(10**6, "Int32")), t), "projection": None}
+    assert_same(gpu_op(spec, t), oracle_op(spec, t), ordered=True)
+    # filter + computed projection fused in one pipeline
+    spec = {"op": "pipeline", "stages": [
+        {"op": "filter", "predicate": resolve(plans.binop("<", C("b"), plans.lit(20, "Int32")), t), "projection": None},
+        {"op": "projection", "exprs": [{"expr": resolve(plans.binop("+", C("a"), plans.lit(1, "Int64")), t), "name": "a1"},
+                                       {"expr": resolve(C("s"), t), "name": "s"}]}]}
+    want = oracle_op(spec["stages"][1], oracle_op(spec["stages"][0], t))
+    assert_same(gpu_op(spec, t), want, ordered=True)
+
+
+def test_filter_two_pass_matches_single_pass(monkeypatch):
+    t = make_table(400001, seed=77, nulls=True)
+    spec = {"op": "filter", "predicate": resolve(plans.binop("<", C("b"), plans.lit(3, "Int32")), t), "projection": [0, 1, 2, 4]}
+    monkeypatch.setenv("SAILGPU_TWO_PASS_MIN", "off")
+    one = gpu_op(spec, t)
+    monkeypatch.setenv("SAILGPU_TWO_PASS_MIN", "1")
+    two = gpu_op(spec, t)
+    assert_same(two, one, ordered=True)
+    assert_same(two, oracle_op(spec, t), ordered=True)
+
+
 @pytest.mark.parametrize("n", [0, 1, 999, 50000])
 @pytest.mark.parametrize("nulls", [False, True])
 @pytest.mark.parametrize("keys", [[], ["b"], ["s"], ["b", "s", "dt"]])
@@ -179,6 +215,21 @@ def test_aggregate_many_groups_multi_batch_growth():
         got = op.collect()
         op.close()
         assert_same(got, oracle_op(spec, whole))
+
+
+@pytest.mark.parametrize("nulls", [False, True])
+@pytest.mark.parametrize("keys", [["b"], ["a"], ["a", "s"]])
+def test_aggregate_cardinality_probe_switches_variant(keys, nulls, monkeypatch):
+    """after the first SAILGPU_CARD_PROBE_ROWS rows the operator reads the group count back and, with many groups,
+    continues with the pipeline variant compiled for the global table only; results must not depend on the switch"""
+    monkeypatch.setenv("SAILGPU_CARD_PROBE_ROWS", "2048")
+    t = make_table(60001, seed=31, nulls=nulls)
+    names = t.schema.names
+    spec = {"op": "aggregate", "mode": "single", "group_by": [{"expr": {"col": names.index(c)}, "name": c} for c in keys],
+            "aggs": [{"fn": "sum", "args": [{"col": names.index("d")}], "name": "sd"}, {"fn": "count", "args": [], "name": "c"},
+                     {"fn": "min", "args": [{"col": names.index("dt")}], "name": "mn"}, {"fn": "avg", "args": [{"col": names.index("d")}], "name": "av"},
+                     {"fn": "sum", "args": [{"col": names.index("f")}], "name": "sf"}]}
+    assert_same(gpu_op(spec, t), oracle_op(spec, t), float_cols={len(keys) + 4})
 
 
 def test_filter_streams_many_batches_in_order():
