@@ -458,7 +458,9 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
   static const int C_STORE[][2] = {{4, 2}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
   static const int C_OTHER[][2] = {{4, 1}, {4, 2}, {2, 1}, {2, 2}, {1, 2}, {1, 1}};
   if (out.sink == SINK_AGG && out.cold_variant) hot_wanted = 0;
-  const int (*cands)[2] = out.sink == SINK_AGG ? (out.cold_variant ? C_AGG_COLD : C_AGG) : out.sink == SINK_STORE ? C_STORE : C_OTHER;
+  // hash-join build and probe pipelines are bound by random-access latency as well (scripts/sweep_ops.sh: 5.4 vs 6.6 ms)
+  const bool latency_bound = out.sink == SINK_BUILD || out.n_probes > 0;
+  const int (*cands)[2] = out.sink == SINK_AGG ? (out.cold_variant ? C_AGG_COLD : C_AGG) : out.sink == SINK_STORE ? C_STORE : latency_bound ? C_AGG_COLD : C_OTHER;
   int best_rpt = 0, best_stages = 0, best_hot = 0;
   if (hot_wanted > 0 && force_hot >= 0) hot_wanted = force_hot;
   for (int pass = 0; pass < 2 && !best_rpt; ++pass) {

@@ -8,6 +8,7 @@
 
 #include "device.hpp"
 #include "kernels.hpp"
+#include "relational.hpp"
 
 namespace sg {
 
@@ -260,6 +261,19 @@ StringExport export_strings(Ctx* ctx, const DevColumn& c, bool as_utf8) {
     out.heap = dev_alloc(ctx, 0);
     return out;
   }
+  if (!as_utf8) {
+    // all strings inline (<= 12 bytes, e.g. flags and codes): the resolved views already are Arrow views -> zero copy
+    BufPtr mx = dev_alloc_zero(ctx, 8);
+    unsigned int max_len = 0;
+    SG_CUDA(launch_max_view_len(c.data->ptr, n, static_cast<unsigned int*>(mx->ptr), ctx->stream));
+    SG_CUDA(cudaMemcpyAsync(&max_len, mx->ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (max_len <= 12) {
+      out.views_or_offsets = c.data;
+      out.heap = dev_alloc(ctx, 0);
+      return out;
+    }
+  }
   BufPtr lens = dev_alloc(ctx, (size_t)n * 4);
   BufPtr offs = dev_alloc(ctx, (size_t)n * 8);
   BufPtr scratch = dev_alloc(ctx, 1026 * 8);
@@ -289,9 +303,27 @@ void* to_host(Ctx* ctx, const void* dptr, size_t bytes, ArrayPriv* p) {
   void* h = malloc(bytes ? bytes : 1);
   SG_CHECK(h != nullptr, SAILGPU_ERR_CUDA, "host allocation failed");
   p->host_allocs.push_back(h);
-  if (bytes) SG_CUDA(cudaMemcpyAsync(h, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ctx->d2h_bytes += bytes;
+  if (!bytes) return h;
+  if (bytes <= Ctx::D2H_SMALL) {
+    if (!ctx->d2h_stage && cudaHostAlloc(&ctx->d2h_stage, Ctx::D2H_STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->d2h_stage = nullptr; }
+    const size_t off = (ctx->d2h_used + 15) & ~(size_t)15;
+    if (ctx->d2h_stage && off + bytes <= Ctx::D2H_STAGE_BYTES) {
+      SG_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d2h_stage) + off, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->d2h_pending.push_back({h, off, bytes});
+      ctx->d2h_used = off + bytes;
+      return h;
+    }
+  }
+  SG_CUDA(cudaMemcpyAsync(h, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return h;
+}
+
+// after the stream has been synchronised: move the bounced pieces to their host buffers
+void finish_small_d2h(Ctx* ctx) {
+  for (auto& it : ctx->d2h_pending) memcpy(it.host, static_cast<const uint8_t*>(ctx->d2h_stage) + it.off, it.bytes);
+  ctx->d2h_pending.clear();
+  ctx->d2h_used = 0;
 }
 
 void export_column(Ctx* ctx, const Field& f, const DevColumn& c, ArrowArray* out, bool to_device) {
@@ -338,6 +370,7 @@ void export_column(Ctx* ctx, const Field& f, const DevColumn& c, ArrowArray* out
 }  // namespace
 
 void export_host_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, ArrowArray* out) {
+  ctx->d2h_pending.clear(); ctx->d2h_used = 0;      // leftovers of an export that failed half way
   auto* p = new ArrayPriv();
   p->buffers.push_back(nullptr);
   p->children.resize(schema.size());
@@ -348,6 +381,7 @@ void export_host_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, ArrowA
     p->child_ptrs[i] = &p->children[i];
   }
   SG_CUDA(cudaStreamSynchronize(ctx->stream));
+  finish_small_d2h(ctx);
   init_array(out, b->rows, 0, p);
   out->n_children = (int64_t)schema.size();
   out->children = p->child_ptrs.data();

@@ -33,6 +33,13 @@ struct Ctx {
   std::atomic<bool> dead{false};     // context destroyed; buffers that outlive it fall back to cudaFree
   // metrics shared by all ops of the context
   std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};
+  // small device->host exports (operator results of a few rows) bounce through one pinned block so that all their
+  // copies are asynchronous and the export costs one synchronisation instead of one per buffer
+  struct D2HItem { void* host; size_t off, bytes; };
+  void* d2h_stage = nullptr;
+  size_t d2h_used = 0;
+  std::vector<D2HItem> d2h_pending;
+  static constexpr size_t D2H_STAGE_BYTES = 1 << 20, D2H_SMALL = 64 << 10;
 };
 
 // set by an atexit hook: CUDA may already be torn down when late destructors run at process exit

@@ -102,7 +102,6 @@ void check_device_error(Ctx* ctx, uint32_t* dev_flag) {
 struct AggTable {
   BufPtr table, state, occ;
   uint64_t capacity = 0;
-  uint64_t rows_bound = 0;     // upper bound on the number of groups (rows fed so far)
 };
 
 struct PipelineOp : Op {
@@ -209,11 +208,20 @@ struct PipelineOp : Op {
   }
 
   // ---- aggregate ------------------------------------------------------------------------------
-  static constexpr uint64_t MAX_CAPACITY = 1ull << 27;
-  static int64_t card_probe_rows() { const char* v = getenv("SAILGPU_CARD_PROBE_ROWS"); return v && *v ? atoll(v) : (1 << 18); }   // tests lower it
-  static constexpr uint64_t CARD_MANY_GROUPS = 256;
-  bool card_known = false, use_cold = false;
+  // The group table is sized for the groups the operator expects, not for its input rows.  Every launch carries a group
+  // limit (half the capacity minus what tiles in flight could still add); CTAs that see the table above it stop taking
+  // tiles and append the ones they still owned to a deferred list.  The host reads (groups, deferred) back at the next
+  // synchronisation point it needs anyway (next push / finish), and if tiles were handed back it grows the table by the
+  // observed groups-per-row ratio, rehashes, and re-launches over the list -- with the pipeline variant compiled for
+  // the global table alone when the input turned out to have many groups.
+  static constexpr uint64_t MIN_CAPACITY = 1ull << 22, MAX_CAPACITY = 1ull << 28;
+  static constexpr uint64_t CARD_MANY_GROUPS = 256, HOT_GROUP_LIMIT = 1 << 16;
+  static uint64_t min_capacity() { const char* v = getenv("SAILGPU_AGG_MIN_CAPACITY"); return v && *v ? next_pow2((uint64_t)atoll(v)) : MIN_CAPACITY; }
+  bool use_cold = false;
   int64_t rows_in_table = 0;
+  struct Pending { BatchPtr batch; std::shared_ptr<CompiledPipeline> cp; BufPtr deferred; int64_t n_tiles = 0; bool active = false; } pend;
+
+  unsigned long long* n_deferred_ptr() { return reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(run.scal.buf->ptr) + 40); }
 
   uint64_t read_n_groups() {
     run.ensure_scratch();
@@ -231,25 +239,14 @@ struct PipelineOp : Op {
     A.n_groups = run.scal.n_groups();
   }
 
-  // make room for `rows` more input rows (each may be a new group)
-  void ensure_capacity(const CompiledPipeline& cp, uint64_t rows) {
-    const AggParams& A0 = cp.agg;
-    if (A0.n_keys == 0) rows = 1;
-    uint64_t need = next_pow2(std::max<uint64_t>(1024, 2 * (tab.rows_bound + rows)));
-    if (need <= tab.capacity) { tab.rows_bound += rows; return; }
-    uint64_t groups = 0;
-    if (tab.capacity) {
-      groups = read_n_groups();
-      tab.rows_bound = groups;
-      need = next_pow2(std::max<uint64_t>(1024, 2 * (groups + rows)));
-      if (need <= tab.capacity) { tab.rows_bound += rows; return; }
-    }
-    SG_CHECK(need <= MAX_CAPACITY, SAILGPU_ERR_UNSUPPORTED, "aggregate needs more than 2^27 group slots in one step");
+  // (re)allocates the table with `cap` slots and moves the `groups` existing entries over
+  void alloc_table(const AggParams& A0, uint64_t cap, uint64_t groups) {
+    SG_CHECK(cap <= MAX_CAPACITY, SAILGPU_ERR_UNSUPPORTED, "aggregate needs more than 2^28 group slots");
     AggTable old = tab;
-    tab.capacity = need;
-    tab.table = dev_alloc(ctx, (size_t)need * A0.entry_words * 8);
-    tab.state = dev_alloc_zero(ctx, (size_t)need * 4);
-    tab.occ = dev_alloc(ctx, (size_t)need * 4);
+    tab.capacity = cap;
+    tab.table = dev_alloc(ctx, (size_t)cap * A0.entry_words * 8);
+    tab.state = dev_alloc_zero(ctx, (size_t)cap * 4);
+    tab.occ = dev_alloc(ctx, (size_t)cap * 4);
     if (old.capacity && groups) {
       AggParams A = A0;
       fill_table(A);
@@ -257,60 +254,81 @@ struct PipelineOp : Op {
       SG_CUDA(launch_agg_rehash(A, static_cast<const uint8_t*>(old.table->ptr), static_cast<const uint32_t*>(old.occ->ptr), groups, run.scal.error(), ctx->stream));
       m.kernel_launches++;
     }
-    tab.rows_bound = groups + rows;
+  }
+
+  // one launch over all tiles of `b` (list == null) or over the listed tiles; tiles handed back land in `deferred_out`
+  void launch_agg(const std::shared_ptr<CompiledPipeline>& cp, const DevBatch& b, const BufPtr& list, int64_t n_list, const BufPtr& deferred_out) {
+    PipelineParams P;
+    run.prepare(P, *cp, b, 0, b.rows);
+    if (list) { P.tile_list = static_cast<const uint32_t*>(list->ptr); P.n_list = n_list; }
+    PipelineAux aux;
+    memset(&aux, 0, sizeof(aux));
+    aux.agg = cp->agg;
+    fill_table(aux.agg);
+    if (deferred_out) {
+      SG_CUDA(cudaMemsetAsync(n_deferred_ptr(), 0, 8, ctx->stream));
+      aux.agg.deferred = static_cast<uint32_t*>(deferred_out->ptr);
+      aux.agg.n_deferred = n_deferred_ptr();
+      const char* fl = getenv("SAILGPU_AGG_FIRST_LIMIT");      // tests: force an early hand-back on the first pass
+      aux.agg.group_limit = (!list && fl && *fl) ? (unsigned long long)atoll(fl) : ~0ull;   // ~0: launch() derives it from the grid
+      // the dictionary variant is only worth running while there are few groups: it hands back early, and the
+      // re-launch (many-groups variant, table sized by the observed ratio) takes over
+      run.group_limit_cap = (cp->cold_variant || list) ? ~0ull : HOT_GROUP_LIMIT;      // re-launches over a list always make progress
+    }
+    run.launch(P, cp, &aux, m);
   }
 
   void push_agg(const BatchPtr& b) {
     Trace tr(ctx, "agg.push");
-    // Cardinality probe: the CTA dictionary / register fast path only pay for a handful of groups.  Once CARD_PROBE_ROWS
-    // rows went in, the group count is read back once; with many groups the rest of the input runs through the variant
-    // compiled for the global table alone (no dictionary, small tiles, 4 CTAs/SM).
-    const int64_t CARD_PROBE_ROWS = card_probe_rows();
-    if (!card_known && rows_in_table >= CARD_PROBE_ROWS && tab.capacity) {
-      use_cold = read_n_groups() > CARD_MANY_GROUPS && getenv("SAILGPU_NO_COLD") == nullptr;
-      card_known = true;
-    }
+    resolve_pending();
+    if (b->rows == 0) return;
     auto cp = run.compiled_for(*b, use_cold);
     if (!agg_cp) agg_cp = cp;
     SG_CHECK(cp->agg.entry_words == agg_cp->agg.entry_words && cp->agg.key_words == agg_cp->agg.key_words, SAILGPU_ERR_UNSUPPORTED,
              "aggregate input batches differ in which key columns carry validity buffers");
-    const int64_t n = b->rows;
-    int64_t done = 0;
-    while (done < n) {
-      int64_t chunk = n - done;
-      if (!card_known && cp->agg.n_keys > 0) {
-        if (rows_in_table >= CARD_PROBE_ROWS) {
-          use_cold = read_n_groups() > CARD_MANY_GROUPS && getenv("SAILGPU_NO_COLD") == nullptr;
-          card_known = true;
-          if (use_cold) cp = run.compiled_for(*b, true);
-        } else if (chunk > 4 * CARD_PROBE_ROWS) {
-          chunk = CARD_PROBE_ROWS;                       // a big first batch: look at its head before committing
-        }
+    const bool grouped = cp->agg.n_keys > 0;
+    if (!tab.capacity) alloc_table(cp->agg, grouped ? min_capacity() : 1024, 0);
+    const int64_t tile_rows = (int64_t)cp->rpt * NT;
+    const int64_t n_tiles = (b->rows + tile_rows - 1) / tile_rows;
+    BufPtr deferred = grouped ? dev_alloc(ctx, (size_t)n_tiles * 4) : nullptr;
+    launch_agg(cp, *b, nullptr, 0, deferred);
+    rows_in_table += b->rows;
+    if (grouped) { pend.batch = b; pend.cp = cp; pend.deferred = deferred; pend.n_tiles = n_tiles; pend.active = true; }
+  }
+
+  // reads back what the last launch handed back and, until nothing is left, grows the table and re-launches over it
+  void resolve_pending() {
+    if (!pend.active) return;
+    Trace tr(ctx, "agg.resolve");
+    for (;;) {
+      unsigned long long gd[3] = {0, 0, 0};      // n_groups @24, cursor @32, n_deferred @40
+      SG_CUDA(cudaMemcpyAsync(gd, run.scal.n_groups(), 24, cudaMemcpyDeviceToHost, ctx->stream));
+      check_device_error(ctx, run.scal.error());   // synchronises
+      const uint64_t groups = gd[0], n_def = gd[2];
+      if (n_def == 0) break;
+      const int64_t tile_rows = (int64_t)pend.cp->rpt * NT;
+      const double rows_def = (double)std::min<int64_t>((int64_t)n_def * tile_rows, pend.batch->rows);
+      const double rows_done = std::max(1.0, (double)rows_in_table - rows_def);
+      // groups still to come, by the ratio seen so far (every row a new group when nothing was processed yet)
+      const double ratio = groups ? std::min(1.0, (double)groups / rows_done) : 1.0;
+      const double est = ratio * rows_def * 1.25 + 1024.0;
+      uint64_t cap = next_pow2((uint64_t)(2.0 * ((double)groups + est)) + 2 * MIN_CAPACITY / 2);
+      if (cap <= tab.capacity) cap = tab.capacity * 2;                 // the estimate fell short: at least double
+      alloc_table(pend.cp->agg, cap, groups);
+      std::shared_ptr<CompiledPipeline> cp = pend.cp;
+      if (!use_cold && groups > CARD_MANY_GROUPS && getenv("SAILGPU_NO_COLD") == nullptr) {
+        auto cold = run.compiled_for(*pend.batch, true);
+        if (cold->rpt == cp->rpt && cold->agg.entry_words == cp->agg.entry_words) { cp = cold; use_cold = true; }   // same tile size: the list carries over
       }
-      if (cp->agg.n_keys > 0) {
-        const int64_t max_chunk = (int64_t)(MAX_CAPACITY / 2) - (int64_t)std::min<uint64_t>(tab.rows_bound, MAX_CAPACITY / 4);
-        if (chunk > max_chunk) {
-          if (tab.capacity) tab.rows_bound = read_n_groups();
-          chunk = std::min<int64_t>(chunk, (int64_t)(MAX_CAPACITY / 2) - (int64_t)tab.rows_bound);
-          chunk &= ~(int64_t)1023;
-          SG_CHECK(chunk > 0, SAILGPU_ERR_UNSUPPORTED, "aggregate exceeds 2^26 groups");
-        }
-      }
-      { Trace t2(ctx, "agg.ensure_capacity"); ensure_capacity(*cp, (uint64_t)chunk); }
-      Trace t3(ctx, "agg.launch");
-      PipelineParams P;
-      run.prepare(P, *cp, *b, done, chunk);
-      PipelineAux aux;
-      memset(&aux, 0, sizeof(aux));
-      aux.agg = cp->agg;
-      fill_table(aux.agg);
-      run.launch(P, cp, &aux, m);
-      done += chunk;
-      rows_in_table += chunk;
+      BufPtr next_deferred = dev_alloc(ctx, (size_t)n_def * 4);
+      launch_agg(cp, *pend.batch, pend.deferred, (int64_t)n_def, next_deferred);
+      pend.cp = cp; pend.deferred = next_deferred;
     }
+    pend = Pending();
   }
 
   BatchPtr extract_agg() {
+    resolve_pending();
     Trace tr(ctx, "agg.extract");
     std::shared_ptr<CompiledPipeline> cp = agg_cp;
     if (!cp) {   // no input at all: compile against an all-valid signature to learn the output layout

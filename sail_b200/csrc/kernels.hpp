@@ -24,7 +24,7 @@ struct AggExtractParams {
 };
 
 cudaError_t launch_pipeline(const KernelArgs& K, int rpt, int n_stages, size_t smem_bytes, int grid, int minb, cudaStream_t stream);
-int pipeline_max_ctas_per_sm(int rpt, int minb, size_t smem_bytes);
+int pipeline_max_ctas_per_sm(int rpt, int minb, size_t smem_bytes, int sink, bool cold);
 cudaError_t launch_tile_popcount(const uint32_t* bits, int64_t n_rows, int tile_rows, int64_t n_tiles, uint32_t* counts, cudaStream_t s);
 cudaError_t launch_agg_rehash(const AggParams& A, const uint8_t* old_table, const uint32_t* old_occ, uint64_t old_groups, uint32_t* err, cudaStream_t s);
 cudaError_t launch_agg_extract(const AggParams& A, const AggExtractParams& X, uint64_t n_groups, uint32_t* err, cudaStream_t s);

@@ -21,6 +21,7 @@ struct Smem {
   int32_t tile[2];
   int32_t hot_n;           // groups in the CTA-local hot dictionary
   int32_t elect;
+  int32_t defer[2];        // AGG with a bounded table: "stop taking tiles" flag, double buffered across iterations
   unsigned long long tile_base;   // COMPACT: exclusive prefix of this tile
   uint32_t warp_sums[33];
 };
@@ -1769,7 +1770,11 @@ __device__ __forceinline__ void sink_partition(const PipelineParams& P, const Pa
 // ================================================================================================
 // the kernel
 // ================================================================================================
-template <int RPT, int MINB>
+// KC (kernel class) splits the instantiations by sink family: the aggregation kernels carry the register accumulators
+// and the bounded-table protocol, the others the ordered compaction / join / partition sinks -- each compiles to less
+// code and keeps its registers for what it runs.
+enum : int { KC_AGG = 0, KC_OTHER = 1, KC_AGG_COLD = 2 };   // KC_AGG_COLD: global table only (no dictionary, no register accumulators)
+template <int RPT, int MINB, int KC>
 __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constant__ KernelArgs K, int n_stages) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem* sm = reinterpret_cast<Smem*>(smem_raw);
@@ -1777,7 +1782,24 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
   const PipelineParams& P0 = K.P[0];
   const int tile_rows = RPT * NT;
   const int64_t n_tiles = (P0.n_rows + tile_rows - 1) / tile_rows;
-  const bool dynamic = P0.sink == SINK_COMPACT && P0.tile_offsets == nullptr;
+  const bool dynamic = KC == KC_OTHER && P0.sink == SINK_COMPACT && P0.tile_offsets == nullptr;
+  // static order walks positions blockIdx.x, +gridDim.x, ...: tile numbers themselves or entries of an explicit list
+  const int64_t n_pos = P0.tile_list ? P0.n_list : n_tiles;
+  auto tile_of = [&](int64_t pos) -> int64_t { return P0.tile_list ? (int64_t)P0.tile_list[pos] : pos; };
+  // bounded aggregation table (AggParams::group_limit): once the table is nearly full this CTA stops taking tiles
+  const bool guarded = KC != KC_OTHER && K.aux[0].agg.deferred != nullptr;
+  auto groups_now = [&]() -> unsigned long long { return *reinterpret_cast<volatile unsigned long long*>(K.aux[0].agg.n_groups); };
+  auto table_full = [&]() -> int { return groups_now() > K.aux[0].agg.group_limit ? 1 : 0; };
+  auto defer_rest = [&](int64_t from) {                   // uniform across the CTA
+    if (from >= n_pos) return;
+    const AggParams& A = K.aux[0].agg;
+    const int64_t cnt = (n_pos - from + gridDim.x - 1) / gridDim.x;
+    __syncthreads();
+    if (threadIdx.x == 0) sm->tile_base = atomicAdd(A.n_deferred, (unsigned long long)cnt);
+    __syncthreads();
+    const unsigned long long base = sm->tile_base;
+    for (int64_t j = threadIdx.x; j < cnt; j += NT) A.deferred[base + j] = (uint32_t)tile_of(from + j * gridDim.x);
+  };
 
   if (threadIdx.x == 0) {
     mbar_init(&sm->full[0], 1);
@@ -1785,8 +1807,9 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
     fence_barrier_init();
     sm->hot_n = 0;
     sm->tile[0] = dynamic ? (int)atomicAdd(P0.ticket, 1u) : (int)blockIdx.x;
+    sm->defer[0] = guarded ? table_full() : 0;
   }
-  if (P0.sink == SINK_AGG) hot_init(K.aux[0].agg, arena);
+  if (KC == KC_AGG) hot_init(K.aux[0].agg, arena);
   __syncthreads();
 
   uint32_t tma_bytes = 0;
@@ -1821,12 +1844,16 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
 #pragma unroll
     for (int j = 0; j < REG_ACCS; ++j) R.v[g][j] = 0;
   R.rows = 0;
+  // `cur` / `nxt` are tile numbers in ticket mode and positions (see n_pos) in static mode
   int64_t cur = sm->tile[0];
+  const int64_t n_end = dynamic ? n_tiles : n_pos;
   uint32_t parity[2] = {0, 0};
   int it = 0;
-  if (cur < n_tiles && issue(cur, 0)) __syncthreads();
+  bool defer = sm->defer[0] != 0;
+  if (defer) { defer_rest(cur); cur = n_end; }
+  if (cur < n_end && issue(dynamic ? cur : tile_of(cur), 0)) __syncthreads();
   for (;; ++it) {
-    if (cur >= n_tiles) break;
+    if (cur >= n_end) break;
     const int s = (n_stages == 2) ? (it & 1) : 0;
     const PipelineParams& P = K.P[s];
     const PipelineAux* aux = &K.aux[s];
@@ -1838,29 +1865,44 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
     } else {
       nxt = cur + gridDim.x;                                  // static stride: no barrier needed
     }
-    if (n_stages == 2 && nxt < n_tiles) issue(nxt, s ^ 1);    // prefetch while this tile is computed (consumed after barrier B)
+    // the group count is read at the top of the tile and only looked at before barrier (B): its latency is hidden
+    unsigned long long g_now = 0;
+    if (guarded && threadIdx.x == 0) g_now = groups_now();
+    const bool prefetched = n_stages == 2 && nxt < n_end && !defer;
+    if (prefetched) issue(dynamic ? nxt : tile_of(nxt), s ^ 1);   // prefetch while this tile is computed (consumed after barrier B)
+    const int64_t cur_tile = dynamic ? cur : tile_of(cur);
     TileCtx c;
-    c.arena = arena; c.stage_off = 0; c.row0 = cur * tile_rows;
+    c.arena = arena; c.stage_off = 0; c.row0 = cur_tile * tile_rows;
     c.nrows = (int)min((int64_t)tile_rows, P.n_rows - c.row0);
     if (P.use_tma && c.nrows == tile_rows) { mbar_wait(&sm->full[s], parity[s]); parity[s] ^= 1; }
 
     vm_exec<RPT>(K.prog[s], P.n_inst, c, P, aux);
-    switch (P.sink) {
-      case SINK_STORE: sink_store<RPT>(P, c); break;
-      case SINK_COMPACT: sink_compact<RPT>(P, c, sm, (int)cur); break;
-      case SINK_AGG:
-        if (aux->agg.cold_only) sink_agg_cold<RPT>(P, aux->agg, c);
-        else if (aux->agg.reg_path) sink_agg_reg<RPT>(P, aux->agg, c, sm, R);
-        else sink_agg<RPT>(P, aux->agg, c, sm);
-        break;
-      case SINK_BUILD: sink_build<RPT>(P, aux->build, c); break;
-      case SINK_PARTITION: sink_partition<RPT>(P, aux->part, c); break;
+    if constexpr (KC == KC_AGG_COLD) {
+      sink_agg_cold<RPT>(P, aux->agg, c);
+    } else if constexpr (KC == KC_AGG) {
+      if (aux->agg.reg_path) sink_agg_reg<RPT>(P, aux->agg, c, sm, R);
+      else sink_agg<RPT>(P, aux->agg, c, sm);
+    } else {
+      switch (P.sink) {
+        case SINK_STORE: sink_store<RPT>(P, c); break;
+        case SINK_COMPACT: sink_compact<RPT>(P, c, sm, (int)cur_tile); break;
+        case SINK_BUILD: sink_build<RPT>(P, aux->build, c); break;
+        case SINK_PARTITION: sink_partition<RPT>(P, aux->part, c); break;
+        default: break;
+      }
     }
+    if (guarded && threadIdx.x == 0) sm->defer[(it + 1) & 1] = g_now > K.aux[0].agg.group_limit ? 1 : 0;
     __syncthreads();                                          // (B) stage s and scratch are free again
-    if (n_stages == 1 && nxt < n_tiles && issue(nxt, 0)) __syncthreads();
+    if (guarded) {
+      const bool was = defer;
+      defer = sm->defer[(it + 1) & 1] != 0;
+      // a tile that is already on its way (prefetched) is still processed; everything after it is handed back
+      if (n_stages == 2 ? (was && !prefetched) : defer) { defer_rest(nxt); break; }
+    }
+    if (n_stages == 1 && nxt < n_end && issue(dynamic ? nxt : tile_of(nxt), 0)) __syncthreads();
     cur = nxt;
   }
-  if (P0.sink == SINK_AGG) {
+  if constexpr (KC == KC_AGG) {
     if (K.aux[0].agg.reg_path) { HotView H = hot_view(K.aux[0].agg, arena); reg_flush(K.aux[0].agg, H, R, sm->hot_n); }
     hot_flush(P0, K.aux[0].agg, arena, sm);
   }
@@ -2056,21 +2098,25 @@ __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, int64_t n, co
 // ================================================================================================
 typedef void (*PipelineFn)(const KernelArgs, int);
 // register budget variants: MINB = resident CTAs per SM the compiler must allow (2 -> 128 regs, 3 -> 80, 4 -> 64)
-static PipelineFn pick_kernel(int rpt, int minb) {
-  if (minb >= 4) return rpt == 1 ? pipeline_kernel<1, 4> : rpt == 2 ? pipeline_kernel<2, 4> : pipeline_kernel<4, 2>;
-  if (minb == 3) return rpt == 1 ? pipeline_kernel<1, 3> : rpt == 2 ? pipeline_kernel<2, 3> : pipeline_kernel<4, 2>;
-  return rpt == 1 ? pipeline_kernel<1, 2> : rpt == 2 ? pipeline_kernel<2, 2> : pipeline_kernel<4, 2>;
+// instantiated variants: dictionary aggregation always runs 2 CTAs/SM (128 registers for the accumulators), the
+// global-table aggregation 4 CTAs/SM, the streaming sinks whatever shared memory allows (2..4)
+static PipelineFn pick_kernel(int rpt, int minb, int sink, bool cold) {
+  if (sink == SINK_AGG && cold) return rpt == 1 ? pipeline_kernel<1, 4, KC_AGG_COLD> : rpt == 2 ? pipeline_kernel<2, 4, KC_AGG_COLD> : pipeline_kernel<4, 2, KC_AGG_COLD>;
+  if (sink == SINK_AGG) return rpt == 1 ? pipeline_kernel<1, 2, KC_AGG> : rpt == 2 ? pipeline_kernel<2, 2, KC_AGG> : pipeline_kernel<4, 2, KC_AGG>;
+  if (minb >= 4 && rpt != 4) return rpt == 1 ? pipeline_kernel<1, 4, KC_OTHER> : pipeline_kernel<2, 4, KC_OTHER>;
+  if (minb >= 3) return rpt == 1 ? pipeline_kernel<1, 3, KC_OTHER> : rpt == 2 ? pipeline_kernel<2, 3, KC_OTHER> : pipeline_kernel<4, 3, KC_OTHER>;
+  return rpt == 1 ? pipeline_kernel<1, 2, KC_OTHER> : rpt == 2 ? pipeline_kernel<2, 2, KC_OTHER> : pipeline_kernel<4, 2, KC_OTHER>;
 }
 cudaError_t launch_pipeline(const KernelArgs& K, int rpt, int n_stages, size_t smem_bytes, int grid, int minb, cudaStream_t stream) {
-  PipelineFn k = pick_kernel(rpt, minb);
+  PipelineFn k = pick_kernel(rpt, minb, K.P[0].sink, K.aux[0].agg.cold_only != 0);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return e;
   k<<<grid, NT, smem_bytes, stream>>>(K, n_stages);
   return cudaGetLastError();
 }
 
-int pipeline_max_ctas_per_sm(int rpt, int minb, size_t smem_bytes) {
-  PipelineFn k = pick_kernel(rpt, minb);
+int pipeline_max_ctas_per_sm(int rpt, int minb, size_t smem_bytes, int sink, bool cold) {
+  PipelineFn k = pick_kernel(rpt, minb, sink, cold);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, NT, smem_bytes) != cudaSuccess) return 0;

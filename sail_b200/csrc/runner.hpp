@@ -28,6 +28,26 @@ struct DevProgram {
 
 inline bool timing_enabled() { static const bool on = getenv("SAILGPU_TIMING") != nullptr; return on; }
 
+// SAILGPU_DUMP=1: prints every compiled pipeline (geometry, inputs, VM program, sink) to stderr
+inline void dump_pipeline(const CompiledPipeline& cp) {
+  static const char* names[] = {"NOP", "UNPACK_BITS", "CONST", "MOV", "CVT", "ADD", "SUB", "MUL", "DIV", "REM", "NEG", "MULW", "MUL128_64", "DIVROUND",
+                                "EQ", "NE", "LT", "LE", "GT", "GE", "AND", "OR", "NOT", "ANDNOT", "SELECT", "STR_EQ_LONG", "STR_LIKE", "DATE_PART", "PROBE", "GATHER"};
+  static const char* sinks[] = {"STORE", "COMPACT", "AGG", "BUILD", "PARTITION"};
+  fprintf(stderr, "[sailgpu pipeline] sink=%s rows/thread=%d stages=%d smem=%zu B (temps %u, stage %u, hot %u) inputs=%zu outs=%zu%s\n",
+          cp.sink >= 0 && cp.sink < 5 ? sinks[cp.sink] : "?", cp.rpt, cp.n_stages, cp.smem_bytes, cp.temps_bytes, cp.stage_bytes, cp.hot_bytes,
+          cp.inputs.size(), cp.outs.size(), cp.cold_variant ? " [cold variant]" : "");
+  for (auto& in : cp.inputs) fprintf(stderr, "  in  col %d%s width %u -> slot %d\n", in.col, in.validity ? " (validity)" : "", in.width, in.slot);
+  for (size_t i = 0; i < cp.prog.size(); ++i) {
+    const VmInst& I = cp.prog[i];
+    const int base = I.op & 0xFF, kind = I.op >> 8;
+    fprintf(stderr, "  %2zu  %-12s k%d dst=%d a=%d b=%d c=%d flags=%u aux=%u imm=%lld\n", i, base < OP_COUNT_ ? names[base] : "?", kind, (int)I.dst, (int)I.a, (int)I.b,
+            (int)I.c, I.flags, I.aux, (long long)I.imm0);
+  }
+  if (cp.sink == SINK_AGG)
+    fprintf(stderr, "  agg keys=%d key_words=%d accs=%d entry_words=%d hot_groups=%d reg_path=%d\n", cp.agg.n_keys, cp.agg.key_words, cp.agg.n_accs, cp.agg.entry_words,
+            cp.agg.hot_groups, cp.agg.reg_path);
+}
+
 struct PipelineRunner {
   Ctx* ctx;
   Schema in_schema;
@@ -36,6 +56,7 @@ struct PipelineRunner {
   std::map<const CompiledPipeline*, DevProgram> programs;
   DevScalars scal;
   int hot_wanted = 8;
+  uint64_t group_limit_cap = ~0ull;      // bounded aggregation: extra cap on the launch's group limit (see PipelineOp)
   std::function<void(PipelineCompiler&, CompiledPipeline&)> custom_sink;   // build / partition sinks
   std::function<void(PipelineCompiler&, CompiledPipeline&)> pre_stages;    // probe ops injected before the stages
 
@@ -71,6 +92,7 @@ struct PipelineRunner {
     if (agg) hot = cp->agg.n_keys == 0 ? 1 : hot_wanted;
     pc.finalize(*cp, ctx, hot);
     cache[cache_key] = cp;
+    if (getenv("SAILGPU_DUMP")) dump_pipeline(*cp);
     return cp;
   }
 
@@ -133,7 +155,7 @@ struct PipelineRunner {
   // Builds the kernel argument block: program, descriptors and parameters resolved for both stages.
   void launch(PipelineParams& P, const std::shared_ptr<CompiledPipeline>& cp, const PipelineAux* aux_host, Metrics& m) {
     program_for(cp);
-    const int64_t n_tiles = (P.n_rows + P.tile_rows - 1) / P.tile_rows;
+    const int64_t n_tiles = P.tile_list ? P.n_list : (P.n_rows + P.tile_rows - 1) / P.tile_rows;
     if (n_tiles == 0) return;
     P.prog = nullptr;
     auto K = std::make_unique<KernelArgs>();
@@ -170,9 +192,18 @@ struct PipelineRunner {
     // resident CTAs per SM: what shared memory allows, then the matching register-budget variant of the kernel
     const int by_smem = std::max(1, (int)(ctx->max_smem / (cp->smem_bytes + 1024)));
     const char* fm = getenv("SAILGPU_MINB");
-    const int minb = fm && *fm ? atoi(fm) : std::min(by_smem, cp->sink == SINK_AGG ? (cp->cold_variant ? 4 : 2) : 3);
-    const int per_sm = std::max(1, std::min(by_smem, pipeline_max_ctas_per_sm(cp->rpt, minb, cp->smem_bytes)));
+    const int minb = fm && *fm ? atoi(fm) : std::min(by_smem, cp->sink == SINK_AGG ? (cp->cold_variant ? 4 : 2) : (cp->sink == SINK_BUILD || cp->n_probes > 0) ? 4 : 3);
+    const int per_sm = std::max(1, std::min(by_smem, pipeline_max_ctas_per_sm(cp->rpt, minb, cp->smem_bytes, cp->sink, cp->cold_variant)));
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * per_sm);
+    if (cp->sink == SINK_AGG && aux_host && aux_host->agg.deferred) {
+      // group limit of a bounded table: half the capacity minus what can still arrive from tiles in flight (a CTA acts
+      // on a table-full reading that is up to two tiles old, so three tiles per CTA) and from the dictionary flushes
+      const uint64_t cap = aux_host->agg.capacity_mask + 1;
+      const uint64_t slack = std::min<uint64_t>(3ull * (uint64_t)grid * (uint64_t)P.tile_rows, (uint64_t)P.n_rows) + (uint64_t)grid * (uint64_t)std::max(0, cp->agg.hot_groups);
+      const uint64_t limit = std::min<uint64_t>(cap / 2 > slack ? cap / 2 - slack : 0, group_limit_cap);
+      for (int st = 0; st < 2; ++st)
+        if (K->aux[st].agg.group_limit == ~0ull) K->aux[st].agg.group_limit = limit;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool timed = timing_enabled();
     if (timed) { SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1)); SG_CUDA(cudaEventRecord(e0, ctx->stream)); }

@@ -154,6 +154,12 @@ struct AggParams {
   unsigned long long* n_groups;   // number of occupied entries
   int32_t cold_only;       // high-cardinality variant: no CTA dictionary, every row goes straight to the global table
   int32_t pad_cold;
+  // Bounded table: the table is sized for the groups the operator expects, not for its input rows.  A CTA that sees
+  // *n_groups above group_limit stops taking tiles and appends the ones it still owned to `deferred`; the host grows the
+  // table and re-launches over that list.  group_limit leaves room for every tile that can still be in flight.
+  unsigned long long group_limit;
+  uint32_t* deferred;             // tile numbers not processed by this launch (null: unguarded launch)
+  unsigned long long* n_deferred;
 };
 
 // Join hash table (build side): open addressing on a 64-bit key hash.
@@ -213,6 +219,8 @@ struct PipelineParams {
   unsigned int* ticket;              // dynamic tile counter
   unsigned long long* out_count;     // total rows kept
   const unsigned long long* tile_offsets;   // COMPACT, two-pass filter: exclusive output offset of every tile (no look-back, static tile order)
+  const uint32_t* tile_list;         // static order over an explicit list of tiles (re-launch over deferred tiles) or null
+  int64_t n_list;
   uint32_t* error_flag;              // bit 0 divide by zero, bit 1 overflow, bit 2 table full, bit 3 unsupported
   int32_t n_probes;
 };

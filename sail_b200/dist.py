@@ -58,6 +58,21 @@ class HostBackend:
     def to_host(self, table):
         return table
 
+    def rows(self, table):
+        return table.num_rows
+
+    def max_over_ranks(self, value: int) -> int:
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return int(value)
+        t = torch.tensor([int(value)], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def run_to_host(self, spec, *tables):
+        return self.run_op(spec, *tables)
+
 
 class GpuBackend:
     """libsailgpu + NCCL: data stays in HBM between the operators and across the exchange."""
@@ -136,6 +151,34 @@ class GpuBackend:
     def exchange(self, parts: list, schema: pa.Schema):
         return [self.engine.exchange(parts, schema, self.ctx)]
 
+    def rows(self, batches):
+        return sum(b.num_rows for b in batches)
+
+    def max_over_ranks(self, value: int) -> int:
+        """agreement on a plan choice: one 8-byte all-reduce on the process group bench.py / the tests initialised"""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return int(value)
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item())
+
+    def run_to_host(self, spec, *inputs):
+        """like run(), but the operator's output is pulled straight into host Arrow memory"""
+        e = self.engine
+        schemas = [i.schema if isinstance(i, pa.Table) else i[0].schema for i in inputs]
+        op = e.GpuExec(spec, schemas, self.ctx)
+        for k, i in enumerate(inputs):
+            for b in ([i] if isinstance(i, pa.Table) else i):
+                op.push(b, k)
+            op.finish(k)
+        t = op.collect()
+        self.launches += op.metrics()["gpu.kernel_launches"]
+        op.close()
+        return t
+
     def to_host(self, batches):
         schema = batches[0].schema
         ident = {"op": "projection", "exprs": [{"expr": {"col": i}, "name": n} for i, n in enumerate(schema.names)]}
@@ -161,3 +204,28 @@ def gather_to_root(backend, data, schema: pa.Schema):
     single = data if isinstance(data, pa.Table) else (data[0] if len(data) == 1 else backend._single(data, schema))
     parts = [single if p == 0 else backend.empty(schema) for p in range(backend.world)]
     return backend.exchange(parts, schema)
+
+
+# partial-aggregate states of at most this many rows per rank are coalesced on the root instead of hash-partitioned
+SMALL_EXCHANGE_ROWS = 1 << 14
+
+
+def final_aggregate(backend, partial, schema: pa.Schema, key_cols: list, final_spec: dict, small_rows: int = SMALL_EXCHANGE_ROWS):
+    """Second phase of a two-phase aggregation across ranks.  Returns (data, on_root): the finalised groups and whether
+    they already sit on rank 0 only.
+
+    * many groups: `RepartitionExec Hash(keys)` + all-to-all, `AggregateExec(FinalPartitioned)` on the owner of each
+      group (the plan Sail's cluster mode runs, module docstring);
+    * a handful of groups on every rank (TPC-H Q1: 4): hash partitioning would cost two exchanges and `world` partition
+      pulls for nothing, so the partial states are coalesced on rank 0 (`CoalescePartitionsExec` +
+      `AggregateExec(Final)`, what DataFusion plans for a single target partition) -- one exchange.
+    The choice must be the same on every rank: it is taken on the maximum partial row count (one 8-byte all-reduce)."""
+    if backend.world == 1:
+        return backend.run(final_spec, partial), True
+    if backend.max_over_ranks(backend.rows(partial)) <= small_rows:
+        gathered = gather_to_root(backend, partial, schema)
+        if backend.rank != 0:
+            return None, True
+        return backend.run(final_spec, gathered), True
+    mine = exchange_by_key(backend, partial, schema, key_cols)
+    return backend.run(final_spec, mine), False

@@ -49,12 +49,23 @@ def _worker(rank, world, port, q):
             flat = [g for o in owners for g in o]
             assert len(flat) == len(set(flat)), f"a group was finalised on two ranks: {owners}"
         root = sdist.gather_to_root(backend, final, final.schema)
+        whole = None
         if rank == 0:
             result = backend.run(sort_node.spec, root)
             whole = plans.execute(sort_node, {"lineitem": tpch.lineitem(0.01, cols)}, oracle_op)
             assert result.equals(whole), (result.to_pylist(), whole.to_pylist())
         else:
             assert root.num_rows == 0
+        # the adaptive second phase: few groups -> coalesced on the root (one exchange); threshold 0 -> hash exchange
+        for small_rows, expect_on_root in ((1 << 14, True), (0, False)):
+            fin, on_root = sdist.final_aggregate(backend, partial, partial.schema, [0, 1], final_node.spec, small_rows=small_rows)
+            assert on_root == expect_on_root
+            if not on_root:
+                fin = sdist.gather_to_root(backend, fin, fin.schema)
+            if rank == 0:
+                assert backend.run_to_host(sort_node.spec, fin).equals(whole)
+            elif on_root:
+                assert fin is None
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         import traceback

@@ -56,6 +56,16 @@ def _worker(rank, world, port, q):
             assert_same(got, want)
         else:
             assert got.num_rows == 0
+        # adaptive second phase: coalesce-on-root for few groups, hash exchange when forced (threshold 0)
+        ident = {"op": "projection", "exprs": [{"expr": {"col": i}, "name": n} for i, n in enumerate(final[0].schema.names)]}
+        for small_rows, expect_on_root in ((1 << 14, True), (0, False)):
+            partial2 = backend.run(partial_node.spec, shard)
+            fin, on_root = sdist.final_aggregate(backend, partial2, partial2[0].schema, [0, 1], final_node.spec, small_rows=small_rows)
+            assert on_root == expect_on_root
+            if not on_root:
+                fin = sdist.gather_to_root(backend, fin, fin[0].schema)
+            if rank == 0:
+                assert_same(backend.run_to_host(ident, fin), want)
         q.put((rank, "ok"))
     except Exception:  # noqa: BLE001
         import traceback

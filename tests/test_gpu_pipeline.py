@@ -219,10 +219,12 @@ def test_aggregate_many_groups_multi_batch_growth():
 
 @pytest.mark.parametrize("nulls", [False, True])
 @pytest.mark.parametrize("keys", [["b"], ["a"], ["a", "s"]])
-def test_aggregate_cardinality_probe_switches_variant(keys, nulls, monkeypatch):
-    """after the first SAILGPU_CARD_PROBE_ROWS rows the operator reads the group count back and, with many groups,
-    continues with the pipeline variant compiled for the global table only; results must not depend on the switch"""
-    monkeypatch.setenv("SAILGPU_CARD_PROBE_ROWS", "2048")
+@pytest.mark.parametrize("first_limit", ["0", "40", "700"])
+def test_aggregate_bounded_table_hands_tiles_back(keys, nulls, first_limit, monkeypatch):
+    """The group table is bounded: CTAs that find it above the launch's group limit hand their remaining tiles back and
+    the operator grows the table, rehashes and re-launches over the deferred list (switching to the many-groups variant
+    of the pipeline).  SAILGPU_AGG_FIRST_LIMIT forces that on the first pass (0: everything is handed back)."""
+    monkeypatch.setenv("SAILGPU_AGG_FIRST_LIMIT", first_limit)
     t = make_table(60001, seed=31, nulls=nulls)
     names = t.schema.names
     spec = {"op": "aggregate", "mode": "single", "group_by": [{"expr": {"col": names.index(c)}, "name": c} for c in keys],
@@ -230,6 +232,28 @@ def test_aggregate_cardinality_probe_switches_variant(keys, nulls, monkeypatch):
                      {"fn": "min", "args": [{"col": names.index("dt")}], "name": "mn"}, {"fn": "avg", "args": [{"col": names.index("d")}], "name": "av"},
                      {"fn": "sum", "args": [{"col": names.index("f")}], "name": "sf"}]}
     assert_same(gpu_op(spec, t), oracle_op(spec, t), float_cols={len(keys) + 4})
+
+
+def test_aggregate_bounded_table_grows_by_itself():
+    """no forcing: 3 M distinct keys overflow the initial 4 M-slot table's group limit, so the natural hand-back /
+    grow / re-launch path runs; sums and counts are checked against numpy"""
+    from sail_b200 import engine
+    n, domain = 4_000_000, 3_000_000
+    rng = np.random.default_rng(5)
+    k = rng.integers(0, domain, n).astype(np.int64)
+    v = rng.integers(-1000, 1000, n).astype(np.int64)
+    t = pa.table({"k": pa.array(k), "v": pa.array(v)})
+    spec = {"op": "aggregate", "mode": "single", "group_by": [{"expr": {"col": 0}, "name": "k"}],
+            "aggs": [{"fn": "sum", "args": [{"col": 1}], "name": "s"}, {"fn": "count", "args": [], "name": "c"}]}
+    got = engine.run_op(spec, t)
+    gk = got.column("k").to_numpy()
+    order = np.argsort(gk)
+    uk, inv, cnt = np.unique(k, return_inverse=True, return_counts=True)
+    sums = np.bincount(inv, weights=v.astype(np.float64)).astype(np.int64)
+    assert got.num_rows == len(uk)
+    assert np.array_equal(gk[order], uk)
+    assert np.array_equal(got.column("s").to_numpy()[order], sums)
+    assert np.array_equal(got.column("c").to_numpy()[order], cnt)
 
 
 def test_filter_streams_many_batches_in_order():
