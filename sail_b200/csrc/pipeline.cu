@@ -429,7 +429,7 @@ __device__ __noinline__ void vm_probe_general(const ProbeParams& P, const TileCt
           if (s.x == 0) break;
           if (s.x == tag) {
             // verify against the build-side key columns
-            const int64_t cand = (int64_t)s.y;
+            const int64_t cand = (int64_t)s.y - 1;                 // slot head = row + 1
             bool eq = true;
             int w = 0;
             for (int i = 0; i < P.n_keys && eq; ++i) {
@@ -487,20 +487,20 @@ __device__ __noinline__ void vm_probe_narrow(const ProbeParams& P, const TileCtx
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     bkey[k] = 0;
-    if (s[k].x == tag[k]) bkey[k] = load_key_word(bcol + (int64_t)s[k].y * bstride, d.width);
+    if (s[k].x == tag[k]) bkey[k] = load_key_word(bcol + ((int64_t)s[k].y - 1) * bstride, d.width);      // slot head = row + 1
   }
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     const int r = threadIdx.x + k * NT;
     int64_t row = -1;
     if (s[k].x != 0) {
-      if (s[k].x == tag[k] && bkey[k] == key[k]) row = (int64_t)s[k].y;
+      if (s[k].x == tag[k] && bkey[k] == key[k]) row = (int64_t)s[k].y - 1;
       else {                                                  // collision: ordinary linear probe from the next slot
         uint64_t idx = (((tag[k] >> 1) & P.capacity_mask) + 1) & P.capacity_mask;
         for (;;) {
           const ulonglong2 cur = *reinterpret_cast<const ulonglong2*>(P.table + idx * 16);
           if (cur.x == 0) break;
-          if (cur.x == tag[k] && load_key_word(bcol + (int64_t)cur.y * bstride, d.width) == key[k]) { row = (int64_t)cur.y; break; }
+          if (cur.x == tag[k] && load_key_word(bcol + ((int64_t)cur.y - 1) * bstride, d.width) == key[k]) { row = (int64_t)cur.y - 1; break; }
           idx = (idx + 1) & P.capacity_mask;
         }
       }
@@ -1603,47 +1603,49 @@ __device__ __forceinline__ bool build_row_has_key(const KeyDesc* keys, const uin
   return true;
 }
 
-__device__ __forceinline__ ulonglong2 ld_slot(const uint8_t* slot) {
-  ulonglong2 s;
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(s.x), "=l"(s.y) : "l"(slot) : "memory");
-  return s;
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const void* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
-// push the pre-linked chain first..last (next[] already links first -> ... -> last) on the slot's stack
-__device__ __forceinline__ void chain_push(const BuildParams& B, uint8_t* slot, ulonglong2 s, unsigned long long tag, long long first, long long last) {
-  for (;;) {
-    B.next[last] = (long long)s.y;
-    __threadfence();
-    const u128 want = ((u128)s.y << 64) | s.x;
-    const u128 prev = atomic_cas_128(slot, want, ((u128)(unsigned long long)first << 64) | tag);
-    if (prev == want) return;
-    s.x = (unsigned long long)prev; s.y = (unsigned long long)(prev >> 64);
-  }
+// Join table slot = { u64 tag (0 = empty; hash | 1), u64 head (row + 1 of the newest row with this key; 0 = none yet) }.
+// The tag is claimed once with a 64-bit CAS and never changes; rows are pushed on the slot's stack with ONE atomic
+// exchange of `head` (wait-free: no retry loop, so a build side with a handful of distinct keys does not collapse into
+// CAS retries), and next[] links them.  The probe runs in a later launch and reads slots with plain loads.
+__device__ __forceinline__ void chain_push(const BuildParams& B, uint8_t* slot, long long first, long long last) {
+  const unsigned long long prev = atomicExch(reinterpret_cast<unsigned long long*>(slot + 8), (unsigned long long)(first + 1));
+  B.next[last] = (long long)prev - 1;                            // -1 ends the chain
+  if ((prev != 0 || first != last) && *reinterpret_cast<volatile uint32_t*>(B.dup_flag) == 0) atomicOr(B.dup_flag, 1u);
 }
-// insert one row; returns the slot it ended up in (nullptr when the table is full)
-__device__ __forceinline__ uint8_t* build_insert_one(const BuildParams& B, const KeyRegs& key, uint64_t h, long long row) {
+// inserts the pre-linked chain first..last (all rows carry `key`); returns the slot (nullptr when the table is full)
+__device__ __forceinline__ uint8_t* build_insert_one(const BuildParams& B, const KeyRegs& key, uint64_t h, long long first, long long last) {
   const unsigned long long tag = h | 1ull;
   uint64_t idx = (h >> 1) & B.capacity_mask;
   for (uint64_t probes = 0; probes <= B.capacity_mask; ++probes) {
     uint8_t* slot = B.table + idx * 16;
-    ulonglong2 s = ld_slot(slot);
-    if (s.x == 0ull) {
-      const u128 prev = atomic_cas_128(slot, (u128)0, ((u128)(unsigned long long)row << 64) | tag);
-      if (prev == 0) return slot;                               // claimed an empty slot (next[row] is already -1)
-      s.x = (unsigned long long)prev; s.y = (unsigned long long)(prev >> 64);
+    unsigned long long t = ld_volatile_u64(slot);
+    if (t == 0ull) {
+      t = atomicCAS(reinterpret_cast<unsigned long long*>(slot), 0ull, tag);
+      if (t == 0ull) { chain_push(B, slot, first, last); return slot; }      // claimed an empty slot
     }
-    if (s.x == tag && build_row_has_key(B.keys, B.key_cols, B.key_stride, B.n_keys, (int64_t)s.y, key)) {
-      atomicOr(B.dup_flag, 1u);                                 // same key: push this row on the chain
-      chain_push(B, slot, s, tag, row, row);
-      return slot;
+    if (t == tag) {
+      // same tag: compare with a row that is already on the chain (the claimer publishes its row right after the CAS)
+      unsigned long long head = ld_volatile_u64(slot + 8);
+      for (uint32_t spins = 0; head == 0ull; ++spins) {
+        if (spins > (1u << 24)) __trap();
+        __nanosleep(20);
+        head = ld_volatile_u64(slot + 8);
+      }
+      if (build_row_has_key(B.keys, B.key_cols, B.key_stride, B.n_keys, (int64_t)head - 1, key)) { chain_push(B, slot, first, last); return slot; }
     }
     idx = (idx + 1) & B.capacity_mask;
   }
   return nullptr;
 }
 
-// HashJoinExec build: one slot {hash tag, head row} per DISTINCT key; rows with an equal key are pushed on the
-// slot's chain (next[]) with a 128-bit CAS.  Lanes of a warp that carry the same key are linked to each other first
-// (__match_any_sync) and pushed with ONE CAS, so a build side with few distinct keys does not serialise on the slot.
+// HashJoinExec build: one slot per DISTINCT key; rows with an equal key are pushed on the slot's chain (next[]).
+// Lanes of a warp that carry the same key are linked to each other first (__match_any_sync) and pushed with ONE
+// exchange, so a build side with few distinct keys costs one atomic per (warp, key).
 template <int RPT>
 __device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildParams& B, const TileCtx& c) {
   const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, P.mask_slot);
@@ -1660,7 +1662,7 @@ __device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildP
     const int leader = __ffs(peers) - 1;
     // step A: the leader of every distinct hash inserts its own row
     uint8_t* slot = nullptr;
-    if (ins && lane == leader) slot = build_insert_one(B, key, h, row);
+    if (ins && lane == leader) slot = build_insert_one(B, key, h, row, row);
     const unsigned long long slot_bits = __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(slot), leader);
     const long long leader_row = __shfl_sync(0xFFFFFFFFu, row, leader);
     slot = reinterpret_cast<uint8_t*>(slot_bits);
@@ -1675,13 +1677,9 @@ __device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildP
       if (nxt >= 0) B.next[row] = next_row;
       const int first = __ffs(chain) - 1, last = 31 - __clz(chain);
       const long long last_row = __shfl_sync(chain, row, last);
-      if (lane == first) {
-        atomicOr(B.dup_flag, 1u);
-        __threadfence();
-        chain_push(B, slot, ld_slot(slot), tag, row, last_row);
-      }
+      if (lane == first) chain_push(B, slot, row, last_row);
     } else if (follower) {
-      build_insert_one(B, key, h, row);                         // same hash, different key (64-bit collision)
+      build_insert_one(B, key, h, row, row);                    // same hash, different key (64-bit collision)
     }
   }
 }

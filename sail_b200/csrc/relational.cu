@@ -70,8 +70,8 @@ __global__ void join_multi_kernel(JoinMultiParams P) {
       for (;;) {
         const ulonglong2 s = *reinterpret_cast<const ulonglong2*>(P.table + idx * 16);
         if (s.x == 0) break;
-        if (s.x == tag && raw_keys_equal(P.build_keys, (int64_t)s.y, P.probe_keys, i, P.n_keys)) {
-          for (int64_t b = (int64_t)s.y; b >= 0; b = P.next[b]) {      // every build row with this key
+        if (s.x == tag && raw_keys_equal(P.build_keys, (int64_t)s.y - 1, P.probe_keys, i, P.n_keys)) {      // slot head = row + 1
+          for (int64_t b = (int64_t)s.y - 1; b >= 0; b = P.next[b]) {      // every build row with this key
             if (P.pass == 1) { P.out_build[out] = b; P.out_probe[out] = i; ++out; }
             if (P.pass >= 1 && P.visited) P.visited[b] = 1;            // pass 2 = mark only (semi / anti joins emitting build rows)
             ++n;
