@@ -287,7 +287,9 @@ struct PipelineOp : Op {
     SG_CHECK(cp->agg.entry_words == agg_cp->agg.entry_words && cp->agg.key_words == agg_cp->agg.key_words, SAILGPU_ERR_UNSUPPORTED,
              "aggregate input batches differ in which key columns carry validity buffers");
     const bool grouped = cp->agg.n_keys > 0;
-    if (!tab.capacity) alloc_table(cp->agg, grouped ? min_capacity() : 1024, 0);
+    // first table: 4 M slots for real inputs, but a final aggregate over a few partial rows gets a few KB (a hand-back
+    // grows it if later batches are bigger)
+    if (!tab.capacity) alloc_table(cp->agg, grouped ? std::min<uint64_t>(min_capacity(), next_pow2(8 * (uint64_t)b->rows + 2048)) : 1024, 0);
     const int64_t tile_rows = (int64_t)cp->rpt * NT;
     const int64_t n_tiles = (b->rows + tile_rows - 1) / tile_rows;
     BufPtr deferred = grouped ? dev_alloc(ctx, (size_t)n_tiles * 4) : nullptr;
