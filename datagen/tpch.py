@@ -221,6 +221,35 @@ def supplier(sf: float, columns=None, strings: str = "view") -> pa.Table:
     return pa.table([_to_arrow(c, a[c], strings) for c in columns], names=columns)
 
 
+# dists.dss p_types / p_cntr: full strings in nested syllable order, equal weights
+P_TYPES = [f"{a} {b} {c}" for a in ("STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO")
+           for b in ("ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED") for c in ("TIN", "NICKEL", "BRASS", "STEEL", "COPPER")]
+P_CONTAINERS = [f"{a} {b}" for a in ("SM", "LG", "MED", "JUMBO", "WRAP") for b in ("CASE", "BOX", "BAG", "JAR", "PKG", "PACK", "CAN", "DRUM")]
+
+
+def part(sf: float, columns=None, strings: str = "view") -> pa.Table:
+    """p_partkey, p_brand ('Brand#MN'), p_type, p_size, p_container, p_retailprice (p_name / p_mfgr / p_comment are not generated)"""
+    n = counts(sf)["part"]
+    a = {"p_partkey": np.empty(n, "i8"), "p_retailprice": np.empty(n, "i8"), "p_size": np.empty(n, "i4"), "p_type": np.empty(n, "u1"),
+         "p_brand": np.empty(n, "i4"), "p_container": np.empty(n, "u1")}
+    lib().tpch_gen_part(ctypes.c_double(sf), ctypes.c_int64(0), ctypes.c_int64(n), _p(a["p_partkey"]), _p(a["p_retailprice"]),
+                        _p(a["p_size"]), _p(a["p_type"]), _p(a["p_brand"]), _p(a["p_container"]))
+    columns = list(columns or ["p_partkey", "p_brand", "p_type", "p_size", "p_container", "p_retailprice"])
+    out = []
+    for c in columns:
+        if c == "p_type":
+            out.append(strings_from_codes(a[c], P_TYPES, strings))
+        elif c == "p_container":
+            out.append(strings_from_codes(a[c], P_CONTAINERS, strings))
+        elif c == "p_brand":
+            brands = sorted(set(int(x) for x in a[c]))
+            codes = np.searchsorted(np.array(brands), a[c])
+            out.append(strings_from_codes(codes, [f"Brand#{b}" for b in brands], strings))
+        else:
+            out.append(_to_arrow(c, a[c], strings))
+    return pa.table(out, names=columns)
+
+
 def nation(strings: str = "view") -> pa.Table:
     keys = np.arange(25, dtype=np.int64)
     names = strings_from_codes(np.arange(25), [n for n, _ in NATIONS], strings)
@@ -237,4 +266,4 @@ def tables(sf: float, strings: str = "view") -> dict:
     """All generated tables (small scale factors only)."""
     return {"lineitem": lineitem(sf, strings=strings), "orders": orders(sf, strings=strings),
             "customer": customer(sf, strings=strings), "supplier": supplier(sf, strings=strings),
-            "nation": nation(strings), "region": region(strings)}
+            "part": part(sf, strings=strings), "nation": nation(strings), "region": region(strings)}

@@ -295,4 +295,49 @@ def q12(strings="Utf8View") -> Node:
     return sort(a, [("l_shipmode", True)])
 
 
-TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q12": q12}
+def q7(strings="Utf8View") -> Node:
+    """test_tpch.plan.yaml:172-209: five CollectLeft joins (the growing intermediate is always the build side), the
+    nation-pair predicate as the residual filter of the last join, date_part in the projection."""
+    supp = scan("supplier", ["s_suppkey", "s_nationkey"])
+    li = filter_(scan("lineitem", ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount", "l_shipdate"]),
+                 and_(binop(">=", col("l_shipdate"), date("1995-01-01")), binop("<=", col("l_shipdate"), date("1996-12-31"))))
+    j1 = hash_join(supp, li, [("s_suppkey", "l_suppkey")],
+                   projection=["s_nationkey", "l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"])
+    ords = scan("orders", ["o_orderkey", "o_custkey"])
+    j2 = hash_join(j1, ords, [("l_orderkey", "o_orderkey")],
+                   projection=["s_nationkey", "l_extendedprice", "l_discount", "l_shipdate", "o_custkey"])
+    cust = scan("customer", ["c_custkey", "c_nationkey"])
+    j3 = hash_join(j2, cust, [("o_custkey", "c_custkey")],
+                   projection=["s_nationkey", "l_extendedprice", "l_discount", "l_shipdate", "c_nationkey"])
+    pair = or_(binop("=", col("n_name"), string("GERMANY", strings)), binop("=", col("n_name"), string("IRAQ", strings)))
+    n1 = project(filter_(scan("nation", ["n_nationkey", "n_name"]), pair), [(col("n_nationkey"), "n1_key"), (col("n_name"), "n1_name")])
+    j4 = hash_join(j3, n1, [("s_nationkey", "n1_key")],
+                   projection=["l_extendedprice", "l_discount", "l_shipdate", "c_nationkey", "n1_name"])
+    n2 = project(filter_(scan("nation", ["n_nationkey", "n_name"]), pair), [(col("n_nationkey"), "n2_key"), (col("n_name"), "n2_name")])
+    cross = or_(and_(binop("=", col("n1_name"), string("GERMANY", strings)), binop("=", col("n2_name"), string("IRAQ", strings))),
+                and_(binop("=", col("n1_name"), string("IRAQ", strings)), binop("=", col("n2_name"), string("GERMANY", strings))))
+    j5 = hash_join(j4, n2, [("c_nationkey", "n2_key")], filter=cross,
+                   projection=["l_extendedprice", "l_discount", "l_shipdate", "n1_name", "n2_name"])
+    p = project(j5, [(col("n1_name"), "supp_nation"), (col("n2_name"), "cust_nation"),
+                     ({"fn": "date_part", "part": "year", "args": [col("l_shipdate")]}, "l_year"), (DISC_PRICE, "volume")])
+    a = two_phase(p, ["supp_nation", "cust_nation", "l_year"], [("sum", col("volume"), "revenue", "Decimal128(32,4)")])
+    return sort(a, [("supp_nation", True), ("cust_nation", True), ("l_year", True)])
+
+
+def q14(strings="Utf8View") -> Node:
+    """test_tpch.plan.yaml:409-425: the filtered lineitem rows are the build side, part the probe side; the promo ratio is
+    a decimal division of the two final sums (the reference guards the divisor with raise_error; division by zero is an
+    error on both paths)."""
+    li = filter_(scan("lineitem", ["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"]),
+                 and_(binop(">=", col("l_shipdate"), date("1995-02-01")), binop("<", col("l_shipdate"), date("1995-03-01"))),
+                 ["l_partkey", "l_extendedprice", "l_discount"])
+    pt = scan("part", ["p_partkey", "p_type"])
+    j = hash_join(li, pt, [("l_partkey", "p_partkey")], projection=["l_extendedprice", "l_discount", "p_type"])
+    p = project(j, [(DISC_PRICE, "__common_expr_1"), "p_type"])
+    promo = {"case": [[{"like": col("p_type"), "pattern": "PROMO%"}, col("__common_expr_1")]], "else": lit(0, "Int32")}
+    a = two_phase(p, [], [("sum", promo, "promo", "Decimal128(32,4)"), ("sum", col("__common_expr_1"), "total", "Decimal128(32,4)")])
+    ratio = binop("/", binop("*", dec(10000, 5, 2), col("promo")), col("total"))
+    return project(a, [(ratio, "promo_revenue")])
+
+
+TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q12": q12, "q14": q14}

@@ -1,4 +1,4 @@
-"""TPC-H Q1/Q3/Q5/Q6 (+Q4, Q12) on one B200 with the tables resident in HBM: wall-clock per query through the C ABI
+"""TPC-H Q1/Q3/Q5/Q6 (+Q4, Q7, Q12, Q14) on one B200 with the tables resident in HBM: wall-clock per query through the C ABI
 (every intermediate stays on the device), rows/s over the scanned rows, and a parity check of each result
 against the oracle at a small scale factor.  Usage: python scripts/bench_tpch.py [SF] [reps]"""
 import json
@@ -12,17 +12,18 @@ from datagen import tpch  # noqa: E402
 from sail_b200 import engine, plans  # noqa: E402
 
 NEEDED = {
-    "lineitem": ["l_orderkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus",
+    "lineitem": ["l_orderkey", "l_partkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus",
                  "l_shipdate", "l_commitdate", "l_receiptdate", "l_shipmode"],
     "orders": ["o_orderkey", "o_custkey", "o_orderdate", "o_orderpriority", "o_shippriority"],
     "customer": ["c_custkey", "c_nationkey", "c_mktsegment"],
     "supplier": ["s_suppkey", "s_nationkey"],
+    "part": ["p_partkey", "p_type"],
 }
 
 
 def load(sf):
     t = {"lineitem": tpch.lineitem(sf, NEEDED["lineitem"]), "orders": tpch.orders(sf, NEEDED["orders"]),
-         "customer": tpch.customer(sf, NEEDED["customer"]), "supplier": tpch.supplier(sf, NEEDED["supplier"]),
+         "customer": tpch.customer(sf, NEEDED["customer"]), "supplier": tpch.supplier(sf, NEEDED["supplier"]), "part": tpch.part(sf, NEEDED["part"]),
          "nation": tpch.nation(), "region": tpch.region()}
     return {k: v.combine_chunks() for k, v in t.items()}
 
@@ -43,7 +44,7 @@ def main():
     dev = {k: (engine.to_device(v, ctx), v.schema.names) for k, v in tables.items()}
     hbm = sum(v.nbytes for v in tables.values())
     results = {}
-    for q in ("q1", "q6", "q3", "q4", "q5", "q12"):
+    for q in ("q1", "q6", "q3", "q4", "q5", "q7", "q12", "q14"):
         plan = plans.TPCH[q]()
         try:
             times, stats = [], {}
