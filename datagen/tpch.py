@@ -224,7 +224,7 @@ def supplier(sf: float, columns=None, strings: str = "view") -> pa.Table:
 # dists.dss p_types / p_cntr: full strings in nested syllable order, equal weights
 P_TYPES = [f"{a} {b} {c}" for a in ("STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO")
            for b in ("ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED") for c in ("TIN", "NICKEL", "BRASS", "STEEL", "COPPER")]
-P_CONTAINERS = [f"{a} {b}" for a in ("SM", "LG", "MED", "JUMBO", "WRAP") for b in ("CASE", "BOX", "BAG", "JAR", "PKG", "PACK", "CAN", "DRUM")]
+P_CONTAINERS = [f"{a} {b}" for a in ("SM", "LG", "MED", "JUMBO", "WRAP") for b in ("CASE", "BOX", "BAG", "JAR", "PACK", "PKG", "CAN", "DRUM")]   # PACK before PKG: part.tbl row 1 is "JUMBO PKG"
 
 
 def part(sf: float, columns=None, strings: str = "view") -> pa.Table:

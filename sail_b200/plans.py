@@ -340,4 +340,33 @@ def q14(strings="Utf8View") -> Node:
     return project(a, [(ratio, "promo_revenue")])
 
 
-TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q12": q12, "q14": q14}
+def q19(strings="Utf8View") -> Node:
+    """test_tpch.plan.yaml:559-575: filtered part is the build side, filtered lineitem the probe side; the three
+    brand/container/quantity/size alternatives are the residual filter of the join (IN lists, decimal ranges)."""
+    def S(v):
+        return string(v, strings)
+
+    def alt(brand, containers, qlo, qhi, size_hi, with_qty):
+        xs = [binop("=", col("p_brand"), S(brand)), {"in": col("p_container"), "set": [S(c) for c in containers]}]
+        if with_qty:
+            xs += [binop(">=", col("l_quantity"), dec(qlo * 100, 15, 2)), binop("<=", col("l_quantity"), dec(qhi * 100, 15, 2))]
+        xs.append(binop("<=", col("p_size"), lit(size_hi, "Int32")))
+        return and_(*xs)
+
+    alts = [("Brand#21", ["SM CASE", "SM BOX", "SM PACK", "SM PKG"], 8, 18, 5),
+            ("Brand#13", ["MED BAG", "MED BOX", "MED PKG", "MED PACK"], 20, 30, 10),
+            ("Brand#52", ["LG CASE", "LG BOX", "LG PACK", "LG PKG"], 30, 40, 15)]
+    pt = filter_(scan("part", ["p_partkey", "p_brand", "p_size", "p_container"]),
+                 and_(or_(*[alt(*a, False) for a in alts]), binop(">=", col("p_size"), lit(1, "Int32"))))
+    qty = or_(*[and_(binop(">=", col("l_quantity"), dec(lo * 100, 15, 2)), binop("<=", col("l_quantity"), dec(hi * 100, 15, 2)))
+                for _, _, lo, hi, _ in alts])
+    li = filter_(scan("lineitem", ["l_partkey", "l_quantity", "l_extendedprice", "l_discount", "l_shipinstruct", "l_shipmode"]),
+                 and_(qty, or_(binop("=", col("l_shipmode"), S("AIR")), binop("=", col("l_shipmode"), S("AIR REG"))),
+                      binop("=", col("l_shipinstruct"), S("DELIVER IN PERSON"))),
+                 ["l_partkey", "l_quantity", "l_extendedprice", "l_discount"])
+    j = hash_join(pt, li, [("p_partkey", "l_partkey")], filter=or_(*[alt(*a, True) for a in alts]),
+                  projection=["l_extendedprice", "l_discount"])
+    return two_phase(j, [], [("sum", DISC_PRICE, "revenue", "Decimal128(32,4)")])
+
+
+TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q12": q12, "q14": q14, "q19": q19}
