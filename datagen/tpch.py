@@ -208,8 +208,14 @@ def customer(sf: float, columns=None, strings: str = "view") -> pa.Table:
          "c_mktsegment": np.empty(n, "u1")}
     lib().tpch_gen_customer(ctypes.c_double(sf), ctypes.c_int64(0), ctypes.c_int64(n),
                             _p(a["c_custkey"]), _p(a["c_nationkey"]), _p(a["c_acctbal"]), _p(a["c_mktsegment"]))
-    columns = list(columns or a.keys())
-    return pa.table([_to_arrow(c, a[c], strings) for c in columns], names=columns)
+    columns = list(columns or list(a.keys()) + ["c_name"])
+
+    def one(c):
+        if c == "c_name":       # dbgen: "Customer#%09d" (18 bytes: always a long view)
+            txt = np.char.add("Customer#", np.char.zfill(a["c_custkey"].astype(str), 9))
+            return pa.array(txt.tolist(), type=pa.string_view() if strings == "view" else pa.string())
+        return _to_arrow(c, a[c], strings)
+    return pa.table([one(c) for c in columns], names=columns)
 
 
 def supplier(sf: float, columns=None, strings: str = "view") -> pa.Table:

@@ -369,4 +369,22 @@ def q19(strings="Utf8View") -> Node:
     return two_phase(j, [], [("sum", DISC_PRICE, "revenue", "Decimal128(32,4)")])
 
 
-TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q12": q12, "q14": q14, "q19": q19}
+def q18(strings="Utf8View", min_qty=313) -> Node:
+    """test_tpch.plan.yaml:529-557: orders x customer x lineitem, LeftSemi against the orders whose quantity sums exceed
+    313 (a grouped aggregate + filter on the probe side), five group keys including an 18-byte name, TopK 100."""
+    del strings
+    ords = scan("orders", ["o_orderkey", "o_custkey", "o_totalprice", "o_orderdate"])
+    cust = scan("customer", ["c_custkey", "c_name"])
+    j1 = hash_join(ords, cust, [("o_custkey", "c_custkey")], projection=["o_orderkey", "o_totalprice", "o_orderdate", "c_custkey", "c_name"])
+    j1 = project(j1, ["c_custkey", "c_name", "o_orderkey", "o_totalprice", "o_orderdate"])
+    li = scan("lineitem", ["l_orderkey", "l_quantity"])
+    j2 = hash_join(j1, li, [("o_orderkey", "l_orderkey")],
+                   projection=["c_custkey", "c_name", "o_orderkey", "o_totalprice", "o_orderdate", "l_quantity"])
+    big = two_phase(scan("lineitem", ["l_orderkey", "l_quantity"]), ["l_orderkey"], [("sum", col("l_quantity"), "q", D152)])
+    big = filter_(big, binop(">", col("q"), dec(min_qty * 100, 14, 2)), ["l_orderkey"])
+    j3 = hash_join(j2, big, [("o_orderkey", "l_orderkey")], join_type="left_semi")
+    a = two_phase(j3, ["c_name", "c_custkey", "o_orderkey", "o_orderdate", "o_totalprice"], [("sum", col("l_quantity"), "sum(l_quantity)", D152)])
+    return sort(a, [("o_totalprice", False), ("o_orderdate", True)], fetch=100)
+
+
+TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q12": q12, "q14": q14, "q18": q18, "q19": q19}

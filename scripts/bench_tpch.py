@@ -14,8 +14,8 @@ from sail_b200 import engine, plans  # noqa: E402
 NEEDED = {
     "lineitem": ["l_orderkey", "l_partkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus",
                  "l_shipdate", "l_commitdate", "l_receiptdate", "l_shipinstruct", "l_shipmode"],
-    "orders": ["o_orderkey", "o_custkey", "o_orderdate", "o_orderpriority", "o_shippriority"],
-    "customer": ["c_custkey", "c_nationkey", "c_mktsegment"],
+    "orders": ["o_orderkey", "o_custkey", "o_totalprice", "o_orderdate", "o_orderpriority", "o_shippriority"],
+    "customer": ["c_custkey", "c_nationkey", "c_mktsegment", "c_name"],
     "supplier": ["s_suppkey", "s_nationkey"],
     "part": ["p_partkey", "p_brand", "p_type", "p_size", "p_container"],
 }
@@ -44,7 +44,7 @@ def main():
     dev = {k: (engine.to_device(v, ctx), v.schema.names) for k, v in tables.items()}
     hbm = sum(v.nbytes for v in tables.values())
     results = {}
-    for q in ("q1", "q6", "q3", "q4", "q5", "q7", "q12", "q14", "q19"):
+    for q in ("q1", "q6", "q3", "q4", "q5", "q7", "q12", "q14", "q18", "q19"):
         plan = plans.TPCH[q]()
         try:
             times, stats = [], {}

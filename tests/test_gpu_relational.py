@@ -128,7 +128,7 @@ def test_hash_repartition(n_parts):
     op.close()
 
 
-@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q12", "q14", "q19"])
+@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q12", "q14", "q18", "q19"])
 def test_tpch_golden_on_gpu(q, golden):
     """whole plans through the C ABI on dbgen SF0.001 == the reference's own snapshot"""
     from datagen import tpch
@@ -146,6 +146,18 @@ def test_tpch_sf01_vs_oracle(q):
     got = plans.execute(plan, tables, gpu_op)
     want = plans.execute(plan, tables, oracle_op)
     assert_same(got, want, ordered=(q != "q3"))   # Q3's top-10 may tie on (revenue, date): compare as sets
+
+
+def test_tpch_q18_with_matches_vs_oracle():
+    """Q18 at the reference's threshold (313) selects nothing below SF1; at 250 the left-semi join, the five-key grouping
+    (18-byte customer names: long views) and the TopK all carry rows"""
+    from datagen import tpch
+    tables = tpch.tables(0.1)
+    plan = plans.q18(min_qty=250)
+    got = plans.execute(plan, tables, gpu_op)
+    want = plans.execute(plan, tables, oracle_op)
+    assert got.num_rows == 100
+    assert_same(got, want, ordered=True)
 
 
 def test_chain_operator_matches_separate_operators():
