@@ -527,6 +527,9 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
     }
     AA.hot_groups = best_hot;
     if (out.cold_variant) { AA.cold_only = 1; AA.reg_path = 0; }
+    // the register fast path keeps its groups in the CTA dictionary: without one (keys wider than HOT_KEY_WORDS words,
+    // or no shared memory left for it) every row has to take the general path
+    if (AA.hot_groups < REG_GROUPS) AA.reg_path = 0;
     AA.hot_smem_off = temps;
   }
   for (ProbeParams* pp : probe_params) {

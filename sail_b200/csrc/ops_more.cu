@@ -98,7 +98,7 @@ struct JoinOp : Op {
     }
     if (n == 0) return;
     brun.init(ctx, bs);
-    brun.custom_sink = [this](PipelineCompiler& pc, CompiledPipeline& cp) { pc.finish_build(cp, lkeys); };
+    brun.custom_sink = [this](PipelineCompiler& pc, CompiledPipeline& cp) { pc.finish_build(cp, lkeys); cp.extra_scratch = CHAIN_CACHE_BYTES; };
     auto cp = brun.compiled_for(*build);
     PipelineParams P;
     brun.prepare(P, *cp, *build, 0, n);
@@ -110,6 +110,7 @@ struct JoinOp : Op {
     aux.build.row_base = 0;
     aux.build.dup_flag = static_cast<uint32_t*>(dupflag->ptr);
     aux.build.next = static_cast<int64_t*>(next->ptr);
+    aux.build.smem_off = cp->scratch_off;
     for (size_t i = 0; i < lkeys.size(); ++i) {
       const DataType& kt = bs[(size_t)lkeys[i]].type;
       aux.build.key_cols[i] = static_cast<const uint8_t*>(build->cols[(size_t)lkeys[i]].data->ptr);
@@ -228,6 +229,7 @@ struct JoinOp : Op {
       return;
     }
     if (b->rows == 0) return;
+    if (swap_applies(*b)) { probe_swapped(b); return; }
     if (general_path()) { probe_general(b); return; }
     if (dup && (jt == "left_semi" || jt == "left_anti")) { mark_all_matches(b); return; }
     PipelineAux aux; memset(&aux, 0, sizeof(aux));
@@ -238,6 +240,62 @@ struct JoinOp : Op {
     aux.probe[0] = it->second;
     BatchPtr out = run_streaming(prun, ctx, b, m, &aux, build_heaps);
     if (probe_streams_output() && out->rows > 0) ready.push_back(out);
+  }
+
+  // ---- duplicate-heavy build side met by a tiny probe batch: execute with the roles exchanged --------------------------
+  // The duplicate path walks, for every probe row, the chain of build rows with its key -- one thread per probe row.  With
+  // a handful of probe rows against millions of build rows (the plans put the growing intermediate on the build side:
+  // TPC-H Q5 / Q7 join it with `nation`) that is a serial walk of ~10^6 dependent loads (measured 560 ms).  An inner join
+  // is symmetric, so such a batch runs through a nested join that builds on the probe batch and streams the build side:
+  // key pairs, residual filter and projection are re-indexed, the output schema is unchanged.  Output order follows the
+  // streamed side (the join reports maintains_input_order = false).
+  bool no_swap = false;
+  bool swap_applies(const DevBatch& b) const {
+    return !no_swap && dup && jt == "inner" && b.rows * 16 < build->rows && getenv("SAILGPU_NO_JOIN_SWAP") == nullptr;
+  }
+  static void remap_cols(Json& j, int nb, int np) {
+    if (j.kind == Json::Obj) {
+      for (auto& kv : j.o) {
+        if (kv.first == "col" && kv.second.kind == Json::Num) {
+          const int i = (int)kv.second.as_int();
+          kv.second.s = std::to_string(i < nb ? i + np : i - nb);
+        } else remap_cols(kv.second, nb, np);
+      }
+    } else if (j.kind == Json::Arr) {
+      for (auto& x : j.a) remap_cols(x, nb, np);
+    }
+  }
+  void probe_swapped(const BatchPtr& b) {
+    const int nb = (int)bs.size(), np = (int)ps.size();
+    auto sw = std::make_unique<JoinOp>();
+    sw->ctx = ctx; sw->kind = "hash_join"; sw->in_schemas = {ps, bs};
+    sw->bs = ps; sw->ps = bs; sw->jt = "inner"; sw->no_swap = true;
+    sw->lkeys = rkeys; sw->rkeys = lkeys;
+    sw->joined = ps;
+    for (auto& f : bs) sw->joined.push_back(f);
+    for (auto& f : sw->joined) f.nullable = true;
+    if (has_filter) { sw->filter_json = filter_json; remap_cols(sw->filter_json, nb, np); sw->has_filter = true; }
+    sw->has_proj = true;
+    const int n_out = has_proj ? (int)projection.size() : nb + np;
+    for (int k = 0; k < n_out; ++k) {
+      const int j = has_proj ? projection[(size_t)k] : k;
+      sw->projection.push_back(j < nb ? j + np : j - nb);
+    }
+    sw->out_schema = out_schema;
+    sw->push(0, b);
+    sw->finish(0);
+    sw->push(1, build);
+    sw->finish(1);
+    for (;;) {
+      BatchPtr o;
+      const bool more = sw->pull(&o);
+      if (o && o->rows > 0) ready.push_back(o);
+      if (!more) break;
+    }
+    m.kernel_launches += sw->m.kernel_launches;
+    m.pipeline_launches += sw->m.pipeline_launches;
+    for (auto& pe : sw->m.pending) m.pending.push_back(pe);
+    sw->m.pending.clear();
   }
 
   BatchPtr project_plain(const BatchPtr& b, int offset) {

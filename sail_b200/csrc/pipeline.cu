@@ -21,6 +21,7 @@ struct Smem {
   int32_t tile[2];
   int32_t hot_n;           // groups in the CTA-local hot dictionary
   int32_t elect;
+  uint32_t cache_count;    // BUILD: occupied entries of the CTA chain cache
   int32_t defer[2];        // AGG with a bounded table: "stop taking tiles" flag, double buffered across iterations
   unsigned long long tile_base;   // COMPACT: exclusive prefix of this tile
   uint32_t warp_sums[33];
@@ -1617,39 +1618,81 @@ __device__ __forceinline__ void chain_push(const BuildParams& B, uint8_t* slot, 
   B.next[last] = (long long)prev - 1;                            // -1 ends the chain
   if ((prev != 0 || first != last) && *reinterpret_cast<volatile uint32_t*>(B.dup_flag) == 0) atomicOr(B.dup_flag, 1u);
 }
-// inserts the pre-linked chain first..last (all rows carry `key`); returns the slot (nullptr when the table is full)
-__device__ __forceinline__ uint8_t* build_insert_one(const BuildParams& B, const KeyRegs& key, uint64_t h, long long first, long long last) {
+// Finds the slot of `key`, claiming an empty one if the key is new.  A claimer publishes its pre-linked chain first..last
+// at once (*pushed = true) so that later arrivals can verify their key against a row of the chain; for an existing key
+// the slot is returned and the caller decides where to push (CTA chain cache or the slot itself).  nullptr: table full.
+__device__ __forceinline__ uint8_t* build_find_or_claim(const BuildParams& B, const KeyRegs& key, uint64_t h, long long first, long long last, bool* pushed) {
   const unsigned long long tag = h | 1ull;
   uint64_t idx = (h >> 1) & B.capacity_mask;
+  *pushed = false;
   for (uint64_t probes = 0; probes <= B.capacity_mask; ++probes) {
     uint8_t* slot = B.table + idx * 16;
     unsigned long long t = ld_volatile_u64(slot);
     if (t == 0ull) {
       t = atomicCAS(reinterpret_cast<unsigned long long*>(slot), 0ull, tag);
-      if (t == 0ull) { chain_push(B, slot, first, last); return slot; }      // claimed an empty slot
+      if (t == 0ull) { chain_push(B, slot, first, last); *pushed = true; return slot; }      // claimed an empty slot
     }
     if (t == tag) {
-      // same tag: compare with a row that is already on the chain (the claimer publishes its row right after the CAS)
+      // same tag: compare with a row that is already on the chain (the claimer publishes its rows right after the CAS)
       unsigned long long head = ld_volatile_u64(slot + 8);
       for (uint32_t spins = 0; head == 0ull; ++spins) {
         if (spins > (1u << 24)) __trap();
         __nanosleep(20);
         head = ld_volatile_u64(slot + 8);
       }
-      if (build_row_has_key(B.keys, B.key_cols, B.key_stride, B.n_keys, (int64_t)head - 1, key)) { chain_push(B, slot, first, last); return slot; }
+      if (build_row_has_key(B.keys, B.key_cols, B.key_stride, B.n_keys, (int64_t)head - 1, key)) return slot;
     }
     idx = (idx + 1) & B.capacity_mask;
   }
   return nullptr;
 }
 
+// CTA chain cache (shared memory, lives for the whole kernel): chains for keys that already own a slot are collected
+// per CTA and pushed on the slot once -- at the end of the kernel, or when the cache runs full.  A build side with a
+// handful of distinct keys (a fact-like intermediate joined to a dimension: TPC-H Q5 / Q7 shapes) otherwise funnels
+// millions of atomic exchanges into a few addresses (measured 37 ns each: 560 ms for an 18 M-row build).
+struct ChainCacheEntry { unsigned long long slot, first; long long last; };
+constexpr int CHAIN_CACHE_ENTRIES = 512;
+__device__ __forceinline__ bool chain_cache_push(const BuildParams& B, ChainCacheEntry* cache, uint32_t* count, uint8_t* slot, long long first, long long last) {
+  const unsigned long long sp = reinterpret_cast<unsigned long long>(slot);
+  uint32_t idx = (uint32_t)mix64(sp) & (CHAIN_CACHE_ENTRIES - 1);
+  for (int probe = 0; probe < 8; ++probe) {
+    ChainCacheEntry* e = cache + idx;
+    const unsigned long long s = atomicCAS(&e->slot, 0ull, sp);
+    if (s == 0ull) atomicAdd(count, 1u);
+    if (s == 0ull || s == sp) {
+      const unsigned long long prev = atomicExch(&e->first, (unsigned long long)(first + 1));
+      if (prev == 0ull) e->last = last;                  // this chain is the bottom of the cached stack
+      else B.next[last] = (long long)prev - 1;
+      return true;
+    }
+    idx = (idx + 1) & (CHAIN_CACHE_ENTRIES - 1);
+  }
+  return false;
+}
+// all threads of the CTA; ends with a barrier
+__device__ __forceinline__ void chain_cache_flush(const BuildParams& B, ChainCacheEntry* cache, uint32_t* count) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < CHAIN_CACHE_ENTRIES; i += NT) {
+    ChainCacheEntry* e = cache + i;
+    if (e->slot) {
+      chain_push(B, reinterpret_cast<uint8_t*>(e->slot), (long long)e->first - 1, e->last);
+      e->slot = 0ull; e->first = 0ull;
+    }
+  }
+  if (threadIdx.x == 0) *count = 0;
+  __syncthreads();
+}
+
 // HashJoinExec build: one slot per DISTINCT key; rows with an equal key are pushed on the slot's chain (next[]).
-// Lanes of a warp that carry the same key are linked to each other first (__match_any_sync) and pushed with ONE
-// exchange, so a build side with few distinct keys costs one atomic per (warp, key).
+// Lanes of a warp that carry the same key are linked to each other first (__match_any_sync); the lowest lane of each
+// group then either claims the key's slot and publishes the group's chain, or -- the key exists already -- parks the
+// chain in the CTA chain cache.
 template <int RPT>
-__device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildParams& B, const TileCtx& c) {
+__device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildParams& B, const TileCtx& c, Smem* sm) {
   const uint8_t* pact = P.mask_slot == NO_SLOT ? nullptr : c.arena + eff(c, P.mask_slot);
   const int lane = threadIdx.x & 31;
+  ChainCacheEntry* cache = reinterpret_cast<ChainCacheEntry*>(c.arena + B.smem_off);
   for (int k = 0; k < RPT; ++k) {
     const int r = threadIdx.x + k * NT;
     const bool live = r < c.nrows && (pact == nullptr || pact[r]);
@@ -1660,26 +1703,28 @@ __device__ __forceinline__ void sink_build(const PipelineParams& P, const BuildP
     const unsigned long long tag = h | 1ull;
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, ins ? tag : (0xFFFFFFFFFFFFFF00ull | (unsigned)lane) & ~1ull);
     const int leader = __ffs(peers) - 1;
-    // step A: the leader of every distinct hash inserts its own row
-    uint8_t* slot = nullptr;
-    if (ins && lane == leader) slot = build_insert_one(B, key, h, row, row);
-    const unsigned long long slot_bits = __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(slot), leader);
     const long long leader_row = __shfl_sync(0xFFFFFFFFu, row, leader);
-    slot = reinterpret_cast<uint8_t*>(slot_bits);
-    // step B: followers whose key really equals the leader's are linked in lane order and pushed once
-    const bool follower = ins && lane != leader && slot != nullptr;
+    // members of a group: the leader and the peers whose key really equals the leader's (equal hash is not enough)
+    const bool follower = ins && lane != leader;
     const bool same = follower && build_row_has_key(B.keys, B.key_cols, B.key_stride, B.n_keys, (int64_t)leader_row, key);
-    const unsigned chain = __ballot_sync(0xFFFFFFFFu, same) & peers;
-    if (same) {
-      const unsigned above = chain & ~((2u << lane) - 1);       // verified peers in higher lanes
+    const bool member = ins && (lane == leader || same);
+    const unsigned cm = __ballot_sync(0xFFFFFFFFu, member) & peers;
+    long long last_row = row;
+    if (member) {
+      const unsigned above = cm & ~((2u << lane) - 1);          // members in higher lanes: link in lane order
       const int nxt = above ? __ffs(above) - 1 : -1;
-      const long long next_row = __shfl_sync(chain, row, nxt >= 0 ? nxt : lane);
+      const long long next_row = __shfl_sync(cm, row, nxt >= 0 ? nxt : lane);
       if (nxt >= 0) B.next[row] = next_row;
-      const int first = __ffs(chain) - 1, last = 31 - __clz(chain);
-      const long long last_row = __shfl_sync(chain, row, last);
-      if (lane == first) chain_push(B, slot, row, last_row);
-    } else if (follower) {
-      build_insert_one(B, key, h, row, row);                    // same hash, different key (64-bit collision)
+      last_row = __shfl_sync(cm, row, 31 - __clz(cm));
+    }
+    if (member && lane == leader) {
+      bool pushed;
+      uint8_t* slot = build_find_or_claim(B, key, h, row, last_row, &pushed);
+      if (slot && !pushed && !chain_cache_push(B, cache, &sm->cache_count, slot, row, last_row)) chain_push(B, slot, row, last_row);
+    } else if (follower && !same) {                             // same hash, different key (64-bit collision)
+      bool pushed;
+      uint8_t* slot = build_find_or_claim(B, key, h, row, row, &pushed);
+      if (slot && !pushed) chain_push(B, slot, row, row);
     }
   }
 }
@@ -1808,6 +1853,11 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
     sm->defer[0] = guarded ? table_full() : 0;
   }
   if (KC == KC_AGG) hot_init(K.aux[0].agg, arena);
+  if (KC == KC_OTHER && P0.sink == SINK_BUILD) {
+    unsigned long long* z = reinterpret_cast<unsigned long long*>(arena + K.aux[0].build.smem_off);
+    for (int i = threadIdx.x; i < CHAIN_CACHE_ENTRIES * 3; i += NT) z[i] = 0ull;
+    if (threadIdx.x == 0) sm->cache_count = 0;
+  }
   __syncthreads();
 
   uint32_t tma_bytes = 0;
@@ -1884,13 +1934,17 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
       switch (P.sink) {
         case SINK_STORE: sink_store<RPT>(P, c); break;
         case SINK_COMPACT: sink_compact<RPT>(P, c, sm, (int)cur_tile); break;
-        case SINK_BUILD: sink_build<RPT>(P, aux->build, c); break;
+        case SINK_BUILD: sink_build<RPT>(P, aux->build, c, sm); break;
         case SINK_PARTITION: sink_partition<RPT>(P, aux->part, c); break;
         default: break;
       }
     }
     if (guarded && threadIdx.x == 0) sm->defer[(it + 1) & 1] = g_now > K.aux[0].agg.group_limit ? 1 : 0;
+    if (KC == KC_OTHER && P.sink == SINK_BUILD && threadIdx.x == 0) sm->defer[(it + 1) & 1] = sm->cache_count > CHAIN_CACHE_ENTRIES / 2 ? 1 : 0;
     __syncthreads();                                          // (B) stage s and scratch are free again
+    if (KC == KC_OTHER && P.sink == SINK_BUILD && sm->defer[(it + 1) & 1]) {      // crowded cache: push everything, start over
+      chain_cache_flush(aux->build, reinterpret_cast<ChainCacheEntry*>(arena + aux->build.smem_off), &sm->cache_count);
+    }
     if (guarded) {
       const bool was = defer;
       defer = sm->defer[(it + 1) & 1] != 0;
@@ -1900,6 +1954,8 @@ __global__ void __launch_bounds__(NT, MINB) pipeline_kernel(const __grid_constan
     if (n_stages == 1 && nxt < n_end && issue(dynamic ? nxt : tile_of(nxt), 0)) __syncthreads();
     cur = nxt;
   }
+  if (KC == KC_OTHER && P0.sink == SINK_BUILD)
+    chain_cache_flush(K.aux[0].build, reinterpret_cast<ChainCacheEntry*>(arena + K.aux[0].build.smem_off), &sm->cache_count);
   if constexpr (KC == KC_AGG) {
     if (K.aux[0].agg.reg_path) { HotView H = hot_view(K.aux[0].agg, arena); reg_flush(K.aux[0].agg, H, R, sm->hot_n); }
     hot_flush(P0, K.aux[0].agg, arena, sm);

@@ -188,7 +188,9 @@ struct BuildParams {
   int64_t* next;           // next[row] = next build row with the same key (-1 ends the chain): duplicates cost O(1)
   const uint8_t* key_cols[MAX_KEYS];   // build key columns (to tell "same key" from "same hash" while inserting)
   uint8_t key_stride[MAX_KEYS];
+  uint32_t smem_off;       // arena offset of the CTA chain cache (CHAIN_CACHE_BYTES)
 };
+constexpr uint32_t CHAIN_CACHE_BYTES = 512 * 24;
 
 struct PartitionParams {
   int32_t n_parts;

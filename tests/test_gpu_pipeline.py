@@ -110,7 +110,7 @@ def test_filter_two_pass_matches_single_pass(monkeypatch):
 
 @pytest.mark.parametrize("n", [0, 1, 999, 50000])
 @pytest.mark.parametrize("nulls", [False, True])
-@pytest.mark.parametrize("keys", [[], ["b"], ["s"], ["b", "s", "dt"]])
+@pytest.mark.parametrize("keys", [[], ["b"], ["s"], ["b", "s", "dt"], ["s", "d", "b"]])      # the last one: 5 key words (no CTA dictionary)
 def test_aggregate_single(n, nulls, keys):
     t = make_table(n, seed=n + 2, nulls=nulls)
     aggs = [("sum", "d"), ("avg", "d"), ("count", None), ("count", "a"), ("min", "a"), ("max", "d"), ("sum", "a"), ("avg", "f"), ("sum", "f"), ("min", "dt")]
@@ -119,6 +119,17 @@ def test_aggregate_single(n, nulls, keys):
             "aggs": [{"fn": fn, "args": [] if c is None else [resolve(C(c), t)], "name": f"{fn}_{c}"} for fn, c in aggs]}
     nk = len(keys)
     assert_same(gpu_op(spec, t), oracle_op(spec, t), float_cols={nk + 7, nk + 8})
+
+
+@pytest.mark.parametrize("nulls", [False, True])
+def test_aggregate_wide_keys_integer_sums(nulls):
+    """sums/counts that qualify for the register fast path, but grouped by more key words than the CTA dictionary holds
+    (TPC-H Q7's shape: two strings + a year): must take the general path"""
+    t = make_table(30011, seed=77, nulls=nulls)
+    names = t.schema.names
+    spec = {"op": "aggregate", "mode": "single", "group_by": [{"expr": {"col": names.index(c)}, "name": c} for c in ("s", "d", "b")],
+            "aggs": [{"fn": "sum", "args": [{"col": names.index("a")}], "name": "sa"}, {"fn": "count", "args": [], "name": "c"}]}
+    assert_same(gpu_op(spec, t), oracle_op(spec, t))
 
 
 def test_two_phase_aggregate():

@@ -61,6 +61,22 @@ def test_hash_join_duplicate_build_keys(jt):
     assert_same(gpu_op(spec, l, r), oracle_op(spec, l, r), float_cols={7})
 
 
+@pytest.mark.parametrize("nulls", [False, True])
+@pytest.mark.parametrize("with_filter", [False, True])
+@pytest.mark.parametrize("proj", [None, [5, 2, 0, 7]])
+def test_hash_join_few_probe_rows_against_duplicate_heavy_build(nulls, with_filter, proj):
+    """a handful of probe rows (with a repeated key) against a build side of 40 000 rows over 12 keys: the operator runs
+    such batches with the roles exchanged (no per-probe-row walk of 3 000-row chains); content must be unchanged"""
+    rng = np.random.default_rng(11)
+    n = 40000
+    l = left_table(n, 21, False, nulls)
+    l = l.set_column(0, "lk", pa.array((rng.integers(0, 12, n) * 3).astype(np.int64), mask=(rng.random(n) < 0.05) if nulls else None))
+    r = right_table(9, 22, 14, nulls)                      # 9 probe rows, keys in {0,3,..,39}: repeats and misses
+    spec = {"op": "hash_join", "join_type": "inner", "on": [[0, 0]], "projection": proj,
+            "filter": plans.binop(">", {"col": 2}, plans.dec(500000, 15, 2)) if with_filter else None}
+    assert_same(gpu_op(spec, l, r), oracle_op(spec, l, r), float_cols={3} if proj else {7})
+
+
 def test_hash_join_two_keys_projection_and_filter():
     l, r = left_table(1500, 5, False, False), right_table(8000, 6, 1500, False)
     spec = {"op": "hash_join", "join_type": "inner", "on": [[0, 0], [1, 1]], "filter": None, "projection": [2, 3, 6]}
