@@ -3,7 +3,7 @@
 Each node is the JSON object a Rust `ExecutionPlan` shim would hand to `sailgpu_op_create`
 (include/sailgpu.h) for the DataFusion operator it replaces.  The shapes follow the reference's
 plan snapshots (python/pysail/tests/spark/__snapshots__/test_tpch.plan.yaml): Q1 `:3-19`,
-Q3 `:72-97`, Q4 `:99-118`, Q5 `:120-156`, Q6, Q12 -- minus the rename-only ProjectionExecs and
+Q3 `:72-97`, Q4 `:99-118`, Q5 `:120-156`, Q6, Q7 `:172-209`, Q12, Q14 `:409-425`, Q18 `:529-557`, Q19 `:559-575` -- minus the rename-only ProjectionExecs and
 the RoundRobinBatch fan-out that pre-sharded tables make unnecessary.
 
 The tree is engine-agnostic: `execute(plan, tables, run_op)` drives it with any callable that maps

@@ -1,5 +1,5 @@
 """GPU parity for HashJoinExec, SortExec/TopK, hash RepartitionExec and whole TPC-H plans
-(Q1,Q3,Q4,Q5,Q6,Q12) through the C ABI, against the oracle and the reference's golden snapshots."""
+(Q1,Q3,Q4,Q5,Q6,Q7,Q12,Q14,Q18,Q19) through the C ABI, against the oracle and the reference's golden snapshots."""
 import decimal
 
 import numpy as np
