@@ -274,6 +274,37 @@ def q5(strings="Utf8View") -> Node:
     return sort(a, [("revenue", False)])
 
 
+def q8(strings="Utf8View") -> Node:
+    """test_tpch.plan.yaml:211-258: seven joins (part -> lineitem -> supplier -> orders -> customer -> nation n1 -> nation n2 ->
+    region), market share = ratio of two sums per order year."""
+    pt = filter_(scan("part", ["p_partkey", "p_type"]), binop("=", col("p_type"), string("LARGE PLATED STEEL", strings)), ["p_partkey"])
+    li = scan("lineitem", ["l_orderkey", "l_partkey", "l_suppkey", "l_extendedprice", "l_discount"])
+    ja = hash_join(pt, li, [("p_partkey", "l_partkey")], projection=["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"])
+    supp = scan("supplier", ["s_suppkey", "s_nationkey"])
+    jb = hash_join(supp, ja, [("s_suppkey", "l_suppkey")], projection=["s_nationkey", "l_orderkey", "l_extendedprice", "l_discount"])
+    jb = project(jb, ["l_orderkey", "l_extendedprice", "l_discount", "s_nationkey"])
+    ords = filter_(scan("orders", ["o_orderkey", "o_custkey", "o_orderdate"]),
+                   and_(binop(">=", col("o_orderdate"), date("1995-01-01")), binop("<=", col("o_orderdate"), date("1996-12-31"))))
+    jc = hash_join(jb, ords, [("l_orderkey", "o_orderkey")],
+                   projection=["l_extendedprice", "l_discount", "s_nationkey", "o_custkey", "o_orderdate"])
+    cust = scan("customer", ["c_custkey", "c_nationkey"])
+    jd = hash_join(jc, cust, [("o_custkey", "c_custkey")],
+                   projection=["l_extendedprice", "l_discount", "s_nationkey", "o_orderdate", "c_nationkey"])
+    n1 = project(scan("nation", ["n_nationkey", "n_regionkey"]), [(col("n_nationkey"), "n1_key"), (col("n_regionkey"), "n1_region")])
+    je = hash_join(n1, jd, [("n1_key", "c_nationkey")],
+                   projection=["n1_region", "l_extendedprice", "l_discount", "s_nationkey", "o_orderdate"])
+    je = project(je, ["l_extendedprice", "l_discount", "s_nationkey", "o_orderdate", "n1_region"])
+    n2 = project(scan("nation", ["n_nationkey", "n_name"]), [(col("n_nationkey"), "n2_key"), (col("n_name"), "n2_name")])
+    jf = hash_join(je, n2, [("s_nationkey", "n2_key")], projection=["l_extendedprice", "l_discount", "o_orderdate", "n1_region", "n2_name"])
+    reg = filter_(scan("region", ["r_regionkey", "r_name"]), binop("=", col("r_name"), string("MIDDLE EAST", strings)), ["r_regionkey"])
+    jg = hash_join(reg, jf, [("r_regionkey", "n1_region")], projection=["l_extendedprice", "l_discount", "o_orderdate", "n2_name"])
+    p = project(jg, [({"fn": "date_part", "part": "year", "args": [col("o_orderdate")]}, "o_year"), (DISC_PRICE, "volume"), (col("n2_name"), "nation")])
+    iraq = {"case": [[binop("=", col("nation"), string("IRAQ", strings)), col("volume")]], "else": lit(0, "Int32")}
+    a = two_phase(p, ["o_year"], [("sum", iraq, "iraq", "Decimal128(32,4)"), ("sum", col("volume"), "total", "Decimal128(32,4)")])
+    r = project(a, ["o_year", (binop("/", col("iraq"), col("total")), "mkt_share")])
+    return sort(r, [("o_year", True)])
+
+
 def q12(strings="Utf8View") -> Node:
     li = filter_(scan("lineitem", ["l_orderkey", "l_shipdate", "l_commitdate", "l_receiptdate", "l_shipmode"]),
                  and_(or_(binop("=", col("l_shipmode"), string("FOB", strings)),
@@ -387,4 +418,4 @@ def q18(strings="Utf8View", min_qty=313) -> Node:
     return sort(a, [("o_totalprice", False), ("o_orderdate", True)], fetch=100)
 
 
-TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q12": q12, "q14": q14, "q18": q18, "q19": q19}
+TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q8": q8, "q12": q12, "q14": q14, "q18": q18, "q19": q19}

@@ -44,7 +44,7 @@ def main():
     dev = {k: (engine.to_device(v, ctx), v.schema.names) for k, v in tables.items()}
     hbm = sum(v.nbytes for v in tables.values())
     results = {}
-    for q in ("q1", "q6", "q3", "q4", "q5", "q7", "q12", "q14", "q18", "q19"):
+    for q in ("q1", "q6", "q3", "q4", "q5", "q7", "q8", "q12", "q14", "q18", "q19"):
         plan = plans.TPCH[q]()
         try:
             times, stats = [], {}

@@ -144,7 +144,7 @@ def test_hash_repartition(n_parts):
     op.close()
 
 
-@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q12", "q14", "q18", "q19"])
+@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q8", "q12", "q14", "q18", "q19"])
 def test_tpch_golden_on_gpu(q, golden):
     """whole plans through the C ABI on dbgen SF0.001 == the reference's own snapshot"""
     from datagen import tpch
@@ -154,7 +154,7 @@ def test_tpch_golden_on_gpu(q, golden):
     assert render.rows(got) == golden[q]["rows"]
 
 
-@pytest.mark.parametrize("q", ["q3", "q4", "q5", "q7", "q12", "q14", "q19"])
+@pytest.mark.parametrize("q", ["q3", "q4", "q5", "q7", "q8", "q12", "q14", "q19"])
 def test_tpch_sf01_vs_oracle(q):
     from datagen import tpch
     tables = tpch.tables(0.1)
