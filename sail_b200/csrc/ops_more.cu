@@ -305,7 +305,27 @@ struct JoinOp : Op {
     for (int p : projection) out->cols.push_back(b->cols[(size_t)(p - offset)]);
     return out;
   }
-  BatchPtr right_outer_nulls(const BatchPtr&) { fail(SAILGPU_ERR_UNSUPPORTED, "right outer join with an empty build side is not supported yet"); }
+  // right outer join against an empty build side: every probe row, build columns all NULL
+  BatchPtr right_outer_nulls(const BatchPtr& b) {
+    SG_CHECK(!has_filter, SAILGPU_ERR_UNSUPPORTED, "residual join filter with join_type 'right' is not supported yet");
+    const int64_t n = b->rows;
+    auto full = std::make_shared<DevBatch>();
+    full->rows = n;
+    for (auto& f : bs) {
+      DevColumn c; c.type = f.type; c.length = n; c.arrow_is_utf8 = f.type.id == TypeId::Utf8;
+      const size_t w = f.type.id == TypeId::Bool ? 0 : f.type.is_string() ? 16 : (size_t)f.type.arrow_width();
+      c.data = dev_alloc_zero(ctx, w ? (size_t)n * w : (size_t)((n + 31) / 32 * 4));      // zero views = empty strings
+      c.validity = dev_alloc_zero(ctx, (size_t)((n + 31) / 32 * 4));
+      c.null_count = n;
+      full->cols.push_back(c);
+    }
+    for (auto& c : b->cols) full->cols.push_back(c);
+    if (!has_proj) return full;
+    auto out = std::make_shared<DevBatch>();
+    out->rows = n;
+    for (int p : projection) out->cols.push_back(full->cols[(size_t)p]);
+    return out;
+  }
 
   // ---- duplicate build keys: count / scan / emit / gather ------------------------------------------
   void fill_raw(RawKeyCol* dst, const DevBatch& bt, const std::vector<int>& keys, const Schema& sch) {

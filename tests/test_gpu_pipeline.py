@@ -97,6 +97,22 @@ def test_filter_two_pass(n, nulls, monkeypatch):
     assert_same(gpu_op(spec, t), want, ordered=True)
 
 
+def test_filter_large_batch_order_and_content_vs_numpy():
+    """8 M rows through the default (two-pass) FilterExec path: exactly the rows numpy selects, in input order"""
+    n = 8_000_003
+    rng = np.random.default_rng(123)
+    a = rng.integers(0, 1000, n).astype(np.int64)
+    b = rng.integers(0, 100, n).astype(np.int32)
+    t = pa.table({"a": pa.array(a), "b": pa.array(b), "i": pa.array(np.arange(n, dtype=np.int64))})
+    for lo, hi in ((0, 1000), (10, 20), (999, 1000), (1000, 1001)):          # everything / 1 % / 0.1 % / nothing
+        pred = plans.and_(plans.binop(">=", {"col": 0}, plans.lit(lo, "Int64")), plans.binop("<", {"col": 0}, plans.lit(hi, "Int64")))
+        got = gpu_op({"op": "filter", "predicate": pred, "projection": [2, 1]}, t)
+        keep = (a >= lo) & (a < hi)
+        assert got.num_rows == int(keep.sum())
+        assert np.array_equal(got.column(0).to_numpy(), np.nonzero(keep)[0])
+        assert np.array_equal(got.column(1).to_numpy(), b[keep])
+
+
 def test_filter_two_pass_matches_single_pass(monkeypatch):
     t = make_table(400001, seed=77, nulls=True)
     spec = {"op": "filter", "predicate": resolve(plans.binop("<", C("b"), plans.lit(3, "Int32")), t), "projection": [0, 1, 2, 4]}

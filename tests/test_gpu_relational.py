@@ -43,8 +43,6 @@ def right_table(n, seed, key_range, nulls):
 def test_hash_join_unique_build(jt, nulls, nl, nr):
     l, r = left_table(nl, 1, False, nulls), right_table(nr, 2, max(nl, 1) * 2, nulls)
     spec = {"op": "hash_join", "join_type": jt, "on": [[0, 0]], "filter": None, "projection": None}
-    if jt == "right" and nl == 0:
-        pytest.skip("right outer with empty build: documented as unsupported")
     assert_same(gpu_op(spec, l, r), oracle_op(spec, l, r), float_cols={7})
 
 
