@@ -93,7 +93,7 @@ using BatchPtr = std::shared_ptr<DevBatch>;
 Schema schema_from_arrow(const ArrowSchema* s);
 void schema_to_arrow(const Schema& s, ArrowSchema* out);
 
-// Host ArrowArray (struct) -> HBM.  Copies on ctx->copy_stream, then makes ctx->stream wait.
+// Host ArrowArray (struct) -> HBM.  Copies are issued on ctx->stream (one stream: allocation, copies and kernels stay ordered).
 BatchPtr import_host_batch(Ctx* ctx, const Schema& schema, ArrowArray* arr);
 // Device ArrowDeviceArray -> batch without copying values (string views are copied + resolved).
 BatchPtr import_device_batch(Ctx* ctx, const Schema& schema, ArrowDeviceArray* arr);
