@@ -219,6 +219,7 @@ struct PipelineOp : Op {
   static uint64_t min_capacity() { const char* v = getenv("SAILGPU_AGG_MIN_CAPACITY"); return v && *v ? next_pow2((uint64_t)atoll(v)) : MIN_CAPACITY; }
   bool use_cold = false;
   int64_t rows_in_table = 0;
+  int64_t known_groups = -1;      // group count read (and error flag checked) by the last resolve_pending(), -1 = stale
   struct Pending { BatchPtr batch; std::shared_ptr<CompiledPipeline> cp; BufPtr deferred; int64_t n_tiles = 0; bool active = false; } pend;
 
   unsigned long long* n_deferred_ptr() { return reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(run.scal.buf->ptr) + 40); }
@@ -295,6 +296,7 @@ struct PipelineOp : Op {
     BufPtr deferred = grouped ? dev_alloc(ctx, (size_t)n_tiles * 4) : nullptr;
     launch_agg(cp, *b, nullptr, 0, deferred);
     rows_in_table += b->rows;
+    known_groups = -1;
     if (grouped) { pend.batch = b; pend.cp = cp; pend.deferred = deferred; pend.n_tiles = n_tiles; pend.active = true; }
   }
 
@@ -307,7 +309,7 @@ struct PipelineOp : Op {
       SG_CUDA(cudaMemcpyAsync(gd, run.scal.n_groups(), 24, cudaMemcpyDeviceToHost, ctx->stream));
       check_device_error(ctx, run.scal.error());   // synchronises
       const uint64_t groups = gd[0], n_def = gd[2];
-      if (n_def == 0) break;
+      if (n_def == 0) { known_groups = (int64_t)groups; break; }      // extract_agg() right after needs no second read-back
       const int64_t tile_rows = (int64_t)pend.cp->rpt * NT;
       const double rows_def = (double)std::min<int64_t>((int64_t)n_def * tile_rows, pend.batch->rows);
       const double rows_done = std::max(1.0, (double)rows_in_table - rows_def);
@@ -341,7 +343,10 @@ struct PipelineOp : Op {
     const AggParams& A0 = cp->agg;
     run.ensure_scratch();
     uint64_t groups = 0;
-    if (tab.capacity) { check_device_error(ctx, run.scal.error()); groups = read_n_groups(); }
+    if (tab.capacity) {
+      if (known_groups >= 0) groups = (uint64_t)known_groups;
+      else { check_device_error(ctx, run.scal.error()); groups = read_n_groups(); }
+    }
     const bool synth = A0.n_keys == 0 && groups == 0;   // global aggregate over zero rows: one row of NULLs / zero counts
     const int64_t rows = synth ? 1 : (int64_t)groups;
     auto out = std::make_shared<DevBatch>();
