@@ -150,6 +150,21 @@ def run_query_dist(backend, specs, inputs, in_schema, host_chunks=None):
     from sail_b200 import dist as sdist
     from sail_b200 import engine
     fused, final, sort = specs
+    if not os.environ.get("SAILGPU_DIST_PYTHON"):
+        # the whole plan, exchanges included, as one chain inside the library (the step-by-step driver below is kept for
+        # comparison: SAILGPU_DIST_PYTHON=1)
+        op = engine.GpuExec(sdist.two_phase_chain(fused, final, [0, 1], [sort]), [in_schema], backend.ctx)
+        if host_chunks is None:
+            for d in inputs:
+                op.push(d.borrow())
+        else:
+            for b in host_chunks:
+                op.push(b)
+        op.finish()
+        out = op.collect()
+        mm = op.metrics()
+        op.close()
+        return (out if backend.rank == 0 else None), mm["gpu.kernel_launches"], mm["gpu.pipeline_kernel_ns"], mm["gpu.pipeline_launches"]
     op1 = engine.GpuExec(fused, [in_schema], backend.ctx)
     if host_chunks is None:
         for d in inputs:
@@ -362,7 +377,7 @@ def main():
             "config": {"workload": f"TPC-H Q1 SF{args.sf:g} per GPU, 1 partition per GPU, Arrow batches resident in HBM",
                        "rows_per_gpu": n_rows, "strings": "Utf8View", "l2": "inputs (6 GB) larger than L2; no flush",
                        "plan": "GpuChainExec{GpuPipelineExec[Filter+Projection+Aggregate(Partial)] -> GpuAggregateExec(FinalPartitioned)"
-                               + (" -> GpuRepartitionExec(Hash) -> NCCL all-to-all" if world > 1 else "")
+                               + (" -> GpuExchangeExec(auto: coalesce on rank 0 | Hash + NCCL all-to-all)" if world > 1 else "")
                                + (" -> GpuSortExec" if SORT_ON_GPU else "") + "}", "parallelism": f"{world} rank(s), lineitem sharded by order range"},
             "e2e": None if e2e_value is None else {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                                                     "ms_per_step": ms_e / e2e_steps, "host_batches": len(chunks)},

@@ -412,6 +412,7 @@ std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<S
 std::unique_ptr<Op> make_sort_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_chain_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
+std::unique_ptr<Op> make_exchange_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 
 std::unique_ptr<Op> make_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs, int partition) {
   (void)partition;
@@ -420,6 +421,7 @@ std::unique_ptr<Op> make_op(Ctx* ctx, const Json& spec, const std::vector<Schema
   if (kind == "sort") return make_sort_op(ctx, spec, inputs);
   if (kind == "repartition") return make_repartition_op(ctx, spec, inputs);
   if (kind == "chain") return make_chain_op(ctx, spec, inputs);
+  if (kind == "exchange") return make_exchange_op(ctx, spec, inputs);
   SG_CHECK(inputs.size() == 1, SAILGPU_ERR_INVALID, "operator '" + kind + "' takes exactly one input");
   auto op = std::make_unique<PipelineOp>();
   op->ctx = ctx; op->kind = kind; op->in_schemas = inputs;

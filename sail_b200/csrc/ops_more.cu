@@ -750,6 +750,96 @@ std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::v
 
 
 // ================================================================================================
+// ExchangeOp -- the shuffle boundary as an operator, so that a whole two-phase aggregation
+//   [partial] -> exchange(auto) -> [final] -> exchange(gather) -> [sort]
+// runs as ONE chain inside the library: no host round trip, no Arrow export/import between the stages.
+//   mode "hash":   RepartitionExec Hash(exprs, world) + all-to-all (partition p -> rank p)
+//   mode "gather": everything to rank `root` (CoalescePartitionsExec / InputMode::Merge)
+//   mode "auto":   hash, unless every rank holds at most `small_rows` rows -- then gather (a handful of partial rows per
+//                  rank, TPC-H Q1: hashing them costs a second exchange for nothing).  The choice is taken on an
+//                  all-gather of the row counts, so every rank takes the same one; a later "gather" exchange of the same
+//                  chain sees that the rows already sit on the root and does not communicate.
+// ================================================================================================
+BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts);
+int64_t exchange_max_rows(Ctx* ctx, int64_t mine);
+std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
+
+struct ExchangeOp : Op {
+  std::string mode = "gather";
+  int root = 0;
+  int64_t small_rows = 1 << 14;
+  Json exprs_json;
+  std::vector<BatchPtr> parts_in;
+  BatchPtr result;
+  bool done = false, pulled = false;
+  bool* on_root_hint = nullptr;     // shared by the exchanges of one chain (owned by the ChainOp)
+
+  void push(int input, const BatchPtr& b) override {
+    SG_CHECK(input == 0, SAILGPU_ERR_INVALID, "exchange has one input");
+    m.input_rows += (uint64_t)b->rows; m.input_batches++;
+    if (b->rows) parts_in.push_back(b);
+  }
+  void finish(int) override {
+    const uint64_t t0 = now_ns();
+    const Schema& sch = in_schemas[0];
+    BatchPtr all = parts_in.empty() ? empty_batch(ctx, sch) : concat_batches(ctx, sch, parts_in);
+    parts_in.clear();
+    const int W = ctx->world;
+    if (W == 1) { result = all; done = true; return; }
+    std::string how = mode;
+    if (how == "auto") how = exchange_max_rows(ctx, all->rows) <= small_rows ? "gather" : "hash";
+    if (how == "gather" && mode == "gather" && on_root_hint && *on_root_hint) {       // an "auto" exchange of this chain already coalesced on the root
+      result = all; done = true; return;
+    }
+    std::vector<BatchPtr> parts((size_t)W);
+    if (how == "gather") {
+      for (int p = 0; p < W; ++p) parts[(size_t)p] = p == root ? all : empty_batch(ctx, sch);
+      if (on_root_hint) *on_root_hint = mode == "auto";
+    } else {
+      if (on_root_hint) *on_root_hint = false;
+      Json spec; spec.kind = Json::Obj;
+      Json opk; opk.kind = Json::Str; opk.s = "repartition";
+      Json sc; sc.kind = Json::Str; sc.s = "hash";
+      Json nn; nn.kind = Json::Num; nn.s = std::to_string(W);
+      spec.o = {{"op", opk}, {"scheme", sc}, {"exprs", exprs_json}, {"n", nn}};
+      auto rp = make_repartition_op(ctx, spec, {sch});
+      if (all->rows) rp->push(0, all);
+      rp->finish(0);
+      for (int p = 0; p < W; ++p) {
+        std::vector<BatchPtr> segs;
+        for (;;) { BatchPtr b; const bool more = rp->pull_partition(p, &b); if (b && b->rows) segs.push_back(b); if (!more) break; }
+        parts[(size_t)p] = segs.empty() ? empty_batch(ctx, sch) : segs.size() == 1 ? segs[0] : concat_batches(ctx, sch, segs);
+      }
+      m.kernel_launches += rp->m.kernel_launches;
+    }
+    result = exchange_batches(ctx, sch, parts);
+    done = true;
+    m.elapsed_compute_ns += now_ns() - t0;
+  }
+  bool pull(BatchPtr* out) override {
+    *out = nullptr;
+    if (done && !pulled) { *out = result; pulled = true; m.output_rows += (uint64_t)result->rows; m.output_batches++; result.reset(); }
+    return !pulled;
+  }
+};
+
+std::unique_ptr<Op> make_exchange_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs) {
+  SG_CHECK(inputs.size() == 1, SAILGPU_ERR_INVALID, "exchange takes one input");
+  auto op = std::make_unique<ExchangeOp>();
+  op->ctx = ctx; op->kind = "exchange"; op->in_schemas = inputs; op->out_schema = inputs[0];
+  const Json* md = spec.find("mode");
+  if (md) op->mode = md->as_str();
+  SG_CHECK(op->mode == "hash" || op->mode == "gather" || op->mode == "auto", SAILGPU_ERR_INVALID, "exchange mode must be hash, gather or auto");
+  const Json* rt = spec.find("root"); if (rt && !rt->is_null()) op->root = (int)rt->as_int();
+  const Json* sr = spec.find("small_rows"); if (sr && !sr->is_null()) op->small_rows = sr->as_int();
+  if (op->mode != "gather") {
+    op->exprs_json = spec.at("exprs");
+    for (auto& e : op->exprs_json.a) (void)parse_expr(e, inputs[0]);          // validate at plan time
+  }
+  return op;
+}
+
+// ================================================================================================
 // A linear chain of GPU operators executed as one island: batches move between the stages as HBM
 // batches inside the library (no Arrow export/import, no host round trip between stages).  This is
 // what the rewrite pass emits for consecutive replaced nodes, e.g. Q1's
@@ -758,6 +848,7 @@ std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::v
 struct ChainOp : Op {
   std::vector<std::unique_ptr<Op>> ops;
   bool finished = false;
+  bool rows_on_root_only = false;   // hint passed from an "auto" exchange to a later "gather" exchange of this chain
   void pump(size_t from) {
     for (size_t i = from; i + 1 < ops.size(); ++i) {
       for (;;) {
@@ -810,6 +901,7 @@ std::unique_ptr<Op> make_chain_op(Ctx* ctx, const Json& spec, const std::vector<
   for (auto& s : spec.at("ops").a) {
     SG_CHECK(s.at("op").as_str() != "hash_join" && s.at("op").as_str() != "repartition", SAILGPU_ERR_UNSUPPORTED, "chain stages must be single-input, single-output operators");
     op->ops.push_back(make_op(ctx, s, {cur}, 0));
+    if (auto* x = dynamic_cast<ExchangeOp*>(op->ops.back().get())) x->on_root_hint = &op->rows_on_root_only;
     cur = op->ops.back()->out_schema;
   }
   SG_CHECK(!op->ops.empty(), SAILGPU_ERR_INVALID, "empty chain");
@@ -855,6 +947,161 @@ namespace { thread_local std::string g_x_error; }
 
 #define NCCL_CALL(expr) do { int _r = (expr); if (_r != 0) sg::fail(SAILGPU_ERR_CUDA, std::string("NCCL error: ") + g_nccl.GetErrorString(_r) + " at " #expr); } while (0)
 
+namespace sg {
+// max over ranks of a row count (one 8-byte all-gather on the context's communicator)
+int64_t exchange_max_rows(Ctx* ctx, int64_t mine) {
+  if (ctx->world == 1) return mine;
+  SG_CHECK(ctx->nccl_comm != nullptr, SAILGPU_ERR_STATE, "sailgpu_ctx_comm_init has not been called");
+  BufPtr d = dev_alloc(ctx, 8), all = dev_alloc(ctx, 8 * (size_t)ctx->world);
+  SG_CUDA(cudaMemcpyAsync(d->ptr, &mine, 8, cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_CALL(g_nccl.AllGather(d->ptr, all->ptr, 1, NCCL_INT64, ctx->nccl_comm, ctx->stream));
+  std::vector<int64_t> h((size_t)ctx->world);
+  SG_CUDA(cudaMemcpyAsync(h.data(), all->ptr, 8 * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(cudaStreamSynchronize(ctx->stream));
+  int64_t mx = 0; for (auto v : h) mx = std::max(mx, v);
+  return mx;
+}
+// all-to-all of world_size device batches over the context's communicator: parts[p] goes to rank p; returns everything
+// that was sent to this rank (rows of rank 0 first, then rank 1, ...)
+BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts) {
+  const int n = (int)parts.size();
+  SG_CHECK(n == ctx->world, SAILGPU_ERR_INVALID, "exchange needs one batch per rank");
+  if (n == 1) return parts[0];
+  BatchPtr out;
+  {
+    SG_CHECK(ctx->nccl_comm != nullptr, SAILGPU_ERR_STATE, "sailgpu_ctx_comm_init has not been called");
+    const int W = n, me = ctx->rank;
+    // 1. counts: rows (and string heap bytes per string column) each rank sends to each rank
+    const size_t ncols = schema.size();
+    const size_t rec = 1 + ncols;                       // rows, heap bytes per column
+    std::vector<int64_t> mine((size_t)W * rec, 0);
+    // strings travel as Arrow views + compact heap: convert through the export path per destination
+    struct SendCol { BufPtr data, validity_bytes, heap; int64_t heap_bytes = 0; };
+    std::vector<std::vector<SendCol>> sc((size_t)W, std::vector<SendCol>(ncols));
+    (void)0;
+    // pass 1: launch the length scans of every (destination, string column) without synchronising
+    struct Pending { int p; size_t ci; BufPtr offs, scratch; int64_t nblocks; };
+    std::vector<Pending> pend;
+    BufPtr totals = dev_alloc_zero(ctx, (size_t)W * ncols * 8 + 8);
+    for (int p = 0; p < W; ++p) {
+      mine[(size_t)p * rec] = parts[(size_t)p]->rows;
+      for (size_t ci = 0; ci < ncols; ++ci) {
+        const DevColumn& col = parts[(size_t)p]->cols[ci];
+        SendCol& sd = sc[(size_t)p][ci];
+        const int64_t k = col.length;
+        if (schema[ci].type.is_string() && k > 0) {
+          BufPtr lens = dev_alloc(ctx, (size_t)k * 4), offs = dev_alloc(ctx, (size_t)k * 8), scratch = dev_alloc(ctx, 1026 * 8);
+          SG_CUDA(launch_view_lengths(col.data->ptr, k, static_cast<uint32_t*>(lens->ptr), 0, ctx->stream));
+          SG_CUDA(launch_exclusive_scan_u32(static_cast<uint32_t*>(lens->ptr), k, static_cast<uint64_t*>(offs->ptr), static_cast<uint64_t*>(scratch->ptr), ctx->stream));
+          const int64_t nblocks = std::min<int64_t>(1024, (k + 4095) / 4096);
+          SG_CUDA(cudaMemcpyAsync(static_cast<uint64_t*>(totals->ptr) + (size_t)p * ncols + ci, static_cast<uint64_t*>(scratch->ptr) + nblocks, 8,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+          pend.push_back({p, ci, offs, scratch, nblocks});
+        } else if (schema[ci].type.id == TypeId::Bool && k > 0) {
+          sd.data = dev_alloc(ctx, (size_t)k);     // booleans travel as bytes
+          SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.data->ptr), static_cast<uint8_t*>(sd.data->ptr), k, 0, ctx->stream));
+        } else sd.data = col.data;
+        if (k > 0) {                              // validity always travels as bytes (1 = valid)
+          sd.validity_bytes = dev_alloc(ctx, (size_t)k);
+          if (col.validity) SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.validity->ptr), static_cast<uint8_t*>(sd.validity_bytes->ptr), k, 0, ctx->stream));
+          else SG_CUDA(cudaMemsetAsync(sd.validity_bytes->ptr, 1, (size_t)k, ctx->stream));
+        }
+      }
+    }
+    // one synchronisation for all heap sizes, then pass 2: compact heaps + Arrow-conformant views
+    std::vector<uint64_t> htot((size_t)W * ncols, 0);
+    if (!pend.empty()) {
+      SG_CUDA(cudaMemcpyAsync(htot.data(), totals->ptr, htot.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    for (auto& q : pend) {
+      const DevColumn& col = parts[(size_t)q.p]->cols[q.ci];
+      SendCol& sd = sc[(size_t)q.p][q.ci];
+      const int64_t k = col.length;
+      sd.heap_bytes = (int64_t)htot[(size_t)q.p * ncols + q.ci];
+      sd.heap = dev_alloc(ctx, (size_t)sd.heap_bytes);
+      sd.data = dev_alloc(ctx, (size_t)k * 16);
+      SG_CUDA(cudaMemcpyAsync(sd.data->ptr, col.data->ptr, (size_t)k * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+      SG_CUDA(launch_views_to_arrow(sd.data->ptr, k, static_cast<uint64_t*>(q.offs->ptr), static_cast<uint8_t*>(sd.heap->ptr), ctx->stream));
+      mine[(size_t)q.p * rec + 1 + q.ci] = sd.heap_bytes;
+    }
+    BufPtr dmine = dev_alloc(ctx, mine.size() * 8), dall = dev_alloc(ctx, mine.size() * 8 * (size_t)W);
+    SG_CUDA(cudaMemcpyAsync(dmine->ptr, mine.data(), mine.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CALL(g_nccl.AllGather(dmine->ptr, dall->ptr, mine.size(), NCCL_INT64, ctx->nccl_comm, ctx->stream));
+    std::vector<int64_t> all(mine.size() * (size_t)W);
+    SG_CUDA(cudaMemcpyAsync(all.data(), dall->ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    auto cnt = [&](int src, int dst, size_t field) { return all[((size_t)src * W + dst) * rec + field]; };
+    // 2. receive layout: rows from rank 0, then rank 1, ...
+    std::vector<int64_t> row_off((size_t)W + 1, 0);
+    for (int s = 0; s < W; ++s) row_off[(size_t)s + 1] = row_off[(size_t)s] + cnt(s, me, 0);
+    const int64_t total_rows = row_off[(size_t)W];
+    out = std::make_shared<DevBatch>();
+    out->rows = total_rows;
+    NCCL_CALL(g_nccl.GroupStart());
+    std::vector<BufPtr> vbytes(ncols), bbytes(ncols);
+    std::vector<std::vector<int64_t>> heap_off(ncols, std::vector<int64_t>((size_t)W + 1, 0));
+    for (size_t ci = 0; ci < ncols; ++ci) {
+      const DataType& t = schema[ci].type;
+      DevColumn col; col.type = t; col.length = total_rows; col.arrow_is_utf8 = t.id == TypeId::Utf8;
+      const bool bits = t.id == TypeId::Bool;
+      const int w = t.is_string() ? 16 : bits ? 1 : t.arrow_width();
+      BufPtr data = dev_alloc(ctx, (size_t)total_rows * w);
+      vbytes[ci] = dev_alloc(ctx, (size_t)total_rows + 4);
+      BufPtr heap;
+      if (t.is_string()) {
+        for (int s = 0; s < W; ++s) heap_off[ci][(size_t)s + 1] = heap_off[ci][(size_t)s] + cnt(s, me, 1 + ci);
+        heap = dev_alloc(ctx, (size_t)heap_off[ci][(size_t)W]);
+        col.heaps = {heap};
+      }
+      for (int peer = 0; peer < W; ++peer) {
+        const SendCol& s = sc[(size_t)peer][ci];
+        const int64_t ks = parts[(size_t)peer]->rows, kr = cnt(peer, me, 0);
+        if (ks) { NCCL_CALL(g_nccl.Send(s.data->ptr, (size_t)ks * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+                  NCCL_CALL(g_nccl.Send(s.validity_bytes->ptr, (size_t)ks, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream)); }
+        if (kr) { NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(data->ptr) + row_off[(size_t)peer] * w, (size_t)kr * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+                  NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(vbytes[ci]->ptr) + row_off[(size_t)peer], (size_t)kr, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream)); }
+        if (t.is_string()) {
+          if (s.heap_bytes) NCCL_CALL(g_nccl.Send(s.heap->ptr, (size_t)s.heap_bytes, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+          const int64_t hb = cnt(peer, me, 1 + ci);
+          if (hb) NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(heap->ptr) + heap_off[ci][(size_t)peer], (size_t)hb, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+        }
+      }
+      if (bits) bbytes[ci] = data; else col.data = data;
+      out->cols.push_back(col);
+    }
+    NCCL_CALL(g_nccl.GroupEnd());
+    // 3. post-process: rebase string views per source segment, pack byte columns
+    BufPtr nullctrs = dev_alloc_zero(ctx, ncols * 8 + 8);
+    for (size_t ci = 0; ci < ncols; ++ci) {
+      DevColumn& col = out->cols[ci];
+      if (schema[ci].type.is_string())
+        for (int s = 0; s < W; ++s) {
+          const int64_t kr = cnt(s, me, 0);
+          if (kr) SG_CUDA(launch_rebase_views(static_cast<uint8_t*>(col.data->ptr) + row_off[(size_t)s] * 16, kr,
+                                              reinterpret_cast<uint64_t>(col.heaps[0]->ptr) + (uint64_t)heap_off[ci][(size_t)s], ctx->stream));
+        }
+      if (bbytes[ci]) {
+        col.data = dev_alloc_zero(ctx, (size_t)((total_rows + 31) / 32 * 4));
+        SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(bbytes[ci]->ptr), static_cast<uint32_t*>(col.data->ptr), total_rows, nullptr, ctx->stream));
+      }
+      col.validity = dev_alloc_zero(ctx, (size_t)((total_rows + 31) / 32 * 4));
+      SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(vbytes[ci]->ptr), static_cast<uint32_t*>(col.validity->ptr), total_rows,
+                                static_cast<unsigned long long*>(nullctrs->ptr) + ci, ctx->stream));
+    }
+    std::vector<unsigned long long> nulls(ncols, 0);
+    SG_CUDA(cudaMemcpyAsync(nulls.data(), nullctrs->ptr, ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t ci = 0; ci < ncols; ++ci) {
+      out->cols[ci].null_count = (int64_t)nulls[ci];
+      if (nulls[ci] == 0) out->cols[ci].validity = nullptr;
+    }
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+  return out;
+}
+}  // namespace sg
+
 extern "C" {
 
 SAILGPU_API int32_t sailgpu_comm_unique_id(uint8_t* out128) {
@@ -893,138 +1140,7 @@ SAILGPU_API int32_t sailgpu_exchange(sailgpu_ctx* c, const struct ArrowSchema* s
       if (!b) b = import_device_batch(ctx, schema, &send[p]);
       parts.push_back(b);
     }
-    BatchPtr out;
-    if (n == 1) out = parts[0];
-    else {
-      SG_CHECK(ctx->nccl_comm != nullptr, SAILGPU_ERR_STATE, "sailgpu_ctx_comm_init has not been called");
-      const int W = n, me = ctx->rank;
-      // 1. counts: rows (and string heap bytes per string column) each rank sends to each rank
-      const size_t ncols = schema.size();
-      const size_t rec = 1 + ncols;                       // rows, heap bytes per column
-      std::vector<int64_t> mine((size_t)W * rec, 0);
-      // strings travel as Arrow views + compact heap: convert through the export path per destination
-      struct SendCol { BufPtr data, validity_bytes, heap; int64_t heap_bytes = 0; };
-      std::vector<std::vector<SendCol>> sc((size_t)W, std::vector<SendCol>(ncols));
-      (void)0;
-      // pass 1: launch the length scans of every (destination, string column) without synchronising
-      struct Pending { int p; size_t ci; BufPtr offs, scratch; int64_t nblocks; };
-      std::vector<Pending> pend;
-      BufPtr totals = dev_alloc_zero(ctx, (size_t)W * ncols * 8 + 8);
-      for (int p = 0; p < W; ++p) {
-        mine[(size_t)p * rec] = parts[(size_t)p]->rows;
-        for (size_t ci = 0; ci < ncols; ++ci) {
-          const DevColumn& col = parts[(size_t)p]->cols[ci];
-          SendCol& sd = sc[(size_t)p][ci];
-          const int64_t k = col.length;
-          if (schema[ci].type.is_string() && k > 0) {
-            BufPtr lens = dev_alloc(ctx, (size_t)k * 4), offs = dev_alloc(ctx, (size_t)k * 8), scratch = dev_alloc(ctx, 1026 * 8);
-            SG_CUDA(launch_view_lengths(col.data->ptr, k, static_cast<uint32_t*>(lens->ptr), 0, ctx->stream));
-            SG_CUDA(launch_exclusive_scan_u32(static_cast<uint32_t*>(lens->ptr), k, static_cast<uint64_t*>(offs->ptr), static_cast<uint64_t*>(scratch->ptr), ctx->stream));
-            const int64_t nblocks = std::min<int64_t>(1024, (k + 4095) / 4096);
-            SG_CUDA(cudaMemcpyAsync(static_cast<uint64_t*>(totals->ptr) + (size_t)p * ncols + ci, static_cast<uint64_t*>(scratch->ptr) + nblocks, 8,
-                                    cudaMemcpyDeviceToDevice, ctx->stream));
-            pend.push_back({p, ci, offs, scratch, nblocks});
-          } else if (schema[ci].type.id == TypeId::Bool && k > 0) {
-            sd.data = dev_alloc(ctx, (size_t)k);     // booleans travel as bytes
-            SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.data->ptr), static_cast<uint8_t*>(sd.data->ptr), k, 0, ctx->stream));
-          } else sd.data = col.data;
-          if (k > 0) {                              // validity always travels as bytes (1 = valid)
-            sd.validity_bytes = dev_alloc(ctx, (size_t)k);
-            if (col.validity) SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.validity->ptr), static_cast<uint8_t*>(sd.validity_bytes->ptr), k, 0, ctx->stream));
-            else SG_CUDA(cudaMemsetAsync(sd.validity_bytes->ptr, 1, (size_t)k, ctx->stream));
-          }
-        }
-      }
-      // one synchronisation for all heap sizes, then pass 2: compact heaps + Arrow-conformant views
-      std::vector<uint64_t> htot((size_t)W * ncols, 0);
-      if (!pend.empty()) {
-        SG_CUDA(cudaMemcpyAsync(htot.data(), totals->ptr, htot.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        SG_CUDA(cudaStreamSynchronize(ctx->stream));
-      }
-      for (auto& q : pend) {
-        const DevColumn& col = parts[(size_t)q.p]->cols[q.ci];
-        SendCol& sd = sc[(size_t)q.p][q.ci];
-        const int64_t k = col.length;
-        sd.heap_bytes = (int64_t)htot[(size_t)q.p * ncols + q.ci];
-        sd.heap = dev_alloc(ctx, (size_t)sd.heap_bytes);
-        sd.data = dev_alloc(ctx, (size_t)k * 16);
-        SG_CUDA(cudaMemcpyAsync(sd.data->ptr, col.data->ptr, (size_t)k * 16, cudaMemcpyDeviceToDevice, ctx->stream));
-        SG_CUDA(launch_views_to_arrow(sd.data->ptr, k, static_cast<uint64_t*>(q.offs->ptr), static_cast<uint8_t*>(sd.heap->ptr), ctx->stream));
-        mine[(size_t)q.p * rec + 1 + q.ci] = sd.heap_bytes;
-      }
-      BufPtr dmine = dev_alloc(ctx, mine.size() * 8), dall = dev_alloc(ctx, mine.size() * 8 * (size_t)W);
-      SG_CUDA(cudaMemcpyAsync(dmine->ptr, mine.data(), mine.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-      NCCL_CALL(g_nccl.AllGather(dmine->ptr, dall->ptr, mine.size(), NCCL_INT64, ctx->nccl_comm, ctx->stream));
-      std::vector<int64_t> all(mine.size() * (size_t)W);
-      SG_CUDA(cudaMemcpyAsync(all.data(), dall->ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      SG_CUDA(cudaStreamSynchronize(ctx->stream));
-      auto cnt = [&](int src, int dst, size_t field) { return all[((size_t)src * W + dst) * rec + field]; };
-      // 2. receive layout: rows from rank 0, then rank 1, ...
-      std::vector<int64_t> row_off((size_t)W + 1, 0);
-      for (int s = 0; s < W; ++s) row_off[(size_t)s + 1] = row_off[(size_t)s] + cnt(s, me, 0);
-      const int64_t total_rows = row_off[(size_t)W];
-      out = std::make_shared<DevBatch>();
-      out->rows = total_rows;
-      NCCL_CALL(g_nccl.GroupStart());
-      std::vector<BufPtr> vbytes(ncols), bbytes(ncols);
-      std::vector<std::vector<int64_t>> heap_off(ncols, std::vector<int64_t>((size_t)W + 1, 0));
-      for (size_t ci = 0; ci < ncols; ++ci) {
-        const DataType& t = schema[ci].type;
-        DevColumn col; col.type = t; col.length = total_rows; col.arrow_is_utf8 = t.id == TypeId::Utf8;
-        const bool bits = t.id == TypeId::Bool;
-        const int w = t.is_string() ? 16 : bits ? 1 : t.arrow_width();
-        BufPtr data = dev_alloc(ctx, (size_t)total_rows * w);
-        vbytes[ci] = dev_alloc(ctx, (size_t)total_rows + 4);
-        BufPtr heap;
-        if (t.is_string()) {
-          for (int s = 0; s < W; ++s) heap_off[ci][(size_t)s + 1] = heap_off[ci][(size_t)s] + cnt(s, me, 1 + ci);
-          heap = dev_alloc(ctx, (size_t)heap_off[ci][(size_t)W]);
-          col.heaps = {heap};
-        }
-        for (int peer = 0; peer < W; ++peer) {
-          const SendCol& s = sc[(size_t)peer][ci];
-          const int64_t ks = parts[(size_t)peer]->rows, kr = cnt(peer, me, 0);
-          if (ks) { NCCL_CALL(g_nccl.Send(s.data->ptr, (size_t)ks * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-                    NCCL_CALL(g_nccl.Send(s.validity_bytes->ptr, (size_t)ks, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream)); }
-          if (kr) { NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(data->ptr) + row_off[(size_t)peer] * w, (size_t)kr * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-                    NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(vbytes[ci]->ptr) + row_off[(size_t)peer], (size_t)kr, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream)); }
-          if (t.is_string()) {
-            if (s.heap_bytes) NCCL_CALL(g_nccl.Send(s.heap->ptr, (size_t)s.heap_bytes, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-            const int64_t hb = cnt(peer, me, 1 + ci);
-            if (hb) NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(heap->ptr) + heap_off[ci][(size_t)peer], (size_t)hb, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-          }
-        }
-        if (bits) bbytes[ci] = data; else col.data = data;
-        out->cols.push_back(col);
-      }
-      NCCL_CALL(g_nccl.GroupEnd());
-      // 3. post-process: rebase string views per source segment, pack byte columns
-      BufPtr nullctrs = dev_alloc_zero(ctx, ncols * 8 + 8);
-      for (size_t ci = 0; ci < ncols; ++ci) {
-        DevColumn& col = out->cols[ci];
-        if (schema[ci].type.is_string())
-          for (int s = 0; s < W; ++s) {
-            const int64_t kr = cnt(s, me, 0);
-            if (kr) SG_CUDA(launch_rebase_views(static_cast<uint8_t*>(col.data->ptr) + row_off[(size_t)s] * 16, kr,
-                                                reinterpret_cast<uint64_t>(col.heaps[0]->ptr) + (uint64_t)heap_off[ci][(size_t)s], ctx->stream));
-          }
-        if (bbytes[ci]) {
-          col.data = dev_alloc_zero(ctx, (size_t)((total_rows + 31) / 32 * 4));
-          SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(bbytes[ci]->ptr), static_cast<uint32_t*>(col.data->ptr), total_rows, nullptr, ctx->stream));
-        }
-        col.validity = dev_alloc_zero(ctx, (size_t)((total_rows + 31) / 32 * 4));
-        SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(vbytes[ci]->ptr), static_cast<uint32_t*>(col.validity->ptr), total_rows,
-                                  static_cast<unsigned long long*>(nullctrs->ptr) + ci, ctx->stream));
-      }
-      std::vector<unsigned long long> nulls(ncols, 0);
-      SG_CUDA(cudaMemcpyAsync(nulls.data(), nullctrs->ptr, ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      SG_CUDA(cudaStreamSynchronize(ctx->stream));
-      for (size_t ci = 0; ci < ncols; ++ci) {
-        out->cols[ci].null_count = (int64_t)nulls[ci];
-        if (nulls[ci] == 0) out->cols[ci].validity = nullptr;
-      }
-      SG_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
+    BatchPtr out = exchange_batches(ctx, schema, parts);
     export_device_batch(ctx, schema, out, recv);
     return SAILGPU_OK;
   } catch (const sg::Error& e) { g_x_error = e.what(); return e.code; }

@@ -229,3 +229,13 @@ def final_aggregate(backend, partial, schema: pa.Schema, key_cols: list, final_s
         return backend.run(final_spec, gathered), True
     mine = exchange_by_key(backend, partial, schema, key_cols)
     return backend.run(final_spec, mine), False
+
+
+def two_phase_chain(partial_spec: dict, final_spec: dict, key_cols: list, tail: list = (), small_rows: int = SMALL_EXCHANGE_ROWS) -> dict:
+    """The whole two-phase aggregation across ranks as ONE operator spec for libsailgpu (`{"op": "chain"}`):
+    partial -> exchange(auto: hash on the group keys, or coalesce on rank 0 when every rank holds few rows) -> final ->
+    exchange(gather to rank 0) -> tail operators (sort).  Nothing leaves HBM or the library between the stages; rank 0
+    pulls the result, the other ranks pull an empty batch.  Same decisions as `final_aggregate` above."""
+    return {"op": "chain", "ops": [partial_spec,
+                                   {"op": "exchange", "mode": "auto", "exprs": [{"col": c} for c in key_cols], "small_rows": small_rows},
+                                   final_spec, {"op": "exchange", "mode": "gather", "root": 0}] + list(tail)}

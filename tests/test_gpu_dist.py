@@ -66,6 +66,18 @@ def _worker(rank, world, port, q):
                 fin = sdist.gather_to_root(backend, fin, fin[0].schema)
             if rank == 0:
                 assert_same(backend.run_to_host(ident, fin), want)
+        # the same plan as ONE chain inside the library (exchange operators), both exchange modes
+        for small_rows in (1 << 14, 0):
+            chain = sdist.two_phase_chain(partial_node.spec, final_node.spec, [0, 1], [ident], small_rows=small_rows)
+            op = engine.GpuExec(chain, [shard.schema], ctx)
+            op.push(shard)
+            op.finish()
+            res = op.collect()
+            op.close()
+            if rank == 0:
+                assert_same(res, want)
+            else:
+                assert res.num_rows == 0
         q.put((rank, "ok"))
     except Exception:  # noqa: BLE001
         import traceback

@@ -62,3 +62,21 @@ def test_unsupported_and_invalid_specs_are_rejected_at_plan_time():
         engine.validate({"op": "hash_join", "join_type": "full", "on": [[0, 0]]}, [s, s])
     with pytest.raises(engine.SailGpuError):
         engine.validate({"op": "nonsense"}, [s])
+
+
+def test_exchange_and_chain_specs_validate_without_a_gpu():
+    """the shuffle boundary as an operator: schema passes through, key expressions are checked at plan time"""
+    from sail_b200 import dist as sdist
+    s = pa.schema([("k", pa.int64()), ("s", pa.string_view()), ("v", pa.decimal128(15, 2))])
+    out = engine.validate({"op": "exchange", "mode": "auto", "exprs": [{"col": 0}, {"col": 1}]}, [s])
+    assert out.names == s.names and [str(f.type) for f in out] == [str(f.type) for f in s]
+    with pytest.raises(engine.SailGpuError):
+        engine.validate({"op": "exchange", "mode": "hash", "exprs": [{"col": 7}]}, [s])
+    with pytest.raises(engine.SailGpuError):
+        engine.validate({"op": "exchange", "mode": "broadcast"}, [s])
+    partial = {"op": "aggregate", "mode": "partial", "group_by": [{"expr": {"col": 0}, "name": "k"}],
+               "aggs": [{"fn": "sum", "args": [{"col": 2}], "name": "sv", "input_type": "Decimal128(15,2)"}]}
+    final = {"op": "aggregate", "mode": "final_partitioned", "group_by": [{"expr": {"col": 0}, "name": "k"}],
+             "aggs": [{"fn": "sum", "name": "sv", "input_type": "Decimal128(15,2)"}]}
+    out = engine.validate(sdist.two_phase_chain(partial, final, [0]), [s])
+    assert out.names == ["k", "sv"] and str(out.field(1).type) == "decimal128(25, 2)"
