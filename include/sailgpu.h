@@ -45,6 +45,9 @@
  *                                           aggregate: one kernel, one pass over HBM)
  *   {"op":"chain","ops":[spec,...]}        (consecutive single-input operators run as one GPU island:
  *                                           batches move between them inside the library, in HBM)
+ *   {"op":"exchange","mode":"hash|gather|auto","exprs":[E],"root":r,"small_rows":k}
+ *                                          (the shuffle boundary inside a chain: hash-repartition + NCCL
+ *                                           all-to-all, or coalesce on rank r; needs sailgpu_ctx_comm_init)
  * Expressions E: {"col":i} {"lit":v,"type":"T"} {"op":"+|-|*|/|%|=|!=|<|<=|>|>=|and|or","l":E,"r":E}
  *   {"not":E} {"neg":E} {"is_null":E} {"is_not_null":E} {"cast":E,"to":"T"}
  *   {"case":[[E,E],...],"else":E|null} {"in":E,"set":[lit,...],"negated":b}
