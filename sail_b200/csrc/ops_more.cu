@@ -948,6 +948,13 @@ namespace { thread_local std::string g_x_error; }
 #define NCCL_CALL(expr) do { int _r = (expr); if (_r != 0) sg::fail(SAILGPU_ERR_CUDA, std::string("NCCL error: ") + g_nccl.GetErrorString(_r) + " at " #expr); } while (0)
 
 namespace sg {
+// uploads the segment table and runs all copies in one launch; *keep holds the table until the stream has used it
+static cudaError_t launch_multi_copy(Ctx* ctx, const std::vector<CopySeg>& segs, BufPtr* keep) {
+  *keep = dev_alloc(ctx, segs.size() * sizeof(CopySeg));
+  cudaError_t e = cudaMemcpyAsync((*keep)->ptr, segs.data(), segs.size() * sizeof(CopySeg), cudaMemcpyHostToDevice, ctx->stream);   // pageable source: staged before return
+  if (e != cudaSuccess) return e;
+  return launch_multi_copy_raw(static_cast<const CopySeg*>((*keep)->ptr), (int)segs.size(), ctx->stream);
+}
 // max over ranks of a row count (one 8-byte all-gather on the context's communicator)
 int64_t exchange_max_rows(Ctx* ctx, int64_t mine) {
   if (ctx->world == 1) return mine;
@@ -1038,39 +1045,94 @@ BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<Batc
     const int64_t total_rows = row_off[(size_t)W];
     out = std::make_shared<DevBatch>();
     out->rows = total_rows;
-    NCCL_CALL(g_nccl.GroupStart());
-    std::vector<BufPtr> vbytes(ncols), bbytes(ncols);
+    std::vector<BufPtr> vbytes(ncols), bbytes(ncols), datas(ncols), heaps(ncols);
     std::vector<std::vector<int64_t>> heap_off(ncols, std::vector<int64_t>((size_t)W + 1, 0));
+    auto width_of = [&](size_t ci) { const DataType& t = schema[ci].type; return t.is_string() ? 16 : t.id == TypeId::Bool ? 1 : t.arrow_width(); };
     for (size_t ci = 0; ci < ncols; ++ci) {
       const DataType& t = schema[ci].type;
       DevColumn col; col.type = t; col.length = total_rows; col.arrow_is_utf8 = t.id == TypeId::Utf8;
-      const bool bits = t.id == TypeId::Bool;
-      const int w = t.is_string() ? 16 : bits ? 1 : t.arrow_width();
-      BufPtr data = dev_alloc(ctx, (size_t)total_rows * w);
+      datas[ci] = dev_alloc(ctx, (size_t)total_rows * width_of(ci));
       vbytes[ci] = dev_alloc(ctx, (size_t)total_rows + 4);
-      BufPtr heap;
       if (t.is_string()) {
         for (int s = 0; s < W; ++s) heap_off[ci][(size_t)s + 1] = heap_off[ci][(size_t)s] + cnt(s, me, 1 + ci);
-        heap = dev_alloc(ctx, (size_t)heap_off[ci][(size_t)W]);
-        col.heaps = {heap};
+        heaps[ci] = dev_alloc(ctx, (size_t)heap_off[ci][(size_t)W]);
+        col.heaps = {heaps[ci]};
       }
-      for (int peer = 0; peer < W; ++peer) {
-        const SendCol& s = sc[(size_t)peer][ci];
-        const int64_t ks = parts[(size_t)peer]->rows, kr = cnt(peer, me, 0);
-        if (ks) { NCCL_CALL(g_nccl.Send(s.data->ptr, (size_t)ks * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-                  NCCL_CALL(g_nccl.Send(s.validity_bytes->ptr, (size_t)ks, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream)); }
-        if (kr) { NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(data->ptr) + row_off[(size_t)peer] * w, (size_t)kr * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-                  NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(vbytes[ci]->ptr) + row_off[(size_t)peer], (size_t)kr, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream)); }
-        if (t.is_string()) {
-          if (s.heap_bytes) NCCL_CALL(g_nccl.Send(s.heap->ptr, (size_t)s.heap_bytes, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-          const int64_t hb = cnt(peer, me, 1 + ci);
-          if (hb) NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(heap->ptr) + heap_off[ci][(size_t)peer], (size_t)hb, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-        }
-      }
-      if (bits) bbytes[ci] = data; else col.data = data;
+      if (t.id == TypeId::Bool) bbytes[ci] = datas[ci]; else col.data = datas[ci];
       out->cols.push_back(col);
     }
+    // Small messages can travel PACKED: all column buffers of one (source, destination) pair in one staging buffer, one
+    // ncclSend/ncclRecv per pair instead of 2-3 per column (a grouped p2p op costs ~8 us: the 4-row partial states of Q1
+    // with 13 columns were 28 ops per peer).  Both sides derive the same layout from the all-gathered counts.
+    constexpr int64_t PACK_LIMIT = 1 << 20;
+    auto a16 = [](int64_t v) { return (v + 15) & ~(int64_t)15; };
+    auto msg_bytes = [&](int src, int dst) {
+      const int64_t k = cnt(src, dst, 0);
+      int64_t tot = 0;
+      for (size_t ci = 0; ci < ncols; ++ci) tot += a16(k * width_of(ci)) + a16(k) + a16(cnt(src, dst, 1 + ci));
+      return k ? tot : 0;
+    };
+    // opt-in (SAILGPU_PACKED_EXCHANGE=1): measured at N=4 it did not pay (4.70 vs 4.45 ms/step) -- the multi-rank overhead of
+    // tiny exchanges is synchronisation latency and rank skew, not the number of grouped p2p operations
+    static const bool no_pack = getenv("SAILGPU_PACKED_EXCHANGE") == nullptr;
+    std::vector<CopySeg> pack_segs, unpack_segs;
+    std::vector<BufPtr> send_stage((size_t)W), recv_stage((size_t)W);
+    for (int peer = 0; peer < W; ++peer) {
+      const int64_t ks = parts[(size_t)peer]->rows, kr = cnt(peer, me, 0);
+      const int64_t sb = msg_bytes(me, peer), rb = msg_bytes(peer, me);
+      if (ks && !no_pack && sb <= PACK_LIMIT) {
+        send_stage[(size_t)peer] = dev_alloc(ctx, (size_t)sb);
+        uint8_t* base = static_cast<uint8_t*>(send_stage[(size_t)peer]->ptr);
+        int64_t off = 0;
+        for (size_t ci = 0; ci < ncols; ++ci) {
+          const SendCol& sd = sc[(size_t)peer][ci];
+          const int64_t db = ks * width_of(ci), hb = schema[ci].type.is_string() ? sd.heap_bytes : 0;
+          pack_segs.push_back({static_cast<const uint8_t*>(sd.data->ptr), base + off, (unsigned long long)db}); off += a16(db);
+          pack_segs.push_back({static_cast<const uint8_t*>(sd.validity_bytes->ptr), base + off, (unsigned long long)ks}); off += a16(ks);
+          if (hb) pack_segs.push_back({static_cast<const uint8_t*>(sd.heap->ptr), base + off, (unsigned long long)hb});
+          off += a16(hb);
+        }
+      }
+      if (kr && !no_pack && rb <= PACK_LIMIT) {
+        recv_stage[(size_t)peer] = dev_alloc(ctx, (size_t)rb);
+        const uint8_t* base = static_cast<const uint8_t*>(recv_stage[(size_t)peer]->ptr);
+        int64_t off = 0;
+        for (size_t ci = 0; ci < ncols; ++ci) {
+          const int w = width_of(ci);
+          const int64_t db = kr * w, hb = cnt(peer, me, 1 + ci);
+          unpack_segs.push_back({base + off, static_cast<uint8_t*>(datas[ci]->ptr) + row_off[(size_t)peer] * w, (unsigned long long)db}); off += a16(db);
+          unpack_segs.push_back({base + off, static_cast<uint8_t*>(vbytes[ci]->ptr) + row_off[(size_t)peer], (unsigned long long)kr}); off += a16(kr);
+          if (hb) unpack_segs.push_back({base + off, static_cast<uint8_t*>(heaps[ci]->ptr) + heap_off[ci][(size_t)peer], (unsigned long long)hb});
+          off += a16(hb);
+        }
+      }
+    }
+    BufPtr seg_keep_a, seg_keep_b;
+    if (!pack_segs.empty()) SG_CUDA(launch_multi_copy(ctx, pack_segs, &seg_keep_a));
+    NCCL_CALL(g_nccl.GroupStart());
+    for (int peer = 0; peer < W; ++peer) {
+      const int64_t ks = parts[(size_t)peer]->rows, kr = cnt(peer, me, 0);
+      if (ks && send_stage[(size_t)peer]) NCCL_CALL(g_nccl.Send(send_stage[(size_t)peer]->ptr, (size_t)msg_bytes(me, peer), NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+      if (kr && recv_stage[(size_t)peer]) NCCL_CALL(g_nccl.Recv(recv_stage[(size_t)peer]->ptr, (size_t)msg_bytes(peer, me), NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+      for (size_t ci = 0; ci < ncols; ++ci) {
+        const DataType& t = schema[ci].type;
+        const int w = width_of(ci);
+        const SendCol& sd = sc[(size_t)peer][ci];
+        if (ks && !send_stage[(size_t)peer]) {
+          NCCL_CALL(g_nccl.Send(sd.data->ptr, (size_t)ks * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+          NCCL_CALL(g_nccl.Send(sd.validity_bytes->ptr, (size_t)ks, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+          if (t.is_string() && sd.heap_bytes) NCCL_CALL(g_nccl.Send(sd.heap->ptr, (size_t)sd.heap_bytes, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+        }
+        if (kr && !recv_stage[(size_t)peer]) {
+          NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(datas[ci]->ptr) + row_off[(size_t)peer] * w, (size_t)kr * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+          NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(vbytes[ci]->ptr) + row_off[(size_t)peer], (size_t)kr, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+          const int64_t hb = cnt(peer, me, 1 + ci);
+          if (t.is_string() && hb) NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(heaps[ci]->ptr) + heap_off[ci][(size_t)peer], (size_t)hb, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+        }
+      }
+    }
     NCCL_CALL(g_nccl.GroupEnd());
+    if (!unpack_segs.empty()) SG_CUDA(launch_multi_copy(ctx, unpack_segs, &seg_keep_b));
     // 3. post-process: rebase string views per source segment, pack byte columns
     BufPtr nullctrs = dev_alloc_zero(ctx, ncols * 8 + 8);
     for (size_t ci = 0; ci < ncols; ++ci) {
