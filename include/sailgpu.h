@@ -171,6 +171,19 @@ SAILGPU_API int32_t sailgpu_op_create(sailgpu_ctx* ctx, const char* spec_json, s
 SAILGPU_API int32_t sailgpu_spec_validate(const char* spec_json, size_t spec_len, const struct ArrowSchema* const* input_schemas,
                                           int32_t n_inputs, struct ArrowSchema* out_schema, char* err_buf, size_t err_cap);
 
+/* Plan-time kernel specialisation.  The library interprets any pipeline at once and, for pipelines that see enough
+ * rows (SAILGPU_JIT_MIN_ROWS, default 4 Mi), compiles a specialised sm_100a kernel with NVRTC the first time; the
+ * cubin is cached next to the library (or in $SAILGPU_JIT_CACHE).  This call moves that compilation to planning time
+ * (the rewrite pass knows the pipelines of a query before the first batch): it generates the kernel for `spec` as it
+ * would run over batches whose column i carries a validity buffer iff bit i of `validity_mask` is set, and with
+ * SAILGPU_JIT_COMPILE stores its cubin in the cache.  No device is touched.  Returns the cubin size (or the source
+ * length without SAILGPU_JIT_COMPILE) and copies the generated source into buf; on failure returns -code and copies
+ * the message.  DataFusion has no counterpart: its operators are ahead-of-time compiled Rust. */
+#define SAILGPU_JIT_COLD_VARIANT 1   /* the high-cardinality variant of an aggregate (global table only) */
+#define SAILGPU_JIT_COMPILE 2
+SAILGPU_API int64_t sailgpu_jit_precompile(const char* spec_json, size_t spec_len, const struct ArrowSchema* const* input_schemas,
+                                           int32_t n_inputs, uint64_t validity_mask, int32_t flags, char* buf, size_t cap);
+
 /* Hand one input batch (struct array, host memory) to the operator.  Takes ownership: the library
  * calls batch->release when it no longer needs the host buffers (after the H2D copy). */
 SAILGPU_API int32_t sailgpu_op_push(sailgpu_op* op, int32_t input_idx, struct ArrowArray* batch);

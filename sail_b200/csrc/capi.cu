@@ -37,6 +37,8 @@ int32_t guard(std::string* err, F&& f) {
 void set_device(const Ctx& c) { SG_CUDA(cudaSetDevice(c.device)); }
 }  // namespace
 
+namespace sg { size_t pipeline_precompile(const Json& spec, const std::vector<Schema>& inputs, uint64_t validity_mask, bool cold, bool compile, std::string* source); }
+
 extern "C" {
 
 // release callback for a borrowed (non-owning) copy of an Arrow array struct: marks it released, frees nothing
@@ -128,6 +130,23 @@ SAILGPU_API int32_t sailgpu_spec_validate(const char* spec_json, size_t spec_len
   return rc;
 }
 
+SAILGPU_API int64_t sailgpu_jit_precompile(const char* spec_json, size_t spec_len, const struct ArrowSchema* const* input_schemas, int32_t n_inputs,
+                                           uint64_t validity_mask, int32_t flags, char* buf, size_t cap) {
+  std::string err, source;
+  size_t cubin = 0;
+  const int32_t rc = guard(&err, [&] {
+    SG_CHECK(spec_json && n_inputs >= 1, SAILGPU_ERR_INVALID, "null argument");
+    Json spec = JsonParser(spec_json, spec_len).parse();
+    std::vector<Schema> ins;
+    for (int i = 0; i < n_inputs; ++i) ins.push_back(schema_from_arrow(input_schemas[i]));
+    cubin = pipeline_precompile(spec, ins, validity_mask, (flags & SAILGPU_JIT_COLD_VARIANT) != 0, (flags & SAILGPU_JIT_COMPILE) != 0, &source);
+  });
+  const std::string& text = rc != 0 ? err : source;
+  if (buf && cap) { const size_t k = std::min(text.size(), cap - 1); memcpy(buf, text.data(), k); buf[k] = 0; }
+  if (rc != 0) return -(int64_t)(rc < 0 ? -rc : rc);
+  return (flags & SAILGPU_JIT_COMPILE) ? (int64_t)cubin : (int64_t)source.size();
+}
+
 SAILGPU_API int32_t sailgpu_op_push(sailgpu_op* h, int32_t input_idx, struct ArrowArray* batch) {
   if (!h) return SAILGPU_ERR_INVALID;
   return guard(&h->last_error, [&] {
@@ -197,12 +216,12 @@ SAILGPU_API int64_t sailgpu_op_metrics(sailgpu_op* h, char* json_buf, size_t cap
                    "{\"output_rows\":%llu,\"output_batches\":%llu,\"input_rows\":%llu,\"input_batches\":%llu,"
                    "\"elapsed_compute\":%llu,\"build_input_rows\":%llu,\"build_input_batches\":%llu,\"build_time\":%llu,"
                    "\"join_time\":%llu,\"gpu.kernel_launches\":%llu,\"gpu.h2d_bytes\":%llu,\"gpu.d2h_bytes\":%llu,"
-                   "\"gpu.pipeline_launches\":%llu,\"gpu.pipeline_kernel_ns\":%llu}",
+                   "\"gpu.pipeline_launches\":%llu,\"gpu.jit_launches\":%llu,\"gpu.pipeline_kernel_ns\":%llu}",
                    (unsigned long long)m.output_rows, (unsigned long long)m.output_batches, (unsigned long long)m.input_rows,
                    (unsigned long long)m.input_batches, (unsigned long long)m.elapsed_compute_ns, (unsigned long long)m.build_input_rows,
                    (unsigned long long)m.build_input_batches, (unsigned long long)m.build_time_ns, (unsigned long long)m.join_time_ns,
                    (unsigned long long)m.kernel_launches, (unsigned long long)h->owner->ctx.h2d_bytes.load(),
-                   (unsigned long long)h->owner->ctx.d2h_bytes.load(), (unsigned long long)h->op->m.pipeline_launches,
+                   (unsigned long long)h->owner->ctx.d2h_bytes.load(), (unsigned long long)h->op->m.pipeline_launches, (unsigned long long)h->op->m.jit_launches,
                    (unsigned long long)h->op->pipeline_kernel_ns());
   if (json_buf && cap) { size_t k = std::min<size_t>((size_t)n, cap - 1); memcpy(json_buf, tmp, k); json_buf[k] = 0; }
   return n + 1;

@@ -496,6 +496,16 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
   }
   out.arena_bytes = temps + out.hot_bytes + (uint32_t)best_stages * stage;
   out.smem_bytes = fixed + out.arena_bytes;
+  {   // snapshot for the kernel specialiser, before ids become offsets
+    JitInfo& J = out.jit;
+    J.prog = prog_; J.slots = slots_; J.inputs = inputs_; J.mask = mask_;
+    J.outs = out.outs; J.out_kinds = out_kinds_; J.agg = out.agg; J.keys = out.keys;
+    for (int j = 0; j < MAX_ACCS; ++j) J.small_acc[j] = small_acc_[j];
+    J.agg.hot_groups = best_hot;
+    if (out.cold_variant) { J.agg.cold_only = 1; J.agg.reg_path = 0; }
+    if (best_hot < REG_GROUPS) J.agg.reg_path = 0;
+    J.valid = true;
+  }
   auto off = [&](uint32_t id) -> uint32_t { return id == NO_SLOT ? NO_SLOT : slots_.at(id).offset; };
   out.prog = prog_;
   for (auto& I : out.prog) {

@@ -45,7 +45,27 @@ struct StageSpec {
 // what one aggregate output column is made of
 struct AggOutSpec { int kind; int a, b; DataType type; bool nullable; DataType in_type; };
 
+// The pipeline before slot ids were rewritten to arena offsets: input of the kernel specialiser (jit.cu), which turns
+// slots into registers and needs to know who reads what.
+struct JitInfo {
+  bool valid = false;
+  std::vector<VmInst> prog;          // operands are slot ids
+  std::vector<SlotInfo> slots;
+  std::vector<InputReg> inputs;      // slot = slot id
+  Val mask;                          // slot < 0 && !is_imm: no filter
+  std::vector<OutputCol> outs;       // slot / valid_slot are ids
+  std::vector<int> out_kinds;        // VmKind of every output value
+  AggParams agg{};                   // keys / accs carry slot ids
+  bool small_acc[MAX_ACCS] = {};
+  std::vector<KeyDesc> keys;
+};
+struct JitKernel;
+
 struct CompiledPipeline {
+  JitInfo jit;
+  std::shared_ptr<JitKernel> jit_kernel;   // specialised kernel, once compiled (jit.cu)
+  bool jit_failed = false;                 // generation / compilation was refused: stay on the interpreter
+  bool jit_checked = false;                // coverage and kernel cache were looked at
   std::vector<VmInst> prog;          // slot ids already rewritten to arena offsets
   std::vector<SlotInfo> slots;
   std::vector<InputReg> inputs;
@@ -196,6 +216,7 @@ class PipelineCompiler {
   bool small_acc_[MAX_ACCS] = {};      // accumulator input is statically below 2^55 (decimal precision <= 16)
   std::vector<OutputCol> outs_;
   std::vector<DataType> out_types_;
+  std::vector<int> out_kinds_;
 
   static int phys_kind(const DataType& t) {
     switch (t.id) {
@@ -321,6 +342,7 @@ class PipelineCompiler {
       o.width = (uint16_t)(t.id == TypeId::Bool ? 0 : t.is_string() ? 16 : t.arrow_width());
       outs_.push_back(o);
       out_types_.push_back(t);
+      out_kinds_.push_back(v.kind);
     }
     out.outs = outs_; out.out_types = out_types_;
   }

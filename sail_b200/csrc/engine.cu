@@ -408,6 +408,30 @@ struct PipelineOp : Op {
   }
 };
 
+// Plan-time specialisation (sailgpu_jit_precompile): compiles the pipeline of `spec` for a batch whose columns carry
+// validity buffers where `validity_mask` has a bit set, writes the specialised kernel's source to *source and, with
+// `compile`, its cubin into the kernel cache -- all without a device (NVRTC cross-compiles for sm_100a).
+size_t pipeline_precompile(const Json& spec, const std::vector<Schema>& inputs, uint64_t validity_mask, bool cold, bool compile, std::string* source) {
+  static Ctx plan_ctx;      // B200 geometry (148 SMs, 227 KB of shared memory per CTA); never touches a device
+  std::unique_ptr<Op> op = make_op(&plan_ctx, spec, inputs, 0);
+  PipelineOp* p = dynamic_cast<PipelineOp*>(op.get());
+  SG_CHECK(p != nullptr, SAILGPU_ERR_UNSUPPORTED, "only filter / projection / aggregate pipelines are specialised");
+  DevBatch shape;
+  for (size_t i = 0; i < inputs[0].size(); ++i) {
+    DevColumn c; c.type = inputs[0][i].type;
+    if (i < 64 && ((validity_mask >> i) & 1)) c.validity = std::make_shared<DevBuf>();
+    shape.cols.push_back(c);
+  }
+  auto cp = p->run.compiled_for(shape, cold);
+  std::string why;
+  SG_CHECK(jit_supported(*cp, &why), SAILGPU_ERR_UNSUPPORTED, "kernel specialiser: " + why);
+  JitPlan plan;
+  SG_CHECK(jit_plan(*cp, plan_ctx.max_smem, &plan), SAILGPU_ERR_UNSUPPORTED, "kernel specialiser: pipeline does not fit in shared memory");
+  const std::string src = jit_generate(*cp, plan);
+  if (source) *source = src;
+  return compile ? jit_precompile_to_cache(src) : 0;
+}
+
 std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_sort_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);

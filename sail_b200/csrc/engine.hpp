@@ -15,7 +15,7 @@ struct Metrics {
   uint64_t input_rows = 0, input_batches = 0, output_rows = 0, output_batches = 0;
   uint64_t elapsed_compute_ns = 0, kernel_launches = 0;
   uint64_t build_input_rows = 0, build_input_batches = 0, build_time_ns = 0, join_time_ns = 0;
-  uint64_t pipeline_launches = 0, pipeline_kernel_ns = 0;
+  uint64_t pipeline_launches = 0, pipeline_kernel_ns = 0, jit_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;   // CUDA events bracketing each pipeline-kernel launch
 };
 

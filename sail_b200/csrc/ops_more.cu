@@ -340,7 +340,7 @@ struct JoinOp : Op {
       SG_CHECK(t.id != TypeId::Bool, SAILGPU_ERR_UNSUPPORTED, "boolean join keys are not supported");
       // the build sink packs <=18-digit decimals from their low 8 bytes; mirror that here
       dst[i].width = (t.is_decimal() && t.precision <= 18) ? 8 : w;
-      SG_CHECK(!(t.is_decimal() && t.precision <= 18), SAILGPU_ERR_UNSUPPORTED, "narrow decimal join keys with duplicate build rows are not supported yet");
+      dst[i].stride = w;
     }
   }
 
@@ -492,6 +492,15 @@ std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<S
   }
   const Json* fj = spec.find("filter");
   if (fj && !fj->is_null()) { op->filter_json = *fj; op->has_filter = true; }
+  // data-independent limits are reported here, at plan time (sailgpu_spec_validate), never after the build side was consumed
+  SG_CHECK(!op->has_filter || op->jt == "inner" || op->jt == "right_semi", SAILGPU_ERR_UNSUPPORTED,
+           "residual join filter with join_type '" + op->jt + "' is not supported yet");
+  for (size_t i = 0; i < op->lkeys.size(); ++i) {
+    const DataType& t = op->bs[(size_t)op->lkeys[i]].type;
+    SG_CHECK(t.id != TypeId::Bool, SAILGPU_ERR_UNSUPPORTED, "boolean join keys are not supported");
+    const int w = t.is_string() ? 16 : t.arrow_width();
+    SG_CHECK(w == 1 || w == 4 || w == 8 || w == 16, SAILGPU_ERR_UNSUPPORTED, "join key of type " + t.str() + " is not supported");
+  }
   const Json* pj = spec.find("projection");
   if (pj && !pj->is_null()) {
     op->has_proj = true;
@@ -608,6 +617,10 @@ std::unique_ptr<Op> make_sort_op(Ctx* ctx, const Json& spec, const std::vector<S
     op->keys.push_back(key);
   }
   SG_CHECK(!op->keys.empty() && op->keys.size() <= 8, SAILGPU_ERR_INVALID, "sort needs 1..8 keys");
+  for (auto& k : op->keys) {      // plan-time limits (sailgpu_spec_validate)
+    SG_CHECK(k.e->kind == Expr::Col, SAILGPU_ERR_UNSUPPORTED, "sort keys must be column references");
+    SG_CHECK(k.e->type.id != TypeId::Float32, SAILGPU_ERR_UNSUPPORTED, "Float32 sort keys");
+  }
   const Json* f = spec.find("fetch");
   if (f && !f->is_null()) op->fetch = f->as_int();
   return op;

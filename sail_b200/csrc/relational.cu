@@ -32,7 +32,7 @@ __device__ __forceinline__ uint64_t raw_key_hash(const RawKeyCol* keys, int n_ke
   for (int i = 0; i < n_keys; ++i) {
     const RawKeyCol& k = keys[i];
     if (col_is_null(k, row)) { *has_null = true; return 0; }
-    const uint8_t* p = k.data + row * k.width;
+    const uint8_t* p = k.data + row * k.stride;
     if (k.width == 16) {
       ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
       h = mix64(h ^ (k.is_view ? view_hash(v) : mix64(v.x ^ mix64(v.y))));
@@ -45,8 +45,8 @@ __device__ __forceinline__ uint64_t raw_key_hash(const RawKeyCol* keys, int n_ke
 }
 __device__ __forceinline__ bool raw_keys_equal(const RawKeyCol* a, int64_t ra, const RawKeyCol* b, int64_t rb, int n_keys) {
   for (int i = 0; i < n_keys; ++i) {
-    const uint8_t* pa = a[i].data + ra * a[i].width;
-    const uint8_t* pb = b[i].data + rb * b[i].width;
+    const uint8_t* pa = a[i].data + ra * a[i].stride;
+    const uint8_t* pb = b[i].data + rb * b[i].stride;
     if (a[i].width == 16) {
       ulonglong2 x = *reinterpret_cast<const ulonglong2*>(pa), y = *reinterpret_cast<const ulonglong2*>(pb);
       if (a[i].is_view ? !view_equal(x, y) : (x.x != y.x || x.y != y.y)) return false;

@@ -10,8 +10,10 @@ namespace sg {
 struct RawKeyCol {
   const uint8_t* data;
   const uint8_t* validity_bits;   // Arrow bitmap or null
-  int32_t width;                  // 1, 4, 8, 16
+  int32_t width;                  // bytes compared / hashed: 1, 4, 8, 16
   int32_t is_view;
+  int32_t stride;                 // bytes between rows (16 for a <=18-digit decimal keyed on its low word)
+  int32_t pad;
 };
 
 struct JoinMultiParams {

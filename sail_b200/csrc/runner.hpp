@@ -3,6 +3,7 @@
 #include <algorithm>
 
 #include "engine.hpp"
+#include "jit.hpp"
 
 namespace sg {
 
@@ -56,6 +57,7 @@ struct PipelineRunner {
   std::map<const CompiledPipeline*, DevProgram> programs;
   DevScalars scal;
   int hot_wanted = 8;
+  int64_t rows_seen = 0;                 // rows launched through this runner (specialisation threshold)
   uint64_t group_limit_cap = ~0ull;      // bounded aggregation: extra cap on the launch's group limit (see PipelineOp)
   std::function<void(PipelineCompiler&, CompiledPipeline&)> custom_sink;   // build / partition sinks
   std::function<void(PipelineCompiler&, CompiledPipeline&)> pre_stages;    // probe ops injected before the stages
@@ -189,17 +191,41 @@ struct PipelineRunner {
         }
       }
     }
+    // Specialised kernel (jit.cu) once the operator has seen enough rows to pay for its compilation, or at once when the
+    // kernel is already cached; everything else -- and every pipeline the specialiser does not cover -- is interpreted.
+    rows_seen += P.n_rows;
+    std::shared_ptr<JitKernel> jk;
+    if (jit_enabled() && P.use_tma && !cp->jit_failed) {
+      jk = cp->jit_kernel;
+      if (!jk) {
+        try {
+          if (!cp->jit_checked) {      // once per compiled pipeline: is it covered, and is its kernel already cached?
+            cp->jit_checked = true;
+            std::string why;
+            if (!jit_supported(*cp, &why)) { cp->jit_failed = true; if (getenv("SAILGPU_JIT_VERBOSE")) fprintf(stderr, "[sailgpu jit] interpreted: %s\n", why.c_str()); }
+            else if (jit_cached(*cp, ctx->max_smem)) jk = cp->jit_kernel = jit_get_kernel(*cp, ctx->max_smem);
+          }
+          if (!jk && !cp->jit_failed && rows_seen >= jit_min_rows()) jk = cp->jit_kernel = jit_get_kernel(*cp, ctx->max_smem);
+        } catch (const Error& e) {
+          cp->jit_failed = true;
+          if (getenv("SAILGPU_JIT_VERBOSE") || getenv("SAILGPU_JIT_STRICT")) fprintf(stderr, "[sailgpu jit] not specialised: %s\n", e.what());
+          if (getenv("SAILGPU_JIT_STRICT")) throw;
+        }
+      }
+    }
     // resident CTAs per SM: what shared memory allows, then the matching register-budget variant of the kernel
     const int by_smem = std::max(1, (int)(ctx->max_smem / (cp->smem_bytes + 1024)));
     const char* fm = getenv("SAILGPU_MINB");
     const int minb = fm && *fm ? atoi(fm) : std::min(by_smem, cp->sink == SINK_AGG ? (cp->cold_variant ? 4 : 2) : (cp->sink == SINK_BUILD || cp->n_probes > 0) ? 4 : 3);
-    const int per_sm = std::max(1, std::min(by_smem, pipeline_max_ctas_per_sm(cp->rpt, minb, cp->smem_bytes, cp->sink, cp->cold_variant)));
+    const int per_sm = jk ? jk->ctas_per_sm : std::max(1, std::min(by_smem, pipeline_max_ctas_per_sm(cp->rpt, minb, cp->smem_bytes, cp->sink, cp->cold_variant)));
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * per_sm);
     if (cp->sink == SINK_AGG && aux_host && aux_host->agg.deferred) {
       // group limit of a bounded table: half the capacity minus what can still arrive from tiles in flight (a CTA acts
-      // on a table-full reading that is up to two tiles old, so three tiles per CTA) and from the dictionary flushes
+      // on a table-full reading that is up to two tiles old, so three tiles per CTA; a specialised kernel has its whole
+      // stage ring in flight) and from the dictionary flushes
       const uint64_t cap = aux_host->agg.capacity_mask + 1;
-      const uint64_t slack = std::min<uint64_t>(3ull * (uint64_t)grid * (uint64_t)P.tile_rows, (uint64_t)P.n_rows) + (uint64_t)grid * (uint64_t)std::max(0, cp->agg.hot_groups);
+      const uint64_t in_flight = jk ? (uint64_t)jk->stages + 1 : 3ull;
+      const uint64_t slack = std::min<uint64_t>(in_flight * (uint64_t)grid * (uint64_t)P.tile_rows, (uint64_t)P.n_rows) + (uint64_t)grid * (uint64_t)std::max(0, cp->agg.hot_groups);
       const uint64_t limit = std::min<uint64_t>(cap / 2 > slack ? cap / 2 - slack : 0, group_limit_cap);
       for (int st = 0; st < 2; ++st)
         if (K->aux[st].agg.group_limit == ~0ull) K->aux[st].agg.group_limit = limit;
@@ -207,7 +233,8 @@ struct PipelineRunner {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool timed = timing_enabled();
     if (timed) { SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1)); SG_CUDA(cudaEventRecord(e0, ctx->stream)); }
-    SG_CUDA(launch_pipeline(*K, cp->rpt, cp->n_stages, cp->smem_bytes, grid, minb, ctx->stream));
+    if (jk) { jit_launch(*jk, *K, grid, ctx->stream); m.jit_launches++; }
+    else SG_CUDA(launch_pipeline(*K, cp->rpt, cp->n_stages, cp->smem_bytes, grid, minb, ctx->stream));
     if (timed) { SG_CUDA(cudaEventRecord(e1, ctx->stream)); m.pending.emplace_back(e0, e1); }
     m.kernel_launches++;
     m.pipeline_launches++;

@@ -75,6 +75,8 @@ def lib():
         L.sailgpu_op_create.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), i32, i32,
                                         ctypes.POINTER(vp), vp]
         L.sailgpu_spec_validate.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), i32, vp, ctypes.c_char_p, ctypes.c_size_t]
+        L.sailgpu_jit_precompile.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), i32, ctypes.c_uint64, i32, ctypes.c_char_p, ctypes.c_size_t]
+        L.sailgpu_jit_precompile.restype = i64
         L.sailgpu_op_push.argtypes = [vp, i32, vp]
         L.sailgpu_op_push_device.argtypes = [vp, i32, vp]
         L.sailgpu_op_finish_input.argtypes = [vp, i32]
@@ -335,6 +337,25 @@ def validate(spec: dict, inputs: list) -> pa.Schema:
     if rc != 0:
         raise SailGpuError(rc, err.value.decode())
     return pa.Schema._import_from_c(ctypes.addressof(out))
+
+
+JIT_COLD_VARIANT, JIT_COMPILE = 1, 2
+
+
+def jit_precompile(spec: dict, inputs: list, validity_mask: int = 0, flags: int = 0) -> tuple[int, str]:
+    """Plan-time kernel specialisation (no GPU needed): returns (cubin bytes or source length, generated CUDA source)
+    of the specialised kernel for `spec`; with JIT_COMPILE the cubin lands in the kernel cache."""
+    text = json.dumps(spec).encode()
+    cs = [_export_schema(s) for s in inputs]
+    arr = (ctypes.c_void_p * len(cs))(*[ctypes.addressof(c) for c in cs])
+    cap = 1 << 20
+    buf = ctypes.create_string_buffer(cap)
+    n = lib().sailgpu_jit_precompile(text, len(text), arr, len(cs), validity_mask, flags, buf, cap)
+    for c in cs:
+        _release_schema(c)
+    if n < 0:
+        raise SailGpuError(int(-n), buf.value.decode())
+    return int(n), buf.value.decode()
 
 
 def run_op(spec: dict, *tables, ctx: Context | None = None) -> pa.Table:
