@@ -1,19 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- TPC-H Q1 (scan + filter + hash-aggregate) at SF10 per GPU: BASELINE.json configs[1].
+"""bench.py -- TPC-H Q1 (scan + filter + hash-aggregate) at SF100 per GPU, lineitem resident in HBM: the configuration
+BASELINE.json quotes its metric on (largest single-GPU config for Q1), plus the hash all-to-all and Q3/Q5 legs.
 
   python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA path through the C ABI)
   python bench.py --impl reference ...                      the reference's CPU algorithm on the host cores
-  torchrun ... bench.py --gpus N ...                        one rank per GPU, lineitem sharded by order range
+  torchrun ... bench.py --gpus N ...                        one rank per GPU, lineitem sharded by order range (weak scaling)
 
-A "step" is one execution of the Q1 physical plan (fused FilterExec+ProjectionExec+AggregateExec
-partial -> AggregateExec final -> SortExec) over the rank's lineitem shard.
-  value : rows/s with the Arrow column buffers already resident in HBM (device batches pushed zero-copy)
-  e2e   : rows/s through the same C ABI with HOST (pinned) Arrow buffers: H2D copies and the D2H of
-          the result are inside the timed region
-  roofline : the dominant kernel (pipeline_kernel) -- algorithmic bytes (100 B/row)
-             / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : oracle/cpipelines.c (C port of the reference's CPU path) on all host cores
-Inputs (6 GB per GPU) are far larger than the 126 MB L2, so no explicit L2 flush is needed.
+A "step" is one execution of the Q1 physical plan (fused FilterExec+ProjectionExec+AggregateExec partial ->
+AggregateExec final -> SortExec) over the rank's lineitem shard, pushed as `chunk-sf`-sized Arrow batches.
+  value    : rows/s with the Arrow column buffers already resident in HBM (device batches pushed zero-copy)
+  e2e      : rows/s through the same C ABI with PAGEABLE host Arrow buffers (what a DataFusion RecordBatch is): staging,
+             H2D copies and the D2H of the result are inside the timed region; measured on the first `e2e-chunks` batches
+  roofline : the dominant kernel -- algorithmic bytes (100 B/row) / its CUDA-event duration, against
+             MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : oracle/cpipelines.c (C port of the reference's CPU path) on all host cores over the same rows
+  exchange : (N > 1) GROUP BY l_orderkey in two phases with the partial states hash-repartitioned over NCCL all-to-all:
+             NVLink bytes per GPU, GB/s against 900 GB/s per direction, parity asserts
+  parity   : every run checks the full-size GPU result against the C port (all ranks' shards, exact integers)
+Inputs are generated on the GPU by datagen/tpch_dbgen_gpu.cu (bit-identical to the host generator, see
+tests/test_gpu_datagen.py); they are far larger than the 126 MB L2, so no explicit L2 flush is needed.
 """
 from __future__ import annotations
 
@@ -33,18 +38,23 @@ os.environ.setdefault("SAILGPU_TIMING", "1")
 Q1_COLS = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
 ALGO_BYTES_PER_ROW = 100      # 4 x Decimal128 + 2 x Utf8View + Date32  
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+NVLINK_GBS_PER_DIR = 900.0
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sf", type=float, default=10.0, help="scale factor PER GPU (weak scaling)")
-    ap.add_argument("--e2e-chunk", type=int, default=1 << 22, help="rows per host batch in the e2e leg")
+    ap.add_argument("--sf", type=float, default=100.0, help="scale factor PER GPU (weak scaling)")
+    ap.add_argument("--chunk-sf", type=float, default=10.0, help="rows of one resident Arrow batch, as a scale factor")
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="host batches of the end-to-end leg (each chunk-sf big)")
+    ap.add_argument("--exchange-sf", type=float, default=30.0, help="per-GPU input of the all-to-all leg (N > 1)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-exchange", action="store_true")
+    ap.add_argument("--skip-joins", action="store_true")
     return ap.parse_args()
 
 
@@ -52,13 +62,18 @@ def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def gen_shard(sf_per_gpu: float, rank: int, world: int):
-    """lineitem rows of orders [rank*O, (rank+1)*O) of an SF(sf*world) database"""
+def shard_chunks(sf_per_gpu: float, chunk_sf: float, rank: int, world: int):
+    """(total sf, [(first order row, orders)]) of this rank's shard of an SF(sf*world) database, cut into chunk-sf pieces"""
     from datagen import tpch
     total_sf = sf_per_gpu * world
-    orders_total = tpch.counts(total_sf)["orders"]
-    per = orders_total // world
-    return tpch.lineitem(total_sf, Q1_COLS, first=rank * per, n=per)
+    per = tpch.counts(total_sf)["orders"] // world
+    step = max(1, min(per, tpch.counts(chunk_sf)["orders"]))
+    first, end, out = rank * per, rank * per + per, []
+    while first < end:
+        n = min(step, end - first)
+        out.append((first, n))
+        first += n
+    return total_sf, out
 
 
 class ClockSampler:
@@ -121,29 +136,6 @@ def q1_specs():
     return {"op": "pipeline", "stages": stages[::-1]}, final.spec, final_sorted.spec
 
 
-def pin_table(ctx, table):
-    """copy every buffer of a single-chunk table into pinned host memory; returns (pinned table, keepalive, bytes)"""
-    import pyarrow as pa
-    from sail_b200 import engine
-    keep, arrays, total = [], [], 0
-    for col in table.columns:
-        arr = col.chunk(0) if col.num_chunks == 1 else col.combine_chunks()
-        bufs = []
-        for b in arr.buffers():
-            if b is None:
-                bufs.append(None)
-                continue
-            p = ctypes.c_void_p()
-            rc = engine.lib().sailgpu_host_alloc(ctx._h, b.size, ctypes.byref(p))
-            assert rc == 0
-            ctypes.memmove(p.value, b.address, b.size)
-            keep.append(p)
-            bufs.append(pa.foreign_buffer(p.value, b.size, base=p))
-            total += b.size
-        arrays.append(pa.Array.from_buffers(arr.type, len(arr), bufs, null_count=arr.null_count, offset=arr.offset))
-    return pa.table(arrays, names=table.schema.names), keep, total
-
-
 def run_query_dist(backend, specs, inputs, in_schema, host_chunks=None):
     """world > 1: fused partial on the shard -> hash repartition + NCCL all-to-all -> final on the owner ->
     gather to rank 0 -> sort there.  Returns (result table on rank 0, launches, kernel ns, kernel launches)."""
@@ -164,7 +156,7 @@ def run_query_dist(backend, specs, inputs, in_schema, host_chunks=None):
         out = op.collect()
         mm = op.metrics()
         op.close()
-        return (out if backend.rank == 0 else None), mm["gpu.kernel_launches"], mm["gpu.pipeline_kernel_ns"], mm["gpu.pipeline_launches"]
+        return (out if backend.rank == 0 else None), mm["gpu.kernel_launches"], mm["gpu.pipeline_kernel_ns"], mm["gpu.pipeline_launches"], mm.get("gpu.jit_launches", 0)
     op1 = engine.GpuExec(fused, [in_schema], backend.ctx)
     if host_chunks is None:
         for d in inputs:
@@ -184,7 +176,7 @@ def run_query_dist(backend, specs, inputs, in_schema, host_chunks=None):
     if not on_root:
         fin = sdist.gather_to_root(backend, fin, fin[0].schema)
     table = backend.run_to_host(sort, fin) if backend.rank == 0 else None
-    return table, m1["gpu.kernel_launches"] + backend.launches, m1["gpu.pipeline_kernel_ns"], m1["gpu.pipeline_launches"]
+    return table, m1["gpu.kernel_launches"] + backend.launches, m1["gpu.pipeline_kernel_ns"], m1["gpu.pipeline_launches"], m1.get("gpu.jit_launches", 0)
 
 
 def run_query(ctx, specs, inputs, in_schema, host_chunks=None):
@@ -207,15 +199,27 @@ def run_query(ctx, specs, inputs, in_schema, host_chunks=None):
     out = op.collect()
     mm = op.metrics()
     op.close()
-    return out, mm["gpu.kernel_launches"], mm["gpu.pipeline_kernel_ns"], mm["gpu.pipeline_launches"]
+    return out, mm["gpu.kernel_launches"], mm["gpu.pipeline_kernel_ns"], mm["gpu.pipeline_launches"], mm.get("gpu.jit_launches", 0)
 
 
 SORT_ON_GPU = True
 DIST_BACKEND = None
 
 
+def merge_q1_rows(parts):
+    """sums per-chunk / per-rank results of the C port: [(flag, status, sum_qty, sum_base, sum_disc_price, sum_charge, sum_disc, count)]"""
+    acc = {}
+    for rows in parts:
+        for r in rows:
+            k = (r[0], r[1])
+            a = acc.setdefault(k, [0] * 6)
+            for j in range(6):
+                a[j] += int(r[2 + j])
+    return sorted((k[0], k[1], *v) for k, v in acc.items())
+
+
 def check_result(table, want_rows):
-    """GPU result vs the C oracle (decimals compared as unscaled integers)."""
+    """GPU result vs the C oracle (decimals compared as unscaled integers; avg columns follow from sum / count)."""
     import decimal
     got = []
     for r in table.to_pylist():
@@ -227,44 +231,140 @@ def check_result(table, want_rows):
     assert sorted(got) == sorted(want), f"GPU Q1 result differs from the CPU oracle:\n{sorted(got)}\n{sorted(want)}"
 
 
-def cpu_q1(table, threads, reps):
+def cpu_q1_chunks(host_tables, threads):
+    """C port of the reference's CPU path over every host chunk: (merged rows, seconds)"""
     from oracle import cpipelines
     from sail_b200 import plans
     cutoff = plans.days("1998-09-24")
-    cpipelines.q1(table.slice(0, min(table.num_rows, 1 << 20)), cutoff, threads)      # warm up / page in
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        rows = cpipelines.q1(table, cutoff, threads)
-    dt = (time.perf_counter() - t0) / reps
-    return rows, dt
+    cpipelines.q1(host_tables[0].slice(0, min(host_tables[0].num_rows, 1 << 20)), cutoff, threads)      # warm up / page in
+    parts, dt = [], 0.0
+    for t in host_tables:
+        t0 = time.perf_counter()
+        parts.append(cpipelines.q1(t, cutoff, threads))
+        dt += time.perf_counter() - t0
+    return merge_q1_rows(parts), dt
 
 
-def e2e_leg(args, ctx, specs, table, stream, world, total_rows):
+def timed_steps(ctx, stream, world, steps, fn):
+    """barrier + synchronise on both sides, CUDA events on the library's stream, MAX over ranks: ms for `steps` calls of fn"""
     import torch
     import torch.distributed as dist
-    n_rows = table.num_rows
-    pinned, keep, h2d_bytes = pin_table(ctx, table)
-    chunks = [pinned.slice(o, args.e2e_chunk).to_batches()[0] for o in range(0, n_rows, args.e2e_chunk)]
-    for _ in range(max(1, min(2, args.warmup))):
-        out_e, _, _, _ = run_query(ctx, specs, None, table.schema, host_chunks=chunks)
     if world > 1:
         dist.barrier()
     ctx.synchronize()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(1, min(args.steps, 5))
-    e2.record(stream)
-    for _ in range(e2e_steps):
-        out_e, _, _, _ = run_query(ctx, specs, None, table.schema, host_chunks=chunks)
-    e3.record(stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
     ctx.synchronize()
-    ms_e = e2.elapsed_time(e3)
+    torch.cuda.synchronize()
     if world > 1:
-        t = torch.tensor([ms_e], device="cuda")
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e = float(t.item())
-    e2e_value = total_rows / (ms_e / e2e_steps / 1e3)
-    d2h_bytes = 0 if out_e is None else sum(b.size for c in out_e.columns for ch in c.chunks for b in ch.buffers() if b is not None)
-    return e2e_value, ms_e, e2e_steps, h2d_bytes, d2h_bytes, chunks, out_e
+        ms = float(t.item())
+    return ms
+
+
+def exchange_leg(args, ctx, stream, rank, world, local):
+    """GROUP BY l_orderkey (sum(l_quantity), count(*)) in two phases; the partial states -- one row per order -- are
+    hash-repartitioned on the key and cross NVLink in one NCCL all-to-all (forced `mode: hash`), the owners finalise.
+    shuffle_write.rs:209-267 / job_graph/planner.rs:80-151 are what this replaces."""
+    import pyarrow as pa
+    import torch.distributed as dist
+    from datagen import tpch_gpu
+    from sail_b200 import engine
+    from oracle import ops as oracle_ops
+    total_sf, chunks = shard_chunks(args.exchange_sf, args.chunk_sf, rank, world)
+    cols = ["l_orderkey", "l_quantity"]
+    gens = [tpch_gpu.generate_buffers(total_sf, f, n, (), cols, local)[1] for f, n in chunks]
+    devs = [g.device_batch(ctx) for g in gens]
+    schema = gens[0].schema
+    aggs = [("sum", {"col": 1}, "sum_qty", "Decimal128(15,2)"), ("count", None, "cnt", None)]
+
+    def agg_spec(mode):
+        merging = mode != "partial"
+        return {"op": "aggregate", "mode": mode, "group_by": [{"expr": {"col": 0}, "name": "l_orderkey"}],
+                "aggs": [dict({"fn": fn, "name": nm, "input_type": it}, **({} if merging else {"args": [] if a is None else [a]})) for fn, a, nm, it in aggs]}
+    chain = {"op": "chain", "ops": [agg_spec("partial"), {"op": "exchange", "mode": "hash", "exprs": [{"col": 0}]}, agg_spec("final_partitioned")]}
+    state = {}
+
+    def run():
+        op = engine.GpuExec(chain, [schema], ctx)
+        for d in devs:
+            op.push(d.borrow())
+        op.finish()
+        state["out"] = op.collect_device()
+        for d in state["out"]:
+            d.schema = op.schema
+        state["schema"] = op.schema
+        state["m"] = op.metrics()
+        op.close()
+    for _ in range(2):
+        run()
+    m0 = state["m"]
+    steps = max(1, min(args.steps, 5))
+    ms = timed_steps(ctx, stream, world, steps, run)
+    m1 = state["m"]
+    sent = (m1["gpu.exchange_sent_bytes"] - m0["gpu.exchange_sent_bytes"]) / steps
+    recv = (m1["gpu.exchange_recv_bytes"] - m0["gpu.exchange_recv_bytes"]) / steps
+    xms = (m1["gpu.exchange_ns"] - m0["gpu.exchange_ns"]) / 1e6 / steps
+    rows_in = sum(g.rows for g in gens)
+    orders = sum(n for _, n in chunks)
+    # ---- parity -----------------------------------------------------------------------------------------------------
+    # (1) exact, per group: the numpy oracle aggregates the first rows of rank 0's shard; every rank filters its share of the
+    #     final result down to those keys; rank 0 merges and compares
+    sample = gens[0].host_table().slice(0, 1 << 20) if rank == 0 else None
+    kmax = [int(sample.column(0)[sample.num_rows - 1].as_py()) if rank == 0 else 0]
+    dist.broadcast_object_list(kmax, src=0)
+    flt = {"op": "filter", "predicate": {"op": "<", "l": {"col": 0}, "r": {"lit": kmax[0], "type": "Int64"}}, "projection": None}
+    fop = engine.GpuExec(flt, [state["schema"]], ctx)
+    for d in state["out"]:
+        fop.push(d.borrow())
+    fop.finish()
+    mine = fop.collect().to_pylist()
+    fop.close()
+    # (2) global: groups, rows and quantity over all ranks against totals the generator / a keyless aggregate give
+    tot = {"op": "aggregate", "mode": "single", "group_by": [], "aggs": [{"fn": "sum", "args": [{"col": 1}], "name": "s"}, {"fn": "sum", "args": [{"col": 2}], "name": "c"},
+                                                                          {"fn": "count", "args": [], "name": "g"}]}
+    top = engine.GpuExec(tot, [state["schema"]], ctx)
+    for d in state["out"]:
+        top.push(d.borrow())
+    top.finish()
+    t_res = top.collect().to_pylist()[0]
+    top.close()
+    qin = {"op": "aggregate", "mode": "single", "group_by": [], "aggs": [{"fn": "sum", "args": [{"col": 1}], "name": "s"}]}
+    qop = engine.GpuExec(qin, [schema], ctx)
+    for d in devs:
+        qop.push(d.borrow())
+    qop.finish()
+    q_in = qop.collect().to_pylist()[0]["s"]
+    qop.close()
+    gathered = [None] * world
+    dist.gather_object({"rows": mine, "sum": t_res["s"] or 0, "cnt": t_res["c"] or 0, "groups": t_res["g"], "in_rows": rows_in, "in_orders": orders, "in_qty": q_in},
+                       gathered if rank == 0 else None, dst=0)
+    res = None
+    if rank == 0:
+        want = oracle_ops.batch_to_arrow(oracle_ops.run_op(agg_spec("single"), oracle_ops.batch_from_arrow(sample))).to_pylist()
+        want = sorted((r["l_orderkey"], r["sum_qty"], r["cnt"]) for r in want if r["l_orderkey"] < kmax[0])
+        got = sorted((r["l_orderkey"], r["sum_qty"], r["cnt"]) for g in gathered for r in g["rows"])
+        assert got == want, f"all-to-all aggregate: {len(got)} sampled groups differ from the oracle's {len(want)}"
+        assert sum(g["groups"] for g in gathered) == sum(g["in_orders"] for g in gathered), "all-to-all aggregate lost or duplicated groups"
+        assert sum(g["cnt"] for g in gathered) == sum(g["in_rows"] for g in gathered), "all-to-all aggregate lost or duplicated rows"
+        assert sum(g["sum"] for g in gathered) == sum(g["in_qty"] for g in gathered), "all-to-all aggregate changed a sum"
+        res = {"workload": f"GROUP BY l_orderkey over SF{args.exchange_sf:g} lineitem per GPU: Partial -> Hash exchange (NCCL all-to-all) -> FinalPartitioned",
+               "rows_per_gpu": rows_in, "groups_per_gpu": orders, "ms_per_step": ms / steps, "value_rows_per_s": rows_in * world / (ms / steps / 1e3),
+               "nvlink_sent_bytes_per_gpu": sent, "nvlink_recv_bytes_per_gpu": recv, "alltoall_ms": xms,
+               "alltoall_gbs_per_gpu_per_dir": (sent / (xms / 1e3) / 1e9) if xms > 0 else None,
+               "nvlink_frac": (sent / (xms / 1e3) / 1e9 / NVLINK_GBS_PER_DIR) if xms > 0 else None,
+               "parity": f"ok: {len(want)} sampled groups exact vs numpy oracle; groups/rows/sum totals over {world} ranks exact"}
+    del devs, gens
+    state.clear()
+    return res
 
 
 def main():
@@ -283,9 +383,10 @@ def main():
 
     import torch
     import torch.distributed as dist
+    torch.cuda.set_device(local)
     if world > 1:
-        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from datagen import tpch_gpu
     from sail_b200 import engine
     global SORT_ON_GPU, DIST_BACKEND
     ctx = engine.Context(local)
@@ -295,101 +396,137 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
         DIST_BACKEND = sdist.GpuBackend(ctx, rank, world)
-    table = gen_shard(args.sf, rank, world).combine_chunks()
-    n_rows = table.num_rows
+    t_gen = time.perf_counter()
+    total_sf, chunks = shard_chunks(args.sf, args.chunk_sf, rank, world)
+    gens = [tpch_gpu.generate_buffers(total_sf, f, n, (), Q1_COLS, local)[1] for f, n in chunks]
+    devs = [g.device_batch(ctx) for g in gens]
+    t_gen = time.perf_counter() - t_gen
+    schema = gens[0].schema
+    n_rows = sum(g.rows for g in gens)
     specs = q1_specs()
     try:
-        engine.GpuExec(specs[2], [engine.GpuExec(specs[1], [engine.GpuExec(specs[0], [table.schema], ctx).schema], ctx).schema], ctx).close()
+        engine.GpuExec(specs[2], [engine.GpuExec(specs[1], [engine.GpuExec(specs[0], [schema], ctx).schema], ctx).schema], ctx).close()
     except engine.SailGpuError:
         SORT_ON_GPU = False
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
 
     # ---- resident leg ---------------------------------------------------------------------------
-    dev = engine.to_device(table, ctx)
-    for _ in range(max(3, args.warmup)):
-        out, _, _, _ = run_query(ctx, specs, [dev], table.schema)
-    sampler = ClockSampler(local)
-    if world > 1:
-        dist.barrier()
-    ctx.synchronize()
-    torch.cuda.synchronize()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    launches = kern_ns = kern_launches = 0
-    for _ in range(args.steps):
-        out, l, kns, kl = run_query(ctx, specs, [dev], table.schema)
-        launches += l
-        kern_ns += kns
-        kern_launches += kl
-    e1.record(stream)
-    ctx.synchronize()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    total_rows = n_rows * world
-    value = total_rows / (ms_per_step / 1e3)
+    acc = {"launches": 0, "kern_ns": 0, "kern_launches": 0, "jit": 0, "out": None}
 
-    # ---- end-to-end leg: host (pinned) Arrow buffers through the C ABI -------------------------------
-    e2e_value = ms_e = None
-    e2e_steps = 1
-    h2d_bytes = d2h_bytes = 0
-    chunks = []
-    out_e = out
-    if not args.skip_e2e:
-        e2e_value, ms_e, e2e_steps, h2d_bytes, d2h_bytes, chunks, out_e = e2e_leg(args, ctx, specs, table, stream, world, total_rows)
-    # ---- CPU baseline (rank 0, N=1 only) + parity of the full-size GPU result ----------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.skip_cpu:
-        threads = os.cpu_count() or 1
-        want_rows, dt = cpu_q1(table, threads, reps=3)
-        check_result(out, want_rows)
-        if not args.skip_e2e:
-            check_result(out_e, want_rows)
-        cpu = {"value": n_rows / dt, "unit": "rows/s", "cores": threads, "kind": "port",
-               "sample": f"full SF{args.sf:g} lineitem ({n_rows} rows) x3, oracle/cpipelines.c (C port of the DataFusion CPU path), all host threads"}
+    def resident_step():
+        out, l, kns, kl, jl = run_query(ctx, specs, devs, schema)
+        acc["out"] = out
+        acc["launches"] += l; acc["kern_ns"] += kns; acc["kern_launches"] += kl; acc["jit"] += jl
+    for _ in range(max(3, args.warmup)):
+        resident_step()
+    acc.update(launches=0, kern_ns=0, kern_launches=0, jit=0)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed_steps(ctx, stream, world, args.steps, resident_step)
+    clocks = sampler.stop()
+    ms_per_step = ms / args.steps
+    total_rows_t = torch.tensor([n_rows], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(total_rows_t)
+    total_rows = int(total_rows_t.item())
+    value = total_rows / (ms_per_step / 1e3)
+    out = acc["out"]
+
+    # ---- host copies: parity of the full-size result against the C port (every rank's shard), CPU baseline, e2e inputs ----
+    host_e2e, cpu, want_rows = [], None, None
+    if not args.skip_cpu:
+        threads = max(1, (os.cpu_count() or 1) // world)
+        parts, dt_cpu = [], 0.0
+        for i, g in enumerate(gens):
+            t = g.host_table()
+            rows_i, dt_i = cpu_q1_chunks([t], threads)
+            parts.append(rows_i)
+            dt_cpu += dt_i
+            if i < args.e2e_chunks and not args.skip_e2e:
+                host_e2e.append(t)
+        mine = merge_q1_rows(parts)
+        gathered = [mine]
+        if world > 1:
+            gathered = [None] * world
+            dist.gather_object(mine, gathered if rank == 0 else None, dst=0)
+        if rank == 0:
+            want_rows = merge_q1_rows(gathered)
+            check_result(out, want_rows)
+            if world == 1:
+                cpu = {"value": n_rows / dt_cpu, "unit": "rows/s", "cores": threads, "kind": "port",
+                       "sample": f"the full SF{args.sf:g} lineitem ({n_rows} rows) once, in {len(gens)} batches, oracle/cpipelines.c (C port of the DataFusion CPU path), all host threads"}
+    elif not args.skip_e2e:
+        host_e2e = [g.host_table() for g in gens[: args.e2e_chunks]]
+
+    # ---- end-to-end leg: PAGEABLE host Arrow buffers through the C ABI -------------------------------------------------
+    e2e = None
+    if not args.skip_e2e and host_e2e:
+        e2e_rows = sum(t.num_rows for t in host_e2e)
+        h2d = sum(b.size for t in host_e2e for c in t.columns for ch in c.chunks for b in ch.buffers() if b is not None)
+        batches = [t.to_batches()[0] for t in host_e2e]
+        st = {}
+
+        def e2e_step():
+            st["out"], _, _, _, _ = run_query(ctx, specs, None, schema, host_chunks=batches)
+        for _ in range(2):
+            e2e_step()
+        e2e_steps = max(1, min(args.steps, 5))
+        ms_e = timed_steps(ctx, stream, world, e2e_steps, e2e_step)
+        rows_t = torch.tensor([e2e_rows], device="cuda", dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(rows_t)
+        out_e = st["out"]
+        d2h = 0 if out_e is None else sum(b.size for c in out_e.columns for ch in c.chunks for b in ch.buffers() if b is not None)
+        if rank == 0 and world == 1 and not args.skip_cpu:      # (N > 1: the resident leg carried the all-rank check)
+            check_result(out_e, merge_q1_rows([parts[i] for i in range(len(host_e2e))]))
+        e2e = {"value": int(rows_t.item()) / (ms_e / e2e_steps / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e / e2e_steps, "host_batches": len(batches), "host_memory": "pageable",
+               "sample": f"the first {len(batches)} of {len(gens)} batches per GPU ({e2e_rows} rows)"}
+    del host_e2e
+
+    # ---- all-to-all leg (N > 1) ------------------------------------------------------------------------------------------
+    exchange = None
+    if world > 1 and not args.skip_exchange:
+        exchange = exchange_leg(args, ctx, stream, rank, world, local)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peak, peak_src = FALLBACK_HBM_GBS, "fallback"
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
-        # the fused stage may run as several launches per step (cardinality-probe chunk + the rest): bytes of all its
-        # launches over the time of all its launches, i.e. the byte-weighted average launch
-        kern_ms = kern_ns / 1e6 / max(1, args.steps)
+        # the fused stage runs as one launch per resident batch: bytes of all its launches over the time of all its launches
+        kern_ms = acc["kern_ns"] / 1e6 / max(1, args.steps)
         achieved = (n_rows * ALGO_BYTES_PER_ROW) / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "q1_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        lps = acc["kern_launches"] / max(1, args.steps)
         line = {
             "metric": "TPC-H Q1 rows/s (scan+filter+hash-aggregate), lineitem resident in HBM",
             "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "i128 (Decimal128) / i64", "data": "synthetic (dbgen-exact TPC-H lineitem)",
+            "dtype": "i128 (Decimal128) / i64", "data": "synthetic (dbgen-exact TPC-H lineitem, generated in HBM)",
             "config": {"workload": f"TPC-H Q1 SF{args.sf:g} per GPU, 1 partition per GPU, Arrow batches resident in HBM",
-                       "rows_per_gpu": n_rows, "strings": "Utf8View", "l2": "inputs (6 GB) larger than L2; no flush",
-                       "plan": "GpuChainExec{GpuPipelineExec[Filter+Projection+Aggregate(Partial)] -> GpuAggregateExec(FinalPartitioned)"
-                               + (" -> GpuExchangeExec(auto: coalesce on rank 0 | Hash + NCCL all-to-all)" if world > 1 else "")
-                               + (" -> GpuSortExec" if SORT_ON_GPU else "") + "}", "parallelism": f"{world} rank(s), lineitem sharded by order range"},
-            "e2e": None if e2e_value is None else {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                                                    "ms_per_step": ms_e / e2e_steps, "host_batches": len(chunks)},
-            "gpu_launches": launches,
+                       "rows_per_gpu": n_rows, "batches_per_gpu": len(gens), "strings": "Utf8View", "l2": "inputs (60 GB at SF100) larger than L2; no flush",
+                       "plan": "GpuChainExec{GpuPipelineExec[Filter+Projection+Aggregate(Partial)] -> "
+                               + ("GpuExchangeExec(auto: coalesce on rank 0 | Hash + NCCL all-to-all) -> " if world > 1 else "")
+                               + "GpuAggregateExec(FinalPartitioned)" + (" -> GpuSortExec" if SORT_ON_GPU else "") + "}",
+                       "parallelism": f"{world} rank(s), lineitem sharded by order range", "datagen_s": round(t_gen, 2),
+                       "parity": "skipped" if args.skip_cpu else f"ok: full-size result of all {world} rank(s) equals the C port (exact integers)"},
+            "e2e": e2e,
+            "gpu_launches": acc["launches"],
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "kernel": "sg::pipeline_kernel", "kernel_ms": kern_ms, "peak_source": peak_src,
-                         "launches_per_step": kern_launches / max(1, args.steps), "algorithmic_bytes_per_launch": n_rows * ALGO_BYTES_PER_ROW},
+                         "traffic": (traffic * n_rows / 59986052) if traffic else None,
+                         "kernel": "sg_jit_kernel (specialised pipeline)" if acc["jit"] else "sg::pipeline_kernel", "kernel_ms": kern_ms, "peak_source": peak_src,
+                         "launches_per_step": lps, "specialised_launches_per_step": acc["jit"] / max(1, args.steps),
+                         "algorithmic_bytes_per_launch": n_rows * ALGO_BYTES_PER_ROW / max(1.0, lps)},
             "cpu_baseline": cpu,
+            "exchange": exchange,
         }
         print(json.dumps(line), flush=True)
-    del dev, out, out_e, chunks
+    del devs, gens, out
     ctx.synchronize()
     if world > 1:
         dist.destroy_process_group()
@@ -397,9 +534,18 @@ def main():
 
 
 def run_reference(args):
-    """The reference arm: the reference's own CPU algorithm for this path (C port: the Rust
-    toolchain and DataFusion are absent from this image), all host threads, same config/metric."""
-    table = gen_shard(args.sf, 0, 1).combine_chunks()
+    """The reference arm: the reference's own CPU algorithm for this path (C port: the Rust toolchain and DataFusion are
+    absent from this image), all host threads, same metric; each step is one pass over a bounded sample (one chunk-sf
+    batch of the workload).  Touches only datagen/ and oracle/ libraries."""
+    from datagen import tpch, tpch_gpu
+    sample_sf = min(args.sf, args.chunk_sf)
+    total_sf, chunks = shard_chunks(args.sf, sample_sf, 0, 1)
+    try:
+        import torch
+        assert torch.cuda.is_available()
+        table = tpch_gpu.generate_buffers(total_sf, chunks[0][0], chunks[0][1], (), Q1_COLS, 0)[1].host_table()
+    except Exception:
+        table = tpch.lineitem(total_sf, Q1_COLS, first=chunks[0][0], n=chunks[0][1]).combine_chunks()
     n_rows = table.num_rows
     threads = os.cpu_count() or 1
     from oracle import cpipelines
@@ -412,13 +558,14 @@ def run_reference(args):
         cpipelines.q1(table, cutoff, threads)
     dt = (time.perf_counter() - t0) / args.steps
     v = n_rows / dt
+    sample = f"one SF{sample_sf:g} batch ({n_rows} rows) of the SF{args.sf:g} workload per step, oracle/cpipelines.c, {threads} threads"
     line = {"impl": "reference", "metric": "TPC-H Q1 rows/s (scan+filter+hash-aggregate), lineitem resident in HBM",
             "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i128 (Decimal128)",
             "data": "synthetic (dbgen-exact TPC-H lineitem)",
-            "config": {"workload": f"TPC-H Q1 SF{args.sf:g}, Arrow batches resident in host memory", "rows": n_rows},
-            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": threads, "kind": "port",
-                             "sample": f"full SF{args.sf:g} lineitem ({n_rows} rows) per step"},
+            "config": {"workload": f"TPC-H Q1 SF{args.sf:g}, Arrow batches resident in host memory; rate measured on a bounded sample, 1 shard on the CPU at every N",
+                       "rows": n_rows, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0

@@ -54,8 +54,11 @@
  *   {"like":E,"pattern":"..","negated":b} {"fn":"date_part|substr",...}
  * Types T: Boolean Int8..Int64 UInt8..UInt64 Float32 Float64 Date32 Decimal128(p,s) Utf8 Utf8View
  *
- * Threading: calls on different handles may run concurrently from any
- * thread; calls on one handle must not overlap.  No thread affinity (the device is set per call).
+ * Threading: any function may be called from any thread (no affinity: the
+ * device is set per call); calls on one handle must not overlap.  A context owns ONE compute stream,
+ * allocation cache and D2H staging block, so calls on handles of the same context are serialised
+ * inside the library (they are correct from any number of threads, they do not overlap on the GPU);
+ * partitions that should run concurrently use one context each -- contexts share nothing.
  * There is NO CPU fallback: every function fails with SAILGPU_ERR_NO_DEVICE if CUDA is unusable.
  */
 #ifndef SAILGPU_H

@@ -35,8 +35,10 @@ int32_t guard(std::string* err, F&& f) {
   }
 }
 void set_device(const Ctx& c) { SG_CUDA(cudaSetDevice(c.device)); }
+using CtxLock = std::lock_guard<std::recursive_mutex>;
 }  // namespace
 
+namespace sg { void set_ctx_error(const std::string& m) { g_ctx_error = m; } }   // ops_more.cu: comm_init / exchange report through sailgpu_ctx_last_error
 namespace sg { size_t pipeline_precompile(const Json& spec, const std::vector<Schema>& inputs, uint64_t validity_mask, bool cold, bool compile, std::string* source); }
 
 extern "C" {
@@ -77,6 +79,7 @@ SAILGPU_API int32_t sailgpu_ctx_create(int32_t device, sailgpu_ctx** out) {
 SAILGPU_API void sailgpu_ctx_destroy(sailgpu_ctx* c) {
   if (!c) return;
   if (sg::g_exiting.load()) return;
+  CtxLock lk(c->ctx.mu);
   cudaSetDevice(c->ctx.device);
   // Batches handed out through pull_device may outlive the context: the (tiny) Ctx block is intentionally never freed,
   // it is only marked dead so that late buffer releases use cudaFree instead of the destroyed stream.
@@ -91,6 +94,7 @@ SAILGPU_API void* sailgpu_ctx_stream(sailgpu_ctx* c) { return c ? (void*)c->ctx.
 SAILGPU_API int32_t sailgpu_ctx_synchronize(sailgpu_ctx* c) {
   return guard(&g_ctx_error, [&] {
     SG_CHECK(c != nullptr, SAILGPU_ERR_INVALID, "null context");
+    CtxLock lk(c->ctx.mu);
     set_device(c->ctx);
     SG_CUDA(cudaStreamSynchronize(c->ctx.stream));
   });
@@ -100,6 +104,7 @@ SAILGPU_API int32_t sailgpu_op_create(sailgpu_ctx* c, const char* spec_json, siz
                           int32_t n_inputs, int32_t partition, sailgpu_op** out, struct ArrowSchema* out_schema) {
   return guard(&g_ctx_error, [&] {
     SG_CHECK(c && spec_json && out && out_schema, SAILGPU_ERR_INVALID, "null argument");
+    CtxLock lk(c->ctx.mu);
     set_device(c->ctx);
     Json spec = JsonParser(spec_json, spec_len).parse();
     std::vector<Schema> ins;
@@ -150,6 +155,7 @@ SAILGPU_API int64_t sailgpu_jit_precompile(const char* spec_json, size_t spec_le
 SAILGPU_API int32_t sailgpu_op_push(sailgpu_op* h, int32_t input_idx, struct ArrowArray* batch) {
   if (!h) return SAILGPU_ERR_INVALID;
   return guard(&h->last_error, [&] {
+    CtxLock lk(h->owner->ctx.mu);
     set_device(h->owner->ctx);
     SG_CHECK(input_idx >= 0 && input_idx < (int)h->op->in_schemas.size(), SAILGPU_ERR_INVALID, "input index out of range");
     SG_CHECK(!h->input_finished[(size_t)input_idx], SAILGPU_ERR_STATE, "push after finish_input");
@@ -161,6 +167,7 @@ SAILGPU_API int32_t sailgpu_op_push(sailgpu_op* h, int32_t input_idx, struct Arr
 SAILGPU_API int32_t sailgpu_op_push_device(sailgpu_op* h, int32_t input_idx, struct ArrowDeviceArray* batch) {
   if (!h) return SAILGPU_ERR_INVALID;
   return guard(&h->last_error, [&] {
+    CtxLock lk(h->owner->ctx.mu);
     set_device(h->owner->ctx);
     SG_CHECK(input_idx >= 0 && input_idx < (int)h->op->in_schemas.size(), SAILGPU_ERR_INVALID, "input index out of range");
     SG_CHECK(!h->input_finished[(size_t)input_idx], SAILGPU_ERR_STATE, "push after finish_input");
@@ -175,6 +182,7 @@ SAILGPU_API int32_t sailgpu_op_push_device(sailgpu_op* h, int32_t input_idx, str
 SAILGPU_API int32_t sailgpu_op_finish_input(sailgpu_op* h, int32_t input_idx) {
   if (!h) return SAILGPU_ERR_INVALID;
   return guard(&h->last_error, [&] {
+    CtxLock lk(h->owner->ctx.mu);
     set_device(h->owner->ctx);
     SG_CHECK(input_idx >= 0 && input_idx < (int)h->op->in_schemas.size(), SAILGPU_ERR_INVALID, "input index out of range");
     if (h->input_finished[(size_t)input_idx]) return;
@@ -187,6 +195,7 @@ SAILGPU_API int32_t sailgpu_op_finish_input(sailgpu_op* h, int32_t input_idx) {
 static int32_t pull_common(sailgpu_op* h, int part, struct ArrowArray* host_out, struct ArrowDeviceArray* dev_out, int32_t* has_more) {
   if (!h) return SAILGPU_ERR_INVALID;
   return guard(&h->last_error, [&] {
+    CtxLock lk(h->owner->ctx.mu);
     set_device(h->owner->ctx);
     SG_CHECK(has_more && (host_out || dev_out), SAILGPU_ERR_INVALID, "null argument");
     BatchPtr b;
@@ -209,20 +218,24 @@ SAILGPU_API int32_t sailgpu_op_pull_partition(sailgpu_op* h, int32_t part, struc
 
 SAILGPU_API int64_t sailgpu_op_metrics(sailgpu_op* h, char* json_buf, size_t cap) {
   if (!h) return -1;
+  CtxLock lk(h->owner->ctx.mu);
   cudaSetDevice(h->owner->ctx.device);
   const Metrics& m = h->op->m;
-  char tmp[1024];
+  char tmp[2048];
   int n = snprintf(tmp, sizeof(tmp),
                    "{\"output_rows\":%llu,\"output_batches\":%llu,\"input_rows\":%llu,\"input_batches\":%llu,"
                    "\"elapsed_compute\":%llu,\"build_input_rows\":%llu,\"build_input_batches\":%llu,\"build_time\":%llu,"
                    "\"join_time\":%llu,\"gpu.kernel_launches\":%llu,\"gpu.h2d_bytes\":%llu,\"gpu.d2h_bytes\":%llu,"
-                   "\"gpu.pipeline_launches\":%llu,\"gpu.jit_launches\":%llu,\"gpu.pipeline_kernel_ns\":%llu}",
+                   "\"gpu.pipeline_launches\":%llu,\"gpu.jit_launches\":%llu,\"gpu.pipeline_kernel_ns\":%llu,"
+                   "\"gpu.exchange_sent_bytes\":%llu,\"gpu.exchange_recv_bytes\":%llu,\"gpu.exchange_ns\":%llu,\"gpu.exchange_calls\":%llu}",
                    (unsigned long long)m.output_rows, (unsigned long long)m.output_batches, (unsigned long long)m.input_rows,
                    (unsigned long long)m.input_batches, (unsigned long long)m.elapsed_compute_ns, (unsigned long long)m.build_input_rows,
                    (unsigned long long)m.build_input_batches, (unsigned long long)m.build_time_ns, (unsigned long long)m.join_time_ns,
                    (unsigned long long)m.kernel_launches, (unsigned long long)h->owner->ctx.h2d_bytes.load(),
                    (unsigned long long)h->owner->ctx.d2h_bytes.load(), (unsigned long long)h->op->m.pipeline_launches, (unsigned long long)h->op->m.jit_launches,
-                   (unsigned long long)h->op->pipeline_kernel_ns());
+                   (unsigned long long)h->op->pipeline_kernel_ns(), (unsigned long long)h->owner->ctx.exch_sent_bytes.load(),
+                   (unsigned long long)h->owner->ctx.exch_recv_bytes.load(), (unsigned long long)h->owner->ctx.exch_ns.load(),
+                   (unsigned long long)h->owner->ctx.exch_calls.load());
   if (json_buf && cap) { size_t k = std::min<size_t>((size_t)n, cap - 1); memcpy(json_buf, tmp, k); json_buf[k] = 0; }
   return n + 1;
 }
@@ -232,6 +245,7 @@ SAILGPU_API const char* sailgpu_last_error(const sailgpu_op* h) { return h ? h->
 SAILGPU_API void sailgpu_op_destroy(sailgpu_op* h) {
   if (!h) return;
   if (sg::g_exiting.load()) return;
+  CtxLock lk(h->owner->ctx.mu);
   cudaSetDevice(h->owner->ctx.device);
   cudaStreamSynchronize(h->owner->ctx.stream);
   delete h;
@@ -240,12 +254,14 @@ SAILGPU_API void sailgpu_op_destroy(sailgpu_op* h) {
 SAILGPU_API int32_t sailgpu_host_alloc(sailgpu_ctx* c, size_t bytes, void** out) {
   return guard(&g_ctx_error, [&] {
     SG_CHECK(c && out, SAILGPU_ERR_INVALID, "null argument");
+    CtxLock lk(c->ctx.mu);
     set_device(c->ctx);
     SG_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
   });
 }
 SAILGPU_API void sailgpu_host_free(sailgpu_ctx* c, void* p) {
   if (!c || !p) return;
+  CtxLock lk(c->ctx.mu);
   cudaSetDevice(c->ctx.device);
   cudaFreeHost(p);
 }

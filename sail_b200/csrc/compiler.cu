@@ -319,11 +319,12 @@ void PipelineCompiler::finish_aggregate(CompiledPipeline& out, const StageSpec& 
     dedup[key] = A.n_accs;
     return A.n_accs++;
   };
-  auto sum_acc = [&](const Val& x, const DataType& t) -> int {
-    if (t.is_decimal()) { const int j = add_acc(ACC_SUM_I128, &x); if (t.precision <= 16 && j < MAX_ACCS) small_acc_[j] = true; return j; }
-    if (t.is_float()) { Val f = convert(x, K_F64); f.vslot = x.vslot; return add_acc(ACC_SUM_F64, &f); }
+  auto ident = [&](const std::string& what, int j) { out.acc_ident[what] = j; return j; };
+  auto sum_acc = [&](const Val& x, const DataType& t, const std::string& id) -> int {
+    if (t.is_decimal()) { const int j = add_acc(ACC_SUM_I128, &x); if (t.precision <= 16 && j < MAX_ACCS) small_acc_[j] = true; return ident("sum|" + id, j); }
+    if (t.is_float()) { Val f = convert(x, K_F64); f.vslot = x.vslot; return ident("sum|" + id, add_acc(ACC_SUM_F64, &f)); }
     Val w = convert(x, K_I64); w.vslot = x.vslot;
-    return add_acc(ACC_SUM_I64, &w);
+    return ident("sum|" + id, add_acc(ACC_SUM_I64, &w));
   };
   auto minmax_acc = [&](bool is_min, const Val& x, const DataType& t) -> int {
     SG_CHECK(!t.is_string() && t.id != TypeId::Bool, SAILGPU_ERR_UNSUPPORTED, "min/max over " + t.str() + " is not supported on the GPU path yet");
@@ -344,7 +345,9 @@ void PipelineCompiler::finish_aggregate(CompiledPipeline& out, const StageSpec& 
   for (auto& a : st.aggs) {
     DataType in_t = a.input_type;
     Val arg; bool has_arg = false;
-    if (!merging && a.has_arg) { ExprPtr x = substitute(a.arg); arg = compile(x); in_t = x->type; has_arg = true; }
+    std::string aid = "*";        // identity of the argument: its expression over the original input columns
+    if (!merging && a.has_arg) { ExprPtr x = substitute(a.arg); arg = compile(x); in_t = x->type; has_arg = true; aid = x->key(); }
+    if (merging) aid = "state" + std::to_string(state_col);
     SG_CHECK(a.fn == "count" || has_arg || merging, SAILGPU_ERR_INVALID, "aggregate '" + a.fn + "' needs an argument");
     AggTypes at = agg_types(a.fn, a.fn == "count" ? T(TypeId::Int64) : in_t);
     auto state_val = [&](size_t k) { return compile(bindings_.at(state_col + k)); };
@@ -357,25 +360,27 @@ void PipelineCompiler::finish_aggregate(CompiledPipeline& out, const StageSpec& 
       if (merging) { Val s = state_val(0); Val w = convert(s, K_I64); w.vslot = s.vslot; j = add_acc(ACC_SUM_I64, &w); A.accs[j].track_seen = 0; }
       else if (has_arg && arg.vslot >= 0) { Val only_valid = arg; j = add_acc(ACC_COUNT, &only_valid); }
       else j = add_acc(ACC_COUNT, nullptr);
+      ident("count|" + aid, j);
       push_out(1, j, 0, T(TypeId::Int64), false);
     } else if (a.fn == "sum") {
       Val x = merging ? state_val(0) : arg;
-      int j = sum_acc(x, merging ? at.state[0] : in_t);
+      int j = sum_acc(x, merging ? at.state[0] : in_t, aid);
       push_out(1, j, 0, at.state[0], A.accs[j].track_seen != 0);
     } else if (a.fn == "min" || a.fn == "max") {
       Val x = merging ? state_val(0) : arg;
-      int j = minmax_acc(a.fn == "min", x, in_t);
+      int j = ident(a.fn + "|" + aid, minmax_acc(a.fn == "min", x, in_t));
       push_out(1, j, 0, in_t, A.accs[j].track_seen != 0);
     } else if (a.fn == "avg") {
       int jc, js;
       if (merging) {
-        Val c = state_val(0); Val w = convert(c, K_I64); w.vslot = c.vslot; jc = add_acc(ACC_SUM_I64, &w); A.accs[jc].track_seen = 0;
+        Val c = state_val(0); Val w = convert(c, K_I64); w.vslot = c.vslot; jc = ident("count|" + aid, add_acc(ACC_SUM_I64, &w)); A.accs[jc].track_seen = 0;
         Val s = state_val(1);
-        js = sum_acc(s, at.state[1]);
+        js = sum_acc(s, at.state[1], "state" + std::to_string(state_col + 1));
       } else {
         if (arg.vslot >= 0) { Val only_valid = arg; jc = add_acc(ACC_COUNT, &only_valid); } else jc = add_acc(ACC_COUNT, nullptr);
-        if (in_t.is_decimal()) js = sum_acc(arg, in_t);
-        else { Val f = convert(arg, K_F64); f.vslot = arg.vslot; js = add_acc(ACC_SUM_F64, &f); }
+        ident("count|" + aid, jc);
+        if (in_t.is_decimal()) js = sum_acc(arg, in_t, aid);
+        else { Val f = convert(arg, K_F64); f.vslot = arg.vslot; js = ident("sumf|" + aid, add_acc(ACC_SUM_F64, &f)); }
       }
       if (partial) {
         push_out(1, jc, 0, T(TypeId::UInt64), false);

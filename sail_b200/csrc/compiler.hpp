@@ -75,6 +75,9 @@ struct CompiledPipeline {
   std::vector<DataType> out_types;
   AggParams agg{};                   // SINK_AGG (table pointers filled at launch)
   std::vector<AggOutSpec> agg_outs;
+  std::map<std::string, int> acc_ident;   // SINK_AGG: "what is accumulated" (function | argument expression) -> accumulator index; the same
+                                     // identities exist under every validity signature, which is how a table is carried over when a
+                                     // later batch brings validity buffers an earlier one did not have (engine.cu: migrate_layout)
   std::vector<KeyDesc> keys;         // SINK_BUILD / SINK_PARTITION key slots
   std::vector<std::string> literals; // device-resident byte strings (LIKE patterns, long string literals)
   std::vector<std::pair<int, int>> literal_fixups;   // (instruction index, literal index) -> imm1 pointer

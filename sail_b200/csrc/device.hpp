@@ -30,11 +30,16 @@ struct Ctx {
   cudaStream_t stream = nullptr;        // compute stream
   cudaStream_t copy_stream = nullptr;   // H2D / D2H stream
   std::string last_error;
+  // One compute stream, one allocation cache and one D2H bounce buffer per context: calls that touch the device are
+  // serialised per context (capi.cu takes this lock), different contexts run concurrently.
+  std::recursive_mutex mu;
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   std::atomic<bool> dead{false};     // context destroyed; buffers that outlive it fall back to cudaFree
   // metrics shared by all ops of the context
   std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};
+  // all-to-all exchanges of this context: bytes put on / taken off NVLink and device time of the grouped send/recv
+  std::atomic<uint64_t> exch_sent_bytes{0}, exch_recv_bytes{0}, exch_ns{0}, exch_calls{0};
   // small device->host exports (operator results of a few rows) bounce through one pinned block so that all their
   // copies are asynchronous and the export costs one synchronisation instead of one per buffer
   struct D2HItem { void* host; size_t off, bytes; };

@@ -279,14 +279,92 @@ struct PipelineOp : Op {
     run.launch(P, cp, &aux, m);
   }
 
-  void push_agg(const BatchPtr& b) {
+  // ---- validity signatures ------------------------------------------------------------------------
+  // The entry layout (null-mask word, seen bits, one counter per nullable avg/count argument) follows from which input
+  // columns carry validity buffers, and Arrow batches of one stream differ in that (a producer drops the bitmap of a
+  // batch without nulls).  The operator therefore keeps the union of the signatures it has seen: a batch that lacks a
+  // bitmap of the union gets an all-ones one, and when a batch widens the union the table is carried over to the wider
+  // layout (migrate_layout).  DataFusion's accumulators take `null_count == 0` fast paths per batch the same way.
+  std::vector<bool> sticky_sig;
+  BufPtr ones; size_t ones_bytes = 0;
+
+  BatchPtr with_union_signature(const BatchPtr& b, bool* widened) {
+    *widened = false;
+    if (sticky_sig.empty()) sticky_sig.assign(b->cols.size(), false);
+    bool same = true;
+    for (size_t i = 0; i < b->cols.size(); ++i) {
+      const bool has = (bool)b->cols[i].validity;
+      if (has && !sticky_sig[i]) { sticky_sig[i] = true; *widened = true; }
+      same &= has == sticky_sig[i];
+    }
+    if (same) return b;
+    const size_t need = (size_t)((b->rows + 31) / 32 * 4);
+    if (!ones || ones_bytes < need) {
+      ones_bytes = std::max<size_t>(need, 1 << 16);
+      ones = dev_alloc(ctx, ones_bytes);
+      SG_CUDA(cudaMemsetAsync(ones->ptr, 0xFF, ones_bytes, ctx->stream));
+    }
+    auto bb = std::make_shared<DevBatch>(*b);
+    for (size_t i = 0; i < bb->cols.size(); ++i)
+      if (sticky_sig[i] && !bb->cols[i].validity) { bb->cols[i].validity = ones; bb->cols[i].null_count = 0; }
+    return bb;
+  }
+
+  static bool same_layout(const CompiledPipeline& a, const CompiledPipeline& b) {
+    const AggParams &x = a.agg, &y = b.agg;
+    if (x.entry_words != y.entry_words || x.key_words != y.key_words || x.has_null_word != y.has_null_word || x.n_accs != y.n_accs) return false;
+    for (int j = 0; j < x.n_accs; ++j)
+      if (x.accs[j].op != y.accs[j].op || x.accs[j].word != y.accs[j].word || x.accs[j].track_seen != y.accs[j].track_seen) return false;
+    return a.acc_ident == b.acc_ident;
+  }
+
+  // the table built under `from`'s layout continues under `to`'s (a superset: more seen bits, a null-mask word, separate
+  // counters where one counter served several aggregates)
+  void migrate_layout(const std::shared_ptr<CompiledPipeline>& from, const std::shared_ptr<CompiledPipeline>& to) {
+    Trace tr(ctx, "agg.migrate");
+    const AggParams &O = from->agg, &N = to->agg;
+    AggMigrateMap M;
+    memset(&M, 0, sizeof(M));
+    M.old_entry_words = (int32_t)O.entry_words; M.old_key_words = O.key_words;
+    M.key_shift = (N.has_null_word && !O.has_null_word) ? 1 : 0;
+    SG_CHECK(N.key_words == O.key_words + M.key_shift && N.has_null_word >= O.has_null_word, SAILGPU_ERR_UNSUPPORTED, "aggregate layouts of two batches cannot be reconciled (group keys)");
+    std::vector<int> src((size_t)N.n_accs, -1);
+    for (auto& kv : to->acc_ident) {
+      auto it = from->acc_ident.find(kv.first);
+      SG_CHECK(it != from->acc_ident.end(), SAILGPU_ERR_UNSUPPORTED, "aggregate layouts of two batches cannot be reconciled (" + kv.first + ")");
+      src[(size_t)kv.second] = it->second;
+    }
+    for (int j = 0; j < N.n_accs; ++j) {
+      SG_CHECK(src[(size_t)j] >= 0 && O.accs[src[(size_t)j]].op == N.accs[j].op, SAILGPU_ERR_UNSUPPORTED, "aggregate layouts of two batches cannot be reconciled (accumulator kinds)");
+      M.acc_src_word[j] = (int16_t)O.accs[src[(size_t)j]].word;
+      M.seen_src[j] = N.accs[j].track_seen ? (O.accs[src[(size_t)j]].track_seen ? (int8_t)src[(size_t)j] : (int8_t)-1) : (int8_t)-2;
+    }
+    check_device_error(ctx, run.scal.error());
+    const uint64_t groups = read_n_groups();
+    AggTable old = tab;
+    tab.table = dev_alloc(ctx, (size_t)tab.capacity * N.entry_words * 8);
+    tab.state = dev_alloc_zero(ctx, (size_t)tab.capacity * 4);
+    tab.occ = dev_alloc(ctx, (size_t)tab.capacity * 4);
+    AggParams A = N;
+    fill_table(A);
+    SG_CUDA(cudaMemsetAsync(run.scal.n_groups(), 0, 8, ctx->stream));
+    SG_CUDA(launch_agg_migrate(A, M, static_cast<const uint8_t*>(old.table->ptr), static_cast<const uint32_t*>(old.occ->ptr), groups, run.scal.error(), ctx->stream));
+    m.kernel_launches++;
+    known_groups = -1;
+  }
+
+  void push_agg(const BatchPtr& b0) {
     Trace tr(ctx, "agg.push");
     resolve_pending();
-    if (b->rows == 0) return;
+    if (b0->rows == 0) return;
+    bool widened = false;
+    const BatchPtr b = with_union_signature(b0, &widened);
     auto cp = run.compiled_for(*b, use_cold);
-    if (!agg_cp) agg_cp = cp;
-    SG_CHECK(cp->agg.entry_words == agg_cp->agg.entry_words && cp->agg.key_words == agg_cp->agg.key_words, SAILGPU_ERR_UNSUPPORTED,
-             "aggregate input batches differ in which key columns carry validity buffers");
+    if (agg_cp && tab.capacity && !same_layout(*agg_cp, *cp)) {
+      SG_CHECK(widened, SAILGPU_ERR_STATE, "aggregate layout changed without a new validity buffer");
+      migrate_layout(agg_cp, cp);
+    }
+    agg_cp = cp;
     const bool grouped = cp->agg.n_keys > 0;
     // first table: 4 M slots for real inputs, but a final aggregate over a few partial rows gets a few KB (a hand-back
     // grows it if later batches are bigger)

@@ -23,6 +23,16 @@ struct AggExtractParams {
   AggOutCol cols[MAX_KEYS + 2 * MAX_ACCS];
 };
 
+// Carrying a group table over to a wider entry layout (a later batch brought validity buffers an earlier one lacked):
+// where every word of a new entry comes from in the old one.
+struct AggMigrateMap {
+  int32_t old_entry_words, old_key_words;
+  int32_t key_shift;                 // 1: the new layout gained the leading null-mask word
+  int32_t pad;
+  int16_t acc_src_word[MAX_ACCS];    // first word (inside the old accumulator area) of the accumulator a new one continues
+  int8_t seen_src[MAX_ACCS];         // old accumulator index whose seen bit carries over; -1: every old contribution was valid (bit set); -2: not tracked
+};
+cudaError_t launch_agg_migrate(const AggParams& A_new, const AggMigrateMap& M, const uint8_t* old_table, const uint32_t* old_occ, uint64_t old_groups, uint32_t* err, cudaStream_t s);
 cudaError_t launch_pipeline(const KernelArgs& K, int rpt, int n_stages, size_t smem_bytes, int grid, int minb, cudaStream_t stream);
 int pipeline_max_ctas_per_sm(int rpt, int minb, size_t smem_bytes, int sink, bool cold);
 cudaError_t launch_tile_popcount(const uint32_t* bits, int64_t n_rows, int tile_rows, int64_t n_tiles, uint32_t* counts, cudaStream_t s);

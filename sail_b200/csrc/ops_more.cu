@@ -895,6 +895,7 @@ struct ChainOp : Op {
     // every stage counts towards gpu.kernel_launches
     for (auto& o : ops) m.kernel_launches += o->m.kernel_launches;
     m.pipeline_launches += ops[0]->m.pipeline_launches;
+    m.jit_launches += ops[0]->m.jit_launches;
     for (auto& p : ops[0]->m.pending) m.pending.push_back(p);
     ops[0]->m.pending.clear();
     m.pipeline_kernel_ns += ops[0]->m.pipeline_kernel_ns;
@@ -956,7 +957,7 @@ constexpr int NCCL_INT8 = 0, NCCL_INT64 = 4;
 }  // namespace
 
 struct sailgpu_ctx { sg::Ctx ctx; };
-namespace { thread_local std::string g_x_error; }
+namespace sg { void set_ctx_error(const std::string& m); }
 
 #define NCCL_CALL(expr) do { int _r = (expr); if (_r != 0) sg::fail(SAILGPU_ERR_CUDA, std::string("NCCL error: ") + g_nccl.GetErrorString(_r) + " at " #expr); } while (0)
 
@@ -1122,7 +1123,16 @@ BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<Batc
     }
     BufPtr seg_keep_a, seg_keep_b;
     if (!pack_segs.empty()) SG_CUDA(launch_multi_copy(ctx, pack_segs, &seg_keep_a));
+    // bytes that cross NVLink (everything except the segment this rank keeps) and the device time of the grouped send/recv
+    {
+      uint64_t sent = 0, recvd = 0;
+      for (int peer = 0; peer < W; ++peer) if (peer != me) { sent += (uint64_t)msg_bytes(me, peer); recvd += (uint64_t)msg_bytes(peer, me); }
+      ctx->exch_sent_bytes += sent; ctx->exch_recv_bytes += recvd; ctx->exch_calls += 1;
+    }
+    cudaEvent_t xe0 = nullptr, xe1 = nullptr;
+    if (timing_enabled()) { SG_CUDA(cudaEventCreate(&xe0)); SG_CUDA(cudaEventCreate(&xe1)); SG_CUDA(cudaEventRecord(xe0, ctx->stream)); }
     NCCL_CALL(g_nccl.GroupStart());
+    struct GroupGuard { bool open = true; ~GroupGuard() { if (open) g_nccl.GroupEnd(); } } group_guard;     // an error below must not leave the group open
     for (int peer = 0; peer < W; ++peer) {
       const int64_t ks = parts[(size_t)peer]->rows, kr = cnt(peer, me, 0);
       if (ks && send_stage[(size_t)peer]) NCCL_CALL(g_nccl.Send(send_stage[(size_t)peer]->ptr, (size_t)msg_bytes(me, peer), NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
@@ -1144,7 +1154,9 @@ BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<Batc
         }
       }
     }
+    group_guard.open = false;
     NCCL_CALL(g_nccl.GroupEnd());
+    if (xe1) SG_CUDA(cudaEventRecord(xe1, ctx->stream));
     if (!unpack_segs.empty()) SG_CUDA(launch_multi_copy(ctx, unpack_segs, &seg_keep_b));
     // 3. post-process: rebase string views per source segment, pack byte columns
     BufPtr nullctrs = dev_alloc_zero(ctx, ncols * 8 + 8);
@@ -1172,6 +1184,11 @@ BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<Batc
       if (nulls[ci] == 0) out->cols[ci].validity = nullptr;
     }
     SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (xe0) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, xe0, xe1) == cudaSuccess) ctx->exch_ns += (uint64_t)((double)ms * 1e6);
+      cudaEventDestroy(xe0); cudaEventDestroy(xe1);
+    }
     }
   return out;
 }
@@ -1190,13 +1207,15 @@ SAILGPU_API int32_t sailgpu_ctx_comm_init(sailgpu_ctx* c, const uint8_t* unique_
     SG_CHECK(c && unique_id128 && world_size >= 1 && rank >= 0 && rank < world_size, SAILGPU_ERR_INVALID, "bad comm_init arguments");
     std::string err;
     SG_CHECK(load_nccl(&err), SAILGPU_ERR_CUDA, err);
+    std::lock_guard<std::recursive_mutex> lk(c->ctx.mu);
     SG_CUDA(cudaSetDevice(c->ctx.device));
     Id128 id; memcpy(id.b, unique_id128, 128);
     void* comm = nullptr;
     NCCL_CALL(g_nccl.CommInitRank(&comm, world_size, id, rank));
     c->ctx.nccl_comm = comm; c->ctx.rank = rank; c->ctx.world = world_size;
     return SAILGPU_OK;
-  } catch (const sg::Error& e) { g_x_error = e.what(); return e.code; }
+  } catch (const sg::Error& e) { sg::set_ctx_error(e.what()); return e.code; }
+  catch (const std::exception& e) { sg::set_ctx_error(std::string("internal error: ") + e.what()); return SAILGPU_ERR_CUDA; }
 }
 
 // all-to-all of n = world_size device batches: batch p goes to rank p; recv = everything sent to this rank
@@ -1205,6 +1224,7 @@ SAILGPU_API int32_t sailgpu_exchange(sailgpu_ctx* c, const struct ArrowSchema* s
   try {
     SG_CHECK(c && schema_c && send && recv, SAILGPU_ERR_INVALID, "null argument");
     Ctx* ctx = &c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     SG_CUDA(cudaSetDevice(ctx->device));
     SG_CHECK(n == ctx->world, SAILGPU_ERR_INVALID, "exchange needs one batch per rank");
     Schema schema = schema_from_arrow(schema_c);
@@ -1218,7 +1238,8 @@ SAILGPU_API int32_t sailgpu_exchange(sailgpu_ctx* c, const struct ArrowSchema* s
     BatchPtr out = exchange_batches(ctx, schema, parts);
     export_device_batch(ctx, schema, out, recv);
     return SAILGPU_OK;
-  } catch (const sg::Error& e) { g_x_error = e.what(); return e.code; }
+  } catch (const sg::Error& e) { sg::set_ctx_error(e.what()); return e.code; }
+  catch (const std::exception& e) { sg::set_ctx_error(std::string("internal error: ") + e.what()); return SAILGPU_ERR_CUDA; }
 }
 
 }  // extern "C"

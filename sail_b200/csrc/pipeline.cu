@@ -1818,6 +1818,24 @@ __global__ void agg_rehash_kernel(AggParams A, const uint8_t* old_table, const u
   }
 }
 
+__global__ void agg_migrate_kernel(AggParams A, AggMigrateMap M, const uint8_t* old_table, const uint32_t* old_occ, uint64_t old_groups, uint32_t* err) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_groups; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(old_table) + (uint64_t)old_occ[i] * M.old_entry_words;
+    KeyRegs key;
+    for (int w = 0; w < MAX_KEY_WORDS; ++w) key.w[w] = 0;
+    for (int w = 0; w < M.old_key_words; ++w) key.w[w + M.key_shift] = src[2 + w];
+    uint64_t* e = agg_find_or_insert(A, key, hash_packed_key(A, key), err);
+    if (!e) continue;
+    uint64_t seen = 0;
+    for (int j = 0; j < A.n_accs; ++j) {
+      for (int w = 0; w < acc_words_of(A.accs[j].op); ++w) e[2 + A.key_words + A.accs[j].word + w] = src[2 + M.old_key_words + M.acc_src_word[j] + w];
+      if (M.seen_src[j] == -1) seen |= 1ull << j;
+      else if (M.seen_src[j] >= 0) seen |= ((src[1] >> M.seen_src[j]) & 1ull) << j;
+    }
+    e[1] = seen;
+  }
+}
+
 __global__ void agg_extract_kernel(AggParams A, AggExtractParams X, uint64_t n_groups, uint32_t* err) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_groups; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t* e = reinterpret_cast<const uint64_t*>(A.table) + (uint64_t)A.occ[i] * A.entry_words;
@@ -2051,6 +2069,12 @@ cudaError_t launch_agg_rehash(const AggParams& A, const uint8_t* old_table, cons
   if (old_groups == 0) return cudaSuccess;
   int grid = (int)std::min<uint64_t>((old_groups + 255) / 256, 148 * 8);
   agg_rehash_kernel<<<grid, 256, 0, s>>>(A, old_table, old_occ, old_groups, err);
+  return cudaGetLastError();
+}
+cudaError_t launch_agg_migrate(const AggParams& A_new, const AggMigrateMap& M, const uint8_t* old_table, const uint32_t* old_occ, uint64_t old_groups, uint32_t* err, cudaStream_t s) {
+  if (old_groups == 0) return cudaSuccess;
+  int grid = (int)std::min<uint64_t>((old_groups + 255) / 256, 148 * 8);
+  agg_migrate_kernel<<<grid, 256, 0, s>>>(A_new, M, old_table, old_occ, old_groups, err);
   return cudaGetLastError();
 }
 cudaError_t launch_agg_extract(const AggParams& A, const AggExtractParams& X, uint64_t n_groups, uint32_t* err, cudaStream_t s) {

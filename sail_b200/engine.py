@@ -394,6 +394,53 @@ def exchange(send: list, schema: pa.Schema, ctx: Context | None = None) -> Devic
     return out
 
 
+_FOREIGN_KEEP = {}     # id -> objects a foreign device batch borrows from (dropped by its release callback)
+
+
+@ctypes.CFUNCTYPE(None, ctypes.c_void_p)
+def _foreign_release(ptr):
+    a = ArrowArrayC.from_address(ptr)
+    _FOREIGN_KEEP.pop(int(a.private_data or 0), None)
+    a.release = None
+
+
+def device_batch_from_buffers(schema: pa.Schema, n_rows: int, tensors: list, ctx: Context | None = None) -> DeviceBatch:
+    """Wraps caller-owned device memory (objects with .data_ptr(), e.g. torch tensors; one values buffer per column, no
+    nulls, strings as inline Utf8View) as an ARROW_DEVICE_CUDA batch -- what a GPU-side producer (a Parquet decoder, the
+    data generator) hands to sailgpu_op_push_device without a copy."""
+    ctx = ctx or default_context()
+    n = len(tensors)
+    assert n == len(schema)
+    children = (ArrowArrayC * n)()
+    child_ptrs = (ctypes.c_void_p * n)()
+    bufs = []
+    for i, t in enumerate(tensors):
+        is_view = schema.field(i).type == pa.string_view()
+        nb = 3 if is_view else 2           # views: validity, views, variadic sizes (no data buffers: every view is inline)
+        b = (ctypes.c_void_p * nb)()
+        b[1] = t.data_ptr()
+        bufs.append(b)
+        c = children[i]
+        c.length, c.null_count, c.offset, c.n_buffers, c.n_children = n_rows, 0, 0, nb, 0
+        c.buffers = ctypes.cast(b, ctypes.c_void_p)
+        c.release = ctypes.cast(_NOOP_RELEASE, ctypes.c_void_p).value
+        child_ptrs[i] = ctypes.addressof(c)
+    d = DeviceBatch(schema)
+    top = (ctypes.c_void_p * 1)()
+    a = d.c.array
+    a.length, a.null_count, a.offset, a.n_buffers, a.n_children = n_rows, 0, 0, 1, n
+    a.buffers = ctypes.cast(top, ctypes.c_void_p)
+    a.children = ctypes.cast(child_ptrs, ctypes.c_void_p)
+    key = id(d)
+    a.private_data = key
+    a.release = ctypes.cast(_foreign_release, ctypes.c_void_p).value
+    _FOREIGN_KEEP[key] = (children, child_ptrs, bufs, top, list(tensors))
+    d.c.device_id = ctx.device
+    d.c.device_type = 2      # ARROW_DEVICE_CUDA
+    d._live = True
+    return d
+
+
 def to_device(table: pa.Table, ctx: Context | None = None) -> DeviceBatch:
     """Upload a table once; the returned DeviceBatch is HBM-resident Arrow (used by the bench's
     'inputs already resident in HBM' leg)."""

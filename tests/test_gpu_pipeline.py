@@ -293,3 +293,83 @@ def test_filter_streams_many_batches_in_order():
     op.finish()
     assert_same(op.collect(), oracle_op(spec, t), ordered=True)
     op.close()
+
+
+@pytest.mark.parametrize("order", ["nulls_first", "nulls_last", "alternating"])
+@pytest.mark.parametrize("keys", [["b"], ["s"], []])
+def test_aggregate_batches_differ_in_validity_buffers(order, keys):
+    """Arrow producers drop the validity buffer of a batch without nulls, so the batches of one stream differ in which
+    columns carry one.  The table layout (null-mask word, seen bits, per-argument counters) must survive that in any order:
+    groups that only appear in null-free batches, all-NULL groups, and nullable group keys."""
+    from sail_b200 import engine
+    rng = np.random.default_rng(5)
+
+    def part(n, with_nulls, lo):
+        b = rng.integers(lo, lo + 6, n).astype(np.int32)
+        s = [f"g{int(x) % 5}" for x in rng.integers(lo, lo + 9, n)]
+        v = [decimal.Decimal(int(x)) / 100 for x in rng.integers(-10**6, 10**6, n)]
+        f = rng.normal(size=n)
+        if with_nulls:
+            mb, ms, mv = rng.random(n) < 0.2, rng.random(n) < 0.2, rng.random(n) < 0.5
+            mv |= b == lo                      # one whole group whose argument is always NULL
+            return pa.table({"b": pa.array(b, mask=mb), "s": pa.array(s, type=pa.string_view(), mask=ms),
+                             "v": pa.array(v, type=pa.decimal128(15, 2), mask=mv), "f": pa.array(f, mask=mv)})
+        return pa.table({"b": pa.array(b), "s": pa.array(s, type=pa.string_view()), "v": pa.array(v, type=pa.decimal128(15, 2)), "f": pa.array(f)})
+
+    clean = [part(5000, False, 0), part(3000, False, 4)]        # group ids 0..9, some only here
+    dirty = [part(4000, True, 2), part(2500, True, 8)]          # group ids 2..13, some only here
+    batches = {"nulls_first": dirty + clean, "nulls_last": clean + dirty, "alternating": [clean[0], dirty[0], clean[1], dirty[1]]}[order]
+    whole = pa.concat_tables(batches)
+    spec = {"op": "aggregate", "mode": "single", "group_by": [{"expr": {"col": whole.schema.names.index(c)}, "name": c} for c in keys],
+            "aggs": [{"fn": "sum", "args": [{"col": 2}], "name": "sv"}, {"fn": "count", "args": [], "name": "c"}, {"fn": "count", "args": [{"col": 2}], "name": "cv"},
+                     {"fn": "min", "args": [{"col": 2}], "name": "mn"}, {"fn": "avg", "args": [{"col": 2}], "name": "av"}, {"fn": "max", "args": [{"col": 3}], "name": "mf"},
+                     {"fn": "avg", "args": [{"col": 3}], "name": "af"}]}
+    op = engine.GpuExec(spec, [whole.schema])
+    for t in batches:
+        op.push(t)
+    op.finish()
+    got = op.collect()
+    op.close()
+    n_key = len(keys)
+    assert_same(got, oracle_op(spec, whole), float_cols=(n_key + 5, n_key + 6))
+
+
+@pytest.mark.parametrize("shared_context", [True, False])
+def test_concurrent_handles_from_two_threads(shared_context):
+    """include/sailgpu.h threading contract: handles may be driven from any threads at once; handles of one context are
+    serialised inside the library, handles of different contexts overlap.  DataFusion polls partitions from a thread pool."""
+    import threading
+    from sail_b200 import engine
+    t = make_table(60000, seed=21, nulls=True)
+    specs = [
+        {"op": "aggregate", "mode": "single", "group_by": [{"expr": resolve(C("b"), t), "name": "b"}],
+         "aggs": [{"fn": "sum", "args": [resolve(C("d"), t)], "name": "sd"}, {"fn": "count", "args": [], "name": "c"}]},
+        {"op": "filter", "predicate": resolve(plans.binop("<", C("b"), plans.lit(25, "Int32")), t), "projection": [0, 2, 4]},
+    ]
+    want = [oracle_op(s, t) for s in specs]
+    ctxs = [engine.default_context(), engine.default_context() if shared_context else engine.Context(0)]
+    errors, got = [], [[None] * 6, [None] * 6]
+
+    def work(k):
+        try:
+            for it in range(6):
+                op = engine.GpuExec(specs[k], [t.schema], ctxs[k])
+                for o in range(0, t.num_rows, 7001):
+                    op.push(t.slice(o, 7001))
+                op.finish()
+                got[k][it] = op.collect()
+                op.close()
+        except Exception as e:      # surfaced below: an exception in a thread would otherwise be lost
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if not shared_context:
+        ctxs[1].close()
+    assert not errors, errors
+    for k in range(2):
+        for it in range(6):
+            assert_same(got[k][it], want[k], ordered=(k == 1))
