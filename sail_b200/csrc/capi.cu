@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" surface declared in include/sailgpu.h.
 #include <cstdio>
 
+#include "h2d.hpp"
 #include "runner.hpp"
 
 using namespace sg;
@@ -67,7 +68,6 @@ SAILGPU_API int32_t sailgpu_ctx_create(int32_t device, sailgpu_ctx** out) {
     c->ctx.sm_count = prop.multiProcessorCount;
     c->ctx.max_smem = prop.sharedMemPerBlockOptin;
     SG_CUDA(cudaStreamCreateWithFlags(&c->ctx.stream, cudaStreamNonBlocking));
-    SG_CUDA(cudaStreamCreateWithFlags(&c->ctx.copy_stream, cudaStreamNonBlocking));
     cudaMemPool_t pool;
     SG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;   // keep freed HBM in the pool: operators re-allocate the same sizes every batch
@@ -85,7 +85,7 @@ SAILGPU_API void sailgpu_ctx_destroy(sailgpu_ctx* c) {
   // it is only marked dead so that late buffer releases use cudaFree instead of the destroyed stream.
   c->ctx.dead.store(true);
   if (c->ctx.stream) { cudaStreamSynchronize(c->ctx.stream); cudaStreamDestroy(c->ctx.stream); c->ctx.stream = nullptr; }
-  if (c->ctx.copy_stream) { cudaStreamDestroy(c->ctx.copy_stream); c->ctx.copy_stream = nullptr; }
+  destroy_pack_pool(&c->ctx);
 }
 
 SAILGPU_API const char* sailgpu_ctx_last_error(const sailgpu_ctx*) { return g_ctx_error.c_str(); }

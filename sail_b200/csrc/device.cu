@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "device.hpp"
+#include "h2d.hpp"
 #include "kernels.hpp"
 #include "relational.hpp"
 
@@ -69,47 +70,68 @@ void schema_to_arrow(const Schema& s, ArrowSchema* out) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-// copy `bytes` from a host or device pointer into a fresh HBM buffer on `stream`
-BufPtr upload(Ctx* ctx, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
-  BufPtr b = dev_alloc(ctx, bytes);
-  if (bytes) SG_CUDA(cudaMemcpyAsync(b->ptr, src, bytes, kind, stream));
-  if (kind == cudaMemcpyHostToDevice) ctx->h2d_bytes += bytes;
-  return b;
-}
-
-// bitmap slice [offset, offset+len) -> bitmap at bit 0.  `on_device` says where src lives.
-BufPtr import_bitmap(Ctx* ctx, const uint8_t* src, int64_t offset, int64_t len, bool on_device, cudaStream_t stream) {
-  const int64_t first_byte = offset >> 3;
-  const int64_t nbytes = ((offset + len + 7) >> 3) - first_byte;
-  if ((offset & 7) == 0) {
-    if (on_device) {
-      auto b = std::make_shared<DevBuf>();   // borrowed: lifetime tied to the batch token held elsewhere
-      b->ptr = const_cast<uint8_t*>(src) + first_byte; b->bytes = (size_t)nbytes; b->on_release = [] {};
-      return b;
-    }
-    return upload(ctx, src + first_byte, (size_t)nbytes, cudaMemcpyHostToDevice, stream);
+// What an import needs besides the column itself: the staged host->device copies (host batches only) and the device
+// work that may only run once the copied bytes are in place (conversions of Utf8 / long views / unaligned bitmaps).
+struct ImportJob {
+  Ctx* ctx;
+  bool on_device;
+  cudaStream_t stream;
+  HostStager stager;
+  std::vector<std::function<void()>> post;
+  ImportJob(Ctx* c, bool dev, cudaStream_t s) : ctx(c), on_device(dev), stream(s), stager(c) {}
+  // `n` elements of `width` bytes from a host (staged, possibly packed on the wire) or device (plain copy) pointer into a fresh HBM buffer
+  BufPtr upload(const void* src, int64_t n, int width, HostCol kind = HostCol::Raw) {
+    const size_t bytes = (size_t)n * (size_t)width;
+    BufPtr b = dev_alloc(ctx, bytes);
+    if (!bytes) return b;
+    if (on_device) SG_CUDA(cudaMemcpyAsync(b->ptr, src, bytes, cudaMemcpyDeviceToDevice, stream));
+    else if (kind == HostCol::Raw) stager.add_raw(b->ptr, src, bytes);
+    else stager.add(kind, b->ptr, src, n, width);
+    return b;
   }
-  BufPtr raw = on_device ? nullptr : upload(ctx, src + first_byte, (size_t)nbytes, cudaMemcpyHostToDevice, stream);
-  const uint8_t* dsrc = on_device ? src + first_byte : static_cast<const uint8_t*>(raw->ptr);
-  BufPtr bytes = dev_alloc(ctx, (size_t)len);
-  SG_CUDA(launch_unpack_bits(dsrc, static_cast<uint8_t*>(bytes->ptr), len, offset & 7, stream));
-  BufPtr bits = dev_alloc_zero(ctx, (size_t)((len + 31) / 32 * 4));
-  SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(bytes->ptr), static_cast<uint32_t*>(bits->ptr), len, nullptr, stream));
-  return bits;
-}
+  // run `f` now (device import: the data is there) or after the staged copies (host import)
+  void after(std::function<void()> f) { if (on_device) f(); else post.push_back(std::move(f)); }
+};
 
 struct ReleaseToken {     // drops the producer's ArrowArray when the last borrowed buffer dies
   ArrowArray arr;
   ~ReleaseToken() { if (arr.release) arr.release(&arr); }
 };
 
-DevColumn import_column(Ctx* ctx, const Field& f, const ArrowArray* a, bool on_device, cudaStream_t stream,
-                        const std::shared_ptr<ReleaseToken>& token) {
+// bitmap slice [offset, offset+len) -> bitmap at bit 0
+BufPtr import_bitmap(ImportJob& J, const uint8_t* src, int64_t offset, int64_t len) {
+  Ctx* ctx = J.ctx;
+  const int64_t first_byte = offset >> 3;
+  const int64_t nbytes = ((offset + len + 7) >> 3) - first_byte;
+  if ((offset & 7) == 0) {
+    if (J.on_device) {
+      auto b = std::make_shared<DevBuf>();   // borrowed: lifetime tied to the batch token held elsewhere
+      b->ptr = const_cast<uint8_t*>(src) + first_byte; b->bytes = (size_t)nbytes; b->on_release = [] {};
+      return b;
+    }
+    return J.upload(src + first_byte, nbytes, 1);
+  }
+  BufPtr raw = J.on_device ? nullptr : J.upload(src + first_byte, nbytes, 1);
+  const uint8_t* dsrc = J.on_device ? src + first_byte : static_cast<const uint8_t*>(raw->ptr);
+  BufPtr bytes = dev_alloc(ctx, (size_t)len);
+  BufPtr bits = dev_alloc_zero(ctx, (size_t)((len + 31) / 32 * 4));
+  cudaStream_t stream = J.stream;
+  J.after([=] {
+    (void)raw;
+    SG_CUDA(launch_unpack_bits(dsrc, static_cast<uint8_t*>(bytes->ptr), len, offset & 7, stream));
+    SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(bytes->ptr), static_cast<uint32_t*>(bits->ptr), len, nullptr, stream));
+  });
+  return bits;
+}
+
+DevColumn import_column(ImportJob& J, const Field& f, const ArrowArray* a, const std::shared_ptr<ReleaseToken>& token) {
+  Ctx* ctx = J.ctx;
+  const bool on_device = J.on_device;
+  cudaStream_t stream = J.stream;
   DevColumn c;
   c.type = f.type;
   c.length = a->length;
   c.null_count = a->null_count;
-  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   auto borrow = [&](const void* p, size_t bytes) {
     auto b = std::make_shared<DevBuf>();
     b->ptr = const_cast<void*>(p); b->bytes = bytes;
@@ -118,7 +140,7 @@ DevColumn import_column(Ctx* ctx, const Field& f, const ArrowArray* a, bool on_d
   };
   const uint8_t* vbits = a->n_buffers > 0 ? static_cast<const uint8_t*>(a->buffers[0]) : nullptr;
   if (vbits && a->null_count != 0 && a->length > 0) {
-    c.validity = import_bitmap(ctx, vbits, a->offset, a->length, on_device, stream);
+    c.validity = import_bitmap(J, vbits, a->offset, a->length);
     if (on_device && c.validity->on_release) c.validity->on_release = [token] {};
     if (c.null_count < 0) c.null_count = -1;   // unknown: treated as "may contain nulls"
   } else {
@@ -128,7 +150,7 @@ DevColumn import_column(Ctx* ctx, const Field& f, const ArrowArray* a, bool on_d
   switch (f.type.id) {
     case TypeId::Bool: {
       const uint8_t* bits = static_cast<const uint8_t*>(a->buffers[1]);
-      c.data = a->length ? import_bitmap(ctx, bits, a->offset, a->length, on_device, stream) : dev_alloc(ctx, 0);
+      c.data = a->length ? import_bitmap(J, bits, a->offset, a->length) : dev_alloc(ctx, 0);
       if (on_device && c.data->on_release) c.data->on_release = [token] {};
       break;
     }
@@ -143,12 +165,16 @@ DevColumn import_column(Ctx* ctx, const Field& f, const ArrowArray* a, bool on_d
         SG_CUDA(cudaStreamSynchronize(stream));
         dbytes = borrow(bytes, (size_t)last);
       } else {
-        doffs = upload(ctx, offs, (size_t)(a->length + 1) * 4, kind, stream);
+        doffs = J.upload(offs, a->length + 1, 4);
         const int32_t last = a->length ? offs[a->length] : 0;
-        dbytes = upload(ctx, bytes, (size_t)last, kind, stream);   // absolute offsets: copy from byte 0
+        dbytes = J.upload(bytes, last, 1);   // absolute offsets: copy from byte 0
       }
       c.data = dev_alloc(ctx, (size_t)a->length * 16);
-      SG_CUDA(launch_utf8_to_views(static_cast<const int32_t*>(doffs->ptr), static_cast<const uint8_t*>(dbytes->ptr), c.data->ptr, a->length, stream));
+      {
+        BufPtr views = c.data;
+        const int64_t n = a->length;
+        J.after([=] { SG_CUDA(launch_utf8_to_views(static_cast<const int32_t*>(doffs->ptr), static_cast<const uint8_t*>(dbytes->ptr), views->ptr, n, stream)); });
+      }
       c.heaps = {dbytes, doffs};
       c.arrow_is_utf8 = true;
       break;
@@ -156,23 +182,28 @@ DevColumn import_column(Ctx* ctx, const Field& f, const ArrowArray* a, bool on_d
     case TypeId::Utf8View: {
       const uint8_t* views = static_cast<const uint8_t*>(a->buffers[1]) + a->offset * 16;
       const int64_t n_data = a->n_buffers - 3;   // validity, views, data..., sizes
-      // views without data buffers are all inline (<= 12 bytes): a device batch can be used in place
-      c.data = (on_device && n_data <= 0) ? borrow(views, (size_t)a->length * 16) : upload(ctx, views, (size_t)a->length * 16, kind, stream);
+      // views without data buffers are all inline (<= 12 bytes): a device batch can be used in place, a host batch travels packed
+      if (on_device && n_data <= 0) c.data = borrow(views, (size_t)a->length * 16);
+      else c.data = J.upload(views, a->length, 16, n_data <= 0 ? HostCol::View16 : HostCol::Raw);
       if (n_data > 0) {
         std::vector<int64_t> sizes((size_t)n_data);
         const int64_t* size_buf = static_cast<const int64_t*>(a->buffers[a->n_buffers - 1]);
         if (on_device) { SG_CUDA(cudaMemcpyAsync(sizes.data(), size_buf, (size_t)n_data * 8, cudaMemcpyDeviceToHost, stream)); SG_CUDA(cudaStreamSynchronize(stream)); }
         else std::memcpy(sizes.data(), size_buf, (size_t)n_data * 8);
-        std::vector<uint64_t> bases((size_t)n_data);
+        auto bases = std::make_shared<std::vector<uint64_t>>((size_t)n_data);
         for (int64_t k = 0; k < n_data; ++k) {
-          BufPtr h = on_device ? borrow(a->buffers[2 + k], (size_t)sizes[k]) : upload(ctx, a->buffers[2 + k], (size_t)sizes[k], kind, stream);
-          bases[(size_t)k] = reinterpret_cast<uint64_t>(h->ptr);
+          BufPtr h = on_device ? borrow(a->buffers[2 + k], (size_t)sizes[k]) : J.upload(a->buffers[2 + k], sizes[k], 1);
+          (*bases)[(size_t)k] = reinterpret_cast<uint64_t>(h->ptr);
           c.heaps.push_back(h);
         }
         BufPtr dbases = dev_alloc(ctx, (size_t)n_data * 8);
-        SG_CUDA(cudaMemcpyAsync(dbases->ptr, bases.data(), (size_t)n_data * 8, cudaMemcpyHostToDevice, stream));
-        SG_CUDA(launch_resolve_views(c.data->ptr, a->length, static_cast<const uint64_t*>(dbases->ptr), stream));
-        SG_CUDA(cudaStreamSynchronize(stream));   // `bases` is a stack vector
+        BufPtr vdata = c.data;
+        const int64_t n = a->length;
+        J.after([=] {
+          SG_CUDA(cudaMemcpyAsync(dbases->ptr, bases->data(), (size_t)n_data * 8, cudaMemcpyHostToDevice, stream));
+          SG_CUDA(launch_resolve_views(vdata->ptr, n, static_cast<const uint64_t*>(dbases->ptr), stream));
+          SG_CUDA(cudaStreamSynchronize(stream));   // `bases` is host memory owned by this closure
+        });
         c.heaps.push_back(dbases);
       }
       break;
@@ -180,7 +211,14 @@ DevColumn import_column(Ctx* ctx, const Field& f, const ArrowArray* a, bool on_d
     default: {
       SG_CHECK(w > 0, SAILGPU_ERR_UNSUPPORTED, "unsupported column type " + f.type.str());
       const uint8_t* p = static_cast<const uint8_t*>(a->buffers[1]) + a->offset * w;
-      c.data = on_device ? borrow(p, (size_t)a->length * w) : upload(ctx, p, (size_t)a->length * w, kind, stream);
+      if (on_device) c.data = borrow(p, (size_t)a->length * w);
+      else {
+        const TypeId id = f.type.id;
+        const HostCol kind = id == TypeId::Decimal128 ? HostCol::Dec128
+                           : (id == TypeId::Int64 || id == TypeId::UInt64) ? HostCol::Int64
+                           : (id == TypeId::Int32 || id == TypeId::UInt32 || id == TypeId::Date32) ? HostCol::Int32 : HostCol::Raw;
+        c.data = J.upload(p, a->length, w, kind);
+      }
     }
   }
   return c;
@@ -196,14 +234,17 @@ BatchPtr import_batch(Ctx* ctx, const Schema& schema, ArrowArray* arr, bool on_d
   arr->release = nullptr;
   auto b = std::make_shared<DevBatch>();
   b->rows = token->arr.length;
+  ImportJob J(ctx, on_device, stream);
   for (size_t i = 0; i < schema.size(); ++i) {
     const ArrowArray* ch = token->arr.children[i];
     SG_CHECK(ch->length == b->rows, SAILGPU_ERR_INVALID, "column length mismatch");
-    b->cols.push_back(import_column(ctx, schema[i], ch, on_device, stream, token));
+    b->cols.push_back(import_column(J, schema[i], ch, token));
   }
   if (!on_device) {
-    // host buffers may be released as soon as the copies have been issued AND completed
-    SG_CUDA(cudaStreamSynchronize(stream));
+    // the packer threads read every host buffer into pinned staging memory before flush() returns; the copies themselves
+    // may still be in flight (the compute stream waits for them through an event), so the next batch can be packed meanwhile
+    J.stager.flush();
+    for (auto& f : J.post) f();
     token.reset();
   }
   return b;

@@ -23,12 +23,14 @@ namespace sg {
       ::sg::fail(SAILGPU_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #call); \
   } while (0)
 
+struct PackPool;
+
 struct Ctx {
   int device = 0;
   int sm_count = 148;
   size_t max_smem = 227 * 1024;
   cudaStream_t stream = nullptr;        // compute stream
-  cudaStream_t copy_stream = nullptr;   // H2D / D2H stream
+  PackPool* pack_pool = nullptr;        // host-batch ingest: packer threads, pinned staging, copy streams (h2d.cu)
   std::string last_error;
   // One compute stream, one allocation cache and one D2H bounce buffer per context: calls that touch the device are
   // serialised per context (capi.cu takes this lock), different contexts run concurrently.

@@ -1,0 +1,280 @@
+// h2d.cu -- packed, pipelined ingest of pageable host Arrow buffers (see h2d.hpp).
+//
+// Replaces, for the GPU path, what arrow::ffi + a plain cudaMemcpy per buffer would do at the boundary the Rust shim
+// crosses per RecordBatch: Arrow's fixed widths are an in-memory format, not a wire format.
+#include "h2d.hpp"
+
+#include <array>
+#include <cstdlib>
+#include <cstring>
+
+namespace sg {
+
+namespace {
+
+constexpr int64_t PIECE_ROWS = 256 * 1024;
+constexpr size_t SLOT_BYTES = (size_t)PIECE_ROWS * 16;     // 4 MiB: one piece of the widest column
+
+enum Enc : int { ENC_RAW = 0, ENC_INT = 1, ENC_VIEW = 2 };
+
+// ---- device side: packed piece -> Arrow layout ---------------------------------------------------
+__global__ void unpack_int_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n, int w_in, int out_width, long long base) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long d;
+    switch (w_in) {
+      case 1: d = src[i]; break;
+      case 2: d = reinterpret_cast<const uint16_t*>(src)[i]; break;
+      case 4: d = reinterpret_cast<const uint32_t*>(src)[i]; break;
+      default: d = reinterpret_cast<const unsigned long long*>(src)[i];
+    }
+    const long long v = (long long)((unsigned long long)base + d);
+    if (out_width == 16) { ulonglong2 w; w.x = (unsigned long long)v; w.y = (unsigned long long)(v >> 63); reinterpret_cast<ulonglong2*>(dst)[i] = w; }
+    else if (out_width == 8) reinterpret_cast<long long*>(dst)[i] = v;
+    else reinterpret_cast<int*>(dst)[i] = (int)v;
+  }
+}
+// packed row: [length byte][L bytes]  ->  16-byte inline view {len:u32, bytes[12]}
+__global__ void unpack_view_kernel(const uint8_t* __restrict__ src, ulonglong2* __restrict__ dst, int64_t n, int L) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* p = src + i * (1 + L);
+    const unsigned len = p[0];
+    unsigned long long lo = len, hi = 0;
+    for (int k = 0; k < L; ++k) {
+      const unsigned long long b = k < (int)len ? p[1 + k] : 0;      // bytes past the string stay zero (Arrow requires zero padding)
+      if (k < 4) lo |= b << (32 + 8 * k); else hi |= b << (8 * (k - 4));
+    }
+    ulonglong2 v; v.x = lo; v.y = hi;
+    dst[i] = v;
+  }
+}
+
+// ---- host side: piece -> staging slot --------------------------------------------------------------
+struct Packed { int enc; size_t bytes; long long base; int w; };
+
+static inline int width_for(unsigned long long range) { return range < (1ull << 8) ? 1 : range < (1ull << 16) ? 2 : range < (1ull << 32) ? 4 : 8; }
+
+template <typename T>
+static void store_deltas(uint8_t* out, const T* vals, size_t stride_elems, int64_t n, long long base, int w) {
+  switch (w) {
+    case 1: for (int64_t i = 0; i < n; ++i) out[i] = (uint8_t)((unsigned long long)vals[i * stride_elems] - (unsigned long long)base); break;
+    case 2: { uint16_t* o = reinterpret_cast<uint16_t*>(out); for (int64_t i = 0; i < n; ++i) o[i] = (uint16_t)((unsigned long long)vals[i * stride_elems] - (unsigned long long)base); break; }
+    case 4: { uint32_t* o = reinterpret_cast<uint32_t*>(out); for (int64_t i = 0; i < n; ++i) o[i] = (uint32_t)((unsigned long long)vals[i * stride_elems] - (unsigned long long)base); break; }
+    default: { uint64_t* o = reinterpret_cast<uint64_t*>(out); for (int64_t i = 0; i < n; ++i) o[i] = (uint64_t)vals[i * stride_elems] - (uint64_t)base; }
+  }
+}
+
+static Packed pack_piece(const HostStager::Item& it, uint8_t* out, bool narrow) {
+  const int64_t n = it.n;
+  if (narrow && it.kind == HostCol::Dec128) {
+    const int64_t* p = reinterpret_cast<const int64_t*>(it.src);
+    int64_t mn = INT64_MAX, mx = INT64_MIN;
+    uint64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      const int64_t lo = p[2 * i], hi = p[2 * i + 1];
+      bad |= (uint64_t)(hi ^ (lo >> 63));
+      mn = lo < mn ? lo : mn; mx = lo > mx ? lo : mx;
+    }
+    if (!bad && n > 0) {
+      const int w = width_for((unsigned long long)mx - (unsigned long long)mn);
+      store_deltas<int64_t>(out, p, 2, n, mn, w);
+      return {ENC_INT, (size_t)n * w, mn, w};
+    }
+  } else if (narrow && it.kind == HostCol::Int64) {
+    const int64_t* p = reinterpret_cast<const int64_t*>(it.src);
+    int64_t mn = INT64_MAX, mx = INT64_MIN;
+    for (int64_t i = 0; i < n; ++i) { mn = p[i] < mn ? p[i] : mn; mx = p[i] > mx ? p[i] : mx; }
+    const int w = n > 0 ? width_for((unsigned long long)mx - (unsigned long long)mn) : 8;
+    if (w < 8) { store_deltas<int64_t>(out, p, 1, n, mn, w); return {ENC_INT, (size_t)n * w, mn, w}; }
+  } else if (narrow && it.kind == HostCol::Int32) {
+    const int32_t* p = reinterpret_cast<const int32_t*>(it.src);
+    int32_t mn = INT32_MAX, mx = INT32_MIN;
+    for (int64_t i = 0; i < n; ++i) { mn = p[i] < mn ? p[i] : mn; mx = p[i] > mx ? p[i] : mx; }
+    const int w = n > 0 ? width_for((unsigned long long)((long long)mx - (long long)mn)) : 4;
+    if (w < 4) { store_deltas<int32_t>(out, p, 1, n, (long long)mn, w); return {ENC_INT, (size_t)n * w, (long long)mn, w}; }
+  } else if (narrow && it.kind == HostCol::View16) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(it.src);      // view = {len, 3 x 4 bytes}
+    uint32_t L = 0;
+    for (int64_t i = 0; i < n; ++i) L = p[4 * i] > L ? p[4 * i] : L;
+    if (L <= 12) {
+      const size_t rb = 1 + L;
+      for (int64_t i = 0; i < n; ++i) {
+        const uint8_t* v = it.src + 16 * i;
+        uint8_t* o = out + rb * (size_t)i;
+        o[0] = (uint8_t)p[4 * i];
+        for (uint32_t k = 0; k < L; ++k) o[1 + k] = v[4 + k];
+      }
+      return {ENC_VIEW, rb * (size_t)n, 0, (int)L};
+    }
+  }
+  const size_t bytes = (size_t)n * (size_t)it.width;
+  memcpy(out, it.src, bytes);
+  return {ENC_RAW, bytes, 0, 0};
+}
+
+}  // namespace
+
+// ---- the pool -----------------------------------------------------------------------------------
+struct PackPool {
+  struct Slot { uint8_t* host = nullptr; uint8_t* dev = nullptr; cudaEvent_t free_ev = nullptr; bool used = false; };
+  struct Worker { std::thread th; std::array<Slot, 2> slots; cudaStream_t stream = nullptr; cudaEvent_t done_ev = nullptr; int turn = 0; bool touched = false; };
+  Ctx* ctx = nullptr;
+  bool narrow = true;
+  std::vector<Worker> workers;
+  Worker inline_w;                 // small batches are staged by the calling thread itself (no wake-ups)
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  const std::vector<HostStager::Item>* work = nullptr;
+  std::atomic<size_t> next{0};
+  size_t total = 0, finished_workers = 0;
+  uint64_t epoch = 0;
+  bool stop = false;
+  std::string error;
+
+  void process(Worker& w, const HostStager::Item& it) {
+    Slot& s = w.slots[(size_t)(w.turn++ & 1)];
+    if (s.used && cudaEventSynchronize(s.free_ev) != cudaSuccess) throw std::runtime_error("staging slot event");
+    const Packed pk = pack_piece(it, s.host, narrow);
+    cudaError_t e;
+    if (pk.enc == ENC_RAW) {
+      e = cudaMemcpyAsync(it.dst, s.host, pk.bytes, cudaMemcpyHostToDevice, w.stream);
+    } else {
+      e = cudaMemcpyAsync(s.dev, s.host, pk.bytes, cudaMemcpyHostToDevice, w.stream);
+      if (e == cudaSuccess) {
+        const int grid = (int)std::min<int64_t>((it.n + 255) / 256, 148 * 4);
+        if (pk.enc == ENC_INT) unpack_int_kernel<<<grid, 256, 0, w.stream>>>(s.dev, it.dst, it.n, pk.w, it.width, pk.base);
+        else unpack_view_kernel<<<grid, 256, 0, w.stream>>>(s.dev, reinterpret_cast<ulonglong2*>(it.dst), it.n, pk.w);
+        e = cudaGetLastError();
+      }
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(s.free_ev, w.stream);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("host staging: ") + cudaGetErrorString(e));
+    s.used = true;
+    w.touched = true;
+    ctx->h2d_bytes += pk.bytes;
+  }
+
+  void run(size_t wi) {
+    cudaSetDevice(ctx->device);
+    Worker& w = workers[wi];
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_work.wait(lk, [&] { return stop || epoch != seen; });
+        if (stop) return;
+        seen = epoch;
+      }
+      std::string err;
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= total) break;
+        try { process(w, (*work)[i]); } catch (const std::exception& e) { err = e.what(); }
+      }
+      if (w.touched) cudaEventRecord(w.done_ev, w.stream);
+      std::lock_guard<std::mutex> lk(mu);
+      if (!err.empty() && error.empty()) error = err;
+      if (++finished_workers == workers.size()) cv_done.notify_all();
+    }
+  }
+};
+
+static PackPool* pool_of(Ctx* ctx) {
+  if (ctx->pack_pool) return ctx->pack_pool;
+  auto* p = new PackPool();
+  p->ctx = ctx;
+  const char* nt = getenv("SAILGPU_PACK_THREADS");
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int n = std::max(1, nt && *nt ? atoi(nt) : std::min(16, std::max(1, hw)));
+  const char* nw = getenv("SAILGPU_H2D_PACK");
+  p->narrow = !(nw && *nw && atoi(nw) == 0);
+  p->workers.resize((size_t)n);
+  auto init_worker = [](PackPool::Worker& w) {
+    SG_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    SG_CUDA(cudaEventCreateWithFlags(&w.done_ev, cudaEventDisableTiming));
+    for (auto& s : w.slots) {
+      SG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.host), SLOT_BYTES, cudaHostAllocDefault));
+      SG_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.dev), SLOT_BYTES));
+      SG_CUDA(cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming));
+    }
+  };
+  for (auto& w : p->workers) init_worker(w);
+  init_worker(p->inline_w);
+  for (size_t i = 0; i < p->workers.size(); ++i) p->workers[i].th = std::thread([p, i] { p->run(i); });
+  ctx->pack_pool = p;
+  return p;
+}
+
+void destroy_pack_pool(Ctx* ctx) {
+  PackPool* p = ctx->pack_pool;
+  if (!p) return;
+  { std::lock_guard<std::mutex> lk(p->mu); p->stop = true; }
+  p->cv_work.notify_all();
+  for (auto& w : p->workers) if (w.th.joinable()) w.th.join();
+  std::vector<PackPool::Worker*> all;
+  for (auto& w : p->workers) all.push_back(&w);
+  all.push_back(&p->inline_w);
+  for (PackPool::Worker* wp : all) {
+    PackPool::Worker& w = *wp;
+    for (auto& s : w.slots) { if (s.host) cudaFreeHost(s.host); if (s.dev) cudaFree(s.dev); if (s.free_ev) cudaEventDestroy(s.free_ev); }
+    if (w.done_ev) cudaEventDestroy(w.done_ev);
+    if (w.stream) cudaStreamDestroy(w.stream);
+  }
+  delete p;
+  ctx->pack_pool = nullptr;
+}
+
+void HostStager::add(HostCol kind, void* dst, const void* src, int64_t n, int width) {
+  if (n <= 0) return;
+  const int64_t piece = kind == HostCol::Raw ? (int64_t)SLOT_BYTES / std::max(1, width) : PIECE_ROWS;
+  for (int64_t o = 0; o < n; o += piece) {
+    const int64_t k = std::min(piece, n - o);
+    items.push_back({kind, static_cast<uint8_t*>(dst) + o * width, static_cast<const uint8_t*>(src) + o * width, k, width});
+  }
+}
+
+void HostStager::flush() {
+  if (items.empty()) return;
+  PackPool* p = pool_of(ctx);
+  // the destination buffers were allocated (stream-ordered) on the compute stream: the copy streams must not start before that
+  cudaEvent_t alloc_ev;
+  SG_CUDA(cudaEventCreateWithFlags(&alloc_ev, cudaEventDisableTiming));
+  SG_CUDA(cudaEventRecord(alloc_ev, ctx->stream));
+  size_t payload = 0;
+  for (auto& it : items) payload += (size_t)it.n * (size_t)it.width;
+  if (payload <= (1u << 20)) {      // a small batch: stage it on this thread
+    PackPool::Worker& w = p->inline_w;
+    SG_CUDA(cudaStreamWaitEvent(w.stream, alloc_ev, 0));
+    SG_CUDA(cudaEventDestroy(alloc_ev));
+    std::string err;
+    try { for (auto& it : items) p->process(w, it); } catch (const std::exception& e) { err = e.what(); }
+    items.clear();
+    SG_CHECK(err.empty(), SAILGPU_ERR_CUDA, err);
+    SG_CUDA(cudaEventRecord(w.done_ev, w.stream));
+    SG_CUDA(cudaStreamWaitEvent(ctx->stream, w.done_ev, 0));
+    return;
+  }
+  for (auto& w : p->workers) SG_CUDA(cudaStreamWaitEvent(w.stream, alloc_ev, 0));
+  SG_CUDA(cudaEventDestroy(alloc_ev));
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->work = &items;
+    p->total = items.size();
+    p->next.store(0);
+    p->finished_workers = 0;
+    p->error.clear();
+    for (auto& w : p->workers) w.touched = false;
+    p->epoch++;
+  }
+  p->cv_work.notify_all();
+  {
+    std::unique_lock<std::mutex> lk(p->mu);
+    p->cv_done.wait(lk, [&] { return p->finished_workers == p->workers.size(); });
+    p->work = nullptr;
+  }
+  items.clear();
+  SG_CHECK(p->error.empty(), SAILGPU_ERR_CUDA, p->error);
+  for (auto& w : p->workers)
+    if (w.touched) SG_CUDA(cudaStreamWaitEvent(ctx->stream, w.done_ev, 0));
+}
+
+}  // namespace sg
