@@ -636,12 +636,36 @@ struct RepartitionOp : Op {
   std::vector<std::deque<BatchPtr>> ready;     // per partition
   bool input_done = false;
   int rr = 0;
+  // RowRoundRobinPartitioner (crates/sail-physical-plan/src/repartition.rs:46-84): row i of the running stream goes to
+  // partition (next_idx + i) % n, next_idx seeded with (input_partition * n) / num_input_partitions
+  bool row_round_robin = false;
+  int64_t next_idx = 0;
+
+  void partition_round_robin(const BatchPtr& b) {
+    const int64_t n = b->rows;
+    JoinOp helper; helper.ctx = ctx;
+    for (int p = 0; p < n_parts; ++p) {
+      const int64_t first = ((int64_t)p - next_idx % n_parts + n_parts) % n_parts;      // first row of this batch that lands in p
+      if (first >= n) continue;
+      const int64_t k = (n - first + n_parts - 1) / n_parts;
+      BufPtr idx = dev_alloc(ctx, (size_t)k * 8);
+      SG_CUDA(launch_iota_stride(static_cast<int64_t*>(idx->ptr), first, n_parts, k, ctx->stream));
+      auto pb = std::make_shared<DevBatch>();
+      pb->rows = k;
+      for (size_t c = 0; c < b->cols.size(); ++c) pb->cols.push_back(helper.gather_column(b->cols[c], in_schemas[0][c], static_cast<const int64_t*>(idx->ptr), k, false));
+      m.kernel_launches += 1 + b->cols.size();
+      ready[(size_t)p].push_back(pb);
+    }
+    next_idx = (next_idx + n) % n_parts;
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));       // the index vectors are released on return
+  }
 
   void push(int input, const BatchPtr& b) override {
     SG_CHECK(input == 0, SAILGPU_ERR_INVALID, "repartition has one input");
     const uint64_t t0 = now_ns();
     m.input_rows += (uint64_t)b->rows; m.input_batches++;
-    if (b->rows) partition(b);
+    if (b->rows && row_round_robin) partition_round_robin(b);
+    else if (b->rows) partition(b);
     m.elapsed_compute_ns += now_ns() - t0;
   }
   void finish(int) override { input_done = true; }
@@ -745,10 +769,21 @@ std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::v
   auto op = std::make_unique<RepartitionOp>();
   op->ctx = ctx; op->kind = "repartition"; op->in_schemas = inputs; op->out_schema = inputs[0];
   const Json* sch = spec.find("scheme");
-  SG_CHECK(!sch || sch->as_str() == "hash", SAILGPU_ERR_UNSUPPORTED,
-           "only Partitioning::Hash is executed on the GPU; round-robin repartitions stay on the reference's CPU path (SURVEY.md 8b)");
+  const std::string scheme = sch ? sch->as_str() : "hash";
+  SG_CHECK(scheme == "hash" || scheme == "round_robin_row", SAILGPU_ERR_UNSUPPORTED,
+           "repartition scheme '" + scheme + "': Partitioning::Hash and the row round-robin of ExplicitRepartitionExec run on the GPU; "
+           "RoundRobinBatch only re-labels whole batches and stays with the reference's stream plumbing (SURVEY.md 8b)");
   op->n_parts = (int)spec.at("n").as_int();
   SG_CHECK(op->n_parts >= 1 && op->n_parts <= 4096, SAILGPU_ERR_INVALID, "partition count out of range");
+  if (scheme == "round_robin_row") {
+    const Json* ip = spec.find("input_partition"); const Json* np = spec.find("num_input_partitions");
+    const int64_t in_part = ip && !ip->is_null() ? ip->as_int() : 0, n_in = np && !np->is_null() ? np->as_int() : 1;
+    SG_CHECK(n_in >= 1 && in_part >= 0 && in_part < n_in, SAILGPU_ERR_INVALID, "input_partition / num_input_partitions out of range");
+    op->row_round_robin = true;
+    op->next_idx = (in_part * op->n_parts) / n_in;
+    op->ready.resize((size_t)op->n_parts);
+    return op;
+  }
   for (auto& e : spec.at("exprs").a) op->exprs.push_back(parse_expr(e, inputs[0]));
   SG_CHECK(!op->exprs.empty() && (int)op->exprs.size() <= MAX_KEYS, SAILGPU_ERR_INVALID, "hash repartition needs 1.." + std::to_string(MAX_KEYS) + " key expressions");
   op->ready.resize((size_t)op->n_parts);

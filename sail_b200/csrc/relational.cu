@@ -349,6 +349,14 @@ cudaError_t launch_iota(int64_t* out, int64_t n, cudaStream_t s) {
   iota_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(out, n);
   return cudaGetLastError();
 }
+__global__ void iota_stride_kernel(int64_t* out, int64_t first, int64_t stride, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = first + i * stride;
+}
+cudaError_t launch_iota_stride(int64_t* out, int64_t first, int64_t stride, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  iota_stride_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(out, first, stride, n);
+  return cudaGetLastError();
+}
 cudaError_t launch_widen_u32(const uint32_t* in, int64_t* out, int64_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   widen_u32_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(in, out, n);

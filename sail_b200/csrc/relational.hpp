@@ -66,6 +66,7 @@ cudaError_t launch_max_view_len(const void* views, int64_t n, unsigned int* out,
 cudaError_t launch_sort_encode(const SortEncodeParams& P, cudaStream_t s);
 cudaError_t radix_sort_indices(const uint8_t* keys, int key_bytes, int64_t n, const RadixScratch& S, const uint32_t* bits, cudaStream_t s, int* launches);
 cudaError_t launch_iota(int64_t* out, int64_t n, cudaStream_t s);
+cudaError_t launch_iota_stride(int64_t* out, int64_t first, int64_t stride, int64_t n, cudaStream_t s);
 cudaError_t launch_widen_u32(const uint32_t* in, int64_t* out, int64_t n, cudaStream_t s);
 // many small device-to-device copies in one launch (packed exchange messages)
 struct CopySeg { const uint8_t* src; uint8_t* dst; unsigned long long bytes; };

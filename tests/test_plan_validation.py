@@ -56,8 +56,15 @@ def test_unsupported_and_invalid_specs_are_rejected_at_plan_time():
         engine.validate({"op": "filter", "predicate": {"col": 7}, "projection": None}, [s])
     assert e.value.code == 1
     with pytest.raises(engine.SailGpuError) as e:
-        engine.validate({"op": "repartition", "scheme": "round_robin_row", "exprs": [], "n": 4}, [s])
-    assert e.value.code == 2            # only Partitioning::Hash runs on the GPU
+        engine.validate({"op": "repartition", "scheme": "round_robin_batch", "n": 4}, [s])
+    assert e.value.code == 2            # Hash and the row round-robin run on the GPU; RoundRobinBatch only re-labels batches
+    assert engine.validate({"op": "repartition", "scheme": "round_robin_row", "n": 4}, [s]).names == ["a", "s"]
+    with pytest.raises(engine.SailGpuError) as e:      # residual filters on outer joins: reported while planning, not after the build side was consumed
+        engine.validate({"op": "hash_join", "join_type": "left", "on": [[0, 0]], "filter": {"op": "<", "l": {"col": 0}, "r": {"col": 2}}}, [s, s])
+    assert e.value.code == 2
+    with pytest.raises(engine.SailGpuError) as e:
+        engine.validate({"op": "sort", "keys": [{"expr": {"op": "+", "l": {"col": 0}, "r": {"col": 0}}, "asc": True}]}, [s])
+    assert e.value.code == 2
     with pytest.raises(engine.SailGpuError):
         engine.validate({"op": "hash_join", "join_type": "full", "on": [[0, 0]]}, [s, s])
     with pytest.raises(engine.SailGpuError):
