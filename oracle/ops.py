@@ -838,6 +838,22 @@ def op_sort(b: Batch, spec: dict) -> Batch:
     return b.take(idx)
 
 
+def concat_batches(parts: list) -> Batch:
+    first = parts[0]
+    cols = []
+    for i, c in enumerate(first.cols):
+        data = np.concatenate([p.cols[i].data for p in parts])
+        valid = None if all(p.cols[i].valid is None for p in parts) else np.concatenate([p.cols[i].validity() for p in parts])
+        cols.append(Col(c.type, data, valid))
+    return Batch(list(first.names), cols)
+
+
+def op_sort_preserving_merge(runs: list, spec: dict) -> Batch:
+    """SortPreservingMergeExec (external; test_tpch.plan.yaml:9-10): stable k-way merge of sorted runs, ties to the earlier run --
+    which is what a stable sort of the runs laid end to end produces."""
+    return op_sort(concat_batches([r for r in runs if r.num_rows] or runs[:1]), spec)
+
+
 def hash_partition_ids(b: Batch, exprs, n_parts: int) -> np.ndarray:
     """Partition id per row for Hash(exprs, n).  The reference's hash function is an unobservable
     implementation detail (SURVEY.md Appendix A 'Exchange'); the property tests pin only that equal
@@ -911,4 +927,6 @@ def run_op(spec: dict, *inputs: Batch):
         return op_sort(inputs[0], spec)
     if kind == "repartition":
         return op_repartition(inputs[0], spec)
+    if kind == "sort_preserving_merge":
+        return op_sort_preserving_merge(list(inputs), spec)
     raise ValueError(kind)

@@ -540,27 +540,24 @@ struct SortOp : Op {
     return false;
   }
 
-  BatchPtr run() {
-    const Schema& sch = in_schemas[0];
-    BatchPtr all = concat_batches(ctx, sch, parts);
-    parts.clear();
+  struct Encoded { BufPtr keys, bits; int key_bytes = 0; };
+
+  // order-preserving fixed-width encoding of the sort keys of every row (memcmp order == requested order)
+  Encoded encode_keys(const BatchPtr& all, const Schema& sch, const std::vector<Key>& ks) {
     const int64_t n = all->rows;
-    if (n == 0) return all;
-    SG_CHECK(n < (1ll << 32), SAILGPU_ERR_UNSUPPORTED, "sort of more than 2^32 rows in one partition");
-    // sort keys must be plain columns of the input (DataFusion plans sort on projected columns)
     SortEncodeParams E; memset(&E, 0, sizeof(E));
-    E.n = n; E.n_keys = (int)keys.size();
+    E.n = n; E.n_keys = (int)ks.size();
     int off = 0;
     BufPtr maxlen = dev_alloc_zero(ctx, 8 * 8);
     std::vector<int> str_keys;
-    for (size_t k = 0; k < keys.size(); ++k) {
-      SG_CHECK(keys[k].e->kind == Expr::Col, SAILGPU_ERR_UNSUPPORTED, "sort keys must be column references");
-      const DevColumn& c = all->cols[(size_t)keys[k].e->col];
-      const DataType& t = sch[(size_t)keys[k].e->col].type;
+    for (size_t k = 0; k < ks.size(); ++k) {
+      SG_CHECK(ks[k].e->kind == Expr::Col, SAILGPU_ERR_UNSUPPORTED, "sort keys must be column references");
+      const DevColumn& c = all->cols[(size_t)ks[k].e->col];
+      const DataType& t = sch[(size_t)ks[k].e->col].type;
       SortKeyCol& s = E.cols[k];
       s.data = static_cast<const uint8_t*>(c.data->ptr);
       s.validity_bits = c.validity ? static_cast<const uint8_t*>(c.validity->ptr) : nullptr;
-      s.asc = keys[k].asc; s.nulls_first = keys[k].nulls_first;
+      s.asc = ks[k].asc; s.nulls_first = ks[k].nulls_first;
       if (t.is_string()) { s.kind = SORT_VIEW; s.width = 16; SG_CUDA(launch_max_view_len(c.data->ptr, n, static_cast<unsigned int*>(maxlen->ptr) + k, ctx->stream)); str_keys.push_back((int)k); }
       else if (t.id == TypeId::Bool) { s.kind = SORT_BOOL; s.width = 1; s.enc_bytes = 1; }
       else if (t.is_float()) { SG_CHECK(t.id == TypeId::Float64, SAILGPU_ERR_UNSUPPORTED, "Float32 sort keys"); s.kind = SORT_F64; s.width = 8; s.enc_bytes = 8; }
@@ -576,13 +573,34 @@ struct SortOp : Op {
         E.cols[k].str_len = (int)lens[k]; E.cols[k].enc_bytes = (int)lens[k] + 4;
       }
     }
-    for (size_t k = 0; k < keys.size(); ++k) { E.cols[k].out_off = off; off += 1 + E.cols[k].enc_bytes; }
+    for (size_t k = 0; k < ks.size(); ++k) { E.cols[k].out_off = off; off += 1 + E.cols[k].enc_bytes; }
     E.key_bytes = off;
-    BufPtr kb = dev_alloc(ctx, (size_t)n * off);
-    BufPtr bits = dev_alloc_zero(ctx, (size_t)off * 8);
-    E.keys = static_cast<uint8_t*>(kb->ptr);
-    E.bits = static_cast<uint32_t*>(bits->ptr);
+    Encoded out;
+    out.key_bytes = off;
+    out.keys = dev_alloc(ctx, (size_t)n * off);
+    out.bits = dev_alloc_zero(ctx, (size_t)off * 8);
+    E.keys = static_cast<uint8_t*>(out.keys->ptr);
+    E.bits = static_cast<uint32_t*>(out.bits->ptr);
     SG_CUDA(launch_sort_encode(E, ctx->stream));
+    m.kernel_launches += 1;
+    return out;
+  }
+
+  BatchPtr take_rows(const BatchPtr& all, const Schema& sch, const int64_t* idx, int64_t take) {
+    auto out = std::make_shared<DevBatch>();
+    out->rows = take;
+    JoinOp helper; helper.ctx = ctx;
+    for (size_t i = 0; i < sch.size(); ++i) out->cols.push_back(helper.gather_column(all->cols[i], sch[i], idx, take, false));
+    m.kernel_launches += sch.size();
+    return out;
+  }
+
+  // full sort: LSD radix over the encoded keys (stable), then one gather per column
+  BatchPtr sort_rows(const BatchPtr& all, const Schema& sch, const std::vector<Key>& ks, int64_t limit) {
+    const int64_t n = all->rows;
+    if (n == 0) return all;
+    SG_CHECK(n < (1ll << 32), SAILGPU_ERR_UNSUPPORTED, "sort of more than 2^32 rows in one partition");
+    Encoded enc = encode_keys(all, sch, ks);
     const int64_t n_chunks = (n + 2047) / 2048;
     BufPtr ia = dev_alloc(ctx, (size_t)n * 4), ib = dev_alloc(ctx, (size_t)n * 4), ka = dev_alloc(ctx, (size_t)n * 8), kbuf = dev_alloc(ctx, (size_t)n * 8),
            hist = dev_alloc(ctx, (size_t)n_chunks * 256 * 4), offs = dev_alloc(ctx, (size_t)n_chunks * 256 * 8), scr = dev_alloc(ctx, 1026 * 8);
@@ -591,38 +609,189 @@ struct SortOp : Op {
     S.kw_a = static_cast<uint64_t*>(ka->ptr); S.kw_b = static_cast<uint64_t*>(kbuf->ptr);
     S.hist = static_cast<uint32_t*>(hist->ptr); S.offs = static_cast<uint64_t*>(offs->ptr); S.scan_scratch = static_cast<uint64_t*>(scr->ptr);
     int sort_launches = 0;
-    SG_CUDA(radix_sort_indices(E.keys, off, n, S, E.bits, ctx->stream, &sort_launches));
-    m.kernel_launches += (uint64_t)(sort_launches + 2);
-    const int64_t take = fetch >= 0 ? std::min<int64_t>(fetch, n) : n;
+    SG_CUDA(radix_sort_indices(static_cast<const uint8_t*>(enc.keys->ptr), enc.key_bytes, n, S, static_cast<const uint32_t*>(enc.bits->ptr), ctx->stream, &sort_launches));
+    m.kernel_launches += (uint64_t)(sort_launches + 1);
+    const int64_t take = limit >= 0 ? std::min<int64_t>(limit, n) : n;
     BufPtr idx = dev_alloc(ctx, (size_t)take * 8);
     SG_CUDA(launch_widen_u32(static_cast<const uint32_t*>(ia->ptr), static_cast<int64_t*>(idx->ptr), take, ctx->stream));
-    auto out = std::make_shared<DevBatch>();
-    out->rows = take;
-    JoinOp helper; helper.ctx = ctx;
-    for (size_t i = 0; i < sch.size(); ++i) out->cols.push_back(helper.gather_column(all->cols[i], sch[i], static_cast<const int64_t*>(idx->ptr), take, false));
+    BatchPtr out = take_rows(all, sch, static_cast<const int64_t*>(idx->ptr), take);
     SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return out;
+  }
+
+  // TopK: radix-select the rows that can be among the first `k` on the leading 8 key bytes (one 8 B/row pass per 11 bits),
+  // then sort only those.  The candidates carry their row number as a last key, so ties come out in input order exactly as
+  // the (stable) full sort would deliver them.  Returns null when the selection does not narrow the input enough.
+  static constexpr int64_t TOPK_MIN_ROWS = 1 << 18, TOPK_MAX_K = 1 << 16;
+  BatchPtr topk_rows(const BatchPtr& all, const Schema& sch, const std::vector<Key>& ks, int64_t k) {
+    const int64_t n = all->rows;
+    Encoded enc = encode_keys(all, sch, ks);
+    const uint8_t* kp = static_cast<const uint8_t*>(enc.keys->ptr);
+    const int total_bits = std::min(64, enc.key_bytes * 8);
+    const int64_t want_at_most = std::max<int64_t>(4 * k, 1 << 16);
+    BufPtr hist = dev_alloc(ctx, 2048 * 4);
+    std::vector<uint32_t> h(2048);
+    int used = 0;
+    uint64_t prefix = 0;
+    int64_t below = 0, cand = n;       // rows strictly before the threshold path / rows on it
+    while (used < total_bits && below + cand > want_at_most) {
+      const int db = std::min(11, total_bits - used);
+      SG_CUDA(cudaMemsetAsync(hist->ptr, 0, 2048 * 4, ctx->stream));
+      SG_CUDA(launch_topk_hist(kp, enc.key_bytes, n, used, prefix, db, static_cast<uint32_t*>(hist->ptr), ctx->stream));
+      SG_CUDA(cudaMemcpyAsync(h.data(), hist->ptr, 2048 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      SG_CUDA(cudaStreamSynchronize(ctx->stream));
+      m.kernel_launches += 1;
+      int64_t run = below;
+      int bin = 0;
+      for (; bin < (1 << db); ++bin) { if (run + h[(size_t)bin] >= k) break; run += h[(size_t)bin]; }
+      if (bin == (1 << db)) bin = (1 << db) - 1;      // k exceeds the row count: everything qualifies
+      below = run; cand = h[(size_t)bin];
+      prefix = (prefix << db) | (uint64_t)bin;
+      used += db;
+    }
+    if (below + cand > std::max<int64_t>(want_at_most, n / 4)) return nullptr;       // heavy ties on the leading bytes: sort everything
+    BufPtr idx = dev_alloc(ctx, (size_t)(below + cand) * 8), ctr = dev_alloc_zero(ctx, 8);
+    SG_CUDA(launch_topk_compact(kp, enc.key_bytes, n, used, prefix, static_cast<int64_t*>(idx->ptr), static_cast<unsigned long long*>(ctr->ptr), ctx->stream));
+    m.kernel_launches += 1;
+    const int64_t nc = below + cand;
+    BatchPtr sub = take_rows(all, sch, static_cast<const int64_t*>(idx->ptr), nc);
+    DevColumn rowno; rowno.type = T(TypeId::Int64); rowno.length = nc; rowno.data = idx;
+    sub->cols.push_back(rowno);
+    Schema sch2 = sch;
+    sch2.push_back({"__row", T(TypeId::Int64), false});
+    std::vector<Key> ks2 = ks;
+    auto re = std::make_shared<Expr>(); re->kind = Expr::Col; re->col = (int)sch.size(); re->type = T(TypeId::Int64); re->nullable = false;
+    ks2.push_back({re, true, true});
+    BatchPtr sorted = sort_rows(sub, sch2, ks2, k);
+    sorted->cols.pop_back();
+    return sorted;
+  }
+
+  BatchPtr run() {
+    const Schema& sch = in_schemas[0];
+    BatchPtr all = concat_batches(ctx, sch, parts);
+    parts.clear();
+    const int64_t n = all->rows;
+    if (n == 0) return all;
+    SG_CHECK(n < (1ll << 32), SAILGPU_ERR_UNSUPPORTED, "sort of more than 2^32 rows in one partition");
+    const char* tk = getenv("SAILGPU_TOPK_MIN_ROWS");       // tests lower it
+    const int64_t topk_min = tk && *tk ? atoll(tk) : TOPK_MIN_ROWS;
+    if (fetch >= 0 && fetch <= TOPK_MAX_K && n >= topk_min && 8 * fetch < n) {
+      BatchPtr t = topk_rows(all, sch, keys, fetch);
+      if (t) return t;
+    }
+    return sort_rows(all, sch, keys, fetch);
+  }
+};
+
+// ================================================================================================
+// SortPreservingMergeExec: k-way merge of sorted runs.  Inputs = the sorted partitions (every input is one run, its
+// batches arrive in order); with "runs":"batches" every pushed batch is a run of its own (what an exchange that gathers
+// the locally sorted partitions of the ranks delivers).  Output = one sorted stream, optionally the first `fetch` rows.
+// ================================================================================================
+struct MergeOp : SortOp {
+  bool runs_are_batches = false;
+  std::vector<std::vector<BatchPtr>> per_input;
+  std::vector<bool> done_in;
+
+  void push(int input, const BatchPtr& b) override {
+    SG_CHECK(input >= 0 && input < (int)per_input.size(), SAILGPU_ERR_INVALID, "merge input index out of range");
+    m.input_rows += (uint64_t)b->rows; m.input_batches++;
+    if (b->rows) per_input[(size_t)input].push_back(b);
+  }
+  void finish(int input) override {
+    SG_CHECK(input >= 0 && input < (int)done_in.size(), SAILGPU_ERR_INVALID, "merge input index out of range");
+    done_in[(size_t)input] = true;
+    input_done = true;
+    for (bool d : done_in) input_done = input_done && d;
+  }
+  bool pull(BatchPtr* out) override {
+    *out = nullptr;
+    if (!input_done) return true;
+    if (emitted) return false;
+    const uint64_t t0 = now_ns();
+    *out = merge();
+    emitted = true;
+    m.elapsed_compute_ns += now_ns() - t0;
+    m.output_rows += (uint64_t)(*out)->rows; m.output_batches++;
+    return false;
+  }
+
+  BatchPtr merge() {
+    const Schema& sch = in_schemas[0];
+    std::vector<BatchPtr> runs;
+    for (auto& in : per_input) {
+      if (in.empty()) continue;
+      if (runs_are_batches) for (auto& b : in) runs.push_back(b);
+      else runs.push_back(in.size() == 1 ? in[0] : concat_batches(ctx, sch, in));
+    }
+    per_input.clear();
+    if (runs.empty()) return empty_batch(ctx, sch);
+    // with a fetch only the first `fetch` rows of every run can reach the output
+    if (fetch >= 0)
+      for (auto& r : runs)
+        if (r->rows > fetch) {
+          BufPtr idx = dev_alloc(ctx, (size_t)fetch * 8);
+          SG_CUDA(launch_iota(static_cast<int64_t*>(idx->ptr), fetch, ctx->stream));
+          r = take_rows(r, sch, static_cast<const int64_t*>(idx->ptr), fetch);
+          SG_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    if (runs.size() == 1) return runs[0];
+    std::vector<int64_t> off(runs.size() + 1, 0);
+    for (size_t i = 0; i < runs.size(); ++i) off[i + 1] = off[i] + runs[i]->rows;
+    BatchPtr all = concat_batches(ctx, sch, runs);
+    const int64_t n = all->rows;
+    Encoded enc = encode_keys(all, sch, keys);
+    BufPtr doff = dev_alloc(ctx, off.size() * 8), perm = dev_alloc(ctx, (size_t)n * 8);
+    SG_CUDA(cudaMemcpyAsync(doff->ptr, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(launch_merge_rank(static_cast<const uint8_t*>(enc.keys->ptr), enc.key_bytes, static_cast<const int64_t*>(doff->ptr), (int)runs.size(), n,
+                              static_cast<int64_t*>(perm->ptr), ctx->stream));
+    m.kernel_launches += 1;
+    const int64_t take = fetch >= 0 ? std::min<int64_t>(fetch, n) : n;
+    BatchPtr out = take_rows(all, sch, static_cast<const int64_t*>(perm->ptr), take);
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));       // `off` is a host vector
     return out;
   }
 };
 
-std::unique_ptr<Op> make_sort_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs) {
-  SG_CHECK(inputs.size() == 1, SAILGPU_ERR_INVALID, "sort takes one input");
-  auto op = std::make_unique<SortOp>();
-  op->ctx = ctx; op->kind = "sort"; op->in_schemas = inputs; op->out_schema = inputs[0];
+static void parse_sort_keys(SortOp* op, const Json& spec, const Schema& in) {
   for (auto& k : spec.at("keys").a) {
     SortOp::Key key;
-    key.e = parse_expr(k.at("expr"), inputs[0]);
+    key.e = parse_expr(k.at("expr"), in);
     const Json* asc = k.find("asc"); key.asc = !asc || asc->kind != Json::Bool || asc->b;
     const Json* nf = k.find("nulls_first"); key.nulls_first = nf && nf->kind == Json::Bool ? nf->b : key.asc;
     op->keys.push_back(key);
   }
-  SG_CHECK(!op->keys.empty() && op->keys.size() <= 8, SAILGPU_ERR_INVALID, "sort needs 1..8 keys");
+  SG_CHECK(!op->keys.empty() && op->keys.size() <= 7, SAILGPU_ERR_INVALID, "sort needs 1..7 keys");
   for (auto& k : op->keys) {      // plan-time limits (sailgpu_spec_validate)
     SG_CHECK(k.e->kind == Expr::Col, SAILGPU_ERR_UNSUPPORTED, "sort keys must be column references");
     SG_CHECK(k.e->type.id != TypeId::Float32, SAILGPU_ERR_UNSUPPORTED, "Float32 sort keys");
   }
   const Json* f = spec.find("fetch");
   if (f && !f->is_null()) op->fetch = f->as_int();
+}
+
+std::unique_ptr<Op> make_merge_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs) {
+  SG_CHECK(!inputs.empty(), SAILGPU_ERR_INVALID, "sort_preserving_merge takes one input per sorted partition");
+  for (auto& s : inputs) {
+    SG_CHECK(s.size() == inputs[0].size(), SAILGPU_ERR_INVALID, "sort_preserving_merge inputs differ in schema");
+    for (size_t i = 0; i < s.size(); ++i) SG_CHECK(s[i].type == inputs[0][i].type, SAILGPU_ERR_INVALID, "sort_preserving_merge inputs differ in schema");
+  }
+  auto op = std::make_unique<MergeOp>();
+  op->ctx = ctx; op->kind = "sort_preserving_merge"; op->in_schemas = inputs; op->out_schema = inputs[0];
+  parse_sort_keys(op.get(), spec, inputs[0]);
+  const Json* r = spec.find("runs");
+  op->runs_are_batches = r && !r->is_null() && r->as_str() == "batches";
+  op->per_input.resize(inputs.size());
+  op->done_in.assign(inputs.size(), false);
+  return op;
+}
+
+std::unique_ptr<Op> make_sort_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs) {
+  SG_CHECK(inputs.size() == 1, SAILGPU_ERR_INVALID, "sort takes one input");
+  auto op = std::make_unique<SortOp>();
+  op->ctx = ctx; op->kind = "sort"; op->in_schemas = inputs; op->out_schema = inputs[0];
+  parse_sort_keys(op.get(), spec, inputs[0]);
   return op;
 }
 
@@ -808,7 +977,7 @@ std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::v
 //                  all-gather of the row counts, so every rank takes the same one; a later "gather" exchange of the same
 //                  chain sees that the rows already sit on the root and does not communicate.
 // ================================================================================================
-BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts);
+BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts, std::vector<int64_t>* source_offsets = nullptr);
 int64_t exchange_max_rows(Ctx* ctx, int64_t mine);
 std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 
@@ -821,6 +990,26 @@ struct ExchangeOp : Op {
   BatchPtr result;
   bool done = false, pulled = false;
   bool* on_root_hint = nullptr;     // shared by the exchanges of one chain (owned by the ChainOp)
+  bool keep_runs = false;           // emit what every source rank sent as a batch of its own (input of a sort-preserving merge)
+  std::deque<BatchPtr> run_batches;
+
+  void split_runs(const std::vector<int64_t>& off) {
+    JoinOp helper; helper.ctx = ctx;
+    const Schema& sch = in_schemas[0];
+    for (size_t s = 0; s + 1 < off.size(); ++s) {
+      const int64_t k = off[s + 1] - off[s];
+      if (k == 0) continue;
+      if (k == result->rows) { run_batches.push_back(result); continue; }
+      BufPtr idx = dev_alloc(ctx, (size_t)k * 8);
+      SG_CUDA(launch_iota_stride(static_cast<int64_t*>(idx->ptr), off[s], 1, k, ctx->stream));
+      auto b = std::make_shared<DevBatch>();
+      b->rows = k;
+      for (size_t c = 0; c < sch.size(); ++c) b->cols.push_back(helper.gather_column(result->cols[c], sch[c], static_cast<const int64_t*>(idx->ptr), k, false));
+      SG_CUDA(cudaStreamSynchronize(ctx->stream));
+      run_batches.push_back(b);
+    }
+    if (run_batches.empty()) run_batches.push_back(result);
+  }
 
   void push(int input, const BatchPtr& b) override {
     SG_CHECK(input == 0, SAILGPU_ERR_INVALID, "exchange has one input");
@@ -833,11 +1022,11 @@ struct ExchangeOp : Op {
     BatchPtr all = parts_in.empty() ? empty_batch(ctx, sch) : concat_batches(ctx, sch, parts_in);
     parts_in.clear();
     const int W = ctx->world;
-    if (W == 1) { result = all; done = true; return; }
+    if (W == 1) { result = all; done = true; if (keep_runs) run_batches.push_back(result); return; }
     std::string how = mode;
     if (how == "auto") how = exchange_max_rows(ctx, all->rows) <= small_rows ? "gather" : "hash";
     if (how == "gather" && mode == "gather" && on_root_hint && *on_root_hint) {       // an "auto" exchange of this chain already coalesced on the root
-      result = all; done = true; return;
+      result = all; done = true; if (keep_runs) run_batches.push_back(result); return;
     }
     std::vector<BatchPtr> parts((size_t)W);
     if (how == "gather") {
@@ -860,12 +1049,20 @@ struct ExchangeOp : Op {
       }
       m.kernel_launches += rp->m.kernel_launches;
     }
-    result = exchange_batches(ctx, sch, parts);
+    std::vector<int64_t> src_off;
+    result = exchange_batches(ctx, sch, parts, keep_runs ? &src_off : nullptr);
+    if (keep_runs) split_runs(src_off);
     done = true;
     m.elapsed_compute_ns += now_ns() - t0;
   }
   bool pull(BatchPtr* out) override {
     *out = nullptr;
+    if (keep_runs) {
+      if (!done) return true;
+      if (!run_batches.empty()) { *out = run_batches.front(); run_batches.pop_front(); m.output_rows += (uint64_t)(*out)->rows; m.output_batches++; }
+      if (run_batches.empty()) { pulled = true; result.reset(); }
+      return !pulled;
+    }
     if (done && !pulled) { *out = result; pulled = true; m.output_rows += (uint64_t)result->rows; m.output_batches++; result.reset(); }
     return !pulled;
   }
@@ -880,6 +1077,7 @@ std::unique_ptr<Op> make_exchange_op(Ctx* ctx, const Json& spec, const std::vect
   SG_CHECK(op->mode == "hash" || op->mode == "gather" || op->mode == "auto", SAILGPU_ERR_INVALID, "exchange mode must be hash, gather or auto");
   const Json* rt = spec.find("root"); if (rt && !rt->is_null()) op->root = (int)rt->as_int();
   const Json* sr = spec.find("small_rows"); if (sr && !sr->is_null()) op->small_rows = sr->as_int();
+  const Json* kr = spec.find("keep_runs"); op->keep_runs = kr && kr->kind == Json::Bool && kr->b;
   if (op->mode != "gather") {
     op->exprs_json = spec.at("exprs");
     for (auto& e : op->exprs_json.a) (void)parse_expr(e, inputs[0]);          // validate at plan time
@@ -1019,10 +1217,10 @@ int64_t exchange_max_rows(Ctx* ctx, int64_t mine) {
 }
 // all-to-all of world_size device batches over the context's communicator: parts[p] goes to rank p; returns everything
 // that was sent to this rank (rows of rank 0 first, then rank 1, ...)
-BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts) {
+BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts, std::vector<int64_t>* source_offsets) {
   const int n = (int)parts.size();
   SG_CHECK(n == ctx->world, SAILGPU_ERR_INVALID, "exchange needs one batch per rank");
-  if (n == 1) return parts[0];
+  if (n == 1) { if (source_offsets) *source_offsets = {0, parts[0]->rows}; return parts[0]; }
   BatchPtr out;
   {
     SG_CHECK(ctx->nccl_comm != nullptr, SAILGPU_ERR_STATE, "sailgpu_ctx_comm_init has not been called");
@@ -1092,6 +1290,7 @@ BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<Batc
     std::vector<int64_t> row_off((size_t)W + 1, 0);
     for (int s = 0; s < W; ++s) row_off[(size_t)s + 1] = row_off[(size_t)s] + cnt(s, me, 0);
     const int64_t total_rows = row_off[(size_t)W];
+    if (source_offsets) *source_offsets = row_off;
     out = std::make_shared<DevBatch>();
     out->rows = total_rows;
     std::vector<BufPtr> vbytes(ncols), bbytes(ncols), datas(ncols), heaps(ncols);

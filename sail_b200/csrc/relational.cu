@@ -344,6 +344,87 @@ cudaError_t radix_sort_indices(const uint8_t* keys, int key_bytes, int64_t n, co
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// TopK selection (SortExec with fetch = k, test_tpch.plan.yaml:27,79; ClickBench ORDER BY .. LIMIT 10): radix SELECT on
+// the leading 8 bytes of the encoded key instead of sorting all n rows.  One level = one streaming pass over 8 B/row:
+// histogram of the next 11 bits among the rows whose consumed prefix equals the threshold path.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t key_word_be(const uint8_t* k, int key_bytes) {      // first 8 key bytes as a big-endian number (zero padded)
+  uint64_t w = 0;
+  const int nb = key_bytes < 8 ? key_bytes : 8;
+  for (int b = 0; b < nb; ++b) w |= (uint64_t)k[b] << (56 - 8 * b);
+  return w;
+}
+__global__ void topk_hist_kernel(const uint8_t* __restrict__ keys, int key_bytes, int64_t n, int used, uint64_t prefix, int digit_bits, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t w = key_word_be(keys + i * key_bytes, key_bytes);
+    if (used == 0 || (w >> (64 - used)) == prefix) atomicAdd(&sh[(uint32_t)((w << used) >> (64 - digit_bits))], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// rows whose leading `used` key bits are <= threshold (every row when used == 0): their indices, in any order
+__global__ void topk_compact_kernel(const uint8_t* __restrict__ keys, int key_bytes, int64_t n, int used, uint64_t threshold, int64_t* __restrict__ out, unsigned long long* counter) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t w = key_word_be(keys + i * key_bytes, key_bytes);
+    const bool take = used == 0 || (w >> (64 - used)) <= threshold;
+    const unsigned m = __ballot_sync(__activemask(), take);
+    if (take) {
+      const unsigned lane = threadIdx.x & 31;
+      const int lead = __ffs(m) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == lead) base = atomicAdd(counter, (unsigned long long)__popc(m));
+      base = __shfl_sync(m, base, lead);
+      out[base + __popc(m & ((1u << lane) - 1))] = i;
+    }
+  }
+}
+cudaError_t launch_topk_hist(const uint8_t* keys, int key_bytes, int64_t n, int used, uint64_t prefix, int digit_bits, uint32_t* hist, cudaStream_t s) {
+  topk_hist_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(keys, key_bytes, n, used, prefix, digit_bits, hist);
+  return cudaGetLastError();
+}
+cudaError_t launch_topk_compact(const uint8_t* keys, int key_bytes, int64_t n, int used, uint64_t threshold, int64_t* out, unsigned long long* counter, cudaStream_t s) {
+  topk_compact_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(keys, key_bytes, n, used, threshold, out, counter);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// k-way merge of sorted runs (SortPreservingMergeExec, test_tpch.plan.yaml:9-10): every row computes its output position
+// directly -- its index in its own run plus, for every other run, the number of rows that sort before it (binary search
+// on the encoded keys; ties go to the earlier run, which makes the merge stable).  No sequential merge loop, no heap.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int key_cmp(const uint8_t* a, const uint8_t* b, int key_bytes) {
+  for (int i = 0; i < key_bytes; ++i) { const int d = (int)a[i] - (int)b[i]; if (d) return d; }
+  return 0;
+}
+__global__ void merge_rank_kernel(const uint8_t* __restrict__ keys, int key_bytes, const int64_t* __restrict__ run_off, int n_runs, int64_t n, int64_t* __restrict__ perm) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = 0;
+    while (r + 1 < n_runs && run_off[r + 1] <= i) ++r;      // (runs are few)
+    const uint8_t* me = keys + i * key_bytes;
+    int64_t pos = i - run_off[r];
+    for (int s = 0; s < n_runs; ++s) {
+      if (s == r) continue;
+      int64_t lo = run_off[s], hi = run_off[s + 1];
+      while (lo < hi) {          // s < r: rows <= me sort first (upper bound); s > r: rows < me (lower bound)
+        const int64_t mid = (lo + hi) >> 1;
+        const int c = key_cmp(keys + mid * key_bytes, me, key_bytes);
+        if (c < 0 || (c == 0 && s < r)) lo = mid + 1; else hi = mid;
+      }
+      pos += lo - run_off[s];
+    }
+    perm[pos] = i;
+  }
+}
+cudaError_t launch_merge_rank(const uint8_t* keys, int key_bytes, const int64_t* run_off, int n_runs, int64_t n, int64_t* perm, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  merge_rank_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(keys, key_bytes, run_off, n_runs, n, perm);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_iota(int64_t* out, int64_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   iota_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(out, n);

@@ -65,6 +65,9 @@ cudaError_t launch_gather_bits(const uint8_t* bits, uint8_t* out, const int64_t*
 cudaError_t launch_max_view_len(const void* views, int64_t n, unsigned int* out, cudaStream_t s);
 cudaError_t launch_sort_encode(const SortEncodeParams& P, cudaStream_t s);
 cudaError_t radix_sort_indices(const uint8_t* keys, int key_bytes, int64_t n, const RadixScratch& S, const uint32_t* bits, cudaStream_t s, int* launches);
+cudaError_t launch_topk_hist(const uint8_t* keys, int key_bytes, int64_t n, int used, uint64_t prefix, int digit_bits, uint32_t* hist /* [2048], zeroed */, cudaStream_t s);
+cudaError_t launch_topk_compact(const uint8_t* keys, int key_bytes, int64_t n, int used, uint64_t threshold, int64_t* out, unsigned long long* counter, cudaStream_t s);
+cudaError_t launch_merge_rank(const uint8_t* keys, int key_bytes, const int64_t* run_off, int n_runs, int64_t n, int64_t* perm, cudaStream_t s);
 cudaError_t launch_iota(int64_t* out, int64_t n, cudaStream_t s);
 cudaError_t launch_iota_stride(int64_t* out, int64_t first, int64_t stride, int64_t n, cudaStream_t s);
 cudaError_t launch_widen_u32(const uint32_t* in, int64_t* out, int64_t n, cudaStream_t s);

@@ -236,6 +236,12 @@ def two_phase_chain(partial_spec: dict, final_spec: dict, key_cols: list, tail: 
     partial -> exchange(auto: hash on the group keys, or coalesce on rank 0 when every rank holds few rows) -> final ->
     exchange(gather to rank 0) -> tail operators (sort).  Nothing leaves HBM or the library between the stages; rank 0
     pulls the result, the other ranks pull an empty batch.  Same decisions as `final_aggregate` above."""
-    return {"op": "chain", "ops": [partial_spec,
-                                   {"op": "exchange", "mode": "auto", "exprs": [{"col": c} for c in key_cols], "small_rows": small_rows},
-                                   final_spec, {"op": "exchange", "mode": "gather", "root": 0}] + list(tail)}
+    tail = list(tail)
+    head = [partial_spec, {"op": "exchange", "mode": "auto", "exprs": [{"col": c} for c in key_cols], "small_rows": small_rows}, final_spec]
+    if tail and tail[0].get("op") == "sort":
+        # SortExec per partition -> SortPreservingMergeExec on the root (test_tpch.plan.yaml:9-10): every rank sorts what it owns, the
+        # sorted runs are gathered as they are and merged, instead of re-sorting the gathered rows
+        s = tail[0]
+        merge = {"op": "sort_preserving_merge", "keys": s["keys"], "fetch": s.get("fetch"), "runs": "batches"}
+        return {"op": "chain", "ops": head + [s, {"op": "exchange", "mode": "gather", "root": 0, "keep_runs": True}, merge] + tail[1:]}
+    return {"op": "chain", "ops": head + [{"op": "exchange", "mode": "gather", "root": 0}] + tail}

@@ -236,7 +236,7 @@ class GpuExec:
 
     def name(self) -> str:
         return {"filter": "GpuFilterExec", "projection": "GpuProjectionExec", "aggregate": "GpuAggregateExec",
-                "hash_join": "GpuHashJoinExec", "sort": "GpuSortExec", "repartition": "GpuRepartitionExec",
+                "hash_join": "GpuHashJoinExec", "sort": "GpuSortExec", "sort_preserving_merge": "GpuSortPreservingMergeExec", "repartition": "GpuRepartitionExec",
                 "pipeline": "GpuPipelineExec", "chain": "GpuChainExec"}.get(self.spec.get("op"), "GpuExec")
 
     def _check(self, rc):

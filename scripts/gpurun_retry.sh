@@ -1,10 +1,11 @@
 #!/bin/bash
-# usage: scripts/gpurun_retry.sh <log file> <timeout s> <command...>   -- retries while the pod answers "busy" (nothing charged)
+# usage: scripts/gpurun_retry.sh <log file> <timeout s> <command...>
+# retries while the pod answers "busy" (nothing charged) or another call of this repo is still in flight
 log=$1; shift; to=$1; shift
-for i in $(seq 1 40); do
+for i in $(seq 1 200); do
   /usr/local/graft/bin/gpurun --timeout "$to" -- "$@" > "$log" 2>&1
   rc=$?
-  if grep -q "status=transient" "$log" || [ $rc -eq 3 ]; then sleep 45; continue; fi
+  if grep -q "status=transient" "$log" || grep -q "already running" "$log" || [ $rc -eq 3 ]; then sleep 40; continue; fi
   exit $rc
 done
 exit 3

@@ -142,6 +142,57 @@ def test_hash_repartition(n_parts):
     op.close()
 
 
+@pytest.mark.parametrize("k", [1, 10, 1000])
+@pytest.mark.parametrize("keys", [[("lk", False)], [("ls", True), ("lv", False)], [("lv", True)], [("lk2", False), ("lk", True)]])
+def test_topk_selection_matches_full_sort(k, keys, monkeypatch):
+    """SortExec with fetch: the radix-select path (candidates by the leading key bytes, then a small sort) returns exactly the
+    rows -- ties included, in input order -- of the stable full sort (the oracle)."""
+    from sail_b200 import engine
+    monkeypatch.setenv("SAILGPU_TOPK_MIN_ROWS", "1000")
+    l = left_table(50021, 31, True, True)
+    names = l.schema.names
+    spec = {"op": "sort", "fetch": k, "keys": [{"expr": {"col": names.index(c)}, "asc": asc, "nulls_first": asc} for c, asc in keys if c in names]}
+    assert_same(gpu_op(spec, l), oracle_op(spec, l), ordered=True)
+
+
+def test_topk_heavy_ties_falls_back_to_the_full_sort(monkeypatch):
+    monkeypatch.setenv("SAILGPU_TOPK_MIN_ROWS", "1000")
+    n = 40000
+    t = pa.table({"k": pa.array(np.zeros(n, dtype=np.int64)), "v": pa.array(np.arange(n, dtype=np.int64))})
+    spec = {"op": "sort", "fetch": 7, "keys": [{"expr": {"col": 0}, "asc": True, "nulls_first": True}]}
+    assert gpu_op(spec, t).column("v").to_pylist() == list(range(7))       # stable: input order among equal keys
+
+
+@pytest.mark.parametrize("fetch", [None, 25])
+@pytest.mark.parametrize("n_runs", [1, 2, 5])
+def test_sort_preserving_merge(n_runs, fetch):
+    """SortPreservingMergeExec: sorted partitions in, one sorted stream out (stable: ties to the earlier partition)"""
+    from sail_b200 import engine
+    l = left_table(30011, 41, True, True)
+    names = l.schema.names
+    keys = [{"expr": {"col": 0}, "asc": True, "nulls_first": True}, {"expr": {"col": len(names) - 1}, "asc": False, "nulls_first": False}]
+    sort = {"op": "sort", "keys": keys, "fetch": None}
+    cut = [l.num_rows * i // n_runs for i in range(n_runs + 1)]
+    runs = [oracle_op(sort, l.slice(cut[i], cut[i + 1] - cut[i])) for i in range(n_runs)]
+    spec = {"op": "sort_preserving_merge", "keys": keys, "fetch": fetch}
+    want = oracle_op(spec, *runs)
+    op = engine.GpuExec(spec, [r.schema for r in runs])
+    for i, r in enumerate(runs):
+        for o in range(0, max(1, r.num_rows), 4099):      # a partition arrives as several batches
+            op.push(r.slice(o, 4099), i)
+        op.finish(i)
+    assert_same(op.collect(), want, ordered=True)
+    op.close()
+    # every pushed batch as a run of its own (what an exchange that gathers sorted partitions hands over)
+    spec2 = dict(spec, runs="batches")
+    op = engine.GpuExec(spec2, [runs[0].schema])
+    for r in runs:
+        op.push(r)
+    op.finish()
+    assert_same(op.collect(), want, ordered=True)
+    op.close()
+
+
 def pull_partition_to_host(op, p, schema):
     from sail_b200 import engine
     parts = []
