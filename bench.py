@@ -155,6 +155,7 @@ def run_query_dist(backend, specs, inputs, in_schema, host_chunks=None):
         op.finish()
         out = op.collect()
         mm = op.metrics()
+        LAST_METRICS.update(mm)
         op.close()
         return (out if backend.rank == 0 else None), mm["gpu.kernel_launches"], mm["gpu.pipeline_kernel_ns"], mm["gpu.pipeline_launches"], mm.get("gpu.jit_launches", 0)
     op1 = engine.GpuExec(fused, [in_schema], backend.ctx)
@@ -198,12 +199,14 @@ def run_query(ctx, specs, inputs, in_schema, host_chunks=None):
     op.finish()
     out = op.collect()
     mm = op.metrics()
+    LAST_METRICS.update(mm)
     op.close()
     return out, mm["gpu.kernel_launches"], mm["gpu.pipeline_kernel_ns"], mm["gpu.pipeline_launches"], mm.get("gpu.jit_launches", 0)
 
 
 SORT_ON_GPU = True
 DIST_BACKEND = None
+LAST_METRICS = {}
 
 
 def merge_q1_rows(parts):
@@ -417,23 +420,23 @@ def main():
         out, l, kns, kl, jl = run_query(ctx, specs, devs, schema)
         acc["out"] = out
         acc["launches"] += l; acc["kern_ns"] += kns; acc["kern_launches"] += kl; acc["jit"] += jl
-    for _ in range(max(3, args.warmup)):
-        resident_step()
-    acc.update(launches=0, kern_ns=0, kern_launches=0, jit=0)
-    sampler = ClockSampler(local)
-    sampler.start()
-    ms = timed_steps(ctx, stream, world, args.steps, resident_step)
-    clocks = sampler.stop()
-    ms_per_step = ms / args.steps
+
+    def resident_leg():
+        for _ in range(max(3, args.warmup)):
+            resident_step()
+        acc.update(launches=0, kern_ns=0, kern_launches=0, jit=0)
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms_ = timed_steps(ctx, stream, world, args.steps, resident_step)
+        return ms_, sampler.stop()
+    ms, clocks = resident_leg()
     total_rows_t = torch.tensor([n_rows], device="cuda", dtype=torch.int64)
     if world > 1:
         dist.all_reduce(total_rows_t)
     total_rows = int(total_rows_t.item())
-    value = total_rows / (ms_per_step / 1e3)
-    out = acc["out"]
 
     # ---- host copies: parity of the full-size result against the C port (every rank's shard), CPU baseline, e2e inputs ----
-    host_e2e, cpu, want_rows = [], None, None
+    host_e2e, cpu, want_rows, notes = [], None, None, []
     if not args.skip_cpu:
         threads = max(1, (os.cpu_count() or 1) // world)
         parts, dt_cpu = [], 0.0
@@ -449,14 +452,31 @@ def main():
         if world > 1:
             gathered = [None] * world
             dist.gather_object(mine, gathered if rank == 0 else None, dst=0)
+        ok = [True]
         if rank == 0:
             want_rows = merge_q1_rows(gathered)
-            check_result(out, want_rows)
+            try:
+                check_result(acc["out"], want_rows)
+            except AssertionError as e:
+                ok[0] = False
+                print(f"[bench] parity FAILED with specialised kernels: {e}", file=sys.stderr)
             if world == 1:
                 cpu = {"value": n_rows / dt_cpu, "unit": "rows/s", "cores": threads, "kind": "port",
                        "sample": f"the full SF{args.sf:g} lineitem ({n_rows} rows) once, in {len(gens)} batches, oracle/cpipelines.c (C port of the DataFusion CPU path), all host threads"}
+        if world > 1:
+            dist.broadcast_object_list(ok, src=0)
+        if not ok[0] and os.environ.get("SAILGPU_JIT", "1") != "0":
+            # never report a number for a wrong result: the interpreter kernel is the reference implementation of the pipeline
+            os.environ["SAILGPU_JIT"] = "0"
+            notes.append("specialised kernels DISABLED for this run: their result differed from the C port (see stderr); numbers are the interpreter's")
+            ms, clocks = resident_leg()
+            if rank == 0:
+                check_result(acc["out"], want_rows)
     elif not args.skip_e2e:
         host_e2e = [g.host_table() for g in gens[: args.e2e_chunks]]
+    ms_per_step = ms / args.steps
+    value = total_rows / (ms_per_step / 1e3)
+    out = acc["out"]
 
     # ---- end-to-end leg: PAGEABLE host Arrow buffers through the C ABI -------------------------------------------------
     e2e = None
@@ -471,16 +491,33 @@ def main():
         for _ in range(2):
             e2e_step()
         e2e_steps = max(1, min(args.steps, 5))
+        wire0 = LAST_METRICS.get("gpu.h2d_bytes", 0)
         ms_e = timed_steps(ctx, stream, world, e2e_steps, e2e_step)
+        wire = (LAST_METRICS.get("gpu.h2d_bytes", 0) - wire0) / e2e_steps
         rows_t = torch.tensor([e2e_rows], device="cuda", dtype=torch.int64)
         if world > 1:
             dist.all_reduce(rows_t)
         out_e = st["out"]
         d2h = 0 if out_e is None else sum(b.size for c in out_e.columns for ch in c.chunks for b in ch.buffers() if b is not None)
         if rank == 0 and world == 1 and not args.skip_cpu:      # (N > 1: the resident leg carried the all-rank check)
-            check_result(out_e, merge_q1_rows([parts[i] for i in range(len(host_e2e))]))
+            want_e = merge_q1_rows([parts[i] for i in range(len(batches))])
+            try:
+                check_result(out_e, want_e)
+            except AssertionError as e:
+                if os.environ.get("SAILGPU_H2D_PACK", "1") == "0":
+                    raise
+                print(f"[bench] e2e parity FAILED with packed host ingest: {e}", file=sys.stderr)
+                os.environ["SAILGPU_H2D_PACK"] = "0"
+                notes.append("packed host ingest DISABLED for the e2e leg: its result differed from the C port (see stderr)")
+                e2e_step()
+                wire0 = LAST_METRICS.get("gpu.h2d_bytes", 0)
+                ms_e = timed_steps(ctx, stream, world, e2e_steps, e2e_step)
+                wire = (LAST_METRICS.get("gpu.h2d_bytes", 0) - wire0) / e2e_steps
+                out_e = st["out"]
+                check_result(out_e, want_e)
         e2e = {"value": int(rows_t.item()) / (ms_e / e2e_steps / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e / e2e_steps, "host_batches": len(batches), "host_memory": "pageable",
+               "ms_per_step": ms_e / e2e_steps, "host_batches": len(batches), "host_memory": "pageable", "pcie_bytes_per_step": wire,
+               "ingest": "packer threads -> pinned staging -> packed wire format (FOR integers, inline views) -> expanded to Arrow in HBM",
                "sample": f"the first {len(batches)} of {len(gens)} batches per GPU ({e2e_rows} rows)"}
     del host_e2e
 
@@ -524,6 +561,7 @@ def main():
                          "algorithmic_bytes_per_launch": n_rows * ALGO_BYTES_PER_ROW / max(1.0, lps)},
             "cpu_baseline": cpu,
             "exchange": exchange,
+            "notes": notes,
         }
         print(json.dumps(line), flush=True)
     del devs, gens, out

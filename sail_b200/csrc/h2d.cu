@@ -235,6 +235,7 @@ void HostStager::add(HostCol kind, void* dst, const void* src, int64_t n, int wi
 void HostStager::flush() {
   if (items.empty()) return;
   PackPool* p = pool_of(ctx);
+  { const char* nw = getenv("SAILGPU_H2D_PACK"); p->narrow = !(nw && *nw && atoi(nw) == 0); }      // read per batch (A/B measurements, fallback)
   // the destination buffers were allocated (stream-ordered) on the compute stream: the copy streams must not start before that
   cudaEvent_t alloc_ev;
   SG_CUDA(cudaEventCreateWithFlags(&alloc_ev, cudaEventDisableTiming));

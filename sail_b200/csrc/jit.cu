@@ -381,7 +381,7 @@ int env_i(const char* n, int d) { const char* v = getenv(n); return v && *v ? at
 
 }  // namespace
 
-bool jit_enabled() { static const bool on = env_i("SAILGPU_JIT", 1) != 0; return on; }
+bool jit_enabled() { return env_i("SAILGPU_JIT", 1) != 0; }      // read per launch: a host can turn specialisation off at run time
 int64_t jit_min_rows() { const char* v = getenv("SAILGPU_JIT_MIN_ROWS"); return v && *v ? atoll(v) : (int64_t)4 << 20; }
 
 bool jit_supported(const CompiledPipeline& cp, std::string* why) {
