@@ -202,18 +202,28 @@ def orders(sf: float, columns=None, strings: str = "view", **kw) -> pa.Table:
     return pa.table([_to_arrow(c, raw[c], strings) for c in columns], names=columns)
 
 
+def _phones(which: int, nationkey: np.ndarray, strings: str) -> pa.Array:
+    n = len(nationkey)
+    raw = np.empty(15 * n, dtype=np.uint8)
+    lib().tpch_gen_phone(ctypes.c_int(which), ctypes.c_int64(0), ctypes.c_int64(n), _p(np.ascontiguousarray(nationkey, dtype=np.int64)), _p(raw))
+    txt = raw.reshape(n, 15).view("S15").ravel()
+    return pa.array([t.decode() for t in txt], type=pa.string_view() if strings == "view" else pa.string())
+
+
 def customer(sf: float, columns=None, strings: str = "view") -> pa.Table:
     n = counts(sf)["customer"]
     a = {"c_custkey": np.empty(n, "i8"), "c_nationkey": np.empty(n, "i8"), "c_acctbal": np.empty(n, "i8"),
          "c_mktsegment": np.empty(n, "u1")}
     lib().tpch_gen_customer(ctypes.c_double(sf), ctypes.c_int64(0), ctypes.c_int64(n),
                             _p(a["c_custkey"]), _p(a["c_nationkey"]), _p(a["c_acctbal"]), _p(a["c_mktsegment"]))
-    columns = list(columns or list(a.keys()) + ["c_name"])
+    columns = list(columns or list(a.keys()) + ["c_name", "c_phone"])
 
     def one(c):
         if c == "c_name":       # dbgen: "Customer#%09d" (18 bytes: always a long view)
             txt = np.char.add("Customer#", np.char.zfill(a["c_custkey"].astype(str), 9))
             return pa.array(txt.tolist(), type=pa.string_view() if strings == "view" else pa.string())
+        if c == "c_phone":
+            return _phones(0, a["c_nationkey"], strings)
         return _to_arrow(c, a[c], strings)
     return pa.table([one(c) for c in columns], names=columns)
 
@@ -223,8 +233,26 @@ def supplier(sf: float, columns=None, strings: str = "view") -> pa.Table:
     a = {"s_suppkey": np.empty(n, "i8"), "s_nationkey": np.empty(n, "i8"), "s_acctbal": np.empty(n, "i8")}
     lib().tpch_gen_supplier(ctypes.c_double(sf), ctypes.c_int64(0), ctypes.c_int64(n),
                             _p(a["s_suppkey"]), _p(a["s_nationkey"]), _p(a["s_acctbal"]))
+    columns = list(columns or list(a.keys()) + ["s_name"])
+
+    def one(c):
+        if c == "s_name":       # dbgen: "Supplier#%09d"
+            txt = np.char.add("Supplier#", np.char.zfill(a["s_suppkey"].astype(str), 9))
+            return pa.array(txt.tolist(), type=pa.string_view() if strings == "view" else pa.string())
+        if c == "s_phone":
+            return _phones(1, a["s_nationkey"], strings)
+        return _to_arrow(c, a[c], strings)
+    return pa.table([one(c) for c in columns], names=columns)
+
+
+def partsupp(sf: float, columns=None, strings: str = "view") -> pa.Table:
+    """ps_partkey, ps_suppkey, ps_availqty, ps_supplycost (ps_comment is not generated)"""
+    n = counts(sf)["part"]
+    a = {"ps_partkey": np.empty(4 * n, "i8"), "ps_suppkey": np.empty(4 * n, "i8"), "ps_availqty": np.empty(4 * n, "i4"), "ps_supplycost": np.empty(4 * n, "i8")}
+    lib().tpch_gen_partsupp(ctypes.c_double(sf), ctypes.c_int64(0), ctypes.c_int64(n), _p(a["ps_partkey"]), _p(a["ps_suppkey"]),
+                            _p(a["ps_availqty"]), _p(a["ps_supplycost"]))
     columns = list(columns or a.keys())
-    return pa.table([_to_arrow(c, a[c], strings) for c in columns], names=columns)
+    return pa.table([decimal_from_int64(a[c]) if c == "ps_supplycost" else _to_arrow(c, a[c], strings) for c in columns], names=columns)
 
 
 # dists.dss p_types / p_cntr: full strings in nested syllable order, equal weights
@@ -272,4 +300,4 @@ def tables(sf: float, strings: str = "view") -> dict:
     """All generated tables (small scale factors only)."""
     return {"lineitem": lineitem(sf, strings=strings), "orders": orders(sf, strings=strings),
             "customer": customer(sf, strings=strings), "supplier": supplier(sf, strings=strings),
-            "part": part(sf, strings=strings), "nation": nation(strings), "region": region(strings)}
+            "part": part(sf, strings=strings), "partsupp": partsupp(sf, strings=strings), "nation": nation(strings), "region": region(strings)}

@@ -286,3 +286,46 @@ void tpch_gen_part(double sf, int64_t first, int64_t n, int64_t *p_partkey,
         stream_row_stop(&size); stream_row_stop(&cntr);
     }
 }
+
+/* partsupp rows of parts [first, first+n): 4 suppliers per part (SUPP_PER_PART); arrays hold 4*n rows.
+ * ps_suppkey: PART_SUPP_BRIDGE (the formula lineitem uses for l_suppkey); ps_availqty = U(1, 9999) on PS_QTY_SD;
+ * ps_supplycost = U(100, 100000) cents on PS_SCST_SD; both streams advance 4 per part row. */
+void tpch_gen_partsupp(double sf, int64_t first, int64_t n, int64_t *ps_partkey, int64_t *ps_suppkey,
+                       int32_t *ps_availqty, int64_t *ps_supplycost) {
+    tpch_counts c = counts_for(sf);
+    stream_t qty, scst;
+    stream_init(&qty, PS_QTY_SD, first); stream_init(&scst, PS_SCST_SD, first);
+    for (int64_t r = 0; r < n; r++) {
+        int64_t pk = first + r + 1;
+        for (int64_t s = 0; s < 4; s++) {
+            int64_t q = stream_uniform(&qty, 1, 9999);
+            int64_t cst = stream_uniform(&scst, 100, 100000);
+            int64_t k = 4 * r + s;
+            if (ps_partkey) ps_partkey[k] = pk;
+            if (ps_suppkey) ps_suppkey[k] = (pk + s * (c.supp / 4 + (pk - 1) / c.supp)) % c.supp + 1;
+            if (ps_availqty) ps_availqty[k] = (int32_t)q;
+            if (ps_supplycost) ps_supplycost[k] = cst;
+        }
+        stream_row_stop(&qty); stream_row_stop(&scst);
+    }
+}
+
+/* phone numbers (gen_phone): "CC-AAA-EEE-NNNN", CC = 10 + nation key, then three uniform draws from the phone stream
+ * (3 per row).  which = 0: customer (C_PHNE_SD), 1: supplier (S_PHNE_SD).  out: 15 bytes per row, no terminator. */
+void tpch_gen_phone(int which, int64_t first, int64_t n, const int64_t *nationkey, char *out) {
+    stream_t ph;
+    stream_init(&ph, which == 0 ? C_PHNE_SD : S_PHNE_SD, first);
+    for (int64_t r = 0; r < n; r++) {
+        int64_t ac = stream_uniform(&ph, 100, 999);
+        int64_t ex = stream_uniform(&ph, 100, 999);
+        int64_t nu = stream_uniform(&ph, 1000, 9999);
+        char buf[32];
+        int cc = (int)(10 + nationkey[r]);
+        buf[0] = (char)('0' + cc / 10); buf[1] = (char)('0' + cc % 10); buf[2] = '-';
+        buf[3] = (char)('0' + ac / 100); buf[4] = (char)('0' + ac / 10 % 10); buf[5] = (char)('0' + ac % 10); buf[6] = '-';
+        buf[7] = (char)('0' + ex / 100); buf[8] = (char)('0' + ex / 10 % 10); buf[9] = (char)('0' + ex % 10); buf[10] = '-';
+        buf[11] = (char)('0' + nu / 1000); buf[12] = (char)('0' + nu / 100 % 10); buf[13] = (char)('0' + nu / 10 % 10); buf[14] = (char)('0' + nu % 10);
+        memcpy(out + 15 * r, buf, 15);
+        stream_row_stop(&ph);
+    }
+}

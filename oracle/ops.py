@@ -806,6 +806,21 @@ def op_hash_join(left: Batch, right: Batch, spec: dict) -> Batch:
     return out if proj is None else out.select(proj)
 
 
+def op_nested_loop_join(left: Batch, right: Batch, spec: dict) -> Batch:
+    """NestedLoopJoinExec, inner (external; test_tpch.plan.yaml:333,661): every (left, right) pair that passes the filter;
+    output = left ++ right then projection, build rows outermost."""
+    assert spec.get("join_type", "inner") == "inner"
+    nl, nr = left.num_rows, right.num_rows
+    li = np.repeat(np.arange(nl, dtype=np.int64), nr)
+    ri = np.tile(np.arange(nr, dtype=np.int64), nl)
+    pair = Batch(left.names + right.names, [c.take(li) for c in left.cols] + [c.take(ri) for c in right.cols])
+    if spec.get("filter") is not None and len(li):
+        p = eval_expr(pair, spec["filter"])
+        pair = pair.take(np.nonzero(p.data & p.validity())[0])
+    proj = spec.get("projection")
+    return pair if proj is None else pair.select(proj)
+
+
 def sort_indices(b: Batch, keys) -> np.ndarray:
     """lexicographic, per-key asc/desc + nulls_first; stable (ties keep input order)."""
     import functools
@@ -927,6 +942,8 @@ def run_op(spec: dict, *inputs: Batch):
         return op_sort(inputs[0], spec)
     if kind == "repartition":
         return op_repartition(inputs[0], spec)
+    if kind == "nested_loop_join":
+        return op_nested_loop_join(inputs[0], inputs[1], spec)
     if kind == "sort_preserving_merge":
         return op_sort_preserving_merge(list(inputs), spec)
     raise ValueError(kind)

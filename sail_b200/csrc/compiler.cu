@@ -258,6 +258,15 @@ Val PipelineCompiler::compile_uncached(const ExprPtr& e) {
       out.vslot = a.vslot;
       return out;
     }
+    case Expr::Substr: {
+      Val a = ensure_slot(compile(e->args[0]));
+      Val out = temp(K_V16);
+      VmInst I{}; I.op = (uint16_t)(OP_SUBSTR | (K_V16 << 8)); I.dst = (uint32_t)out.slot; I.a = (uint32_t)a.slot; I.b = I.c = NO_SLOT;
+      I.sa = (uint8_t)a.stride; I.imm0 = (uint64_t)e->sub_start; I.imm1 = (uint64_t)e->sub_len;
+      prog_.push_back(I);
+      out.vslot = a.vslot;
+      return out;
+    }
     case Expr::DatePart: {
       Val a = compile(e->args[0]);
       Val d = emit1(OP_DATE_PART, K_I32, K_I32, a, (uint16_t)(e->op == "year" ? 0 : e->op == "month" ? 1 : 2));

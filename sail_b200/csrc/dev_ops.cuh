@@ -179,4 +179,38 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const void* p) {
   return v;
 }
 
+// substr(view, start, count) in characters (UTF-8): the result is an inline view when it fits in 12 bytes, otherwise it
+// points into the source string (a result longer than 12 bytes implies a long source, whose bytes the batch keeps alive)
+__device__ __forceinline__ uint8_t view_byte(const ulonglong2& v, uint32_t i) {
+  if ((uint32_t)v.x <= 12) return i < 4 ? (uint8_t)(v.x >> (32 + 8 * i)) : (uint8_t)(v.y >> (8 * (i - 4)));
+  return reinterpret_cast<const uint8_t*>(v.y)[i];
+}
+__device__ __forceinline__ ulonglong2 view_substr(const ulonglong2& v, long long start, long long count) {
+  const uint32_t n = (uint32_t)v.x;
+  const long long c0 = start - 1;
+  uint32_t b0 = n, b1 = n;
+  long long ci = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if ((view_byte(v, i) & 0xC0) != 0x80) {          // first byte of a character
+      if (ci == c0) b0 = i;
+      if (count >= 0 && ci == c0 + count) { b1 = i; break; }
+      ++ci;
+    }
+  }
+  if (b0 > b1) b0 = b1;
+  const uint32_t rl = b1 - b0;
+  ulonglong2 r; r.x = rl; r.y = 0;
+  if (rl <= 12) {
+    for (uint32_t k = 0; k < rl; ++k) {
+      const unsigned long long b = view_byte(v, b0 + k);
+      if (k < 4) r.x |= b << (32 + 8 * k); else r.y |= b << (8 * (k - 4));
+    }
+  } else {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(v.y) + b0;
+    for (uint32_t k = 0; k < 4; ++k) r.x |= (unsigned long long)p[k] << (32 + 8 * k);
+    r.y = reinterpret_cast<unsigned long long>(p);
+  }
+  return r;
+}
+
 }  // namespace sg

@@ -513,6 +513,7 @@ size_t pipeline_precompile(const Json& spec, const std::vector<Schema>& inputs, 
 std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_sort_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_merge_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
+std::unique_ptr<Op> make_nlj_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_chain_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 std::unique_ptr<Op> make_exchange_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
@@ -521,6 +522,7 @@ std::unique_ptr<Op> make_op(Ctx* ctx, const Json& spec, const std::vector<Schema
   (void)partition;
   const std::string kind = spec.at("op").as_str();
   if (kind == "hash_join") return make_join_op(ctx, spec, inputs);
+  if (kind == "nested_loop_join") return make_nlj_op(ctx, spec, inputs);
   if (kind == "sort") return make_sort_op(ctx, spec, inputs);
   if (kind == "sort_preserving_merge") return make_merge_op(ctx, spec, inputs);
   if (kind == "repartition") return make_repartition_op(ctx, spec, inputs);

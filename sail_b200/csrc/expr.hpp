@@ -15,7 +15,7 @@ struct Expr;
 using ExprPtr = std::shared_ptr<Expr>;
 
 struct Expr {
-  enum Kind { Col, Lit, Bin, Not, Neg, IsNull, IsNotNull, Cast, Case, Like, DatePart } kind = Col;
+  enum Kind { Col, Lit, Bin, Not, Neg, IsNull, IsNotNull, Cast, Case, Like, DatePart, Substr } kind = Col;
   DataType type;
   bool nullable = false;
   // Col
@@ -28,6 +28,7 @@ struct Expr {
   // Bin / Like / DatePart
   std::string op;        // "+", "=", "and", ... ; LIKE pattern ; date part
   bool negated = false;
+  long long sub_start = 1, sub_len = -1;     // Substr: 1-based first character, character count (-1: to the end)
   std::vector<ExprPtr> args;   // Bin: l, r ; Case: w0,t0,w1,t1,...,[else]
   bool has_else = false;
 
@@ -231,6 +232,19 @@ inline ExprPtr parse_expr(const Json& j, const Schema& in) {
       e->args = {parse_expr(j.at("args").a.at(0), in)};
       SG_CHECK(e->args[0]->type.id == TypeId::Date32, SAILGPU_ERR_UNSUPPORTED, "date_part on " + e->args[0]->type.str());
       e->type = T(TypeId::Int32); e->nullable = e->args[0]->nullable;
+      return e;
+    }
+    if (fn == "substr") {      // substr(str, start[, length]) with literal positions (Spark / DataFusion character semantics)
+      e->kind = Expr::Substr;
+      e->args = {parse_expr(j.at("args").a.at(0), in)};
+      SG_CHECK(e->args[0]->type.is_string(), SAILGPU_ERR_INVALID, "substr needs a string operand");
+      e->sub_start = j.at("start").as_int();
+      const Json* ln = j.find("length");
+      e->sub_len = ln && !ln->is_null() ? ln->as_int() : -1;
+      SG_CHECK(e->sub_start >= 1, SAILGPU_ERR_UNSUPPORTED, "substr with a start position below 1 is not supported on the GPU path yet");
+      SG_CHECK(!(ln && !ln->is_null()) || e->sub_len >= 0, SAILGPU_ERR_INVALID, "substr with a negative length");
+      e->op = "substr:" + std::to_string(e->sub_start) + ":" + std::to_string(e->sub_len);
+      e->type = e->args[0]->type; e->nullable = e->args[0]->nullable;
       return e;
     }
     fail(SAILGPU_ERR_UNSUPPORTED, "scalar function '" + fn + "' is not implemented on the GPU path");

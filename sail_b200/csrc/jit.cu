@@ -193,6 +193,9 @@ struct Emitter {
         def(I.dst, K_B, std::string("((inb && jit_like(") + operand(I.a, K_V16, I.sa) + ", reinterpret_cast<const uint8_t*>(K.prog[0][" + std::to_string(pc) + "].imm1), " +
                             std::to_string((uint32_t)I.imm0) + "u, " + std::to_string(I.aux & 0xFF) + ")) != " + (((I.aux >> 8) & 1) ? "true" : "false") + ")");
         break;
+      case OP_SUBSTR:
+        def(I.dst, K_V16, "(inb ? view_substr(" + operand(I.a, K_V16, I.sa) + ", " + std::to_string((long long)I.imm0) + "ll, " + std::to_string((long long)I.imm1) + "ll) : mkv16(0ull, 0ull))");
+        break;
       case OP_DATE_PART: def(I.dst, K_I32, "jit_date_part(" + operand(I.a, K_I32, I.sa) + ", " + std::to_string(I.aux) + ")"); break;
       default: throw Unsupported{"VM instruction " + std::to_string(base)};
     }

@@ -462,7 +462,7 @@ struct JoinOp : Op {
   }
 };
 
-std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs) {
+static std::unique_ptr<Op> make_plain_join_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs) {
   SG_CHECK(inputs.size() == 2, SAILGPU_ERR_INVALID, "hash_join takes two inputs (build = left, probe = right)");
   auto op = std::make_unique<JoinOp>();
   op->ctx = ctx; op->kind = "hash_join"; op->in_schemas = inputs;
@@ -493,7 +493,7 @@ std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<S
   const Json* fj = spec.find("filter");
   if (fj && !fj->is_null()) { op->filter_json = *fj; op->has_filter = true; }
   // data-independent limits are reported here, at plan time (sailgpu_spec_validate), never after the build side was consumed
-  SG_CHECK(!op->has_filter || op->jt == "inner" || op->jt == "right_semi", SAILGPU_ERR_UNSUPPORTED,
+  SG_CHECK(!op->has_filter || op->jt == "inner" || op->jt == "right_semi" || op->jt == "left_semi" || op->jt == "left_anti", SAILGPU_ERR_UNSUPPORTED,
            "residual join filter with join_type '" + op->jt + "' is not supported yet");
   for (size_t i = 0; i < op->lkeys.size(); ++i) {
     const DataType& t = op->bs[(size_t)op->lkeys[i]].type;
@@ -508,6 +508,254 @@ std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<S
   }
   if (op->has_proj) for (int i : op->projection) op->out_schema.push_back(op->joined[(size_t)i]);
   else op->out_schema = op->joined;
+  return op;
+}
+
+// ================================================================================================
+// LeftSemi / LeftAnti joins WITH a residual filter (TPC-H Q21: `exists (.. l2.l_suppkey <> l1.l_suppkey)`,
+// test_tpch.plan.yaml:621-622).  A build row qualifies when SOME key-matching probe row passes the filter, so matches have
+// to be enumerated as pairs.  Composed from the two joins the library already has: the build side gets a row-number column;
+// an inner join with the filter yields the row numbers of the build rows that found a partner; a filter-less semi / anti
+// join of the build side against those numbers emits the result.
+// ================================================================================================
+struct FilteredSemiJoinOp : Op {
+  std::unique_ptr<Op> pairs, pick;
+  std::vector<BatchPtr> bparts;
+  std::deque<BatchPtr> ready;
+  bool build_done = false, probe_done = false, finished = false;
+
+  static Json jnum(int64_t v) { Json j; j.kind = Json::Num; j.s = std::to_string(v); return j; }
+  static Json jstr(const std::string& v) { Json j; j.kind = Json::Str; j.s = v; return j; }
+  static Json jarr(std::vector<Json> v) { Json j; j.kind = Json::Arr; j.a = std::move(v); return j; }
+
+  void drain(Op& from, Op* to) {
+    for (;;) {
+      BatchPtr b;
+      const bool more = from.pull(&b);
+      if (b && b->rows > 0) { if (to) to->push(1, b); else ready.push_back(b); }
+      if (!b || !more) break;
+    }
+  }
+  void push(int input, const BatchPtr& b) override {
+    if (input == 0) { SG_CHECK(!build_done, SAILGPU_ERR_STATE, "build input already finished"); bparts.push_back(b); m.build_input_rows += (uint64_t)b->rows; m.build_input_batches++; return; }
+    SG_CHECK(input == 1 && build_done, input == 1 ? SAILGPU_ERR_STATE : SAILGPU_ERR_INVALID, "hash_join: the build input must be finished before the probe input is pushed");
+    m.input_rows += (uint64_t)b->rows; m.input_batches++;
+    pairs->push(1, b);
+    drain(*pairs, pick.get());
+  }
+  void finish(int input) override {
+    if (input == 0) {
+      const Schema& bs = in_schemas[0];
+      BatchPtr build = bparts.empty() ? empty_batch(ctx, bs) : concat_batches(ctx, bs, bparts);
+      bparts.clear();
+      auto with_id = std::make_shared<DevBatch>(*build);
+      DevColumn id; id.type = T(TypeId::Int64); id.length = build->rows;
+      id.data = dev_alloc(ctx, (size_t)build->rows * 8);
+      SG_CUDA(launch_iota(static_cast<int64_t*>(id.data->ptr), build->rows, ctx->stream));
+      with_id->cols.push_back(id);
+      pairs->push(0, with_id); pairs->finish(0);
+      pick->push(0, with_id); pick->finish(0);
+      build_done = true;
+      return;
+    }
+    probe_done = true;
+    pairs->finish(1);
+    drain(*pairs, pick.get());
+    pick->finish(1);
+    drain(*pick, nullptr);
+    finished = true;
+    m.kernel_launches += pairs->m.kernel_launches + pick->m.kernel_launches;
+  }
+  bool pull(BatchPtr* out) override {
+    *out = nullptr;
+    if (!ready.empty()) { *out = ready.front(); ready.pop_front(); m.output_rows += (uint64_t)(*out)->rows; m.output_batches++; }
+    return !ready.empty() || !finished;
+  }
+};
+
+std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs) {
+  SG_CHECK(inputs.size() == 2, SAILGPU_ERR_INVALID, "hash_join takes two inputs (build = left, probe = right)");
+  const Json* jtj = spec.find("join_type");
+  const std::string jt = jtj ? jtj->as_str() : "inner";
+  const Json* fj = spec.find("filter");
+  if (!((jt == "left_semi" || jt == "left_anti") && fj && !fj->is_null())) return make_plain_join_op(ctx, spec, inputs);
+  // validates keys / projection / filter types exactly as the plain operator would (its output schema is ours)
+  auto plain = make_plain_join_op(ctx, spec, inputs);
+  auto op = std::make_unique<FilteredSemiJoinOp>();
+  op->ctx = ctx; op->kind = "hash_join"; op->in_schemas = inputs; op->out_schema = plain->out_schema;
+  (void)parse_expr(*fj, [&] { Schema s = inputs[0]; for (auto& f : inputs[1]) s.push_back(f); return s; }());
+  const int nb = (int)inputs[0].size();
+  Schema bs_id = inputs[0];
+  bs_id.push_back({"__row", T(TypeId::Int64), false});
+  // (a) inner join with the filter; columns of (build ++ __row ++ probe): probe column j sits at nb + 1 + j
+  Json fmap = *fj;
+  std::function<void(Json&)> shift = [&](Json& j) {
+    if (j.kind == Json::Obj) {
+      for (auto& kv : j.o) {
+        if (kv.first == "col" && kv.second.kind == Json::Num) { const int i = (int)kv.second.as_int(); if (i >= nb) kv.second.s = std::to_string(i + 1); }
+        else shift(kv.second);
+      }
+    } else if (j.kind == Json::Arr) for (auto& x : j.a) shift(x);
+  };
+  shift(fmap);
+  Json a; a.kind = Json::Obj;
+  a.o = {{"op", FilteredSemiJoinOp::jstr("hash_join")}, {"join_type", FilteredSemiJoinOp::jstr("inner")}, {"on", spec.at("on")}, {"filter", fmap},
+         {"projection", FilteredSemiJoinOp::jarr({FilteredSemiJoinOp::jnum(nb)})}};
+  op->pairs = make_plain_join_op(ctx, a, {bs_id, inputs[1]});
+  // (b) semi / anti join of the build side against the row numbers that found a partner
+  std::vector<Json> proj;
+  const Json* pj = spec.find("projection");
+  if (pj && !pj->is_null()) for (auto& x : pj->a) proj.push_back(x);
+  else for (int i = 0; i < nb; ++i) proj.push_back(FilteredSemiJoinOp::jnum(i));
+  Json b; b.kind = Json::Obj;
+  b.o = {{"op", FilteredSemiJoinOp::jstr("hash_join")}, {"join_type", FilteredSemiJoinOp::jstr(jt)},
+         {"on", FilteredSemiJoinOp::jarr({FilteredSemiJoinOp::jarr({FilteredSemiJoinOp::jnum(nb), FilteredSemiJoinOp::jnum(0)})})},
+         {"projection", FilteredSemiJoinOp::jarr(proj)}};
+  Schema ids = {{"__row", T(TypeId::Int64), true}};
+  op->pick = make_plain_join_op(ctx, b, {bs_id, ids});
+  return op;
+}
+
+// ================================================================================================
+// NestedLoopJoinExec (inner) with a small build side: what DataFusion plans for the scalar-subquery shapes of TPC-H Q11 /
+// Q22 (test_tpch.plan.yaml:333,661 -- the left child is a one-row aggregate).  Every build row turns into literals of a
+// Filter -> Projection pipeline over the probe batches, so the join is one pass of the tile pipeline per build row and
+// inherits its expression support (and its specialised kernels).  Build sides beyond a few dozen rows are refused.
+// ================================================================================================
+struct NestedLoopJoinOp : Op {
+  static constexpr int64_t MAX_BUILD_ROWS = 64;
+  Schema ls, rs, joined;
+  ExprPtr filter;                     // over `joined` (left ++ right); null: cross join
+  std::vector<int> projection;        // into `joined`
+  std::vector<BatchPtr> lparts;
+  std::vector<std::unique_ptr<PipelineRunner>> runs;   // one per build row
+  std::deque<BatchPtr> pending, ready;
+  bool left_done = false, right_done = false;
+
+  static ExprPtr literal_of(Ctx* ctx, const DevColumn& c, const DataType& t, int64_t row) {
+    auto e = std::make_shared<Expr>();
+    e->kind = Expr::Lit; e->type = t;
+    if (c.validity) {
+      uint8_t byte = 0;
+      SG_CUDA(cudaMemcpyAsync(&byte, static_cast<const uint8_t*>(c.validity->ptr) + (row >> 3), 1, cudaMemcpyDeviceToHost, ctx->stream));
+      SG_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (!((byte >> (row & 7)) & 1)) { e->lit_null = true; e->nullable = true; return e; }
+    }
+    if (t.id == TypeId::Bool) {
+      uint8_t byte = 0;
+      SG_CUDA(cudaMemcpyAsync(&byte, static_cast<const uint8_t*>(c.data->ptr) + (row >> 3), 1, cudaMemcpyDeviceToHost, ctx->stream));
+      SG_CUDA(cudaStreamSynchronize(ctx->stream));
+      e->lit_i = (byte >> (row & 7)) & 1;
+      return e;
+    }
+    const int w = t.is_string() ? 16 : t.arrow_width();
+    uint8_t raw[16] = {0};
+    SG_CUDA(cudaMemcpyAsync(raw, static_cast<const uint8_t*>(c.data->ptr) + row * w, (size_t)w, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (t.is_string()) {
+      uint32_t len; memcpy(&len, raw, 4);
+      e->lit_s.resize(len);
+      if (len <= 12) memcpy(&e->lit_s[0], raw + 4, len);
+      else {
+        uint64_t ptr; memcpy(&ptr, raw + 8, 8);       // resolved view: absolute device pointer
+        SG_CUDA(cudaMemcpyAsync(&e->lit_s[0], reinterpret_cast<const void*>(ptr), len, cudaMemcpyDeviceToHost, ctx->stream));
+        SG_CUDA(cudaStreamSynchronize(ctx->stream));
+      }
+    } else if (t.id == TypeId::Float64) { memcpy(&e->lit_f, raw, 8); }
+    else if (t.id == TypeId::Float32) { float f; memcpy(&f, raw, 4); e->lit_f = f; }
+    else if (w == 16) { u128 v; memcpy(&v, raw, 16); e->lit_i = (i128)v; }
+    else if (w == 8) { int64_t v; memcpy(&v, raw, 8); e->lit_i = t.is_unsigned_int() ? (i128)(uint64_t)v : (i128)v; }
+    else if (w == 4) { int32_t v; memcpy(&v, raw, 4); e->lit_i = t.is_unsigned_int() ? (i128)(uint32_t)v : (i128)v; }
+    else if (w == 2) { int16_t v; memcpy(&v, raw, 2); e->lit_i = t.is_unsigned_int() ? (i128)(uint16_t)v : (i128)v; }
+    else { int8_t v; memcpy(&v, raw, 1); e->lit_i = t.is_unsigned_int() ? (i128)(uint8_t)v : (i128)v; }
+    return e;
+  }
+  // expression over (left ++ right) -> expression over right with the build row's values as literals
+  ExprPtr bind_row(const ExprPtr& e, const std::vector<ExprPtr>& lits) const {
+    if (e->kind == Expr::Col) {
+      if (e->col < (int)ls.size()) return lits[(size_t)e->col];
+      auto c = std::make_shared<Expr>(*e);
+      c->col = e->col - (int)ls.size();
+      return c;
+    }
+    if (e->kind == Expr::Lit) return e;
+    auto c = std::make_shared<Expr>(*e);
+    for (auto& a : c->args) a = bind_row(a, lits);
+    return c;
+  }
+
+  void build_runners() {
+    BatchPtr left = lparts.empty() ? empty_batch(ctx, ls) : concat_batches(ctx, ls, lparts);
+    lparts.clear();
+    SG_CHECK(left->rows <= MAX_BUILD_ROWS, SAILGPU_ERR_UNSUPPORTED,
+             "nested loop join with " + std::to_string(left->rows) + " build rows (the GPU path covers the scalar-subquery shapes: at most " + std::to_string(MAX_BUILD_ROWS) + ")");
+    for (int64_t r = 0; r < left->rows; ++r) {
+      std::vector<ExprPtr> lits;
+      for (size_t c = 0; c < ls.size(); ++c) lits.push_back(literal_of(ctx, left->cols[c], ls[c].type, r));
+      auto run = std::make_unique<PipelineRunner>();
+      run->init(ctx, rs);
+      if (filter) { StageSpec f; f.kind = StageSpec::Filter; f.predicate = bind_row(filter, lits); run->stages.push_back(f); }
+      StageSpec p; p.kind = StageSpec::Projection;
+      for (size_t k = 0; k < projection.size(); ++k) {
+        const int j = projection[k];
+        ExprPtr e;
+        if (j < (int)ls.size()) e = lits[(size_t)j];
+        else { e = std::make_shared<Expr>(); e->kind = Expr::Col; e->col = j - (int)ls.size(); e->type = rs[(size_t)e->col].type; e->nullable = rs[(size_t)e->col].nullable; }
+        p.exprs.push_back(e); p.names.push_back(out_schema[k].name);
+      }
+      run->stages.push_back(p);
+      runs.push_back(std::move(run));
+    }
+  }
+  void probe(const BatchPtr& b) {
+    if (b->rows == 0) return;
+    for (auto& run : runs) {
+      BatchPtr out = run_streaming(*run, ctx, b, m, nullptr, {});
+      if (out->rows > 0) ready.push_back(out);
+    }
+  }
+  void push(int input, const BatchPtr& b) override {
+    const uint64_t t0 = now_ns();
+    if (input == 0) { SG_CHECK(!left_done, SAILGPU_ERR_STATE, "build input already finished"); lparts.push_back(b); m.build_input_rows += (uint64_t)b->rows; m.build_input_batches++; return; }
+    SG_CHECK(input == 1, SAILGPU_ERR_INVALID, "nested_loop_join has two inputs");
+    m.input_rows += (uint64_t)b->rows; m.input_batches++;
+    if (!left_done) { pending.push_back(b); return; }
+    probe(b);
+    m.elapsed_compute_ns += now_ns() - t0;
+  }
+  void finish(int input) override {
+    if (input == 0) {
+      left_done = true;
+      build_runners();
+      while (!pending.empty()) { probe(pending.front()); pending.pop_front(); }
+    } else right_done = true;
+  }
+  bool pull(BatchPtr* out) override {
+    *out = nullptr;
+    if (!ready.empty()) { *out = ready.front(); ready.pop_front(); m.output_rows += (uint64_t)(*out)->rows; m.output_batches++; }
+    return !ready.empty() || !(left_done && right_done);
+  }
+};
+
+std::unique_ptr<Op> make_nlj_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs) {
+  SG_CHECK(inputs.size() == 2, SAILGPU_ERR_INVALID, "nested_loop_join takes two inputs (build = left, probe = right)");
+  auto op = std::make_unique<NestedLoopJoinOp>();
+  op->ctx = ctx; op->kind = "nested_loop_join"; op->in_schemas = inputs;
+  op->ls = inputs[0]; op->rs = inputs[1];
+  const Json* jt = spec.find("join_type");
+  SG_CHECK(!jt || jt->as_str() == "inner", SAILGPU_ERR_UNSUPPORTED, "nested_loop_join: only join_type 'inner' runs on the GPU path");
+  op->joined = op->ls;
+  for (auto& f : op->rs) op->joined.push_back(f);
+  const Json* fj = spec.find("filter");
+  if (fj && !fj->is_null()) {
+    op->filter = parse_expr(*fj, op->joined);
+    SG_CHECK(op->filter->type.id == TypeId::Bool, SAILGPU_ERR_INVALID, "join filter must be boolean");
+  }
+  const Json* pj = spec.find("projection");
+  if (pj && !pj->is_null()) {
+    for (auto& x : pj->a) { const int i = (int)x.as_int(); SG_CHECK(i >= 0 && i < (int)op->joined.size(), SAILGPU_ERR_INVALID, "join projection index out of range"); op->projection.push_back(i); }
+  } else for (size_t i = 0; i < op->joined.size(); ++i) op->projection.push_back((int)i);
+  for (int i : op->projection) op->out_schema.push_back(op->joined[(size_t)i]);
   return op;
 }
 

@@ -633,6 +633,17 @@ __device__ __forceinline__ void vm_exec(const VmInst* prog, int n_inst, const Ti
         }
         break;
       }
+      case OP_SUBSTR: {
+        const uint8_t* pa = c.arena + eff(c, I.a);
+        uint8_t* pd = c.arena + eff(c, I.dst);
+        for (int k = 0; k < RPT; ++k) {
+          const int r = threadIdx.x + k * NT;
+          ulonglong2 v; v.x = 0; v.y = 0;
+          if (r < c.nrows) v = view_substr(*reinterpret_cast<const ulonglong2*>(pa + r * I.sa), (long long)I.imm0, (long long)I.imm1);
+          *reinterpret_cast<ulonglong2*>(pd + r * 16) = v;
+        }
+        break;
+      }
       case OP_PROBE: vm_probe<RPT>(aux->probe[I.aux], c, I.c); break;
       case OP_GATHER: vm_gather<RPT>(I, c); break;
       default: break;

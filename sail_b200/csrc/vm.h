@@ -51,6 +51,7 @@ enum VmBase : uint16_t {
   OP_DATE_PART,     // dst(I32) <- part(aux: 0 year 1 month 2 day) of Date32 a
   OP_PROBE,         // hash-join probe: aux = probe index (see ProbeParams)
   OP_GATHER,        // dst(kind) <- build column [imm1 ptr] at row id slot a (I64), masked by active; aux = elem width
+  OP_SUBSTR,        // dst(V16) <- substr(view a, imm0 = 1-based start character, imm1 = character count or -1): UTF-8 aware
   OP_COUNT_
 };
 enum : uint16_t { F_IMM_A = 1, F_IMM_B = 2 };

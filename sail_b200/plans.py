@@ -135,6 +135,19 @@ def hash_join(build: Node, probe: Node, on: list, join_type="inner", projection=
     return Node(spec, [build, probe], list(names if projection is None else projection))
 
 
+def nested_loop_join(build: Node, probe: Node, filter=None, projection=None) -> Node:
+    """NestedLoopJoinExec, inner: build = left child (the one-row scalar subquery in TPC-H Q11 / Q22)"""
+    names = build.names + probe.names
+    spec = {"op": "nested_loop_join", "join_type": "inner",
+            "filter": None if filter is None else resolve(filter, names),
+            "projection": None if projection is None else [names.index(c) for c in projection]}
+    return Node(spec, [build, probe], list(names if projection is None else projection))
+
+
+def substr(e, start: int, length: int | None = None):
+    return {"fn": "substr", "args": [e], "start": start, "length": length}
+
+
 def sort(child: Node, keys: list, fetch=None) -> Node:
     """keys: (column name, asc) -- Spark default null ordering: ASC NULLS FIRST / DESC NULLS LAST"""
     ks = [{"expr": resolve(col(k), child.names), "asc": asc, "nulls_first": asc} for k, asc in keys]
@@ -418,4 +431,71 @@ def q18(strings="Utf8View", min_qty=313) -> Node:
     return sort(a, [("o_totalprice", False), ("o_orderdate", True)], fetch=100)
 
 
-TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q8": q8, "q12": q12, "q14": q14, "q18": q18, "q19": q19}
+def q11(strings="Utf8View", nation="ALGERIA") -> Node:
+    """test_tpch.plan.yaml:324-363: the HAVING threshold is a scalar subquery -> NestedLoopJoinExec against a one-row aggregate"""
+    def joined():
+        nat = filter_(scan("nation", ["n_nationkey", "n_name"]), binop("=", col("n_name"), string(nation, strings)), ["n_nationkey"])
+        sp = hash_join(scan("supplier", ["s_suppkey", "s_nationkey"]), scan("partsupp", ["ps_partkey", "ps_suppkey", "ps_availqty", "ps_supplycost"]),
+                       [("s_suppkey", "ps_suppkey")], projection=["s_nationkey", "ps_partkey", "ps_availqty", "ps_supplycost"])
+        return hash_join(nat, sp, [("n_nationkey", "s_nationkey")], projection=["ps_partkey", "ps_availqty", "ps_supplycost"])
+    value = binop("*", col("ps_supplycost"), col("ps_availqty"))
+    total = two_phase(joined(), [], [("sum", value, "total", "Decimal128(26,2)")])
+    thr = project(total, [(binop("*", col("total"), dec(1000000, 10, 10)), "threshold")])
+    per = two_phase(joined(), ["ps_partkey"], [("sum", value, "value", "Decimal128(26,2)")])
+    per = project(per, ["ps_partkey", "value", ({"cast": col("value"), "to": "Decimal128(38,12)"}, "value_cmp")])
+    j = nested_loop_join(thr, per, binop(">", col("value_cmp"), col("threshold")), ["ps_partkey", "value"])
+    return sort(j, [("value", False)])
+
+
+def q17(strings="Utf8View", brand="Brand#42", container="LG BAG") -> Node:
+    """test_tpch.plan.yaml:504-527: the correlated avg() is decorrelated into a grouped aggregate joined back with a residual filter"""
+    pt = filter_(scan("part", ["p_partkey", "p_brand", "p_container"]),
+                 and_(binop("=", col("p_brand"), string(brand, strings)), binop("=", col("p_container"), string(container, strings))), ["p_partkey"])
+    j1 = hash_join(pt, scan("lineitem", ["l_partkey", "l_quantity", "l_extendedprice"]), [("p_partkey", "l_partkey")],
+                   projection=["p_partkey", "l_quantity", "l_extendedprice"])
+    j1 = project(j1, ["l_quantity", "l_extendedprice", "p_partkey"])
+    avgq = two_phase(project(scan("lineitem", ["l_partkey", "l_quantity"]), [(col("l_partkey"), "k"), (col("l_quantity"), "q")]),
+                     ["k"], [("avg", col("q"), "avg_q", D152)])
+    thr = project(avgq, [(binop("*", dec(2, 1, 1), col("avg_q")), "limit_q"), "k"])
+    j2 = hash_join(j1, thr, [("p_partkey", "k")], filter=binop("<", col("l_quantity"), col("limit_q")), projection=["l_extendedprice"])
+    a = two_phase(j2, [], [("sum", col("l_extendedprice"), "s", D152)])
+    return project(a, [(binop("/", col("s"), dec(70, 2, 1)), "avg_yearly")])
+
+
+def q21(strings="Utf8View", nation="ARGENTINA") -> Node:
+    """test_tpch.plan.yaml:608-645: EXISTS / NOT EXISTS with `l_suppkey <>` become LeftSemi / LeftAnti joins with a residual filter"""
+    late = binop(">", col("l_receiptdate"), col("l_commitdate"))
+    nat = filter_(scan("nation", ["n_nationkey", "n_name"]), binop("=", col("n_name"), string(nation, strings)), ["n_nationkey"])
+    l1 = filter_(scan("lineitem", ["l_orderkey", "l_suppkey", "l_commitdate", "l_receiptdate"]), late, ["l_orderkey", "l_suppkey"])
+    ja = hash_join(scan("supplier", ["s_suppkey", "s_name", "s_nationkey"]), l1, [("s_suppkey", "l_suppkey")],
+                   projection=["s_name", "s_nationkey", "l_orderkey", "l_suppkey"])
+    of = filter_(scan("orders", ["o_orderkey", "o_orderstatus"]), binop("=", col("o_orderstatus"), string("F", strings)), ["o_orderkey"])
+    jb = hash_join(ja, of, [("l_orderkey", "o_orderkey")], projection=["s_name", "s_nationkey", "l_orderkey", "l_suppkey"])
+    jc = hash_join(nat, jb, [("n_nationkey", "s_nationkey")], projection=["s_name", "l_orderkey", "l_suppkey"])
+    l2 = project(scan("lineitem", ["l_orderkey", "l_suppkey"]), [(col("l_orderkey"), "l2_orderkey"), (col("l_suppkey"), "l2_suppkey")])
+    semi = hash_join(jc, l2, [("l_orderkey", "l2_orderkey")], join_type="left_semi", filter=binop("!=", col("l2_suppkey"), col("l_suppkey")))
+    l3 = project(filter_(scan("lineitem", ["l_orderkey", "l_suppkey", "l_commitdate", "l_receiptdate"]), late, ["l_orderkey", "l_suppkey"]),
+                 [(col("l_orderkey"), "l3_orderkey"), (col("l_suppkey"), "l3_suppkey")])
+    anti = hash_join(semi, l3, [("l_orderkey", "l3_orderkey")], join_type="left_anti", filter=binop("!=", col("l3_suppkey"), col("l_suppkey")),
+                     projection=["s_name"])
+    a = two_phase(anti, ["s_name"], [("count", None, "numwait", None)])
+    return sort(a, [("numwait", False), ("s_name", True)], fetch=100)
+
+
+def q22(strings="Utf8View", codes=("24", "34", "16", "30", "33", "14", "13")) -> Node:
+    """test_tpch.plan.yaml:647-680: substr() country codes, NOT EXISTS as RightAnti, avg() threshold as a NestedLoopJoinExec"""
+    code = substr(col("c_phone"), 1, 2)
+    in_codes = {"in": code, "set": [string(c, strings) for c in codes], "negated": False}
+    cust = filter_(scan("customer", ["c_custkey", "c_phone", "c_acctbal"]), in_codes)
+    anti = hash_join(scan("orders", ["o_custkey"]), cust, [("o_custkey", "c_custkey")], join_type="right_anti", projection=["c_phone", "c_acctbal"])
+    right = project(anti, ["c_phone", "c_acctbal", ({"cast": col("c_acctbal"), "to": "Decimal128(19,6)"}, "bal_cmp")])
+    pos = filter_(scan("customer", ["c_phone", "c_acctbal"]), and_(binop(">", col("c_acctbal"), dec(0, 15, 2)), in_codes), ["c_acctbal"])
+    avgb = two_phase(pos, [], [("avg", col("c_acctbal"), "avg_bal", D152)])
+    j = nested_loop_join(avgb, right, binop(">", col("bal_cmp"), col("avg_bal")), ["c_phone", "c_acctbal"])
+    p = project(j, [(code, "cntrycode"), "c_acctbal"])
+    a = two_phase(p, ["cntrycode"], [("count", None, "numcust", None), ("sum", col("c_acctbal"), "totacctbal", D152)])
+    return sort(a, [("cntrycode", True)])
+
+
+TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q8": q8, "q11": q11, "q12": q12, "q14": q14, "q17": q17, "q18": q18, "q19": q19,
+        "q21": q21, "q22": q22}

@@ -240,7 +240,7 @@ def test_row_round_robin_streaming(n_parts, in_part, n_in):
     op.close()
 
 
-@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q8", "q12", "q14", "q18", "q19"])
+@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q8", "q11", "q12", "q14", "q17", "q18", "q19", "q21", "q22"])
 def test_tpch_golden_on_gpu(q, golden):
     """whole plans through the C ABI on dbgen SF0.001 == the reference's own snapshot"""
     from datagen import tpch
@@ -250,7 +250,7 @@ def test_tpch_golden_on_gpu(q, golden):
     assert render.rows(got) == golden[q]["rows"]
 
 
-@pytest.mark.parametrize("q", ["q3", "q4", "q5", "q7", "q8", "q12", "q14", "q19"])
+@pytest.mark.parametrize("q", ["q3", "q4", "q5", "q7", "q8", "q11", "q12", "q14", "q17", "q19", "q21", "q22"])
 def test_tpch_sf01_vs_oracle(q):
     from datagen import tpch
     tables = tpch.tables(0.1)
@@ -258,6 +258,38 @@ def test_tpch_sf01_vs_oracle(q):
     got = plans.execute(plan, tables, gpu_op)
     want = plans.execute(plan, tables, oracle_op)
     assert_same(got, want, ordered=(q != "q3"))   # Q3's top-10 may tie on (revenue, date): compare as sets
+
+
+@pytest.mark.parametrize("jt", ["left_semi", "left_anti"])
+@pytest.mark.parametrize("dups", [False, True])
+def test_semi_anti_join_with_residual_filter(jt, dups):
+    """EXISTS / NOT EXISTS with an inequality on a non-key column (TPC-H Q21): a build row qualifies when SOME key-matching probe
+    row passes the filter -- not when the first one does"""
+    l = left_table(20000, 71, dups, True)
+    r = right_table(30000, 72, 9000, True)
+    spec = {"op": "hash_join", "join_type": jt, "mode": "collect_left", "on": [[0, 0]],
+            "filter": {"op": "!=", "l": {"col": 1}, "r": {"col": 5}}, "projection": [0, 2, 3]}       # lk2 != rk2
+    assert_same(gpu_op(spec, l, r), oracle_op(spec, l, r))
+
+
+def test_nested_loop_join_small_build_side():
+    """NestedLoopJoinExec (inner): every build row becomes the literals of a filter + projection pass over the probe batches"""
+    build = pa.table({"lo": pa.array([10, 500, None], type=pa.int64()), "tag": pa.array(["a", "bb", "ccc"], type=pa.string_view())})
+    r = right_table(5000, 73, 300, True)
+    spec = {"op": "nested_loop_join", "join_type": "inner", "filter": {"op": ">", "l": {"col": 2}, "r": {"col": 0}}, "projection": [1, 0, 2, 4]}
+    assert_same(gpu_op(spec, build, r), oracle_op(spec, build, r))
+    cross = {"op": "nested_loop_join", "join_type": "inner", "filter": None, "projection": None}
+    assert_same(gpu_op(cross, build.slice(0, 2), r.slice(0, 100)), oracle_op(cross, build.slice(0, 2), r.slice(0, 100)))
+
+
+def test_substr_matches_the_oracle():
+    t = pa.table({"s": pa.array(["25-989-741-2988", "", "a", "héllo wörld, a longer string value", None, "abcdefghijklmnop"], type=pa.string_view())})
+    for start, length in [(1, 2), (2, None), (4, 20), (30, 5), (1, 0), (7, 13)]:
+        spec = {"op": "projection", "exprs": [{"expr": {"fn": "substr", "args": [{"col": 0}], "start": start, "length": length}, "name": "x"}]}
+        assert_same(gpu_op(spec, t), oracle_op(spec, t), ordered=True)
+    flt = {"op": "filter", "predicate": {"in": {"fn": "substr", "args": [{"col": 0}], "start": 1, "length": 2},
+                                         "set": [{"lit": "25", "type": "Utf8View"}, {"lit": "ab", "type": "Utf8View"}], "negated": False}, "projection": None}
+    assert_same(gpu_op(flt, t), oracle_op(flt, t), ordered=True)
 
 
 def test_tpch_q18_with_matches_vs_oracle():

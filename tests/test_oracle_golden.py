@@ -12,7 +12,7 @@ def run_oracle(spec, *tables):
     return ops.batch_to_arrow(out)
 
 
-@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q8", "q12", "q14", "q18", "q19"])
+@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q8", "q11", "q12", "q14", "q17", "q18", "q19", "q21", "q22"])
 @pytest.mark.parametrize("strings", ["view", "utf8"])
 def test_tpch_golden(q, strings, golden):
     from datagen import tpch

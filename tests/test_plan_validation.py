@@ -17,7 +17,7 @@ def walk(node, tables, fn):
     return out
 
 
-@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q8", "q12", "q14", "q18", "q19"])
+@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q8", "q11", "q12", "q14", "q17", "q18", "q19", "q21", "q22"])
 def test_output_schema_of_every_plan_node_matches_the_oracle(q, tpch_tiny):
     seen = []
 
