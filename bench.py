@@ -370,6 +370,148 @@ def exchange_leg(args, ctx, stream, rank, world, local):
     return res
 
 
+def joins_leg(args, ctx, stream, local):
+    """BASELINE configs[2]: TPC-H Q3 and Q5 at SF100 on one B200 (3- and 6-way hash joins + aggregate), tables resident in HBM.
+    Per query: wall-clock of the whole operator tree (CUDA events on the library's stream), rows/s over the scanned rows, the
+    fraction of the HBM roofline on the compulsory input bytes, a CPU PROXY (pyarrow Acero, all host
+    threads -- not Sail: the Rust reference does not build here) on the first chunk-sf batch of orders, and two parity checks:
+    exact equality with the proxy on that batch, and additivity over all order-range chunks at full size (facts are disjoint
+    by order key, so the whole result must be the combination of the chunk results)."""
+    import decimal
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    import torch
+    from datagen import tpch, tpch_gpu
+    from sail_b200 import engine, plans
+    sf = args.sf
+    LC = ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount", "l_shipdate"]
+    OC = ["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"]
+    dims_host = {"customer": tpch.customer(sf, ["c_custkey", "c_nationkey", "c_mktsegment"]).combine_chunks(),
+                 "supplier": tpch.supplier(sf, ["s_suppkey", "s_nationkey"]).combine_chunks(), "nation": tpch.nation(), "region": tpch.region()}
+    dims = {k: (engine.to_device(v, ctx), v.schema.names) for k, v in dims_host.items()}
+
+    def facts(first, n):
+        o, l = tpch_gpu.generate_buffers(sf, first, n, OC, LC, local)
+        return o, l
+
+    def dev_of(o, l):
+        d = dict(dims)
+        d["orders"] = (o.device_batch(ctx), OC)
+        d["lineitem"] = (l.device_batch(ctx), LC)
+        return d
+
+    def run_gpu(plan, dev):
+        out = plans.execute_gpu(plan, dev, ctx)
+        spec = {"op": "projection", "exprs": [{"expr": {"col": i}, "name": n} for i, n in enumerate(out[0].schema.names)]}
+        op = engine.GpuExec(spec, [out[0].schema], ctx)
+        for d in out:
+            op.push(d)
+        op.finish()
+        t = op.collect()
+        op.close()
+        return t
+
+    def rows_of(t):
+        return [tuple(r.values()) for r in t.to_pylist()]
+    one = pa.scalar(decimal.Decimal("1"), pa.decimal128(10, 0))
+
+    def acero_q3(T):
+        cust = T["customer"].filter(pc.equal(T["customer"]["c_mktsegment"], "BUILDING")).select(["c_custkey"])
+        o = T["orders"].filter(pc.less(T["orders"]["o_orderdate"], pa.scalar(plans.days("1995-03-15"), pa.int32()).cast(pa.date32())))
+        j1 = o.join(cust, keys="o_custkey", right_keys="c_custkey", join_type="inner")
+        li = T["lineitem"].filter(pc.greater(T["lineitem"]["l_shipdate"], pa.scalar(plans.days("1995-03-15"), pa.int32()).cast(pa.date32())))
+        li = li.append_column("rev", pc.multiply(li["l_extendedprice"], pc.subtract(one, li["l_discount"]))).select(["l_orderkey", "rev"])
+        j2 = li.join(j1.select(["o_orderkey", "o_orderdate", "o_shippriority"]), keys="l_orderkey", right_keys="o_orderkey", join_type="inner")
+        g = j2.group_by(["l_orderkey", "o_orderdate", "o_shippriority"]).aggregate([("rev", "sum")])
+        g = g.sort_by([("rev_sum", "descending"), ("o_orderdate", "ascending")]).slice(0, 10)
+        return [(r["l_orderkey"], r["rev_sum"], r["o_orderdate"], r["o_shippriority"]) for r in g.to_pylist()]
+
+    def acero_q5(T):
+        reg = T["region"].filter(pc.equal(T["region"]["r_name"], "AFRICA")).select(["r_regionkey"])
+        nat = T["nation"].join(reg, keys="n_regionkey", right_keys="r_regionkey", join_type="inner").select(["n_nationkey", "n_name"])
+        cust = T["customer"].select(["c_custkey", "c_nationkey"]).join(nat, keys="c_nationkey", right_keys="n_nationkey", join_type="inner")
+        od = T["orders"]["o_orderdate"]
+        lo, hi = pa.scalar(plans.days("1994-01-01"), pa.int32()).cast(pa.date32()), pa.scalar(plans.days("1995-01-01"), pa.int32()).cast(pa.date32())
+        o = T["orders"].filter(pc.and_(pc.greater_equal(od, lo), pc.less(od, hi))).select(["o_orderkey", "o_custkey"])
+        o = o.join(cust, keys="o_custkey", right_keys="c_custkey", join_type="inner").select(["o_orderkey", "c_nationkey", "n_name"])
+        li = T["lineitem"]
+        li = li.append_column("rev", pc.multiply(li["l_extendedprice"], pc.subtract(one, li["l_discount"]))).select(["l_orderkey", "l_suppkey", "rev"])
+        j = li.join(o, keys="l_orderkey", right_keys="o_orderkey", join_type="inner")
+        j = j.join(T["supplier"], keys=["l_suppkey", "c_nationkey"], right_keys=["s_suppkey", "s_nationkey"], join_type="inner")
+        g = j.group_by(["n_name"]).aggregate([("rev", "sum")])
+        return sorted(((r["n_name"], r["rev_sum"]) for r in g.to_pylist()), key=lambda x: -x[1])
+    QUERIES = {"q3": (plans.q3, acero_q3, lambda r: (r[0], r[1], r[2], r[3]),
+                      # customer 24 B + orders 24 B + lineitem 44 B per row (SURVEY.md 8d: Q3 compulsory input)
+                      lambda nl, no, nc: nl * 44 + no * 24 + nc * 24),
+               "q5": (plans.q5, acero_q5, lambda r: (r[0], r[1]),
+                      lambda nl, no, nc: nl * 48 + no * 20 + nc * 16)}
+    res = {}
+    total_orders = tpch.counts(sf)["orders"]
+    chunk = max(1, min(total_orders, tpch.counts(args.chunk_sf)["orders"]))
+    # ---- timing at full size ---------------------------------------------------------------------------------------------
+    o_all, l_all = facts(0, total_orders)
+    dev_all = dev_of(o_all, l_all)
+    whole = {}
+    for q, (mk, _, _, bytes_of) in QUERIES.items():
+        plan = mk()
+        run_gpu(plan, dev_all)                                   # warm-up (kernel specialisation, allocation cache)
+        best = None
+        for _ in range(3):
+            ctx.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            whole[q] = run_gpu(plan, dev_all)
+            e1.record(stream)
+            ctx.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+        scanned = l_all.rows + o_all.rows + dims_host["customer"].num_rows + (dims_host["supplier"].num_rows + 30 if q == "q5" else 0)
+        nbytes = bytes_of(l_all.rows, o_all.rows, dims_host["customer"].num_rows)
+        res[q] = {"ms": best, "scanned_rows": scanned, "rows_per_s": scanned / (best / 1e3), "compulsory_input_bytes": nbytes,
+                  "achieved_gbs": nbytes / (best / 1e3) / 1e9}
+    del dev_all, o_all, l_all
+    # ---- parity: chunk 0 against the proxy; all chunks against the whole ----------------------------------------------------
+    per_chunk = {q: [] for q in QUERIES}
+    first = 0
+    ci = 0
+    while first < total_orders:
+        n = min(chunk, total_orders - first)
+        o, l = facts(first, n)
+        dev = dev_of(o, l)
+        for q, (mk, acero, key, _) in QUERIES.items():
+            got = rows_of(run_gpu(mk(), dev))
+            per_chunk[q].append(got)
+            if ci == 0:
+                T = dict(dims_host)
+                T["orders"], T["lineitem"] = o.host_table(), l.host_table()
+                pa.set_cpu_count(os.cpu_count() or 1)
+                t0 = time.perf_counter()
+                want = acero(T)
+                dt = time.perf_counter() - t0
+                g = sorted(got, key=repr) if q == "q3" else got
+                w = sorted(want, key=repr) if q == "q3" else want
+                assert [tuple(map(str, r)) for r in g] == [tuple(map(str, r)) for r in w], f"{q}: GPU result of the first SF{args.chunk_sf:g} batch differs from pyarrow Acero:\n{g[:5]}\n{w[:5]}"
+                rows_c = l.rows + o.rows + dims_host["customer"].num_rows
+                res[q]["cpu_proxy"] = {"kind": "proxy (pyarrow Acero, not Sail)", "cores": pa.cpu_count(), "ms": dt * 1e3, "rows_per_s": rows_c / dt,
+                                       "sample": f"orders [0, {n}) of SF{sf:g} = an SF{args.chunk_sf:g}-sized batch ({rows_c} rows)"}
+        del dev, o, l
+        first += n
+        ci += 1
+    # Q5: revenue per nation adds up over chunks; Q3: the global top-10 is the top-10 of the per-chunk top-10s (groups are orders)
+    acc = {}
+    for rows in per_chunk["q5"]:
+        for name, rev in rows:
+            acc[name] = acc.get(name, 0) + rev
+    w5 = {r[0]: r[1] for r in rows_of(whole["q5"])}
+    assert acc == w5, f"q5: full-size result is not the sum of its {ci} order-range chunks"
+    cand = sorted((r for rows in per_chunk["q3"] for r in rows), key=lambda r: (-r[1], r[2]))[:10]
+    w3 = rows_of(whole["q3"])
+    assert sorted(map(repr, cand)) == sorted(map(repr, w3)), "q3: full-size top-10 is not the top-10 of its chunks' top-10s"
+    for q in QUERIES:
+        res[q]["parity"] = f"ok: first SF{args.chunk_sf:g} batch equals pyarrow Acero exactly; full-size result equals the combination of {ci} order-range chunks"
+    return res
+
+
 def main():
     args = parse_args()
     rank, world, local = dist_env()
@@ -526,6 +668,19 @@ def main():
     if world > 1 and not args.skip_exchange:
         exchange = exchange_leg(args, ctx, stream, rank, world, local)
 
+    # ---- Q3 / Q5 at the same scale (N = 1: BASELINE configs[2]) ---------------------------------------------------------------
+    joins = None
+    if world == 1 and not args.skip_joins:
+        del devs, gens
+        devs, gens = [], [None] * len(chunks)
+        ctx.synchronize()
+        try:
+            joins = joins_leg(args, ctx, stream, local)
+        except Exception as e:      # reported, never hidden: the Q1 line above stands on its own
+            import traceback
+            traceback.print_exc()
+            joins = {"error": f"{type(e).__name__}: {e}"[:600]}
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peak, peak_src = FALLBACK_HBM_GBS, "fallback"
@@ -539,6 +694,9 @@ def main():
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         lps = acc["kern_launches"] / max(1, args.steps)
+        if joins and "error" not in joins:
+            for jq in joins.values():
+                jq["roofline_frac"] = jq["achieved_gbs"] / peak
         line = {
             "metric": "TPC-H Q1 rows/s (scan+filter+hash-aggregate), lineitem resident in HBM",
             "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -561,6 +719,7 @@ def main():
                          "algorithmic_bytes_per_launch": n_rows * ALGO_BYTES_PER_ROW / max(1.0, lps)},
             "cpu_baseline": cpu,
             "exchange": exchange,
+            "joins": joins,
             "notes": notes,
         }
         print(json.dumps(line), flush=True)

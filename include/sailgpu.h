@@ -26,8 +26,9 @@
  *     crates/sail-execution/src/plan/shuffle_write.rs:209-267,               sailgpu_ctx_comm_init,
  *     plan/shuffle_read.rs:107-117                                           sailgpu_exchange
  *
- * Data crosses the boundary as Arrow C Data Interface structs (host memory; the library copies
- * host<->HBM itself from/to pinned staging) or Arrow C *Device* Data Interface structs
+ * Data crosses the boundary as Arrow C Data Interface structs (host memory, pageable is fine: packer
+ * threads of the library range-check every column piece, write it in a narrow wire format into pinned
+ * staging memory and expand it back to Arrow in HBM, sail_b200/csrc/h2d.cu) or Arrow C *Device* Data Interface structs
  * (ARROW_DEVICE_CUDA: buffers already in HBM, zero copy -- how consecutive GPU operators chain
  * without bouncing through the host).  No torch types, no C++ types: plain pointers and sizes.
  *
@@ -37,21 +38,29 @@
  *   {"op":"aggregate","mode":"partial|final|final_partitioned|single",
  *    "group_by":[{"expr":E,"name":".."}],"aggs":[{"fn":"sum|avg|count|min|max","args":[E],
  *    "name":"..","input_type":"T"}]}
- *   {"op":"hash_join","join_type":"inner|left|right_semi|...","on":[[l,r],...],"filter":E|null,
- *    "projection":[...]|null}              (input 0 = build = LEFT child, input 1 = probe)
- *   {"op":"sort","keys":[{"expr":E,"asc":bool,"nulls_first":bool}],"fetch":k|null}
+ *   {"op":"hash_join","join_type":"inner|left|right|left_semi|left_anti|right_semi|right_anti","on":[[l,r],...],
+ *    "filter":E|null,"projection":[...]|null}   (input 0 = build = LEFT child, input 1 = probe; residual filters with
+ *                                           inner, right_semi, left_semi and left_anti)
+ *   {"op":"nested_loop_join","join_type":"inner","filter":E|null,"projection":[...]|null}
+ *                                          (NestedLoopJoinExec with a small build side: the scalar-subquery shapes)
+ *   {"op":"sort","keys":[{"expr":E,"asc":bool,"nulls_first":bool}],"fetch":k|null}     (fetch: TopK by radix selection)
+ *   {"op":"sort_preserving_merge","keys":[...],"fetch":k|null,"runs":"inputs|batches"}
+ *                                          (SortPreservingMergeExec: one input per sorted partition, k-way merge)
  *   {"op":"repartition","scheme":"hash","exprs":[E],"n":N}
+ *   {"op":"repartition","scheme":"round_robin_row","n":N,"input_partition":i,"num_input_partitions":m}
+ *                                          (RowRoundRobinPartitioner of ExplicitRepartitionExec, repartition.rs:46-84)
  *   {"op":"pipeline","stages":[spec,...]}  (fused chain of filter/projection ending in at most one
  *                                           aggregate: one kernel, one pass over HBM)
  *   {"op":"chain","ops":[spec,...]}        (consecutive single-input operators run as one GPU island:
  *                                           batches move between them inside the library, in HBM)
- *   {"op":"exchange","mode":"hash|gather|auto","exprs":[E],"root":r,"small_rows":k}
+ *   {"op":"exchange","mode":"hash|gather|auto","exprs":[E],"root":r,"small_rows":k,"keep_runs":bool}
  *                                          (the shuffle boundary inside a chain: hash-repartition + NCCL
  *                                           all-to-all, or coalesce on rank r; needs sailgpu_ctx_comm_init)
  * Expressions E: {"col":i} {"lit":v,"type":"T"} {"op":"+|-|*|/|%|=|!=|<|<=|>|>=|and|or","l":E,"r":E}
  *   {"not":E} {"neg":E} {"is_null":E} {"is_not_null":E} {"cast":E,"to":"T"}
  *   {"case":[[E,E],...],"else":E|null} {"in":E,"set":[lit,...],"negated":b}
- *   {"like":E,"pattern":"..","negated":b} {"fn":"date_part|substr",...}
+ *   {"like":E,"pattern":"..","negated":b} {"fn":"date_part","part":"year|month|day","args":[E]}
+ *   {"fn":"substr","args":[E],"start":s,"length":n|null}   (1-based, in characters)
  * Types T: Boolean Int8..Int64 UInt8..UInt64 Float32 Float64 Date32 Decimal128(p,s) Utf8 Utf8View
  *
  * Threading: any function may be called from any thread (no affinity: the
