@@ -183,6 +183,30 @@ SAILGPU_API int32_t sailgpu_op_create(sailgpu_ctx* ctx, const char* spec_json, s
 SAILGPU_API int32_t sailgpu_spec_validate(const char* spec_json, size_t spec_len, const struct ArrowSchema* const* input_schemas,
                                           int32_t n_inputs, struct ArrowSchema* out_schema, char* err_buf, size_t err_cap);
 
+/* Parquet column chunks -> Arrow columns in HBM (the scan before the operator path: DataFusion's DataSourceExec(ParquetSource),
+ * crates/sail-data-source/src/listing/planner.rs:47, task_runner/core.rs:115-133).  The caller reads the footer (the Rust side
+ * already does, through the `parquet` crate) and hands over, per projected column of ONE row group, the bytes of its column chunk
+ * exactly as stored in the file (dictionary page first) plus what the footer says about it; the chunk crosses PCIe as stored and is
+ * decoded on the device (page headers and RLE run headers are walked on the host, every value is produced by a GPU thread).
+ * `schema` names the Arrow type each column decodes to (Int32/Date32, Int64, Float64, Decimal128 from FIXED_LEN_BYTE_ARRAY /
+ * INT32 / INT64, Utf8View from BYTE_ARRAY).  Covered: data pages V1/V2, PLAIN and dictionary encodings, flat optional columns,
+ * uncompressed pages; anything else returns SAILGPU_ERR_UNSUPPORTED and the caller keeps its CPU reader for that file. */
+typedef struct sailgpu_parquet_column {
+  const uint8_t* chunk;      /* host pointer: first byte of the column chunk (its dictionary page, else its first data page) */
+  uint64_t chunk_len;        /* total_compressed_size of the chunk */
+  int32_t physical_type;     /* parquet::Type: 1 INT32, 2 INT64, 5 DOUBLE, 6 BYTE_ARRAY, 7 FIXED_LEN_BYTE_ARRAY */
+  int32_t type_length;       /* FIXED_LEN_BYTE_ARRAY length, else 0 */
+  int32_t max_def_level;     /* 0 required, 1 optional */
+  int32_t codec;             /* parquet::CompressionCodec: 0 UNCOMPRESSED */
+  int64_t num_values;
+} sailgpu_parquet_column;
+SAILGPU_API int32_t sailgpu_parquet_decode(sailgpu_ctx* ctx, const struct ArrowSchema* schema, const sailgpu_parquet_column* cols,
+                                           int32_t n_cols, int64_t n_rows, struct ArrowDeviceArray* out);
+/* Plan-time / diagnostic companion: walks the pages and run headers of column `column` on the host only and reports what it
+ * found as JSON ({"pages":..,"dense":non-null values,"dict_count":..,...}); fails exactly where sailgpu_parquet_decode would. */
+SAILGPU_API int32_t sailgpu_parquet_inspect(const struct ArrowSchema* schema, const sailgpu_parquet_column* cols, int32_t n_cols,
+                                            int64_t n_rows, int32_t column, char* buf, size_t cap);
+
 /* Plan-time kernel specialisation.  The library interprets any pipeline at once and, for pipelines that see enough
  * rows (SAILGPU_JIT_MIN_ROWS, default 4 Mi), compiles a specialised sm_100a kernel with NVRTC the first time; the
  * cubin is cached next to the library (or in $SAILGPU_JIT_CACHE).  This call moves that compilation to planning time

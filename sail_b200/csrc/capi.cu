@@ -42,6 +42,12 @@ using CtxLock = std::lock_guard<std::recursive_mutex>;
 namespace sg { void set_ctx_error(const std::string& m) { g_ctx_error = m; } }   // ops_more.cu: comm_init / exchange report through sailgpu_ctx_last_error
 namespace sg { size_t pipeline_precompile(const Json& spec, const std::vector<Schema>& inputs, uint64_t validity_mask, bool cold, bool compile, std::string* source); }
 
+namespace sg {
+struct ParquetColumnDesc { const uint8_t* chunk; uint64_t chunk_len; int32_t physical_type, type_length, max_def_level, codec; int64_t num_values; };
+DevColumn decode_parquet_column(Ctx* ctx, const Field& f, const ParquetColumnDesc& c, int64_t n_rows);
+std::string parquet_plan_summary(const Field& f, const ParquetColumnDesc& c, int64_t n_rows);
+}
+
 extern "C" {
 
 // release callback for a borrowed (non-owning) copy of an Arrow array struct: marks it released, frees nothing
@@ -150,6 +156,39 @@ SAILGPU_API int64_t sailgpu_jit_precompile(const char* spec_json, size_t spec_le
   if (buf && cap) { const size_t k = std::min(text.size(), cap - 1); memcpy(buf, text.data(), k); buf[k] = 0; }
   if (rc != 0) return -(int64_t)(rc < 0 ? -rc : rc);
   return (flags & SAILGPU_JIT_COMPILE) ? (int64_t)cubin : (int64_t)source.size();
+}
+
+// host-only: what the page / run-header walk found in one column chunk, as JSON (no device is touched)
+SAILGPU_API int32_t sailgpu_parquet_inspect(const struct ArrowSchema* schema_c, const sailgpu_parquet_column* cols, int32_t n_cols, int64_t n_rows, int32_t column,
+                                            char* buf, size_t cap) {
+  std::string err, out;
+  const int32_t rc = guard(&err, [&] {
+    SG_CHECK(schema_c && cols && column >= 0 && column < n_cols, SAILGPU_ERR_INVALID, "bad argument");
+    Schema schema = schema_from_arrow(schema_c);
+    SG_CHECK((int)schema.size() == n_cols, SAILGPU_ERR_INVALID, "parquet: column count mismatch");
+    ParquetColumnDesc d{cols[column].chunk, cols[column].chunk_len, cols[column].physical_type, cols[column].type_length, cols[column].max_def_level, cols[column].codec, cols[column].num_values};
+    out = parquet_plan_summary(schema[(size_t)column], d, n_rows);
+  });
+  const std::string& text = rc != 0 ? err : out;
+  if (buf && cap) { const size_t k = std::min(text.size(), cap - 1); memcpy(buf, text.data(), k); buf[k] = 0; }
+  return rc;
+}
+SAILGPU_API int32_t sailgpu_parquet_decode(sailgpu_ctx* c, const struct ArrowSchema* schema_c, const sailgpu_parquet_column* cols, int32_t n_cols, int64_t n_rows,
+                                           struct ArrowDeviceArray* out) {
+  return guard(&g_ctx_error, [&] {
+    SG_CHECK(c && schema_c && cols && out && n_rows >= 0, SAILGPU_ERR_INVALID, "null argument");
+    CtxLock lk(c->ctx.mu);
+    set_device(c->ctx);
+    Schema schema = schema_from_arrow(schema_c);
+    SG_CHECK((int)schema.size() == n_cols, SAILGPU_ERR_INVALID, "parquet: " + std::to_string(n_cols) + " column chunks for a schema of " + std::to_string(schema.size()) + " fields");
+    auto b = std::make_shared<DevBatch>();
+    b->rows = n_rows;
+    for (int i = 0; i < n_cols; ++i) {
+      ParquetColumnDesc d{cols[i].chunk, cols[i].chunk_len, cols[i].physical_type, cols[i].type_length, cols[i].max_def_level, cols[i].codec, cols[i].num_values};
+      b->cols.push_back(decode_parquet_column(&c->ctx, schema[(size_t)i], d, n_rows));
+    }
+    export_device_batch(&c->ctx, schema, b, out);
+  });
 }
 
 SAILGPU_API int32_t sailgpu_op_push(sailgpu_op* h, int32_t input_idx, struct ArrowArray* batch) {

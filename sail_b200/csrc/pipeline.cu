@@ -2094,6 +2094,14 @@ cudaError_t launch_agg_extract(const AggParams& A, const AggExtractParams& X, ui
   agg_extract_kernel<<<grid, 256, 0, s>>>(A, X, n_groups, err);
   return cudaGetLastError();
 }
+__global__ void u32_to_bytes_kernel(const uint32_t* __restrict__ in, uint8_t* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] ? 1 : 0;
+}
+cudaError_t launch_u32_to_bytes(const uint32_t* in, uint8_t* out, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  u32_to_bytes_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(in, out, n);
+  return cudaGetLastError();
+}
 cudaError_t launch_pack_bytes(const uint8_t* bytes, uint32_t* bits, int64_t n, unsigned long long* null_count, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);

@@ -77,6 +77,8 @@ def lib():
         L.sailgpu_spec_validate.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), i32, vp, ctypes.c_char_p, ctypes.c_size_t]
         L.sailgpu_jit_precompile.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), i32, ctypes.c_uint64, i32, ctypes.c_char_p, ctypes.c_size_t]
         L.sailgpu_jit_precompile.restype = i64
+        L.sailgpu_parquet_decode.argtypes = [vp, vp, vp, i32, i64, vp]
+        L.sailgpu_parquet_inspect.argtypes = [vp, vp, i32, i64, i32, ctypes.c_char_p, ctypes.c_size_t]
         L.sailgpu_op_push.argtypes = [vp, i32, vp]
         L.sailgpu_op_push_device.argtypes = [vp, i32, vp]
         L.sailgpu_op_finish_input.argtypes = [vp, i32]
@@ -439,6 +441,73 @@ def device_batch_from_buffers(schema: pa.Schema, n_rows: int, tensors: list, ctx
     d.c.device_type = 2      # ARROW_DEVICE_CUDA
     d._live = True
     return d
+
+
+class ParquetColumnC(ctypes.Structure):
+    _fields_ = [("chunk", ctypes.c_void_p), ("chunk_len", ctypes.c_uint64), ("physical_type", ctypes.c_int32), ("type_length", ctypes.c_int32),
+                ("max_def_level", ctypes.c_int32), ("codec", ctypes.c_int32), ("num_values", ctypes.c_int64)]
+
+
+_PQ_PHYSICAL = {"BOOLEAN": 0, "INT32": 1, "INT64": 2, "INT96": 3, "FLOAT": 4, "DOUBLE": 5, "BYTE_ARRAY": 6, "FIXED_LEN_BYTE_ARRAY": 7}
+_PQ_CODEC = {"UNCOMPRESSED": 0, "SNAPPY": 1, "GZIP": 2, "LZO": 3, "BROTLI": 4, "LZ4": 5, "ZSTD": 6, "LZ4_RAW": 7}
+
+
+def _parquet_descriptors(file_bytes, row_group: int, columns: list | None):
+    import pyarrow.parquet as pq
+    buf = pa.py_buffer(file_bytes)
+    f = pq.ParquetFile(pa.BufferReader(buf))
+    rg = f.metadata.row_group(row_group)
+    names = [f.schema.column(i).name for i in range(rg.num_columns)]
+    columns = list(columns or names)
+    fields, cols = [], (ParquetColumnC * len(columns))()
+    for k, name in enumerate(columns):
+        i = names.index(name)
+        cm, cs = rg.column(i), f.schema.column(i)
+        t = f.schema_arrow.field(name).type
+        if pa.types.is_string(t) or pa.types.is_large_string(t):
+            t = pa.string_view()
+        fields.append(pa.field(name, t, nullable=cs.max_definition_level > 0))
+        start = cm.data_page_offset
+        if cm.has_dictionary_page and cm.dictionary_page_offset is not None:
+            start = min(start, cm.dictionary_page_offset)
+        c = cols[k]
+        c.chunk = buf.address + start
+        c.chunk_len = cm.total_compressed_size
+        c.physical_type = _PQ_PHYSICAL[cm.physical_type]
+        c.type_length = cs.length if cm.physical_type == "FIXED_LEN_BYTE_ARRAY" else 0
+        c.max_def_level = cs.max_definition_level
+        c.codec = _PQ_CODEC.get(cm.compression, 99)
+        c.num_values = cm.num_values
+    return buf, pa.schema(fields), cols, rg.num_rows
+
+
+def parquet_decode(file_bytes, row_group: int = 0, columns: list | None = None, ctx: Context | None = None) -> DeviceBatch:
+    """One row group of a Parquet file (bytes in host memory) decoded on the device: the footer is read here with pyarrow (the
+    Rust side uses the `parquet` crate), the column chunks go to sailgpu_parquet_decode as stored."""
+    ctx = ctx or default_context()
+    buf, schema, cols, n_rows = _parquet_descriptors(file_bytes, row_group, columns)
+    cschema = _export_schema(schema)
+    d = DeviceBatch(schema)
+    rc = lib().sailgpu_parquet_decode(ctx._h, ctypes.addressof(cschema), ctypes.addressof(cols), len(cols), n_rows, ctypes.addressof(d.c))
+    _release_schema(cschema)
+    del buf
+    if rc != 0:
+        raise SailGpuError(rc, lib().sailgpu_ctx_last_error(None).decode())
+    d._live = True
+    return d
+
+
+def parquet_inspect(file_bytes, column: int, row_group: int = 0, columns: list | None = None) -> dict:
+    """Host-only: what the page / run-header walk of sailgpu_parquet_decode finds in one column chunk (no GPU needed)."""
+    buf, schema, cols, n_rows = _parquet_descriptors(file_bytes, row_group, columns)
+    cschema = _export_schema(schema)
+    out = ctypes.create_string_buffer(1024)
+    rc = lib().sailgpu_parquet_inspect(ctypes.addressof(cschema), ctypes.addressof(cols), len(cols), n_rows, column, out, 1024)
+    _release_schema(cschema)
+    del buf
+    if rc != 0:
+        raise SailGpuError(rc, out.value.decode())
+    return json.loads(out.value.decode())
 
 
 def to_device(table: pa.Table, ctx: Context | None = None) -> DeviceBatch:
