@@ -76,6 +76,14 @@ def shard_chunks(sf_per_gpu: float, chunk_sf: float, rank: int, world: int):
     return total_sf, out
 
 
+def gen_shard(sf_per_gpu: float, rank: int, world: int):
+    """host-generated lineitem shard (the C generator): kept for the diagnostic scripts under scripts/"""
+    from datagen import tpch
+    total_sf = sf_per_gpu * world
+    per = tpch.counts(total_sf)["orders"] // world
+    return tpch.lineitem(total_sf, Q1_COLS, first=rank * per, n=per)
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region (NVML, every 2 ms; nvidia-smi as fallback)."""
     REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}

@@ -28,7 +28,7 @@ def main():
                 bench.run_query(ctx, specs, [dev], table.schema)
             tot = launches = 0
             for _ in range(5):
-                _, _, kns, kl = bench.run_query(ctx, specs, [dev], table.schema)
+                _, _, kns, kl, _ = bench.run_query(ctx, specs, [dev], table.schema)
                 tot += kns
                 launches += kl
             ms = tot / 1e6 / launches
