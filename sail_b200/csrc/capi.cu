@@ -89,6 +89,7 @@ SAILGPU_API void sailgpu_ctx_destroy(sailgpu_ctx* c) {
   cudaSetDevice(c->ctx.device);
   // Batches handed out through pull_device may outlive the context: the (tiny) Ctx block is intentionally never freed,
   // it is only marked dead so that late buffer releases use cudaFree instead of the destroyed stream.
+  c->ctx.shared_objects.clear();      // compiled pipelines and their literal buffers
   c->ctx.dead.store(true);
   if (c->ctx.stream) { cudaStreamSynchronize(c->ctx.stream); cudaStreamDestroy(c->ctx.stream); c->ctx.stream = nullptr; }
   destroy_pack_pool(&c->ctx);

@@ -156,6 +156,18 @@ struct Json {
   bool as_bool() const { SG_CHECK(kind == Bool, SAILGPU_ERR_INVALID, "spec: expected bool"); return b; }
   const std::string& as_str() const { SG_CHECK(kind == Str, SAILGPU_ERR_INVALID, "spec: expected string"); return s; }
 };
+// canonical text of a spec (cache keys)
+inline void json_dump(const Json& j, std::string* out) {
+  switch (j.kind) {
+    case Json::Null: *out += "null"; break;
+    case Json::Bool: *out += j.b ? "true" : "false"; break;
+    case Json::Num: *out += j.s; break;
+    case Json::Str: *out += '"'; *out += j.s; *out += '"'; break;
+    case Json::Arr: *out += '['; for (auto& x : j.a) { json_dump(x, out); *out += ','; } *out += ']'; break;
+    case Json::Obj: *out += '{'; for (auto& kv : j.o) { *out += kv.first; *out += ':'; json_dump(kv.second, out); *out += ','; } *out += '}'; break;
+  }
+}
+
 
 class JsonParser {
  public:

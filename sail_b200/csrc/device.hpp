@@ -30,6 +30,9 @@ struct Ctx {
   int sm_count = 148;
   size_t max_smem = 227 * 1024;
   cudaStream_t stream = nullptr;        // compute stream
+  // compiled pipelines shared by every operator instance created from the same spec over the same schema (engine.cu): an
+  // executor creates one operator per partition and per query run, the tile program / specialised kernel is built once
+  std::map<std::string, std::shared_ptr<void>> shared_objects;
   PackPool* pack_pool = nullptr;        // host-batch ingest: packer threads, pinned staging, copy streams (h2d.cu)
   std::string last_error;
   // One compute stream, one allocation cache and one D2H bounce buffer per context: calls that touch the device are

@@ -161,9 +161,11 @@ struct PipelineOp : Op {
   static constexpr int64_t TWO_PASS_MIN_ROWS = 1 << 18;
   PipelineRunner mask_run, sel_run;
   bool two_pass_ready = false;
+  std::string share_key;
   void setup_two_pass() {
     const Schema& in = run.in_schema;
     mask_run.init(ctx, in);
+    if (!share_key.empty()) mask_run.share(share_key + "#mask");
     StageSpec f; f.kind = StageSpec::Filter; f.predicate = run.stages[0].predicate;
     mask_run.stages.push_back(f);
     mask_run.custom_sink = [](PipelineCompiler& pc, CompiledPipeline& cp) { pc.finish_mask_store(cp); };
@@ -171,6 +173,7 @@ struct PipelineOp : Op {
     Field mf; mf.name = "__mask"; mf.type.id = TypeId::Bool; mf.nullable = false;
     in2.push_back(mf);
     sel_run.init(ctx, in2);
+    if (!share_key.empty()) sel_run.share(share_key + "#select");
     sel_run.stages = run.stages;
     StageSpec& s0 = sel_run.stages[0];
     auto me = std::make_shared<Expr>(); me->kind = Expr::Col; me->col = (int)in.size(); me->type.id = TypeId::Bool; me->nullable = false;
@@ -541,6 +544,13 @@ std::unique_ptr<Op> make_op(Ctx* ctx, const Json& spec, const std::vector<Schema
     Schema next;
     op->run.stages.push_back(parse_stage(*s, cur, &next));
     cur = next;
+  }
+  {   // operators created from the same spec over the same schema share their compiled pipelines (and specialised kernels)
+    std::string key = "pipeline|";
+    json_dump(spec, &key);
+    for (auto& f : inputs[0]) { key += '|'; key += f.type.str(); key += f.nullable ? '?' : '!'; }
+    op->share_key = key;
+    op->run.share(key);
   }
   op->has_agg = op->run.stages.back().kind == StageSpec::Aggregate;
   for (size_t i = 0; i + 1 < op->run.stages.size(); ++i)

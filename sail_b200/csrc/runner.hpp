@@ -49,12 +49,25 @@ inline void dump_pipeline(const CompiledPipeline& cp) {
             cp.agg.hot_groups, cp.agg.reg_path);
 }
 
+// what a runner compiles; shared between runners of identical operators (PipelineRunner::share)
+struct RunnerShared {
+  std::map<std::vector<bool>, std::shared_ptr<CompiledPipeline>> cache;
+  std::map<const CompiledPipeline*, DevProgram> programs;
+};
+
 struct PipelineRunner {
   Ctx* ctx;
   Schema in_schema;
   std::vector<StageSpec> stages;
-  std::map<std::vector<bool>, std::shared_ptr<CompiledPipeline>> cache;
-  std::map<const CompiledPipeline*, DevProgram> programs;
+  std::shared_ptr<RunnerShared> shared_state = std::make_shared<RunnerShared>();
+  // adopt the compiled pipelines of every earlier operator with this key on this context (plain filter / projection /
+  // aggregate pipelines only: join and partition pipelines bake per-operator pointers into their programs)
+  void share(const std::string& key) {
+    if (!ctx || ctx->stream == nullptr) return;          // plan-time validation / precompilation: no device context
+    auto it = ctx->shared_objects.find(key);
+    if (it == ctx->shared_objects.end()) ctx->shared_objects.emplace(key, std::static_pointer_cast<void>(shared_state));
+    else shared_state = std::static_pointer_cast<RunnerShared>(it->second);
+  }
   DevScalars scal;
   int hot_wanted = 8;
   int64_t rows_seen = 0;                 // rows launched through this runner (specialisation threshold)
@@ -70,6 +83,7 @@ struct PipelineRunner {
     for (auto& c : b.cols) sig.push_back((bool)c.validity);
     std::vector<bool> cache_key = sig;
     cache_key.push_back(cold_variant);
+    auto& cache = shared_state->cache;
     auto it = cache.find(cache_key);
     if (it != cache.end()) return it->second;
     auto cp = std::make_shared<CompiledPipeline>();
@@ -99,6 +113,7 @@ struct PipelineRunner {
   }
 
   DevProgram& program_for(const std::shared_ptr<CompiledPipeline>& cp) {
+    auto& programs = shared_state->programs;
     auto it = programs.find(cp.get());
     if (it == programs.end()) {
       DevProgram dp;
