@@ -318,12 +318,14 @@ __device__ __forceinline__ void jit_cold_rows(const KernelArgs& K, const typenam
 // per-thread register partials of the integer fast path (tier 2)
 template <class G> struct JitAggRegs { int64_t v[REG_GROUPS][G::N_ACCS > 0 ? G::N_ACCS : 1]; int rows; };
 
+// Warp-collective (full-mask shuffles): nothing in here may depend on the dictionary size, which other warps change
+// asynchronously -- every register group is flushed, groups that do not exist yet hold zeros.
 template <class G>
-__device__ __forceinline__ void jit_reg_flush(const JitHot& H, JitAggRegs<G>& R, int hot_n) {
+__device__ __forceinline__ void jit_reg_flush(const JitHot& H, JitAggRegs<G>& R) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int g = 0; g < REG_GROUPS; ++g) {
-    if (g < hot_n) {
+    {
       uint64_t* wa = H.wacc + (size_t)g * jit_aw<G>();
 #pragma unroll
       for (int j = 0; j < G::N_ACCS; ++j) {
@@ -361,7 +363,9 @@ __device__ __forceinline__ void jit_agg_reg_tile(const KernelArgs& K, const type
   int gid[G::RPT];
   uint32_t fpv[G::RPT];
   bool miss = false;
-  const int n0 = (int)lds_acquire_u32(&sm->dict_n);
+  // the lanes of a warp leave the mbarrier wait one by one and other warps grow the dictionary meanwhile: lane 0's reading is
+  // broadcast so that the warp collectives below are executed by all lanes or by none
+  const int n0 = __shfl_sync(0xFFFFFFFFu, (int)lds_acquire_u32(&sm->dict_n), 0);
 #pragma unroll
   for (int k = 0; k < G::RPT; ++k) {
     gid[k] = -1; fpv[k] = 0;
@@ -425,7 +429,7 @@ __device__ __forceinline__ void jit_agg_reg_tile(const KernelArgs& K, const type
     }
   }
   R.rows += G::RPT;
-  if (R.rows >= JIT_REG_FLUSH) jit_reg_flush<G>(H, R, (int)lds_acquire_u32(&sm->dict_n));
+  if (R.rows >= JIT_REG_FLUSH) jit_reg_flush<G>(H, R);
   bool anycold = false;
 #pragma unroll
   for (int k = 0; k < G::RPT; ++k) anycold |= rows[k].live && gid[k] < 0;
@@ -440,7 +444,7 @@ __device__ __forceinline__ void jit_agg_dict_tile(const KernelArgs& K, const typ
   int gid[G::RPT];
   uint32_t fpv[G::RPT];
   bool miss = false;
-  const int n0 = (int)lds_acquire_u32(&sm->dict_n);
+  const int n0 = __shfl_sync(0xFFFFFFFFu, (int)lds_acquire_u32(&sm->dict_n), 0);      // warp-uniform (see jit_agg_reg_tile)
 #pragma unroll
   for (int k = 0; k < G::RPT; ++k) {
     gid[k] = -1; fpv[k] = 0;
@@ -464,7 +468,7 @@ __device__ __forceinline__ void jit_agg_dict_tile(const KernelArgs& K, const typ
       }
     }
   }
-  const int hot_n = (int)lds_acquire_u32(&sm->dict_n);
+  const int hot_n = __shfl_sync(0xFFFFFFFFu, (int)lds_acquire_u32(&sm->dict_n), 0);      // every gid of this warp is below it
   bool anyhot = false;
 #pragma unroll
   for (int k = 0; k < G::RPT; ++k) anyhot |= rows[k].live && gid[k] >= 0;
@@ -781,6 +785,7 @@ __device__ __forceinline__ void jit_main(const KernelArgs& K) {
     }
     __syncwarp();
     mbar_wait(&sm->full[s], (uint32_t)((it / S) & 1));
+    __syncwarp();
     const long long tn = sm->tile_no[s];
     if (tn < 0) break;
     const int64_t tile = tn & ~JIT_PARTIAL;
@@ -816,7 +821,7 @@ __device__ __forceinline__ void jit_main(const KernelArgs& K) {
     if (lane == 0) mbar_arrive(&sm->empty[s]);
   }
   if constexpr (G::SINK == SINK_AGG) {
-    if constexpr (G::AGG_TIER == 2) { const JitHot H = jit_hot<G>(scratch); jit_reg_flush<G>(H, R, (int)lds_acquire_u32(&sm->dict_n)); }
+    if constexpr (G::AGG_TIER == 2) { const JitHot H = jit_hot<G>(scratch); jit_reg_flush<G>(H, R); }
     __syncthreads();
     jit_hot_flush<G>(K, sm, scratch);
   }
