@@ -4,6 +4,8 @@
 // crosses per RecordBatch: Arrow's fixed widths are an in-memory format, not a wire format.
 #include "h2d.hpp"
 
+#include <sched.h>
+
 #include <array>
 #include <cstdlib>
 #include <cstring>
@@ -48,63 +50,48 @@ __global__ void unpack_view_kernel(const uint8_t* __restrict__ src, ulonglong2* 
   }
 }
 
-// ---- host side: piece -> staging slot --------------------------------------------------------------
+// ---- host side: piece -> staging slot (loops in h2d_pack.cpp: AVX-512 / AVX2 / baseline clones) -------
 struct Packed { int enc; size_t bytes; long long base; int w; };
+}  // namespace
+extern "C" {
+void sg_scan_dec128(const int64_t* p, int64_t n, int64_t* mn, int64_t* mx, uint64_t* bad);
+void sg_scan_i64(const int64_t* p, int64_t n, int64_t* mn, int64_t* mx);
+void sg_scan_i32(const int32_t* p, int64_t n, int32_t* mn, int32_t* mx);
+uint32_t sg_scan_view_maxlen(const uint32_t* p, int64_t n);
+void sg_pack_i64(uint8_t* out, const int64_t* vals, int64_t stride, int64_t n, int64_t base, int w);
+void sg_pack_i32(uint8_t* out, const int32_t* vals, int64_t n, int32_t base, int w);
+void sg_pack_views(uint8_t* out, const uint8_t* views, int64_t n, uint32_t L);
+}
+namespace {
 
 static inline int width_for(unsigned long long range) { return range < (1ull << 8) ? 1 : range < (1ull << 16) ? 2 : range < (1ull << 32) ? 4 : 8; }
 
-template <typename T>
-static void store_deltas(uint8_t* out, const T* vals, size_t stride_elems, int64_t n, long long base, int w) {
-  switch (w) {
-    case 1: for (int64_t i = 0; i < n; ++i) out[i] = (uint8_t)((unsigned long long)vals[i * stride_elems] - (unsigned long long)base); break;
-    case 2: { uint16_t* o = reinterpret_cast<uint16_t*>(out); for (int64_t i = 0; i < n; ++i) o[i] = (uint16_t)((unsigned long long)vals[i * stride_elems] - (unsigned long long)base); break; }
-    case 4: { uint32_t* o = reinterpret_cast<uint32_t*>(out); for (int64_t i = 0; i < n; ++i) o[i] = (uint32_t)((unsigned long long)vals[i * stride_elems] - (unsigned long long)base); break; }
-    default: { uint64_t* o = reinterpret_cast<uint64_t*>(out); for (int64_t i = 0; i < n; ++i) o[i] = (uint64_t)vals[i * stride_elems] - (uint64_t)base; }
-  }
-}
-
 static Packed pack_piece(const HostStager::Item& it, uint8_t* out, bool narrow) {
   const int64_t n = it.n;
-  if (narrow && it.kind == HostCol::Dec128) {
+  if (narrow && n > 0 && it.kind == HostCol::Dec128) {
     const int64_t* p = reinterpret_cast<const int64_t*>(it.src);
-    int64_t mn = INT64_MAX, mx = INT64_MIN;
-    uint64_t bad = 0;
-    for (int64_t i = 0; i < n; ++i) {
-      const int64_t lo = p[2 * i], hi = p[2 * i + 1];
-      bad |= (uint64_t)(hi ^ (lo >> 63));
-      mn = lo < mn ? lo : mn; mx = lo > mx ? lo : mx;
-    }
-    if (!bad && n > 0) {
+    int64_t mn, mx; uint64_t bad;
+    sg_scan_dec128(p, n, &mn, &mx, &bad);
+    if (!bad) {
       const int w = width_for((unsigned long long)mx - (unsigned long long)mn);
-      store_deltas<int64_t>(out, p, 2, n, mn, w);
+      sg_pack_i64(out, p, 2, n, mn, w);
       return {ENC_INT, (size_t)n * w, mn, w};
     }
-  } else if (narrow && it.kind == HostCol::Int64) {
+  } else if (narrow && n > 0 && it.kind == HostCol::Int64) {
     const int64_t* p = reinterpret_cast<const int64_t*>(it.src);
-    int64_t mn = INT64_MAX, mx = INT64_MIN;
-    for (int64_t i = 0; i < n; ++i) { mn = p[i] < mn ? p[i] : mn; mx = p[i] > mx ? p[i] : mx; }
-    const int w = n > 0 ? width_for((unsigned long long)mx - (unsigned long long)mn) : 8;
-    if (w < 8) { store_deltas<int64_t>(out, p, 1, n, mn, w); return {ENC_INT, (size_t)n * w, mn, w}; }
-  } else if (narrow && it.kind == HostCol::Int32) {
+    int64_t mn, mx;
+    sg_scan_i64(p, n, &mn, &mx);
+    const int w = width_for((unsigned long long)mx - (unsigned long long)mn);
+    if (w < 8) { sg_pack_i64(out, p, 1, n, mn, w); return {ENC_INT, (size_t)n * w, mn, w}; }
+  } else if (narrow && n > 0 && it.kind == HostCol::Int32) {
     const int32_t* p = reinterpret_cast<const int32_t*>(it.src);
-    int32_t mn = INT32_MAX, mx = INT32_MIN;
-    for (int64_t i = 0; i < n; ++i) { mn = p[i] < mn ? p[i] : mn; mx = p[i] > mx ? p[i] : mx; }
-    const int w = n > 0 ? width_for((unsigned long long)((long long)mx - (long long)mn)) : 4;
-    if (w < 4) { store_deltas<int32_t>(out, p, 1, n, (long long)mn, w); return {ENC_INT, (size_t)n * w, (long long)mn, w}; }
-  } else if (narrow && it.kind == HostCol::View16) {
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(it.src);      // view = {len, 3 x 4 bytes}
-    uint32_t L = 0;
-    for (int64_t i = 0; i < n; ++i) L = p[4 * i] > L ? p[4 * i] : L;
-    if (L <= 12) {
-      const size_t rb = 1 + L;
-      for (int64_t i = 0; i < n; ++i) {
-        const uint8_t* v = it.src + 16 * i;
-        uint8_t* o = out + rb * (size_t)i;
-        o[0] = (uint8_t)p[4 * i];
-        for (uint32_t k = 0; k < L; ++k) o[1 + k] = v[4 + k];
-      }
-      return {ENC_VIEW, rb * (size_t)n, 0, (int)L};
-    }
+    int32_t mn, mx;
+    sg_scan_i32(p, n, &mn, &mx);
+    const int w = width_for((unsigned long long)((long long)mx - (long long)mn));
+    if (w < 4) { sg_pack_i32(out, p, n, mn, w); return {ENC_INT, (size_t)n * w, (long long)mn, w}; }
+  } else if (narrow && n > 0 && it.kind == HostCol::View16) {
+    const uint32_t L = sg_scan_view_maxlen(reinterpret_cast<const uint32_t*>(it.src), n);
+    if (L <= 12) { sg_pack_views(out, it.src, n, L); return {ENC_VIEW, (size_t)(1 + L) * (size_t)n, 0, (int)L}; }
   }
   const size_t bytes = (size_t)n * (size_t)it.width;
   memcpy(out, it.src, bytes);
@@ -182,9 +169,18 @@ static PackPool* pool_of(Ctx* ctx) {
   if (ctx->pack_pool) return ctx->pack_pool;
   auto* p = new PackPool();
   p->ctx = ctx;
+  // packer threads: the CPUs this process may use (affinity mask, cgroup quota), shared by the ranks of the node, at most 32
   const char* nt = getenv("SAILGPU_PACK_THREADS");
-  const int hw = (int)std::thread::hardware_concurrency();
-  const int n = std::max(1, nt && *nt ? atoi(nt) : std::min(16, std::max(1, hw)));
+  int avail = (int)std::thread::hardware_concurrency();
+  { cpu_set_t set; if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = std::min(avail > 0 ? avail : 1 << 20, (int)CPU_COUNT(&set)); }
+  if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    long long quota = 0, period = 0;
+    if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0) avail = std::min<long long>(avail, (quota + period - 1) / period);
+    fclose(f);
+  }
+  const char* lw = getenv("LOCAL_WORLD_SIZE");
+  const int ranks = std::max(1, lw && *lw ? atoi(lw) : ctx->world);
+  const int n = std::max(1, nt && *nt ? atoi(nt) : std::min(32, std::max(2, avail / ranks)));
   const char* nw = getenv("SAILGPU_H2D_PACK");
   p->narrow = !(nw && *nw && atoi(nw) == 0);
   p->workers.resize((size_t)n);
