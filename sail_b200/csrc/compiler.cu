@@ -467,6 +467,11 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
   // aggregation wants 2 CTAs/SM of 512-row tiles; plain projection streams best with big double-buffered tiles;
   // compaction / join / partition sinks prefer big single-stage tiles and more resident CTAs
   static const int C_AGG[][2] = {{2, 1}, {1, 2}, {2, 2}, {1, 1}, {4, 1}, {4, 2}};
+  // with the kernel specialiser on, dictionary aggregation uses 256-row tiles: the specialised kernel (which inherits the tile
+  // size so that tile lists stay valid across both kernels) keeps one row per thread in registers without spills -- measured on
+  // Q1 SF10: 1.49 ms against 1.95 ms with two rows per thread (profiles/r02_jit_sweep.txt); the interpreter, which now only sees
+  // small inputs, loses a few percent
+  static const int C_AGG_JIT[][2] = {{1, 2}, {1, 1}, {2, 1}, {2, 2}, {4, 1}, {4, 2}};
   // high-cardinality aggregation is bound by the latency of the global table: small tiles, 4 CTAs/SM (64 registers)
   static const int C_AGG_COLD[][2] = {{2, 1}, {2, 2}, {1, 2}, {1, 1}, {4, 1}, {4, 2}};
   static const int C_STORE[][2] = {{4, 2}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
@@ -474,7 +479,9 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
   if (out.sink == SINK_AGG && out.cold_variant) hot_wanted = 0;
   // hash-join build and probe pipelines are bound by random-access latency as well (scripts/sweep_ops.sh: 5.4 vs 6.6 ms)
   const bool latency_bound = out.sink == SINK_BUILD || out.n_probes > 0;
-  const int (*cands)[2] = out.sink == SINK_AGG ? (out.cold_variant ? C_AGG_COLD : C_AGG) : out.sink == SINK_STORE ? C_STORE : latency_bound ? C_AGG_COLD : C_OTHER;
+  const bool jit_on = getenv("SAILGPU_JIT") == nullptr || atoi(getenv("SAILGPU_JIT")) != 0;
+  const int (*cands)[2] = out.sink == SINK_AGG ? (out.cold_variant ? C_AGG_COLD : (jit_on && out.n_probes == 0) ? C_AGG_JIT : C_AGG)
+                          : out.sink == SINK_STORE ? C_STORE : latency_bound ? C_AGG_COLD : C_OTHER;
   int best_rpt = 0, best_stages = 0, best_hot = 0;
   if (hot_wanted > 0 && force_hot >= 0) hot_wanted = force_hot;
   for (int pass = 0; pass < 2 && !best_rpt; ++pass) {
