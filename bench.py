@@ -58,6 +58,19 @@ def parse_args():
     return ap.parse_args()
 
 
+def host_cores() -> int:
+    """CPUs this process can actually run on: the affinity mask cut by the cgroup CPU quota (the GPU boxes show 128 logical
+    CPUs under a 16-CPU quota; threads beyond the quota only add context switches)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -404,8 +417,8 @@ def joins_leg(args, ctx, stream, local):
 
     def dev_of(o, l):
         d = dict(dims)
-        d["orders"] = (o.device_batch(ctx), OC)
-        d["lineitem"] = (l.device_batch(ctx), LC)
+        d["orders"] = ([x.device_batch(ctx) for x in o] if isinstance(o, list) else o.device_batch(ctx), OC)
+        d["lineitem"] = ([x.device_batch(ctx) for x in l] if isinstance(l, list) else l.device_batch(ctx), LC)
         return d
 
     def run_gpu(plan, dev):
@@ -457,8 +470,17 @@ def joins_leg(args, ctx, stream, local):
     total_orders = tpch.counts(sf)["orders"]
     chunk = max(1, min(total_orders, tpch.counts(args.chunk_sf)["orders"]))
     # ---- timing at full size ---------------------------------------------------------------------------------------------
-    o_all, l_all = facts(0, total_orders)
+    # the tables are resident as batches of chunk-sf order ranges (what a scan hands the operators), all pushed into one operator tree
+    o_all, l_all = [], []
+    first = 0
+    while first < total_orders:
+        n = min(chunk, total_orders - first)
+        o, l = facts(first, n)
+        o_all.append(o)
+        l_all.append(l)
+        first += n
     dev_all = dev_of(o_all, l_all)
+    l_rows, o_rows = sum(x.rows for x in l_all), sum(x.rows for x in o_all)
     whole = {}
     for q, (mk, _, _, bytes_of) in QUERIES.items():
         plan = mk()
@@ -473,8 +495,8 @@ def joins_leg(args, ctx, stream, local):
             ctx.synchronize()
             ms = e0.elapsed_time(e1)
             best = ms if best is None or ms < best else best
-        scanned = l_all.rows + o_all.rows + dims_host["customer"].num_rows + (dims_host["supplier"].num_rows + 30 if q == "q5" else 0)
-        nbytes = bytes_of(l_all.rows, o_all.rows, dims_host["customer"].num_rows)
+        scanned = l_rows + o_rows + dims_host["customer"].num_rows + (dims_host["supplier"].num_rows + 30 if q == "q5" else 0)
+        nbytes = bytes_of(l_rows, o_rows, dims_host["customer"].num_rows)
         res[q] = {"ms": best, "scanned_rows": scanned, "rows_per_s": scanned / (best / 1e3), "compulsory_input_bytes": nbytes,
                   "achieved_gbs": nbytes / (best / 1e3) / 1e9}
     del dev_all, o_all, l_all
@@ -492,7 +514,7 @@ def joins_leg(args, ctx, stream, local):
             if ci == 0:
                 T = dict(dims_host)
                 T["orders"], T["lineitem"] = o.host_table(), l.host_table()
-                pa.set_cpu_count(os.cpu_count() or 1)
+                pa.set_cpu_count(host_cores())
                 t0 = time.perf_counter()
                 want = acero(T)
                 dt = time.perf_counter() - t0
@@ -588,7 +610,7 @@ def main():
     # ---- host copies: parity of the full-size result against the C port (every rank's shard), CPU baseline, e2e inputs ----
     host_e2e, cpu, want_rows, notes = [], None, None, []
     if not args.skip_cpu:
-        threads = max(1, (os.cpu_count() or 1) // world)
+        threads = max(1, host_cores() // world)
         parts, dt_cpu = [], 0.0
         for i, g in enumerate(gens):
             t = g.host_table()
@@ -752,7 +774,7 @@ def run_reference(args):
     except Exception:
         table = tpch.lineitem(total_sf, Q1_COLS, first=chunks[0][0], n=chunks[0][1]).combine_chunks()
     n_rows = table.num_rows
-    threads = os.cpu_count() or 1
+    threads = host_cores()
     from oracle import cpipelines
     from sail_b200 import plans
     cutoff = plans.days("1998-09-24")

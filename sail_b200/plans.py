@@ -163,15 +163,17 @@ def execute(node: Node, tables: dict, run_op):
 
 def execute_gpu(node: Node, dev_tables: dict, ctx=None, stats: dict | None = None):
     """Runs the plan through libsailgpu with every intermediate batch staying in HBM (device hand-off between
-    operators).  dev_tables: {table: (DeviceBatch, schema names)} resident inputs; returns a list of DeviceBatch.
+    operators).  dev_tables: {table: (DeviceBatch or a list of them, schema names)} resident inputs; returns a list of DeviceBatch.
     stats (optional) collects per-operator metrics keyed by a running node number."""
     from . import engine
     if node.spec["op"] == "scan":
         dev, names = dev_tables[node.spec["table"]]
         idx = [names.index(c) for c in node.spec["columns"]]
         spec = {"op": "projection", "exprs": [{"expr": {"col": i}, "name": names[i]} for i in idx]}
-        op = engine.GpuExec(spec, [dev.schema], ctx)
-        op.push(dev.borrow())
+        devs = dev if isinstance(dev, (list, tuple)) else [dev]          # a table may be resident as several batches
+        op = engine.GpuExec(spec, [devs[0].schema], ctx)
+        for d in devs:
+            op.push(d.borrow())
         op.finish()
         out = op.collect_device()
         for d in out:
