@@ -198,8 +198,10 @@ def lineitem(sf: float, columns=None, strings: str = "view", **kw) -> pa.Table:
 
 def orders(sf: float, columns=None, strings: str = "view", **kw) -> pa.Table:
     columns = list(columns or ORDERS_ALL)
-    raw = gen_orders_lineitem_numpy(sf, columns, (), **kw)
-    return pa.table([_to_arrow(c, raw[c], strings) for c in columns], names=columns)
+    gen = [c for c in columns if c != "o_comment"]
+    raw = gen_orders_lineitem_numpy(sf, gen or ["o_orderkey"], (), **kw)
+    n_rows = len(raw[(gen or ["o_orderkey"])[0]])
+    return pa.table([comments(c, n_rows, strings, kw.get("first", 0)) if c == "o_comment" else _to_arrow(c, raw[c], strings) for c in columns], names=columns)
 
 
 def _phones(which: int, nationkey: np.ndarray, strings: str) -> pa.Array:
@@ -208,6 +210,97 @@ def _phones(which: int, nationkey: np.ndarray, strings: str) -> pa.Array:
     lib().tpch_gen_phone(ctypes.c_int(which), ctypes.c_int64(0), ctypes.c_int64(n), _p(np.ascontiguousarray(nationkey, dtype=np.int64)), _p(raw))
     txt = raw.reshape(n, 15).view("S15").ravel()
     return pa.array([t.decode() for t in txt], type=pa.string_view() if strings == "view" else pa.string())
+
+
+# dists.dss "colors" (p_name draws five of them per part)
+COLORS = ("almond antique aquamarine azure beige bisque black blanched blue blush brown burlywood burnished chartreuse chiffon chocolate "
+          "coral cornflower cornsilk cream cyan dark deep dim dodger drab firebrick floral forest frosted gainsboro ghost goldenrod green "
+          "grey honeydew hot indian ivory khaki lace lavender lawn lemon light lime linen magenta maroon medium metallic midnight mint "
+          "misty moccasin navajo navy olive orange orchid pale papaya peach peru pink plum powder puff purple red rose rosy royal saddle "
+          "salmon sandy seashell sienna sky slate smoke snow spring steel tan thistle tomato turquoise violet wheat white yellow").split()
+assert len(COLORS) == 92
+
+_NOUNS = ("foxes ideas theodolites pinto beans instructions dependencies excuses platelets asymptotes courts dolphins multipliers sauternes "
+          "warthogs frets dinos attainments somas patterns forges braids frays warhorses dugouts notornis epitaphs pearls tithes waters orbits "
+          "gifts sheaves depths sentiments decoys realms pains grouches escapades packages requests accounts deposits").split()
+_VERBS = ("sleep wake are cajole haggle nag use boost affix detect integrate maintain nod was lose sublate solve thrash promise engage "
+          "hinder print x-ray breach eat grow impress mold poach serve run dazzle snooze doze unwind kindle play hang believe doubt").split()
+_ADJS = ("furious sly careful blithe quick fluffy slow quiet ruthless thin close dogged daring brave stealthy permanent enticing idle busy "
+         "regular final ironic even bold silent special pending unusual express").split()
+_ADVS = ("sometimes always never furiously slyly carefully blithely quickly fluffily slowly quietly ruthlessly thinly closely doggedly "
+         "daringly bravely stealthily permanently enticingly idly busily regularly finally ironically evenly boldly silently").split()
+_PREPS = ("about above according to across after against along alongside of among around at atop before behind beneath beside besides "
+          "between beyond by despite during except for from in place of inside instead of into near of on outside over past since through "
+          "throughout to toward under until up upon without with within").split()
+_POOL = None
+TEXT_POOL_BYTES = 1 << 20
+
+
+def text_pool() -> bytes:
+    """The comment pool.  dbgen pre-generates 300 MB of sentences from the grammar in dists.dss; that grammar is not restated
+    here, so this pool (1 MiB of adverb/adjective/noun/verb sentences over dbgen's word lists, fixed seed) is NOT dbgen's: the
+    comment columns are realistic (`special requests`, `express packages` ... occur) but do not reproduce dbgen's bytes, and
+    the three golden snapshots that depend on comment text (q2's output is empty; q10's c_comment column; q13's filter) are
+    pinned only as far as they do not."""
+    global _POOL
+    if _POOL is None:
+        rng = np.random.RandomState(933588178 % (2 ** 31))
+        out, size = [], 0
+        while size < TEXT_POOL_BYTES + 256:
+            k = rng.randint(0, 4)
+            w = lambda L: L[rng.randint(0, len(L))]
+            if k == 0:
+                sent = f"{w(_ADVS)} {w(_ADJS)} {w(_NOUNS)} {w(_VERBS)} {w(_PREPS)} the {w(_ADJS)} {w(_NOUNS)}"
+            elif k == 1:
+                sent = f"{w(_ADJS)} {w(_NOUNS)} {w(_VERBS)} {w(_ADVS)}"
+            elif k == 2:
+                sent = f"{w(_NOUNS)} {w(_VERBS)} {w(_ADVS)} {w(_PREPS)} the {w(_ADVS)} {w(_ADJS)} {w(_NOUNS)}"
+            else:
+                sent = f"{w(_ADJS)}, {w(_ADJS)} {w(_NOUNS)} {w(_PREPS)} the {w(_NOUNS)} {w(_VERBS)}"
+            sent += ".;:?!"[rng.randint(0, 5)] if rng.randint(0, 8) == 0 else "."
+            out.append(sent + " ")
+            size += len(sent) + 1
+        _POOL = "".join(out).encode()[:TEXT_POOL_BYTES]
+    return _POOL
+
+
+_TEXT_STREAMS = {"o_comment": (12, 49), "c_comment": (31, 73), "s_comment": (36, 63)}   # Seed[] index, average length
+
+
+def comments(column: str, n: int, strings: str = "view", first: int = 0) -> pa.Array:
+    """dbgen's TEXT(): offset and length draws on the column's own stream, cut out of text_pool()"""
+    stream, avg = _TEXT_STREAMS[column]
+    lo, hi = int(avg * 0.4), int(avg * 1.6)
+    off, ln = np.empty(n, "i8"), np.empty(n, "i4")
+    pool = text_pool()
+    lib().tpch_gen_text(ctypes.c_int(stream), ctypes.c_int64(first), ctypes.c_int64(n), ctypes.c_int64(lo), ctypes.c_int64(hi),
+                        ctypes.c_int64(len(pool)), _p(off), _p(ln))
+    vals = [pool[o:o + l].decode() for o, l in zip(off.tolist(), ln.tolist())]
+    if column == "s_comment":       # mk_supp: "Customer <noise>Complaints|Recommends" overwrites part of a few comments
+        kind = np.empty(n, "u1")
+        lib().tpch_gen_bbb(ctypes.c_int64(first), ctypes.c_int64(n), _p(kind))
+        for i in np.nonzero(kind)[0].tolist():
+            word = "Complaints" if kind[i] == 1 else "Recommends"
+            t = vals[i]
+            if len(t) < 25:
+                t = t + " " * (25 - len(t))
+            vals[i] = t[:3] + "Customer " + t[12:len(t) - 10] + word
+    return pa.array(vals, type=pa.string_view() if strings == "view" else pa.string())
+
+
+def addresses(which: int, n: int, strings: str = "view", first: int = 0) -> pa.Array:
+    ln, raw = np.empty(n, "i4"), np.zeros(40 * n, dtype=np.uint8)
+    lib().tpch_gen_address(ctypes.c_int(which), ctypes.c_int64(first), ctypes.c_int64(n), _p(ln), _p(raw))
+    rows = raw.reshape(n, 40)
+    vals = [bytes(rows[i, :l]).decode() for i, l in enumerate(ln.tolist())]
+    return pa.array(vals, type=pa.string_view() if strings == "view" else pa.string())
+
+
+def part_names(n: int, strings: str = "view", first: int = 0) -> pa.Array:
+    idx = np.empty(5 * n, dtype=np.uint8)
+    lib().tpch_gen_pname(ctypes.c_int64(first), ctypes.c_int64(n), ctypes.c_int(1), _p(idx))
+    vals = [" ".join(COLORS[j] for j in row) for row in idx.reshape(n, 5).tolist()]
+    return pa.array(vals, type=pa.string_view() if strings == "view" else pa.string())
 
 
 def customer(sf: float, columns=None, strings: str = "view") -> pa.Table:
@@ -224,6 +317,10 @@ def customer(sf: float, columns=None, strings: str = "view") -> pa.Table:
             return pa.array(txt.tolist(), type=pa.string_view() if strings == "view" else pa.string())
         if c == "c_phone":
             return _phones(0, a["c_nationkey"], strings)
+        if c == "c_address":
+            return addresses(0, n, strings)
+        if c == "c_comment":
+            return comments(c, n, strings)
         return _to_arrow(c, a[c], strings)
     return pa.table([one(c) for c in columns], names=columns)
 
@@ -241,6 +338,10 @@ def supplier(sf: float, columns=None, strings: str = "view") -> pa.Table:
             return pa.array(txt.tolist(), type=pa.string_view() if strings == "view" else pa.string())
         if c == "s_phone":
             return _phones(1, a["s_nationkey"], strings)
+        if c == "s_address":
+            return addresses(1, n, strings)
+        if c == "s_comment":
+            return comments(c, n, strings)
         return _to_arrow(c, a[c], strings)
     return pa.table([one(c) for c in columns], names=columns)
 
@@ -262,7 +363,7 @@ P_CONTAINERS = [f"{a} {b}" for a in ("SM", "LG", "MED", "JUMBO", "WRAP") for b i
 
 
 def part(sf: float, columns=None, strings: str = "view") -> pa.Table:
-    """p_partkey, p_brand ('Brand#MN'), p_type, p_size, p_container, p_retailprice (p_name / p_mfgr / p_comment are not generated)"""
+    """p_partkey, p_name, p_mfgr, p_brand ('Brand#MN'), p_type, p_size, p_container, p_retailprice (p_comment is not generated)"""
     n = counts(sf)["part"]
     a = {"p_partkey": np.empty(n, "i8"), "p_retailprice": np.empty(n, "i8"), "p_size": np.empty(n, "i4"), "p_type": np.empty(n, "u1"),
          "p_brand": np.empty(n, "i4"), "p_container": np.empty(n, "u1")}
@@ -275,6 +376,10 @@ def part(sf: float, columns=None, strings: str = "view") -> pa.Table:
             out.append(strings_from_codes(a[c], P_TYPES, strings))
         elif c == "p_container":
             out.append(strings_from_codes(a[c], P_CONTAINERS, strings))
+        elif c == "p_name":
+            out.append(part_names(n, strings))
+        elif c == "p_mfgr":       # mk_part: brand = mfgr * 10 + U(1, 5)
+            out.append(strings_from_codes(a["p_brand"] // 10 - 1, [f"Manufacturer#{m}" for m in range(1, 6)], strings))
         elif c == "p_brand":
             brands = sorted(set(int(x) for x in a[c]))
             codes = np.searchsorted(np.array(brands), a[c])
@@ -298,6 +403,8 @@ def region(strings: str = "view") -> pa.Table:
 
 def tables(sf: float, strings: str = "view") -> dict:
     """All generated tables (small scale factors only)."""
-    return {"lineitem": lineitem(sf, strings=strings), "orders": orders(sf, strings=strings),
-            "customer": customer(sf, strings=strings), "supplier": supplier(sf, strings=strings),
-            "part": part(sf, strings=strings), "partsupp": partsupp(sf, strings=strings), "nation": nation(strings), "region": region(strings)}
+    return {"lineitem": lineitem(sf, strings=strings), "orders": orders(sf, ORDERS_ALL + ["o_comment"], strings=strings),
+            "customer": customer(sf, ["c_custkey", "c_nationkey", "c_acctbal", "c_mktsegment", "c_name", "c_phone", "c_address", "c_comment"], strings=strings),
+            "supplier": supplier(sf, ["s_suppkey", "s_nationkey", "s_acctbal", "s_name", "s_phone", "s_address", "s_comment"], strings=strings),
+            "part": part(sf, ["p_partkey", "p_brand", "p_type", "p_size", "p_container", "p_retailprice", "p_name", "p_mfgr"], strings=strings),
+            "partsupp": partsupp(sf, strings=strings), "nation": nation(strings), "region": region(strings)}

@@ -329,3 +329,65 @@ void tpch_gen_phone(int which, int64_t first, int64_t n, const int64_t *nationke
         stream_row_stop(&ph);
     }
 }
+
+/* p_name (mk_part: agg_str(&colors, 5, P_NAME_SD)): the 92 colour words are permuted per row with a Fisher-Yates pass over the whole
+ * list (92 draws: the stream's boundary) and the first five are joined by blanks.  out5: 5 colour indices per row.
+ * reset = 1 starts every row from the identity permutation (seedless parallel generation; what the golden results need). */
+void tpch_gen_pname(int64_t first, int64_t n, int reset, uint8_t *out5) {
+    stream_t nm;
+    stream_init(&nm, P_NAME_SD, first);
+    int perm[92];
+    for (int i = 0; i < 92; i++) perm[i] = i;
+    for (int64_t r = 0; r < n; r++) {
+        if (reset) for (int i = 0; i < 92; i++) perm[i] = i;
+        for (int i = 0; i < 92; i++) {
+            int64_t src = stream_uniform(&nm, i, 91);
+            int t = perm[src]; perm[src] = perm[i]; perm[i] = t;
+        }
+        for (int i = 0; i < 5; i++) out5[5 * r + i] = (uint8_t)perm[i];
+        stream_row_stop(&nm);
+    }
+}
+
+/* c_address / s_address (V_STR(25) = a_rnd(10, 40)): one length draw, then one draw per five characters, six bits per character
+ * from dbgen's alpha_num table.  which = 0: customer (C_ADDR_SD), 1: supplier (S_ADDR_SD).  out40: 40 bytes per row. */
+void tpch_gen_address(int which, int64_t first, int64_t n, int32_t *len, char *out40) {
+    static const char alpha_num[] = "0123456789abcdefghijklmnopqrstuvwxyz ABCDEFGHIJKLMNOPQRSTUVWXYZ,";
+    stream_t ad;
+    stream_init(&ad, which == 0 ? C_ADDR_SD : S_ADDR_SD, first);
+    for (int64_t r = 0; r < n; r++) {
+        int64_t l = stream_uniform(&ad, 10, 40), bits = 0;
+        for (int64_t i = 0; i < l; i++) {
+            if (i % 5 == 0) bits = stream_uniform(&ad, 0, 2147483647);
+            out40[40 * r + i] = alpha_num[bits & 077];
+            bits >>= 6;
+        }
+        len[r] = (int32_t)l;
+        stream_row_stop(&ad);
+    }
+}
+
+/* supplier "Better Business Bureau" marks (mk_supp): bad_press = U(1, 10000) on BBB_CMNT_SD; at most 10 in 10000 suppliers carry
+ * "Customer ... Complaints" (type draw U(0,100) on BBB_TYPE_SD below 50) or "Customer ... Recommends".  kind: 0 none, 1, 2. */
+void tpch_gen_bbb(int64_t first, int64_t n, uint8_t *kind) {
+    stream_t bp, ty;
+    stream_init(&bp, BBB_CMNT_SD, first); stream_init(&ty, BBB_TYPE_SD, first);
+    for (int64_t r = 0; r < n; r++) {
+        int64_t bad = stream_uniform(&bp, 1, 10000), t = stream_uniform(&ty, 0, 100);
+        kind[r] = bad <= 10 ? (t < 50 ? 1 : 2) : 0;
+        stream_row_stop(&bp); stream_row_stop(&ty);
+    }
+}
+
+/* comment columns (TEXT(avg) = dbg_text): dbgen cuts every comment out of one pre-generated text pool -- offset = U(0, pool - max),
+ * length = U(min, max), both on the column's stream (two draws per row).  The pool itself needs dbgen's grammar tables, which this
+ * repository does not restate: the draws are dbgen's, the pool is datagen/tpch.py's own (see text_pool()).  stream: the Seed[] index. */
+void tpch_gen_text(int stream, int64_t first, int64_t n, int64_t min, int64_t max, int64_t pool, int64_t *off, int32_t *len) {
+    stream_t tx;
+    stream_init(&tx, stream, first);
+    for (int64_t r = 0; r < n; r++) {
+        off[r] = stream_uniform(&tx, 0, pool - max);
+        len[r] = (int32_t)stream_uniform(&tx, min, max);
+        stream_row_stop(&tx);
+    }
+}

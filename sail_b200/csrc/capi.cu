@@ -40,7 +40,8 @@ using CtxLock = std::lock_guard<std::recursive_mutex>;
 }  // namespace
 
 namespace sg { void set_ctx_error(const std::string& m) { g_ctx_error = m; } }   // ops_more.cu: comm_init / exchange report through sailgpu_ctx_last_error
-namespace sg { size_t pipeline_precompile(const Json& spec, const std::vector<Schema>& inputs, uint64_t validity_mask, bool cold, bool compile, std::string* source); }
+namespace sg { void pipeline_static_check(const Json& spec, const std::vector<Schema>& inputs);
+size_t pipeline_precompile(const Json& spec, const std::vector<Schema>& inputs, uint64_t validity_mask, bool cold, bool compile, std::string* source); }
 
 namespace sg {
 struct ParquetColumnDesc { const uint8_t* chunk; uint64_t chunk_len; int32_t physical_type, type_length, max_def_level, codec; int64_t num_values; };
@@ -136,6 +137,7 @@ SAILGPU_API int32_t sailgpu_spec_validate(const char* spec_json, size_t spec_len
     std::vector<Schema> ins;
     for (int i = 0; i < n_inputs; ++i) ins.push_back(schema_from_arrow(input_schemas[i]));
     std::unique_ptr<Op> op = make_op(nullptr, spec, ins, 0);
+    pipeline_static_check(spec, ins);
     schema_to_arrow(op->out_schema, out_schema);
   });
   if (rc != 0 && err_buf && err_cap) { const size_t k = std::min(err.size(), err_cap - 1); memcpy(err_buf, err.data(), k); err_buf[k] = 0; }

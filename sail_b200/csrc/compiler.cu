@@ -474,13 +474,15 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
   static const int C_AGG_JIT[][2] = {{1, 2}, {1, 1}, {2, 1}, {2, 2}, {4, 1}, {4, 2}};
   // high-cardinality aggregation is bound by the latency of the global table: small tiles, 4 CTAs/SM (64 registers)
   static const int C_AGG_COLD[][2] = {{2, 1}, {2, 2}, {1, 2}, {1, 1}, {4, 1}, {4, 2}};
+  // the many-groups variant takes over the dictionary variant's deferred TILE list in the middle of a batch: same tile size
+  static const int C_AGG_COLD_JIT[][2] = {{1, 2}, {1, 1}, {2, 1}, {2, 2}, {4, 1}, {4, 2}};
   static const int C_STORE[][2] = {{4, 2}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
   static const int C_OTHER[][2] = {{4, 1}, {4, 2}, {2, 1}, {2, 2}, {1, 2}, {1, 1}};
   if (out.sink == SINK_AGG && out.cold_variant) hot_wanted = 0;
   // hash-join build and probe pipelines are bound by random-access latency as well (scripts/sweep_ops.sh: 5.4 vs 6.6 ms)
   const bool latency_bound = out.sink == SINK_BUILD || out.n_probes > 0;
   const bool jit_on = getenv("SAILGPU_JIT") == nullptr || atoi(getenv("SAILGPU_JIT")) != 0;
-  const int (*cands)[2] = out.sink == SINK_AGG ? (out.cold_variant ? C_AGG_COLD : (jit_on && out.n_probes == 0) ? C_AGG_JIT : C_AGG)
+  const int (*cands)[2] = out.sink == SINK_AGG ? ((jit_on && out.n_probes == 0) ? (out.cold_variant ? C_AGG_COLD_JIT : C_AGG_JIT) : out.cold_variant ? C_AGG_COLD : C_AGG)
                           : out.sink == SINK_STORE ? C_STORE : latency_bound ? C_AGG_COLD : C_OTHER;
   int best_rpt = 0, best_stages = 0, best_hot = 0;
   if (hot_wanted > 0 && force_hot >= 0) hot_wanted = force_hot;

@@ -385,6 +385,7 @@ struct PipelineOp : Op {
   void resolve_pending() {
     if (!pend.active) return;
     Trace tr(ctx, "agg.resolve");
+    uint64_t prev_def = 0;
     for (;;) {
       unsigned long long gd[3] = {0, 0, 0};      // n_groups @24, cursor @32, n_deferred @40
       SG_CUDA(cudaMemcpyAsync(gd, run.scal.n_groups(), 24, cudaMemcpyDeviceToHost, ctx->stream));
@@ -398,12 +399,19 @@ struct PipelineOp : Op {
       const double ratio = groups ? std::min(1.0, (double)groups / rows_done) : 1.0;
       const double est = ratio * rows_def * 1.25 + 1024.0;
       uint64_t cap = next_pow2((uint64_t)(2.0 * ((double)groups + est)) + 2 * MIN_CAPACITY / 2);
-      if (cap <= tab.capacity) cap = tab.capacity * 2;                 // the estimate fell short: at least double
-      alloc_table(pend.cp->agg, cap, groups);
+      // a hand-back does not always mean a full table: the dictionary variant gives up at HOT_GROUP_LIMIT groups whatever the
+      // capacity.  The table only grows when the estimate asks for it, or when a re-launch at this capacity made no progress.
+      const bool stuck = prev_def != 0 && n_def >= prev_def;
+      if (cap <= tab.capacity && stuck) cap = tab.capacity * 2;
+      prev_def = n_def;
+      if (cap > tab.capacity) alloc_table(pend.cp->agg, cap, groups);
       std::shared_ptr<CompiledPipeline> cp = pend.cp;
       if (!use_cold && groups > CARD_MANY_GROUPS && getenv("SAILGPU_NO_COLD") == nullptr) {
         auto cold = run.compiled_for(*pend.batch, true);
-        if (cold->rpt == cp->rpt && cold->agg.entry_words == cp->agg.entry_words) { cp = cold; use_cold = true; }   // same tile size: the list carries over
+        if (cold->agg.entry_words == cp->agg.entry_words) {
+          use_cold = true;                                    // later batches start on the many-groups variant
+          if (cold->rpt == cp->rpt) cp = cold;                // same tile size: this batch's deferred list carries over
+        }
       }
       BufPtr next_deferred = dev_alloc(ctx, (size_t)n_def * 4);
       launch_agg(cp, *pend.batch, pend.deferred, (int64_t)n_def, next_deferred);
@@ -511,6 +519,21 @@ size_t pipeline_precompile(const Json& spec, const std::vector<Schema>& inputs, 
   const std::string src = jit_generate(*cp, plan);
   if (source) *source = src;
   return compile ? jit_precompile_to_cache(src) : 0;
+}
+
+// Plan-time limits of a filter / projection / aggregate pipeline (sailgpu_spec_validate): the tile program is compiled against the
+// B200 geometry for a batch without validity buffers, so that the data-independent limits -- "more than 6 group keys", "group key
+// wider than 64 bytes", "does not fit in shared memory" ... -- are answered while planning, never after the first batch arrived.
+// (Validity buffers add one column buffer each; a batch whose nullable columns push a pipeline over the 20-buffer limit is still
+// reported at push time as SAILGPU_ERR_UNSUPPORTED.)  Touches no device.
+void pipeline_static_check(const Json& spec, const std::vector<Schema>& inputs) {
+  static Ctx plan_ctx;
+  std::unique_ptr<Op> op = make_op(&plan_ctx, spec, inputs, 0);
+  PipelineOp* p = dynamic_cast<PipelineOp*>(op.get());
+  if (p == nullptr) return;
+  DevBatch shape;
+  for (auto& f : inputs[0]) { DevColumn c; c.type = f.type; shape.cols.push_back(c); }
+  p->run.compiled_for(shape, false);
 }
 
 std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);

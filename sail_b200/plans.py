@@ -499,5 +499,143 @@ def q22(strings="Utf8View", codes=("24", "34", "16", "30", "33", "14", "13")) ->
     return sort(a, [("cntrycode", True)])
 
 
+def like(e, pattern: str, negated=False):
+    return {"like": e, "pattern": pattern, "negated": negated}
+
+
+def q2(strings="Utf8View", size=48, type_suffix="%TIN", region="ASIA") -> Node:
+    """test_tpch.plan.yaml [02]: the correlated min(ps_supplycost) is decorrelated into a grouped aggregate over the same
+    region's suppliers, joined back on (partkey, cost); eight output columns, four of them long strings; TopK 100 on four keys."""
+    def region_keys():
+        return filter_(scan("region", ["r_regionkey", "r_name"]), binop("=", col("r_name"), string(region, strings)), ["r_regionkey"])
+    pt = filter_(scan("part", ["p_partkey", "p_mfgr", "p_type", "p_size"]),
+                 and_(binop("=", col("p_size"), lit(size, "Int32")), like(col("p_type"), type_suffix)), ["p_partkey", "p_mfgr"])
+    j1 = hash_join(scan("partsupp", ["ps_partkey", "ps_suppkey", "ps_supplycost"]), pt, [("ps_partkey", "p_partkey")],
+                   projection=["ps_suppkey", "ps_supplycost", "p_partkey", "p_mfgr"])
+    j1 = project(j1, ["p_partkey", "p_mfgr", "ps_suppkey", "ps_supplycost"])
+    sup = scan("supplier", ["s_suppkey", "s_name", "s_address", "s_nationkey", "s_phone", "s_acctbal", "s_comment"])
+    j2 = hash_join(sup, j1, [("s_suppkey", "ps_suppkey")],
+                   projection=["s_name", "s_address", "s_nationkey", "s_phone", "s_acctbal", "s_comment", "p_partkey", "p_mfgr", "ps_supplycost"])
+    j2 = project(j2, ["p_partkey", "p_mfgr", "s_name", "s_address", "s_nationkey", "s_phone", "s_acctbal", "s_comment", "ps_supplycost"])
+    j3 = hash_join(j2, scan("nation", ["n_nationkey", "n_name", "n_regionkey"]), [("s_nationkey", "n_nationkey")],
+                   projection=["p_partkey", "p_mfgr", "s_name", "s_address", "s_phone", "s_acctbal", "s_comment", "ps_supplycost", "n_name", "n_regionkey"])
+    j4 = hash_join(region_keys(), j3, [("r_regionkey", "n_regionkey")],
+                   projection=["p_partkey", "p_mfgr", "s_name", "s_address", "s_phone", "s_acctbal", "s_comment", "ps_supplycost", "n_name"])
+    k1 = hash_join(scan("supplier", ["s_suppkey", "s_nationkey"]),
+                   project(scan("partsupp", ["ps_partkey", "ps_suppkey", "ps_supplycost"]), [(col("ps_partkey"), "k_partkey"), (col("ps_suppkey"), "k_suppkey"), (col("ps_supplycost"), "k_cost")]),
+                   [("s_suppkey", "k_suppkey")], projection=["s_nationkey", "k_partkey", "k_cost"])
+    k1 = project(k1, ["k_partkey", "k_cost", "s_nationkey"])
+    k2 = hash_join(scan("nation", ["n_nationkey", "n_regionkey"]), k1, [("n_nationkey", "s_nationkey")], projection=["n_regionkey", "k_partkey", "k_cost"])
+    k2 = project(k2, ["k_partkey", "k_cost", "n_regionkey"])
+    k3 = hash_join(region_keys(), k2, [("r_regionkey", "n_regionkey")], projection=["k_partkey", "k_cost"])
+    mn = two_phase(k3, ["k_partkey"], [("min", col("k_cost"), "min_cost", D152)])
+    mn = project(mn, ["min_cost", "k_partkey"])
+    j5 = hash_join(j4, mn, [("p_partkey", "k_partkey"), ("ps_supplycost", "min_cost")],
+                   projection=["p_partkey", "p_mfgr", "s_name", "s_address", "s_phone", "s_acctbal", "s_comment", "n_name"])
+    p = project(j5, ["s_acctbal", "s_name", "n_name", "p_partkey", "p_mfgr", "s_address", "s_phone", "s_comment"])
+    return sort(p, [("s_acctbal", False), ("n_name", True), ("s_name", True), ("p_partkey", True)], fetch=100)
+
+
+def q9(strings="Utf8View", colour="moccasin") -> Node:
+    """test_tpch.plan.yaml [09]: p_name LIKE '%colour%' on a 5-word string, five inner joins (one on two keys against a
+    duplicate-key build side), profit = price * (1 - discount) - cost * quantity grouped by nation and order year."""
+    del strings
+    pt = filter_(scan("part", ["p_partkey", "p_name"]), like(col("p_name"), f"%{colour}%"), ["p_partkey"])
+    LI = ["l_orderkey", "l_partkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount"]
+    j1 = hash_join(pt, scan("lineitem", LI), [("p_partkey", "l_partkey")], projection=LI)
+    j2 = hash_join(scan("supplier", ["s_suppkey", "s_nationkey"]), j1, [("s_suppkey", "l_suppkey")], projection=["s_nationkey"] + LI)
+    j2 = project(j2, LI + ["s_nationkey"])
+    j3 = hash_join(j2, scan("partsupp", ["ps_partkey", "ps_suppkey", "ps_supplycost"]), [("l_suppkey", "ps_suppkey"), ("l_partkey", "ps_partkey")],
+                   projection=["l_orderkey", "l_quantity", "l_extendedprice", "l_discount", "s_nationkey", "ps_supplycost"])
+    j4 = hash_join(j3, scan("orders", ["o_orderkey", "o_orderdate"]), [("l_orderkey", "o_orderkey")],
+                   projection=["l_quantity", "l_extendedprice", "l_discount", "s_nationkey", "ps_supplycost", "o_orderdate"])
+    j5 = hash_join(j4, scan("nation", ["n_nationkey", "n_name"]), [("s_nationkey", "n_nationkey")])
+    amount = binop("-", DISC_PRICE, binop("*", col("ps_supplycost"), col("l_quantity")))          # Decimal128(33,4)
+    p = project(j5, [(col("n_name"), "nation"), ({"fn": "date_part", "part": "year", "args": [col("o_orderdate")]}, "o_year"), (amount, "amount")])
+    a = two_phase(p, ["nation", "o_year"], [("sum", col("amount"), "sum_profit", "Decimal128(33,4)")])
+    return sort(a, [("nation", True), ("o_year", False)])
+
+
+def q10(strings="Utf8View", first="1993-07-01", last="1993-10-01") -> Node:
+    """test_tpch.plan.yaml [10]: three inner joins, then an aggregate on SEVEN group keys (four of them strings, three longer
+    than a view's inline 12 bytes), TopK 20 on the sum."""
+    ords = filter_(scan("orders", ["o_orderkey", "o_custkey", "o_orderdate"]),
+                   and_(binop(">=", col("o_orderdate"), date(first)), binop("<", col("o_orderdate"), date(last))), ["o_orderkey", "o_custkey"])
+    C = ["c_custkey", "c_name", "c_address", "c_nationkey", "c_phone", "c_acctbal", "c_comment"]
+    j1 = hash_join(ords, scan("customer", C), [("o_custkey", "c_custkey")], projection=["o_orderkey"] + C)
+    j1 = project(j1, C + ["o_orderkey"])
+    li = filter_(scan("lineitem", ["l_orderkey", "l_extendedprice", "l_discount", "l_returnflag"]),
+                 binop("=", col("l_returnflag"), string("R", strings)), ["l_orderkey", "l_extendedprice", "l_discount"])
+    j2 = hash_join(j1, li, [("o_orderkey", "l_orderkey")], projection=C + ["l_extendedprice", "l_discount"])
+    j3 = hash_join(scan("nation", ["n_nationkey", "n_name"]), j2, [("n_nationkey", "c_nationkey")],
+                   projection=["n_name", "c_custkey", "c_name", "c_address", "c_phone", "c_acctbal", "c_comment", "l_extendedprice", "l_discount"])
+    j3 = project(j3, ["c_custkey", "c_name", "c_address", "c_phone", "c_acctbal", "c_comment", "l_extendedprice", "l_discount", "n_name"])
+    a = two_phase(j3, ["c_custkey", "c_name", "c_acctbal", "c_phone", "n_name", "c_address", "c_comment"],
+                  [("sum", DISC_PRICE, "revenue", "Decimal128(32,4)")])
+    p = project(a, ["c_custkey", "c_name", "revenue", "c_acctbal", "n_name", "c_address", "c_phone", "c_comment"])
+    return sort(p, [("revenue", False)], fetch=20)
+
+
+def q13(strings="Utf8View", w1="express", w2="requests") -> Node:
+    """test_tpch.plan.yaml [13]: LEFT join (customers without orders keep a NULL order key), count(o_orderkey) skips the NULLs,
+    then a second aggregate over the counts; the filter is NOT LIKE on a long comment column."""
+    del strings
+    ords = filter_(scan("orders", ["o_orderkey", "o_custkey", "o_comment"]), like(col("o_comment"), f"%{w1}%{w2}%", True), ["o_orderkey", "o_custkey"])
+    j = hash_join(scan("customer", ["c_custkey"]), ords, [("c_custkey", "o_custkey")], join_type="left", projection=["c_custkey", "o_orderkey"])
+    a1 = two_phase(j, ["c_custkey"], [("count", col("o_orderkey"), "c_count", "Int64")])
+    a2 = two_phase(project(a1, ["c_count"]), ["c_count"], [("count", None, "custdist", None)])
+    return sort(a2, [("custdist", False), ("c_count", False)])
+
+
+def q15(strings="Utf8View", first="1996-08-01", last="1996-11-01") -> Node:
+    """test_tpch.plan.yaml [15].1: the revenue view is planned twice -- once under max() (a keyless aggregate over a grouped
+    one), once joined to supplier -- and the two meet in a join on the Decimal128(38,4) revenue itself."""
+    del strings
+
+    def revenue():
+        li = filter_(scan("lineitem", ["l_suppkey", "l_extendedprice", "l_discount", "l_shipdate"]),
+                     and_(binop(">=", col("l_shipdate"), date(first)), binop("<", col("l_shipdate"), date(last))), ["l_suppkey", "l_extendedprice", "l_discount"])
+        return two_phase(li, ["l_suppkey"], [("sum", DISC_PRICE, "total_revenue", "Decimal128(32,4)")])
+    mx = two_phase(project(revenue(), ["total_revenue"]), [], [("max", col("total_revenue"), "max_revenue", "Decimal128(38,4)")])
+    sup = scan("supplier", ["s_suppkey", "s_name", "s_address", "s_phone"])
+    j1 = hash_join(sup, project(revenue(), [(col("l_suppkey"), "supplier_no"), "total_revenue"]), [("s_suppkey", "supplier_no")],
+                   projection=["s_suppkey", "s_name", "s_address", "s_phone", "total_revenue"])
+    j2 = hash_join(mx, j1, [("max_revenue", "total_revenue")], projection=["s_suppkey", "s_name", "s_address", "s_phone", "total_revenue"])
+    return sort(j2, [("s_suppkey", True)])
+
+
+def q16(strings="Utf8View", brand="Brand#14", type_prefix="SMALL PLATED%", sizes=(14, 6, 5, 31, 49, 15, 41, 47)) -> Node:
+    """test_tpch.plan.yaml [16]: NOT IN (subquery) as LeftAnti, count(DISTINCT) as two stacked aggregates (the inner one has
+    group keys only), != / NOT LIKE / IN-list filter."""
+    pt = filter_(scan("part", ["p_partkey", "p_brand", "p_type", "p_size"]),
+                 and_(binop("!=", col("p_brand"), string(brand, strings)), like(col("p_type"), type_prefix, True),
+                      {"in": col("p_size"), "set": [lit(v, "Int32") for v in sizes], "negated": False}))
+    j1 = hash_join(scan("partsupp", ["ps_partkey", "ps_suppkey"]), pt, [("ps_partkey", "p_partkey")], projection=["ps_suppkey", "p_brand", "p_type", "p_size"])
+    bad = filter_(scan("supplier", ["s_suppkey", "s_comment"]), like(col("s_comment"), "%Customer%Complaints%"), ["s_suppkey"])
+    anti = hash_join(j1, bad, [("ps_suppkey", "s_suppkey")], join_type="left_anti")
+    d = two_phase(anti, ["p_brand", "p_type", "p_size", (col("ps_suppkey"), "alias1")], [])
+    c = two_phase(d, ["p_brand", "p_type", "p_size"], [("count", col("alias1"), "supplier_cnt", "Int64")])
+    return sort(c, [("supplier_cnt", False), ("p_brand", True), ("p_type", True), ("p_size", True)])
+
+
+def q20(strings="Utf8View", colour="blanched", nation="KENYA", first="1993-01-01", last="1994-01-01") -> Node:
+    """test_tpch.plan.yaml [20]: IN (subquery) chains become RightSemi / LeftSemi joins; the correlated 0.5 * sum(l_quantity)
+    is a grouped aggregate joined on two keys with a residual `availqty > half` filter in Decimal128(23,3)."""
+    nat = filter_(scan("nation", ["n_nationkey", "n_name"]), binop("=", col("n_name"), string(nation, strings)), ["n_nationkey"])
+    j1 = hash_join(nat, scan("supplier", ["s_suppkey", "s_name", "s_address", "s_nationkey"]), [("n_nationkey", "s_nationkey")],
+                   projection=["s_suppkey", "s_name", "s_address"])
+    pt = filter_(scan("part", ["p_partkey", "p_name"]), like(col("p_name"), f"{colour}%"), ["p_partkey"])
+    rs = hash_join(pt, scan("partsupp", ["ps_partkey", "ps_suppkey", "ps_availqty"]), [("p_partkey", "ps_partkey")], join_type="right_semi")
+    li = filter_(scan("lineitem", ["l_partkey", "l_suppkey", "l_quantity", "l_shipdate"]),
+                 and_(binop(">=", col("l_shipdate"), date(first)), binop("<", col("l_shipdate"), date(last))), ["l_partkey", "l_suppkey", "l_quantity"])
+    ag = two_phase(li, ["l_partkey", "l_suppkey"], [("sum", col("l_quantity"), "sum_qty", D152)])
+    half = {"cast": binop("*", dec(5, 1, 1), col("sum_qty")), "to": "Decimal128(23,3)"}
+    thr = project(ag, [(half, "half_qty"), "l_partkey", "l_suppkey"])
+    j2 = hash_join(rs, thr, [("ps_partkey", "l_partkey"), ("ps_suppkey", "l_suppkey")],
+                   filter=binop(">", {"cast": col("ps_availqty"), "to": "Decimal128(23,3)"}, col("half_qty")), projection=["ps_suppkey"])
+    semi = hash_join(j1, j2, [("s_suppkey", "ps_suppkey")], join_type="left_semi", projection=["s_name", "s_address"])
+    return sort(semi, [("s_name", True)])
+
+
 TPCH = {"q1": q1, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q8": q8, "q11": q11, "q12": q12, "q14": q14, "q17": q17, "q18": q18, "q19": q19,
-        "q21": q21, "q22": q22}
+        "q21": q21, "q22": q22, "q2": q2, "q9": q9, "q10": q10, "q13": q13, "q15": q15, "q16": q16, "q20": q20}

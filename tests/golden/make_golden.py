@@ -17,7 +17,10 @@ def main():
     out = {}
     for block in text.split("\n---\n")[1:]:
         m = re.search(r'name: "test_derived_tpch_query_result\[(\d+)\](\.\d+)?"', block)
-        if not m or m.group(2):
+        if not m:
+            continue
+        # Q15 is three statements (create view / select / drop view): the select is snapshot [15].1
+        if (m.group(2) or "") != (".1" if int(m.group(1)) == 15 else ""):
             continue
         lines = [ln.strip().strip("'") for ln in block.splitlines() if ln.strip().strip("'").startswith("| ")]
         rows = [[c.strip() for c in ln.strip("|").split("|")] for ln in lines]

@@ -240,7 +240,7 @@ def test_row_round_robin_streaming(n_parts, in_part, n_in):
     op.close()
 
 
-@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q8", "q11", "q12", "q14", "q17", "q18", "q19", "q21", "q22"])
+@pytest.mark.parametrize("q", ["q1", "q2", "q3", "q4", "q5", "q6", "q7", "q8", "q9", "q11", "q12", "q14", "q15", "q16", "q17", "q18", "q19", "q20", "q21", "q22"])
 def test_tpch_golden_on_gpu(q, golden):
     """whole plans through the C ABI on dbgen SF0.001 == the reference's own snapshot"""
     from datagen import tpch
@@ -250,7 +250,7 @@ def test_tpch_golden_on_gpu(q, golden):
     assert render.rows(got) == golden[q]["rows"]
 
 
-@pytest.mark.parametrize("q", ["q3", "q4", "q5", "q7", "q8", "q11", "q12", "q14", "q17", "q19", "q21", "q22"])
+@pytest.mark.parametrize("q", ["q2", "q3", "q4", "q5", "q7", "q8", "q9", "q11", "q12", "q13", "q14", "q15", "q16", "q17", "q19", "q20", "q21", "q22"])
 def test_tpch_sf01_vs_oracle(q):
     from datagen import tpch
     tables = tpch.tables(0.1)

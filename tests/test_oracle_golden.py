@@ -12,7 +12,7 @@ def run_oracle(spec, *tables):
     return ops.batch_to_arrow(out)
 
 
-@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q6", "q7", "q8", "q11", "q12", "q14", "q17", "q18", "q19", "q21", "q22"])
+@pytest.mark.parametrize("q", ["q1", "q2", "q3", "q4", "q5", "q6", "q7", "q8", "q9", "q10", "q11", "q12", "q14", "q15", "q16", "q17", "q18", "q19", "q20", "q21", "q22"])
 @pytest.mark.parametrize("strings", ["view", "utf8"])
 def test_tpch_golden(q, strings, golden):
     from datagen import tpch
@@ -22,7 +22,14 @@ def test_tpch_golden(q, strings, golden):
     got = plans.execute(plan, tables, run_oracle)
     want = golden[q]
     assert got.schema.names == want["columns"]
-    assert render.rows(got) == want["rows"]
+    assert drop_unpinned(q, render.rows(got)) == drop_unpinned(q, want["rows"])
+
+
+def drop_unpinned(q, rows):
+    """Q10 returns c_comment: dbgen cuts comments out of a text pool built from a grammar this repository does not restate
+    (datagen/tpch.py::text_pool), so that ONE column is left out of the comparison (the snapshot also trims its trailing blanks); every other column of every query is exact.
+    (Q13 filters on comment text and is therefore not pinned at all: tests/test_gpu_relational.py checks it against the oracle.)"""
+    return [[c.strip() for c in r[:-1]] for r in rows] if q == "q10" else rows      # (the snapshot table also trims an address that starts with a blank)
 
 
 def test_c_pipelines_match_golden_and_python_oracle(golden):
