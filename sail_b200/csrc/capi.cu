@@ -40,7 +40,8 @@ using CtxLock = std::lock_guard<std::recursive_mutex>;
 }  // namespace
 
 namespace sg { void set_ctx_error(const std::string& m) { g_ctx_error = m; } }   // ops_more.cu: comm_init / exchange report through sailgpu_ctx_last_error
-namespace sg { void pipeline_static_check(const Json& spec, const std::vector<Schema>& inputs);
+namespace sg { void resolve_exchange_timing(Ctx* ctx);
+void pipeline_static_check(const Json& spec, const std::vector<Schema>& inputs);
 size_t pipeline_precompile(const Json& spec, const std::vector<Schema>& inputs, uint64_t validity_mask, bool cold, bool compile, std::string* source); }
 
 namespace sg {
@@ -264,6 +265,7 @@ SAILGPU_API int64_t sailgpu_op_metrics(sailgpu_op* h, char* json_buf, size_t cap
   cudaSetDevice(h->owner->ctx.device);
   const Metrics& m = h->op->m;
   char tmp[2048];
+  sg::resolve_exchange_timing(&h->owner->ctx);
   int n = snprintf(tmp, sizeof(tmp),
                    "{\"output_rows\":%llu,\"output_batches\":%llu,\"input_rows\":%llu,\"input_batches\":%llu,"
                    "\"elapsed_compute\":%llu,\"build_input_rows\":%llu,\"build_input_batches\":%llu,\"build_time\":%llu,"

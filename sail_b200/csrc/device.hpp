@@ -45,6 +45,7 @@ struct Ctx {
   std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};
   // all-to-all exchanges of this context: bytes put on / taken off NVLink and device time of the grouped send/recv
   std::atomic<uint64_t> exch_sent_bytes{0}, exch_recv_bytes{0}, exch_ns{0}, exch_calls{0};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> exch_events;      // grouped send/recv of finished exchanges, not yet read (resolve_exchange_timing)
   // small device->host exports (operator results of a few rows) bounce through one pinned block so that all their
   // copies are asynchronous and the export costs one synchronisation instead of one per buffer
   struct D2HItem { void* host; size_t off, bytes; };

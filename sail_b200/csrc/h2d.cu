@@ -14,8 +14,17 @@ namespace sg {
 
 namespace {
 
-constexpr int64_t PIECE_ROWS = 256 * 1024;
-constexpr size_t SLOT_BYTES = (size_t)PIECE_ROWS * 16;     // 4 MiB: one piece of the widest column
+constexpr int64_t MAX_PIECE_ROWS = 256 * 1024;
+constexpr size_t SLOT_BYTES = (size_t)MAX_PIECE_ROWS * 16;     // 4 MiB: one piece of the widest column
+// rows per piece: SAILGPU_PACK_PIECE_ROWS (a multiple of 1024, at most 256 Ki) -- a piece is scanned and then packed, so it should
+// still be in the packing core's L2 when the second loop reads it
+static int64_t piece_rows() {      // read per batch: A/B measurements in one process
+  const char* e = getenv("SAILGPU_PACK_PIECE_ROWS");
+  const int64_t r = e && *e ? atoll(e) : 64 * 1024;
+  return std::max<int64_t>(1024, std::min<int64_t>(MAX_PIECE_ROWS, r / 1024 * 1024));
+}
+// SAILGPU_PACK_DRY=1 (measurements only): pieces are packed but neither copied nor expanded -- the host side of the ingest alone
+static bool pack_dry() { const char* e = getenv("SAILGPU_PACK_DRY"); return e && *e && atoi(e) != 0; }
 
 enum Enc : int { ENC_RAW = 0, ENC_INT = 1, ENC_VIEW = 2 };
 
@@ -121,6 +130,7 @@ struct PackPool {
     Slot& s = w.slots[(size_t)(w.turn++ & 1)];
     if (s.used && cudaEventSynchronize(s.free_ev) != cudaSuccess) throw std::runtime_error("staging slot event");
     const Packed pk = pack_piece(it, s.host, narrow);
+    if (pack_dry()) { ctx->h2d_bytes += pk.bytes; return; }
     cudaError_t e;
     if (pk.enc == ENC_RAW) {
       e = cudaMemcpyAsync(it.dst, s.host, pk.bytes, cudaMemcpyHostToDevice, w.stream);
@@ -221,7 +231,7 @@ void destroy_pack_pool(Ctx* ctx) {
 
 void HostStager::add(HostCol kind, void* dst, const void* src, int64_t n, int width) {
   if (n <= 0) return;
-  const int64_t piece = kind == HostCol::Raw ? (int64_t)SLOT_BYTES / std::max(1, width) : PIECE_ROWS;
+  const int64_t piece = kind == HostCol::Raw ? (int64_t)SLOT_BYTES / std::max(1, width) : piece_rows();
   for (int64_t o = 0; o < n; o += piece) {
     const int64_t k = std::min(piece, n - o);
     items.push_back({kind, static_cast<uint8_t*>(dst) + o * width, static_cast<const uint8_t*>(src) + o * width, k, width});

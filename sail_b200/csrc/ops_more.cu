@@ -1225,8 +1225,7 @@ std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::v
 //                  all-gather of the row counts, so every rank takes the same one; a later "gather" exchange of the same
 //                  chain sees that the rows already sit on the root and does not communicate.
 // ================================================================================================
-BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts, std::vector<int64_t>* source_offsets = nullptr);
-int64_t exchange_max_rows(Ctx* ctx, int64_t mine);
+BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts, std::vector<int64_t>* source_offsets = nullptr, int64_t abort_above_rows = -1);
 std::unique_ptr<Op> make_repartition_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs);
 
 struct ExchangeOp : Op {
@@ -1271,16 +1270,21 @@ struct ExchangeOp : Op {
     parts_in.clear();
     const int W = ctx->world;
     if (W == 1) { result = all; done = true; if (keep_runs) run_batches.push_back(result); return; }
-    std::string how = mode;
-    if (how == "auto") how = exchange_max_rows(ctx, all->rows) <= small_rows ? "gather" : "hash";
-    if (how == "gather" && mode == "gather" && on_root_hint && *on_root_hint) {       // an "auto" exchange of this chain already coalesced on the root
+    std::vector<int64_t> src_off;
+    if (mode == "gather" && on_root_hint && *on_root_hint) {       // an "auto" exchange of this chain already coalesced on the root
       result = all; done = true; if (keep_runs) run_batches.push_back(result); return;
     }
     std::vector<BatchPtr> parts((size_t)W);
-    if (how == "gather") {
+    bool sent = false;
+    if (mode == "gather" || mode == "auto") {
+      // "auto" tries the coalescing layout first: the all-gathered count table of that attempt tells every rank whether some
+      // rank holds more than small_rows rows -- if so nothing was sent and the rows are hash-partitioned instead
       for (int p = 0; p < W; ++p) parts[(size_t)p] = p == root ? all : empty_batch(ctx, sch);
-      if (on_root_hint) *on_root_hint = mode == "auto";
-    } else {
+      result = exchange_batches(ctx, sch, parts, keep_runs ? &src_off : nullptr, mode == "auto" ? small_rows : -1);
+      sent = result != nullptr;
+      if (on_root_hint) *on_root_hint = sent && mode == "auto";
+    }
+    if (!sent) {
       if (on_root_hint) *on_root_hint = false;
       Json spec; spec.kind = Json::Obj;
       Json opk; opk.kind = Json::Str; opk.s = "repartition";
@@ -1296,9 +1300,8 @@ struct ExchangeOp : Op {
         parts[(size_t)p] = segs.empty() ? empty_batch(ctx, sch) : segs.size() == 1 ? segs[0] : concat_batches(ctx, sch, segs);
       }
       m.kernel_launches += rp->m.kernel_launches;
+      result = exchange_batches(ctx, sch, parts, keep_runs ? &src_off : nullptr);
     }
-    std::vector<int64_t> src_off;
-    result = exchange_batches(ctx, sch, parts, keep_runs ? &src_off : nullptr);
     if (keep_runs) split_runs(src_off);
     done = true;
     m.elapsed_compute_ns += now_ns() - t0;
@@ -1450,229 +1453,225 @@ static cudaError_t launch_multi_copy(Ctx* ctx, const std::vector<CopySeg>& segs,
   if (e != cudaSuccess) return e;
   return launch_multi_copy_raw(static_cast<const CopySeg*>((*keep)->ptr), (int)segs.size(), ctx->stream);
 }
-// max over ranks of a row count (one 8-byte all-gather on the context's communicator)
-int64_t exchange_max_rows(Ctx* ctx, int64_t mine) {
-  if (ctx->world == 1) return mine;
-  SG_CHECK(ctx->nccl_comm != nullptr, SAILGPU_ERR_STATE, "sailgpu_ctx_comm_init has not been called");
-  BufPtr d = dev_alloc(ctx, 8), all = dev_alloc(ctx, 8 * (size_t)ctx->world);
-  SG_CUDA(cudaMemcpyAsync(d->ptr, &mine, 8, cudaMemcpyHostToDevice, ctx->stream));
-  NCCL_CALL(g_nccl.AllGather(d->ptr, all->ptr, 1, NCCL_INT64, ctx->nccl_comm, ctx->stream));
-  std::vector<int64_t> h((size_t)ctx->world);
-  SG_CUDA(cudaMemcpyAsync(h.data(), all->ptr, 8 * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
-  SG_CUDA(cudaStreamSynchronize(ctx->stream));
-  int64_t mx = 0; for (auto v : h) mx = std::max(mx, v);
-  return mx;
-}
 // all-to-all of world_size device batches over the context's communicator: parts[p] goes to rank p; returns everything
-// that was sent to this rank (rows of rank 0 first, then rank 1, ...)
-BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts, std::vector<int64_t>* source_offsets) {
+// that was sent to this rank (rows of rank 0 first, then rank 1, ...).
+//
+// ONE host synchronisation per exchange: everything the ranks must agree on -- rows, string-heap bytes and "carries a validity
+// buffer" per (source, destination, column) -- is assembled ON THE DEVICE (the heap sizes come out of the length scans without
+// being read back), all-gathered, and read back once.  The layout of every send and receive follows from that table on every
+// rank; null counts of the result are not read back (validity travels only for columns where some source has a bitmap, and the
+// result then reports null_count = -1, "unknown").
+// abort_above_rows >= 0: if any rank contributes more rows than that, nothing is sent and nullptr is returned on EVERY rank
+// (the decision is taken on the all-gathered table) -- the "auto" exchange tries the coalescing layout first this way.
+BatchPtr exchange_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts, std::vector<int64_t>* source_offsets, int64_t abort_above_rows) {
   const int n = (int)parts.size();
   SG_CHECK(n == ctx->world, SAILGPU_ERR_INVALID, "exchange needs one batch per rank");
   if (n == 1) { if (source_offsets) *source_offsets = {0, parts[0]->rows}; return parts[0]; }
-  BatchPtr out;
-  {
-    SG_CHECK(ctx->nccl_comm != nullptr, SAILGPU_ERR_STATE, "sailgpu_ctx_comm_init has not been called");
-    const int W = n, me = ctx->rank;
-    // 1. counts: rows (and string heap bytes per string column) each rank sends to each rank
-    const size_t ncols = schema.size();
-    const size_t rec = 1 + ncols;                       // rows, heap bytes per column
-    std::vector<int64_t> mine((size_t)W * rec, 0);
-    // strings travel as Arrow views + compact heap: convert through the export path per destination
-    struct SendCol { BufPtr data, validity_bytes, heap; int64_t heap_bytes = 0; };
-    std::vector<std::vector<SendCol>> sc((size_t)W, std::vector<SendCol>(ncols));
-    (void)0;
-    // pass 1: launch the length scans of every (destination, string column) without synchronising
-    struct Pending { int p; size_t ci; BufPtr offs, scratch; int64_t nblocks; };
-    std::vector<Pending> pend;
-    BufPtr totals = dev_alloc_zero(ctx, (size_t)W * ncols * 8 + 8);
-    for (int p = 0; p < W; ++p) {
-      mine[(size_t)p * rec] = parts[(size_t)p]->rows;
-      for (size_t ci = 0; ci < ncols; ++ci) {
-        const DevColumn& col = parts[(size_t)p]->cols[ci];
-        SendCol& sd = sc[(size_t)p][ci];
-        const int64_t k = col.length;
-        if (schema[ci].type.is_string() && k > 0) {
-          BufPtr lens = dev_alloc(ctx, (size_t)k * 4), offs = dev_alloc(ctx, (size_t)k * 8), scratch = dev_alloc(ctx, 1026 * 8);
-          SG_CUDA(launch_view_lengths(col.data->ptr, k, static_cast<uint32_t*>(lens->ptr), 0, ctx->stream));
-          SG_CUDA(launch_exclusive_scan_u32(static_cast<uint32_t*>(lens->ptr), k, static_cast<uint64_t*>(offs->ptr), static_cast<uint64_t*>(scratch->ptr), ctx->stream));
-          const int64_t nblocks = std::min<int64_t>(1024, (k + 4095) / 4096);
-          SG_CUDA(cudaMemcpyAsync(static_cast<uint64_t*>(totals->ptr) + (size_t)p * ncols + ci, static_cast<uint64_t*>(scratch->ptr) + nblocks, 8,
-                                  cudaMemcpyDeviceToDevice, ctx->stream));
-          pend.push_back({p, ci, offs, scratch, nblocks});
-        } else if (schema[ci].type.id == TypeId::Bool && k > 0) {
-          sd.data = dev_alloc(ctx, (size_t)k);     // booleans travel as bytes
-          SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.data->ptr), static_cast<uint8_t*>(sd.data->ptr), k, 0, ctx->stream));
-        } else sd.data = col.data;
-        if (k > 0) {                              // validity always travels as bytes (1 = valid)
-          sd.validity_bytes = dev_alloc(ctx, (size_t)k);
-          if (col.validity) SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.validity->ptr), static_cast<uint8_t*>(sd.validity_bytes->ptr), k, 0, ctx->stream));
-          else SG_CUDA(cudaMemsetAsync(sd.validity_bytes->ptr, 1, (size_t)k, ctx->stream));
-        }
+  SG_CHECK(ctx->nccl_comm != nullptr, SAILGPU_ERR_STATE, "sailgpu_ctx_comm_init has not been called");
+  const int W = n, me = ctx->rank;
+  const size_t ncols = schema.size();
+  const size_t rec = 1 + 2 * ncols;                   // rows | heap bytes per column | has-validity per column
+  std::vector<int64_t> mine((size_t)W * rec, 0);
+  // 1. length scans of every (destination, string column): the totals stay on the device
+  struct Pending { int p; size_t ci; BufPtr offs, scratch; int64_t nblocks; };
+  std::vector<Pending> pend;
+  for (int p = 0; p < W; ++p) {
+    mine[(size_t)p * rec] = parts[(size_t)p]->rows;
+    for (size_t ci = 0; ci < ncols; ++ci) {
+      const DevColumn& col = parts[(size_t)p]->cols[ci];
+      const int64_t k = col.length;
+      mine[(size_t)p * rec + 1 + ncols + ci] = (k > 0 && col.validity) ? 1 : 0;
+      if (schema[ci].type.is_string() && k > 0) {
+        BufPtr lens = dev_alloc(ctx, (size_t)k * 4), offs = dev_alloc(ctx, (size_t)k * 8), scratch = dev_alloc(ctx, 1026 * 8);
+        SG_CUDA(launch_view_lengths(col.data->ptr, k, static_cast<uint32_t*>(lens->ptr), 0, ctx->stream));
+        SG_CUDA(launch_exclusive_scan_u32(static_cast<uint32_t*>(lens->ptr), k, static_cast<uint64_t*>(offs->ptr), static_cast<uint64_t*>(scratch->ptr), ctx->stream));
+        pend.push_back({p, ci, offs, scratch, std::min<int64_t>(1024, (k + 4095) / 4096)});
       }
     }
-    // one synchronisation for all heap sizes, then pass 2: compact heaps + Arrow-conformant views
-    std::vector<uint64_t> htot((size_t)W * ncols, 0);
-    if (!pend.empty()) {
-      SG_CUDA(cudaMemcpyAsync(htot.data(), totals->ptr, htot.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      SG_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
-    for (auto& q : pend) {
-      const DevColumn& col = parts[(size_t)q.p]->cols[q.ci];
-      SendCol& sd = sc[(size_t)q.p][q.ci];
+  }
+  BufPtr dmine = dev_alloc(ctx, mine.size() * 8), dall = dev_alloc(ctx, mine.size() * 8 * (size_t)W);
+  SG_CUDA(cudaMemcpyAsync(dmine->ptr, mine.data(), mine.size() * 8, cudaMemcpyHostToDevice, ctx->stream));     // pageable source: staged before return
+  for (auto& q : pend)
+    SG_CUDA(cudaMemcpyAsync(static_cast<int64_t*>(dmine->ptr) + (size_t)q.p * rec + 1 + q.ci, static_cast<uint64_t*>(q.scratch->ptr) + q.nblocks, 8,
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+  NCCL_CALL(g_nccl.AllGather(dmine->ptr, dall->ptr, mine.size(), NCCL_INT64, ctx->nccl_comm, ctx->stream));
+  std::vector<int64_t> all(mine.size() * (size_t)W);
+  SG_CUDA(cudaMemcpyAsync(all.data(), dall->ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(cudaStreamSynchronize(ctx->stream));                                                                  // the one synchronisation
+  auto cnt = [&](int src, int dst, size_t field) { return all[((size_t)src * W + dst) * rec + field]; };
+  if (abort_above_rows >= 0) {
+    int64_t mx = 0;
+    for (int s = 0; s < W; ++s) { int64_t r = 0; for (int d = 0; d < W; ++d) r += cnt(s, d, 0); mx = std::max(mx, r); }
+    if (mx > abort_above_rows) return nullptr;
+  }
+  // validity of column ci travels to `dst` iff some source has a bitmap there
+  auto vneed = [&](int dst, size_t ci) { for (int s = 0; s < W; ++s) if (cnt(s, dst, 1 + ncols + ci)) return true; return false; };
+  // 2. what this rank sends: compact string heaps + Arrow-conformant views, validity as bytes where the destination expects it
+  struct SendCol { BufPtr data, validity_bytes, heap; int64_t heap_bytes = 0; };
+  std::vector<std::vector<SendCol>> sc((size_t)W, std::vector<SendCol>(ncols));
+  for (int p = 0; p < W; ++p)
+    for (size_t ci = 0; ci < ncols; ++ci) {
+      const DevColumn& col = parts[(size_t)p]->cols[ci];
+      SendCol& sd = sc[(size_t)p][ci];
       const int64_t k = col.length;
-      sd.heap_bytes = (int64_t)htot[(size_t)q.p * ncols + q.ci];
-      sd.heap = dev_alloc(ctx, (size_t)sd.heap_bytes);
-      sd.data = dev_alloc(ctx, (size_t)k * 16);
-      SG_CUDA(cudaMemcpyAsync(sd.data->ptr, col.data->ptr, (size_t)k * 16, cudaMemcpyDeviceToDevice, ctx->stream));
-      SG_CUDA(launch_views_to_arrow(sd.data->ptr, k, static_cast<uint64_t*>(q.offs->ptr), static_cast<uint8_t*>(sd.heap->ptr), ctx->stream));
-      mine[(size_t)q.p * rec + 1 + q.ci] = sd.heap_bytes;
+      if (k == 0) continue;
+      if (schema[ci].type.id == TypeId::Bool) {
+        sd.data = dev_alloc(ctx, (size_t)k);     // booleans travel as bytes
+        SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.data->ptr), static_cast<uint8_t*>(sd.data->ptr), k, 0, ctx->stream));
+      } else if (!schema[ci].type.is_string()) sd.data = col.data;
+      if (vneed(p, ci)) {
+        sd.validity_bytes = dev_alloc(ctx, (size_t)k);
+        if (col.validity) SG_CUDA(launch_unpack_bits(static_cast<const uint8_t*>(col.validity->ptr), static_cast<uint8_t*>(sd.validity_bytes->ptr), k, 0, ctx->stream));
+        else SG_CUDA(cudaMemsetAsync(sd.validity_bytes->ptr, 1, (size_t)k, ctx->stream));
+      }
     }
-    BufPtr dmine = dev_alloc(ctx, mine.size() * 8), dall = dev_alloc(ctx, mine.size() * 8 * (size_t)W);
-    SG_CUDA(cudaMemcpyAsync(dmine->ptr, mine.data(), mine.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    NCCL_CALL(g_nccl.AllGather(dmine->ptr, dall->ptr, mine.size(), NCCL_INT64, ctx->nccl_comm, ctx->stream));
-    std::vector<int64_t> all(mine.size() * (size_t)W);
-    SG_CUDA(cudaMemcpyAsync(all.data(), dall->ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    SG_CUDA(cudaStreamSynchronize(ctx->stream));
-    auto cnt = [&](int src, int dst, size_t field) { return all[((size_t)src * W + dst) * rec + field]; };
-    // 2. receive layout: rows from rank 0, then rank 1, ...
-    std::vector<int64_t> row_off((size_t)W + 1, 0);
-    for (int s = 0; s < W; ++s) row_off[(size_t)s + 1] = row_off[(size_t)s] + cnt(s, me, 0);
-    const int64_t total_rows = row_off[(size_t)W];
-    if (source_offsets) *source_offsets = row_off;
-    out = std::make_shared<DevBatch>();
-    out->rows = total_rows;
-    std::vector<BufPtr> vbytes(ncols), bbytes(ncols), datas(ncols), heaps(ncols);
-    std::vector<std::vector<int64_t>> heap_off(ncols, std::vector<int64_t>((size_t)W + 1, 0));
-    auto width_of = [&](size_t ci) { const DataType& t = schema[ci].type; return t.is_string() ? 16 : t.id == TypeId::Bool ? 1 : t.arrow_width(); };
+  for (auto& q : pend) {
+    const DevColumn& col = parts[(size_t)q.p]->cols[q.ci];
+    SendCol& sd = sc[(size_t)q.p][q.ci];
+    const int64_t k = col.length;
+    sd.heap_bytes = cnt(me, q.p, 1 + q.ci);
+    sd.heap = dev_alloc(ctx, (size_t)sd.heap_bytes);
+    sd.data = dev_alloc(ctx, (size_t)k * 16);
+    SG_CUDA(cudaMemcpyAsync(sd.data->ptr, col.data->ptr, (size_t)k * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    SG_CUDA(launch_views_to_arrow(sd.data->ptr, k, static_cast<uint64_t*>(q.offs->ptr), static_cast<uint8_t*>(sd.heap->ptr), ctx->stream));
+  }
+  // 3. receive layout: rows from rank 0, then rank 1, ...
+  std::vector<int64_t> row_off((size_t)W + 1, 0);
+  for (int s = 0; s < W; ++s) row_off[(size_t)s + 1] = row_off[(size_t)s] + cnt(s, me, 0);
+  const int64_t total_rows = row_off[(size_t)W];
+  if (source_offsets) *source_offsets = row_off;
+  BatchPtr out = std::make_shared<DevBatch>();
+  out->rows = total_rows;
+  std::vector<BufPtr> vbytes(ncols), bbytes(ncols), datas(ncols), heaps(ncols);
+  std::vector<char> vrecv(ncols, 0);
+  std::vector<std::vector<int64_t>> heap_off(ncols, std::vector<int64_t>((size_t)W + 1, 0));
+  auto width_of = [&](size_t ci) { const DataType& t = schema[ci].type; return t.is_string() ? 16 : t.id == TypeId::Bool ? 1 : t.arrow_width(); };
+  for (size_t ci = 0; ci < ncols; ++ci) {
+    const DataType& t = schema[ci].type;
+    DevColumn col; col.type = t; col.length = total_rows; col.arrow_is_utf8 = t.id == TypeId::Utf8;
+    datas[ci] = dev_alloc(ctx, (size_t)total_rows * width_of(ci));
+    vrecv[ci] = vneed(me, ci) ? 1 : 0;
+    if (vrecv[ci]) vbytes[ci] = dev_alloc(ctx, (size_t)total_rows + 4);
+    if (t.is_string()) {
+      for (int s = 0; s < W; ++s) heap_off[ci][(size_t)s + 1] = heap_off[ci][(size_t)s] + cnt(s, me, 1 + ci);
+      heaps[ci] = dev_alloc(ctx, (size_t)heap_off[ci][(size_t)W]);
+      col.heaps = {heaps[ci]};
+    }
+    if (t.id == TypeId::Bool) bbytes[ci] = datas[ci]; else col.data = datas[ci];
+    out->cols.push_back(col);
+  }
+  // Small messages can travel PACKED: all column buffers of one (source, destination) pair in one staging buffer, one
+  // ncclSend/ncclRecv per pair instead of 2-3 per column.  Both sides derive the same layout from the all-gathered table.
+  // Opt-in (SAILGPU_PACKED_EXCHANGE=1): measured at N=4 it did not pay (4.70 vs 4.45 ms/step).
+  constexpr int64_t PACK_LIMIT = 1 << 20;
+  auto a16 = [](int64_t v) { return (v + 15) & ~(int64_t)15; };
+  auto msg_bytes = [&](int src, int dst) {
+    const int64_t k = cnt(src, dst, 0);
+    int64_t tot = 0;
+    for (size_t ci = 0; ci < ncols; ++ci) tot += a16(k * width_of(ci)) + (vneed(dst, ci) ? a16(k) : 0) + a16(cnt(src, dst, 1 + ci));
+    return k ? tot : 0;
+  };
+  static const bool no_pack = getenv("SAILGPU_PACKED_EXCHANGE") == nullptr;
+  std::vector<CopySeg> pack_segs, unpack_segs;
+  std::vector<BufPtr> send_stage((size_t)W), recv_stage((size_t)W);
+  for (int peer = 0; peer < W; ++peer) {
+    const int64_t ks = parts[(size_t)peer]->rows, kr = cnt(peer, me, 0);
+    const int64_t sb = msg_bytes(me, peer), rb = msg_bytes(peer, me);
+    if (ks && !no_pack && sb <= PACK_LIMIT) {
+      send_stage[(size_t)peer] = dev_alloc(ctx, (size_t)sb);
+      uint8_t* base = static_cast<uint8_t*>(send_stage[(size_t)peer]->ptr);
+      int64_t off = 0;
+      for (size_t ci = 0; ci < ncols; ++ci) {
+        const SendCol& sd = sc[(size_t)peer][ci];
+        const int64_t db = ks * width_of(ci), hb = schema[ci].type.is_string() ? sd.heap_bytes : 0;
+        pack_segs.push_back({static_cast<const uint8_t*>(sd.data->ptr), base + off, (unsigned long long)db}); off += a16(db);
+        if (sd.validity_bytes) { pack_segs.push_back({static_cast<const uint8_t*>(sd.validity_bytes->ptr), base + off, (unsigned long long)ks}); off += a16(ks); }
+        if (hb) pack_segs.push_back({static_cast<const uint8_t*>(sd.heap->ptr), base + off, (unsigned long long)hb});
+        off += a16(hb);
+      }
+    }
+    if (kr && !no_pack && rb <= PACK_LIMIT) {
+      recv_stage[(size_t)peer] = dev_alloc(ctx, (size_t)rb);
+      const uint8_t* base = static_cast<const uint8_t*>(recv_stage[(size_t)peer]->ptr);
+      int64_t off = 0;
+      for (size_t ci = 0; ci < ncols; ++ci) {
+        const int w = width_of(ci);
+        const int64_t db = kr * w, hb = cnt(peer, me, 1 + ci);
+        unpack_segs.push_back({base + off, static_cast<uint8_t*>(datas[ci]->ptr) + row_off[(size_t)peer] * w, (unsigned long long)db}); off += a16(db);
+        if (vrecv[ci]) { unpack_segs.push_back({base + off, static_cast<uint8_t*>(vbytes[ci]->ptr) + row_off[(size_t)peer], (unsigned long long)kr}); off += a16(kr); }
+        if (hb) unpack_segs.push_back({base + off, static_cast<uint8_t*>(heaps[ci]->ptr) + heap_off[ci][(size_t)peer], (unsigned long long)hb});
+        off += a16(hb);
+      }
+    }
+  }
+  BufPtr seg_keep_a, seg_keep_b;
+  if (!pack_segs.empty()) SG_CUDA(launch_multi_copy(ctx, pack_segs, &seg_keep_a));
+  // bytes that cross NVLink (everything except the segment this rank keeps) and the device time of the grouped send/recv
+  {
+    uint64_t sent = 0, recvd = 0;
+    for (int peer = 0; peer < W; ++peer) if (peer != me) { sent += (uint64_t)msg_bytes(me, peer); recvd += (uint64_t)msg_bytes(peer, me); }
+    ctx->exch_sent_bytes += sent; ctx->exch_recv_bytes += recvd; ctx->exch_calls += 1;
+  }
+  cudaEvent_t xe0 = nullptr, xe1 = nullptr;
+  if (timing_enabled()) { SG_CUDA(cudaEventCreate(&xe0)); SG_CUDA(cudaEventCreate(&xe1)); SG_CUDA(cudaEventRecord(xe0, ctx->stream)); }
+  NCCL_CALL(g_nccl.GroupStart());
+  struct GroupGuard { bool open = true; ~GroupGuard() { if (open) g_nccl.GroupEnd(); } } group_guard;     // an error below must not leave the group open
+  for (int peer = 0; peer < W; ++peer) {
+    const int64_t ks = parts[(size_t)peer]->rows, kr = cnt(peer, me, 0);
+    if (ks && send_stage[(size_t)peer]) NCCL_CALL(g_nccl.Send(send_stage[(size_t)peer]->ptr, (size_t)msg_bytes(me, peer), NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+    if (kr && recv_stage[(size_t)peer]) NCCL_CALL(g_nccl.Recv(recv_stage[(size_t)peer]->ptr, (size_t)msg_bytes(peer, me), NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
     for (size_t ci = 0; ci < ncols; ++ci) {
       const DataType& t = schema[ci].type;
-      DevColumn col; col.type = t; col.length = total_rows; col.arrow_is_utf8 = t.id == TypeId::Utf8;
-      datas[ci] = dev_alloc(ctx, (size_t)total_rows * width_of(ci));
-      vbytes[ci] = dev_alloc(ctx, (size_t)total_rows + 4);
-      if (t.is_string()) {
-        for (int s = 0; s < W; ++s) heap_off[ci][(size_t)s + 1] = heap_off[ci][(size_t)s] + cnt(s, me, 1 + ci);
-        heaps[ci] = dev_alloc(ctx, (size_t)heap_off[ci][(size_t)W]);
-        col.heaps = {heaps[ci]};
+      const int w = width_of(ci);
+      const SendCol& sd = sc[(size_t)peer][ci];
+      if (ks && !send_stage[(size_t)peer]) {
+        NCCL_CALL(g_nccl.Send(sd.data->ptr, (size_t)ks * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+        if (sd.validity_bytes) NCCL_CALL(g_nccl.Send(sd.validity_bytes->ptr, (size_t)ks, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+        if (t.is_string() && sd.heap_bytes) NCCL_CALL(g_nccl.Send(sd.heap->ptr, (size_t)sd.heap_bytes, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
       }
-      if (t.id == TypeId::Bool) bbytes[ci] = datas[ci]; else col.data = datas[ci];
-      out->cols.push_back(col);
-    }
-    // Small messages can travel PACKED: all column buffers of one (source, destination) pair in one staging buffer, one
-    // ncclSend/ncclRecv per pair instead of 2-3 per column (a grouped p2p op costs ~8 us: the 4-row partial states of Q1
-    // with 13 columns were 28 ops per peer).  Both sides derive the same layout from the all-gathered counts.
-    constexpr int64_t PACK_LIMIT = 1 << 20;
-    auto a16 = [](int64_t v) { return (v + 15) & ~(int64_t)15; };
-    auto msg_bytes = [&](int src, int dst) {
-      const int64_t k = cnt(src, dst, 0);
-      int64_t tot = 0;
-      for (size_t ci = 0; ci < ncols; ++ci) tot += a16(k * width_of(ci)) + a16(k) + a16(cnt(src, dst, 1 + ci));
-      return k ? tot : 0;
-    };
-    // opt-in (SAILGPU_PACKED_EXCHANGE=1): measured at N=4 it did not pay (4.70 vs 4.45 ms/step) -- the multi-rank overhead of
-    // tiny exchanges is synchronisation latency and rank skew, not the number of grouped p2p operations
-    static const bool no_pack = getenv("SAILGPU_PACKED_EXCHANGE") == nullptr;
-    std::vector<CopySeg> pack_segs, unpack_segs;
-    std::vector<BufPtr> send_stage((size_t)W), recv_stage((size_t)W);
-    for (int peer = 0; peer < W; ++peer) {
-      const int64_t ks = parts[(size_t)peer]->rows, kr = cnt(peer, me, 0);
-      const int64_t sb = msg_bytes(me, peer), rb = msg_bytes(peer, me);
-      if (ks && !no_pack && sb <= PACK_LIMIT) {
-        send_stage[(size_t)peer] = dev_alloc(ctx, (size_t)sb);
-        uint8_t* base = static_cast<uint8_t*>(send_stage[(size_t)peer]->ptr);
-        int64_t off = 0;
-        for (size_t ci = 0; ci < ncols; ++ci) {
-          const SendCol& sd = sc[(size_t)peer][ci];
-          const int64_t db = ks * width_of(ci), hb = schema[ci].type.is_string() ? sd.heap_bytes : 0;
-          pack_segs.push_back({static_cast<const uint8_t*>(sd.data->ptr), base + off, (unsigned long long)db}); off += a16(db);
-          pack_segs.push_back({static_cast<const uint8_t*>(sd.validity_bytes->ptr), base + off, (unsigned long long)ks}); off += a16(ks);
-          if (hb) pack_segs.push_back({static_cast<const uint8_t*>(sd.heap->ptr), base + off, (unsigned long long)hb});
-          off += a16(hb);
-        }
-      }
-      if (kr && !no_pack && rb <= PACK_LIMIT) {
-        recv_stage[(size_t)peer] = dev_alloc(ctx, (size_t)rb);
-        const uint8_t* base = static_cast<const uint8_t*>(recv_stage[(size_t)peer]->ptr);
-        int64_t off = 0;
-        for (size_t ci = 0; ci < ncols; ++ci) {
-          const int w = width_of(ci);
-          const int64_t db = kr * w, hb = cnt(peer, me, 1 + ci);
-          unpack_segs.push_back({base + off, static_cast<uint8_t*>(datas[ci]->ptr) + row_off[(size_t)peer] * w, (unsigned long long)db}); off += a16(db);
-          unpack_segs.push_back({base + off, static_cast<uint8_t*>(vbytes[ci]->ptr) + row_off[(size_t)peer], (unsigned long long)kr}); off += a16(kr);
-          if (hb) unpack_segs.push_back({base + off, static_cast<uint8_t*>(heaps[ci]->ptr) + heap_off[ci][(size_t)peer], (unsigned long long)hb});
-          off += a16(hb);
-        }
+      if (kr && !recv_stage[(size_t)peer]) {
+        NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(datas[ci]->ptr) + row_off[(size_t)peer] * w, (size_t)kr * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+        if (vrecv[ci]) NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(vbytes[ci]->ptr) + row_off[(size_t)peer], (size_t)kr, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
+        const int64_t hb = cnt(peer, me, 1 + ci);
+        if (t.is_string() && hb) NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(heaps[ci]->ptr) + heap_off[ci][(size_t)peer], (size_t)hb, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
       }
     }
-    BufPtr seg_keep_a, seg_keep_b;
-    if (!pack_segs.empty()) SG_CUDA(launch_multi_copy(ctx, pack_segs, &seg_keep_a));
-    // bytes that cross NVLink (everything except the segment this rank keeps) and the device time of the grouped send/recv
-    {
-      uint64_t sent = 0, recvd = 0;
-      for (int peer = 0; peer < W; ++peer) if (peer != me) { sent += (uint64_t)msg_bytes(me, peer); recvd += (uint64_t)msg_bytes(peer, me); }
-      ctx->exch_sent_bytes += sent; ctx->exch_recv_bytes += recvd; ctx->exch_calls += 1;
-    }
-    cudaEvent_t xe0 = nullptr, xe1 = nullptr;
-    if (timing_enabled()) { SG_CUDA(cudaEventCreate(&xe0)); SG_CUDA(cudaEventCreate(&xe1)); SG_CUDA(cudaEventRecord(xe0, ctx->stream)); }
-    NCCL_CALL(g_nccl.GroupStart());
-    struct GroupGuard { bool open = true; ~GroupGuard() { if (open) g_nccl.GroupEnd(); } } group_guard;     // an error below must not leave the group open
-    for (int peer = 0; peer < W; ++peer) {
-      const int64_t ks = parts[(size_t)peer]->rows, kr = cnt(peer, me, 0);
-      if (ks && send_stage[(size_t)peer]) NCCL_CALL(g_nccl.Send(send_stage[(size_t)peer]->ptr, (size_t)msg_bytes(me, peer), NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-      if (kr && recv_stage[(size_t)peer]) NCCL_CALL(g_nccl.Recv(recv_stage[(size_t)peer]->ptr, (size_t)msg_bytes(peer, me), NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-      for (size_t ci = 0; ci < ncols; ++ci) {
-        const DataType& t = schema[ci].type;
-        const int w = width_of(ci);
-        const SendCol& sd = sc[(size_t)peer][ci];
-        if (ks && !send_stage[(size_t)peer]) {
-          NCCL_CALL(g_nccl.Send(sd.data->ptr, (size_t)ks * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-          NCCL_CALL(g_nccl.Send(sd.validity_bytes->ptr, (size_t)ks, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-          if (t.is_string() && sd.heap_bytes) NCCL_CALL(g_nccl.Send(sd.heap->ptr, (size_t)sd.heap_bytes, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-        }
-        if (kr && !recv_stage[(size_t)peer]) {
-          NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(datas[ci]->ptr) + row_off[(size_t)peer] * w, (size_t)kr * w, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-          NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(vbytes[ci]->ptr) + row_off[(size_t)peer], (size_t)kr, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-          const int64_t hb = cnt(peer, me, 1 + ci);
-          if (t.is_string() && hb) NCCL_CALL(g_nccl.Recv(static_cast<uint8_t*>(heaps[ci]->ptr) + heap_off[ci][(size_t)peer], (size_t)hb, NCCL_INT8, peer, ctx->nccl_comm, ctx->stream));
-        }
+  }
+  group_guard.open = false;
+  NCCL_CALL(g_nccl.GroupEnd());
+  if (xe1) { SG_CUDA(cudaEventRecord(xe1, ctx->stream)); ctx->exch_events.emplace_back(xe0, xe1); }      // read when metrics are asked for
+  if (!unpack_segs.empty()) SG_CUDA(launch_multi_copy(ctx, unpack_segs, &seg_keep_b));
+  // 4. post-process (no read-back): rebase string views per source segment, pack byte columns into Arrow bitmaps
+  for (size_t ci = 0; ci < ncols; ++ci) {
+    DevColumn& col = out->cols[ci];
+    if (schema[ci].type.is_string())
+      for (int s = 0; s < W; ++s) {
+        const int64_t kr = cnt(s, me, 0);
+        if (kr) SG_CUDA(launch_rebase_views(static_cast<uint8_t*>(col.data->ptr) + row_off[(size_t)s] * 16, kr,
+                                            reinterpret_cast<uint64_t>(col.heaps[0]->ptr) + (uint64_t)heap_off[ci][(size_t)s], ctx->stream));
       }
+    if (bbytes[ci]) {
+      col.data = dev_alloc_zero(ctx, (size_t)((total_rows + 31) / 32 * 4));
+      SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(bbytes[ci]->ptr), static_cast<uint32_t*>(col.data->ptr), total_rows, nullptr, ctx->stream));
     }
-    group_guard.open = false;
-    NCCL_CALL(g_nccl.GroupEnd());
-    if (xe1) SG_CUDA(cudaEventRecord(xe1, ctx->stream));
-    if (!unpack_segs.empty()) SG_CUDA(launch_multi_copy(ctx, unpack_segs, &seg_keep_b));
-    // 3. post-process: rebase string views per source segment, pack byte columns
-    BufPtr nullctrs = dev_alloc_zero(ctx, ncols * 8 + 8);
-    for (size_t ci = 0; ci < ncols; ++ci) {
-      DevColumn& col = out->cols[ci];
-      if (schema[ci].type.is_string())
-        for (int s = 0; s < W; ++s) {
-          const int64_t kr = cnt(s, me, 0);
-          if (kr) SG_CUDA(launch_rebase_views(static_cast<uint8_t*>(col.data->ptr) + row_off[(size_t)s] * 16, kr,
-                                              reinterpret_cast<uint64_t>(col.heaps[0]->ptr) + (uint64_t)heap_off[ci][(size_t)s], ctx->stream));
-        }
-      if (bbytes[ci]) {
-        col.data = dev_alloc_zero(ctx, (size_t)((total_rows + 31) / 32 * 4));
-        SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(bbytes[ci]->ptr), static_cast<uint32_t*>(col.data->ptr), total_rows, nullptr, ctx->stream));
-      }
+    if (vrecv[ci] && total_rows > 0) {
       col.validity = dev_alloc_zero(ctx, (size_t)((total_rows + 31) / 32 * 4));
-      SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(vbytes[ci]->ptr), static_cast<uint32_t*>(col.validity->ptr), total_rows,
-                                static_cast<unsigned long long*>(nullctrs->ptr) + ci, ctx->stream));
-    }
-    std::vector<unsigned long long> nulls(ncols, 0);
-    SG_CUDA(cudaMemcpyAsync(nulls.data(), nullctrs->ptr, ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    SG_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (size_t ci = 0; ci < ncols; ++ci) {
-      out->cols[ci].null_count = (int64_t)nulls[ci];
-      if (nulls[ci] == 0) out->cols[ci].validity = nullptr;
-    }
-    SG_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (xe0) {
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, xe0, xe1) == cudaSuccess) ctx->exch_ns += (uint64_t)((double)ms * 1e6);
-      cudaEventDestroy(xe0); cudaEventDestroy(xe1);
-    }
-    }
+      SG_CUDA(launch_pack_bytes(static_cast<const uint8_t*>(vbytes[ci]->ptr), static_cast<uint32_t*>(col.validity->ptr), total_rows, nullptr, ctx->stream));
+      col.null_count = -1;
+    } else col.null_count = 0;
+  }
+  // the staging buffers of this call are released stream-ordered (dev_alloc): nothing to wait for
   return out;
+}
+
+// device time of the grouped send/recv of finished exchanges -> gpu.exchange_ns (called when metrics are read)
+void resolve_exchange_timing(Ctx* ctx) {
+  for (auto& ev : ctx->exch_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) ctx->exch_ns += (uint64_t)((double)ms * 1e6);
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  ctx->exch_events.clear();
 }
 }  // namespace sg
 
