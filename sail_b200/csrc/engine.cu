@@ -526,6 +526,8 @@ size_t pipeline_precompile(const Json& spec, const std::vector<Schema>& inputs, 
 // wider than 64 bytes", "does not fit in shared memory" ... -- are answered while planning, never after the first batch arrived.
 // (Validity buffers add one column buffer each; a batch whose nullable columns push a pipeline over the 20-buffer limit is still
 // reported at push time as SAILGPU_ERR_UNSUPPORTED.)  Touches no device.
+static thread_local bool g_in_static_check = false;
+std::unique_ptr<Op> make_wide_agg_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs, const Schema& out_schema);
 void pipeline_static_check(const Json& spec, const std::vector<Schema>& inputs) {
   static Ctx plan_ctx;
   std::unique_ptr<Op> op = make_op(&plan_ctx, spec, inputs, 0);
@@ -579,6 +581,15 @@ std::unique_ptr<Op> make_op(Ctx* ctx, const Json& spec, const std::vector<Schema
   for (size_t i = 0; i + 1 < op->run.stages.size(); ++i)
     SG_CHECK(op->run.stages[i].kind != StageSpec::Aggregate, SAILGPU_ERR_INVALID, "aggregate must be the last stage of a pipeline");
   op->out_schema = cur;
+  // a group key the hash table cannot pack (more than 6 keys / 64 bytes): grouping by sorting instead (ops_more.cu WideAggOp)
+  if (kind == "aggregate" && !g_in_static_check) {
+    bool wide = false;
+    g_in_static_check = true;
+    try { pipeline_static_check(spec, inputs); }
+    catch (const Error& e) { wide = e.code == SAILGPU_ERR_UNSUPPORTED && std::string(e.what()).find("group key") != std::string::npos; }
+    g_in_static_check = false;
+    if (wide) return make_wide_agg_op(ctx, spec, inputs, cur);
+  }
   return op;
 }
 

@@ -1044,6 +1044,151 @@ std::unique_ptr<Op> make_sort_op(Ctx* ctx, const Json& spec, const std::vector<S
 }
 
 // ================================================================================================
+// AggregateExec whose group key does not fit the hash table (more than 6 keys or more than 64 packed key bytes; TPC-H Q10
+// groups by seven columns, four of them strings): grouping by SORTING.  The key expressions are evaluated as columns, encoded
+// with the sort operator's order-preserving encoding and radix-sorted; runs of equal keys get dense group numbers; the
+// aggregate itself then runs through the ordinary hash pipeline on that ONE Int64 key; the key columns of the result are
+// gathered from one representative row per group.  DataFusion's GroupValuesRows handles such keys in its row format
+// (datafusion physical-plan aggregates/group_values) -- same result rows, unspecified order.
+// ================================================================================================
+std::unique_ptr<Op> make_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs, int partition);
+
+struct WideAggOp : Op {
+  Json spec;
+  std::vector<BatchPtr> parts;
+  bool input_done = false, emitted = false;
+  int n_keys = 0;
+  bool merging = false;
+
+  static Json jnum(int64_t v) { Json j; j.kind = Json::Num; j.s = std::to_string(v); return j; }
+  static Json jstr(const std::string& v) { Json j; j.kind = Json::Str; j.s = v; return j; }
+  static Json jobj(std::vector<std::pair<std::string, Json>> v) { Json j; j.kind = Json::Obj; j.o = std::move(v); return j; }
+  static Json jarr(std::vector<Json> v) { Json j; j.kind = Json::Arr; j.a = std::move(v); return j; }
+  static Json jcol(int64_t i) { return jobj({{"col", jnum(i)}}); }
+
+  void push(int input, const BatchPtr& b) override {
+    SG_CHECK(input == 0, SAILGPU_ERR_INVALID, "aggregate has one input");
+    m.input_rows += (uint64_t)b->rows; m.input_batches++;
+    if (b->rows) parts.push_back(b);
+  }
+  void finish(int) override { input_done = true; }
+  bool pull(BatchPtr* out) override {
+    *out = nullptr;
+    if (!input_done) return true;
+    if (emitted) return false;
+    const uint64_t t0 = now_ns();
+    *out = run();
+    emitted = true;
+    m.elapsed_compute_ns += now_ns() - t0;
+    m.output_rows += (uint64_t)(*out)->rows; m.output_batches++;
+    return false;
+  }
+
+  BatchPtr through(const Json& sub_spec, const Schema& in, const BatchPtr& b, Schema* out_schema) {
+    std::unique_ptr<Op> op = make_op(ctx, sub_spec, {in}, 0);
+    if (b->rows) op->push(0, b);
+    op->finish(0);
+    std::vector<BatchPtr> outs;
+    for (;;) { BatchPtr o; const bool more = op->pull(&o); if (o && o->rows) outs.push_back(o); if (!more) break; }
+    m.kernel_launches += op->m.kernel_launches;
+    if (out_schema) *out_schema = op->out_schema;
+    return outs.empty() ? empty_batch(ctx, op->out_schema) : outs.size() == 1 ? outs[0] : concat_batches(ctx, op->out_schema, outs);
+  }
+
+  BatchPtr run() {
+    const Schema& in = in_schemas[0];
+    if (parts.empty()) return empty_batch(ctx, out_schema);
+    BatchPtr all = parts.size() == 1 ? parts[0] : concat_batches(ctx, in, parts);
+    parts.clear();
+    const int64_t n = all->rows;
+    SG_CHECK(n < (1ll << 32), SAILGPU_ERR_UNSUPPORTED, "sort-based grouping of more than 2^32 rows in one partition");
+    // 1. the group expressions as columns
+    const Json& gb = spec.at("group_by");
+    std::vector<Json> kex;
+    for (size_t i = 0; i < gb.a.size(); ++i) kex.push_back(jobj({{"expr", gb.a[i].at("expr")}, {"name", jstr("__k" + std::to_string(i))}}));
+    Schema ks;
+    BatchPtr kb = through(jobj({{"op", jstr("projection")}, {"exprs", jarr(kex)}}), in, all, &ks);
+    // 2. rows in key order
+    SortOp so; so.ctx = ctx;
+    std::vector<SortOp::Key> keys;
+    for (int i = 0; i < n_keys; ++i) keys.push_back({parse_expr(jcol(i), ks), true, true});
+    SortOp::Encoded enc = so.encode_keys(kb, ks, keys);
+    const int64_t n_chunks = (n + 2047) / 2048;
+    BufPtr ia = dev_alloc(ctx, (size_t)n * 4), ib = dev_alloc(ctx, (size_t)n * 4), ka = dev_alloc(ctx, (size_t)n * 8), kbuf = dev_alloc(ctx, (size_t)n * 8),
+           hist = dev_alloc(ctx, (size_t)n_chunks * 256 * 4), offs = dev_alloc(ctx, (size_t)n_chunks * 256 * 8), scr = dev_alloc(ctx, 1026 * 8);
+    RadixScratch S;
+    S.idx_a = static_cast<uint32_t*>(ia->ptr); S.idx_b = static_cast<uint32_t*>(ib->ptr);
+    S.kw_a = static_cast<uint64_t*>(ka->ptr); S.kw_b = static_cast<uint64_t*>(kbuf->ptr);
+    S.hist = static_cast<uint32_t*>(hist->ptr); S.offs = static_cast<uint64_t*>(offs->ptr); S.scan_scratch = static_cast<uint64_t*>(scr->ptr);
+    int sort_launches = 0;
+    SG_CUDA(radix_sort_indices(static_cast<const uint8_t*>(enc.keys->ptr), enc.key_bytes, n, S, static_cast<const uint32_t*>(enc.bits->ptr), ctx->stream, &sort_launches));
+    // 3. runs of equal keys -> dense group numbers, one representative row per group
+    BufPtr heads = dev_alloc(ctx, (size_t)n * 4), before = dev_alloc(ctx, (size_t)n * 8), scr2 = dev_alloc(ctx, 1026 * 8);
+    SG_CUDA(launch_group_heads(static_cast<const uint8_t*>(enc.keys->ptr), enc.key_bytes, S.idx_a, n, static_cast<uint32_t*>(heads->ptr), ctx->stream));
+    SG_CUDA(launch_exclusive_scan_u32(static_cast<const uint32_t*>(heads->ptr), n, static_cast<uint64_t*>(before->ptr), static_cast<uint64_t*>(scr2->ptr), ctx->stream));
+    uint64_t n_groups = 0;
+    SG_CUDA(cudaMemcpyAsync(&n_groups, static_cast<uint64_t*>(scr2->ptr) + std::min<int64_t>(1024, (n + 4095) / 4096), 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    DevColumn gid; gid.type = T(TypeId::Int64); gid.length = n; gid.data = dev_alloc(ctx, (size_t)n * 8);
+    BufPtr rep = dev_alloc(ctx, (size_t)n_groups * 8);
+    SG_CUDA(launch_assign_groups(S.idx_a, static_cast<const uint32_t*>(heads->ptr), static_cast<const uint64_t*>(before->ptr), n,
+                                 static_cast<int64_t*>(gid.data->ptr), static_cast<int64_t*>(rep->ptr), ctx->stream));
+    m.kernel_launches += (uint64_t)sort_launches + 4;
+    // 4. the aggregate on the group number.  Merging modes find their state columns by position (after the keys): [gid | states];
+    //    the others address input columns by index: [inputs | gid]
+    auto agg_in = std::make_shared<DevBatch>();
+    agg_in->rows = n;
+    Schema ain;
+    Field gf; gf.name = "__gid"; gf.type = T(TypeId::Int64); gf.nullable = false;
+    int gid_col = 0;
+    if (merging) {
+      ain.push_back(gf); agg_in->cols.push_back(gid);
+      for (size_t i = (size_t)n_keys; i < in.size(); ++i) { ain.push_back(in[i]); agg_in->cols.push_back(all->cols[i]); }
+    } else {
+      ain = in; agg_in->cols = all->cols;
+      gid_col = (int)in.size();
+      ain.push_back(gf); agg_in->cols.push_back(gid);
+    }
+    std::vector<std::pair<std::string, Json>> so2;
+    for (auto& kv : spec.o) {
+      if (kv.first == "group_by") so2.push_back({"group_by", jarr({jobj({{"expr", jcol(gid_col)}, {"name", jstr("__gid")}})})});
+      else so2.push_back(kv);
+    }
+    Schema aos;
+    BatchPtr agg = through(jobj(so2), ain, agg_in, &aos);
+    SG_CHECK((uint64_t)agg->rows == n_groups, SAILGPU_ERR_STATE, "sort-based grouping: group count mismatch");
+    // 5. key columns of the result: the representative row of each output group
+    JoinOp helper; helper.ctx = ctx;
+    DevColumn repc; repc.type = T(TypeId::Int64); repc.length = (int64_t)n_groups; repc.data = rep;
+    DevColumn pick = helper.gather_column(repc, gf, static_cast<const int64_t*>(agg->cols[0].data->ptr), agg->rows, false);
+    auto out = std::make_shared<DevBatch>();
+    out->rows = agg->rows;
+    for (int i = 0; i < n_keys; ++i) {
+      DevColumn c = helper.gather_column(kb->cols[(size_t)i], ks[(size_t)i], static_cast<const int64_t*>(pick.data->ptr), agg->rows, false);
+      out->cols.push_back(c);
+    }
+    for (size_t i = 1; i < agg->cols.size(); ++i) out->cols.push_back(agg->cols[i]);
+    m.kernel_launches += (uint64_t)n_keys + 1;
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return out;
+  }
+};
+
+std::unique_ptr<Op> make_wide_agg_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs, const Schema& out_schema) {
+  auto op = std::make_unique<WideAggOp>();
+  op->ctx = ctx; op->kind = "aggregate"; op->in_schemas = inputs; op->out_schema = out_schema; op->spec = spec;
+  op->n_keys = (int)spec.at("group_by").a.size();
+  const std::string mode = spec.at("mode").as_str();
+  op->merging = mode == "final" || mode == "final_partitioned";
+  SG_CHECK(op->n_keys >= 1 && op->n_keys <= 7, SAILGPU_ERR_UNSUPPORTED, "sort-based grouping takes 1 to 7 group keys");
+  for (int i = 0; i < op->n_keys; ++i) {
+    const DataType& t = out_schema[(size_t)i].type;
+    SG_CHECK(t.id != TypeId::Float32, SAILGPU_ERR_UNSUPPORTED, "Float32 group keys");
+  }
+  return op;
+}
+
+// ================================================================================================
 // RepartitionExec Hash(exprs, n): histogram -> offsets -> scatter (two passes of SINK_PARTITION)
 // ================================================================================================
 struct RepartitionOp : Op {

@@ -425,6 +425,32 @@ cudaError_t launch_merge_rank(const uint8_t* keys, int key_bytes, const int64_t*
   return cudaGetLastError();
 }
 
+// sort-based grouping (aggregates whose group key does not fit the hash table's packed key): rows in key order, `heads` marks
+// the first row of every run of equal encoded keys
+__global__ void group_heads_kernel(const uint8_t* __restrict__ keys, int key_bytes, const uint32_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ heads) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    heads[i] = (i == 0 || key_cmp(keys + (int64_t)idx[i] * key_bytes, keys + (int64_t)idx[i - 1] * key_bytes, key_bytes) != 0) ? 1u : 0u;
+}
+cudaError_t launch_group_heads(const uint8_t* keys, int key_bytes, const uint32_t* idx, int64_t n, uint32_t* heads, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  group_heads_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(keys, key_bytes, idx, n, heads);
+  return cudaGetLastError();
+}
+// group number of every input row (dense, in key order) and one representative input row per group
+__global__ void assign_groups_kernel(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ heads, const uint64_t* __restrict__ before, int64_t n,
+                                     int64_t* __restrict__ gid_of_row, int64_t* __restrict__ rep) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = (int64_t)before[i] + (int64_t)heads[i] - 1;      // heads before i, plus this one
+    gid_of_row[idx[i]] = g;
+    if (heads[i]) rep[g] = (int64_t)idx[i];
+  }
+}
+cudaError_t launch_assign_groups(const uint32_t* idx, const uint32_t* heads, const uint64_t* before, int64_t n, int64_t* gid_of_row, int64_t* rep, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  assign_groups_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(idx, heads, before, n, gid_of_row, rep);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_iota(int64_t* out, int64_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   iota_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(out, n);

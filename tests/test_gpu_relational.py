@@ -240,24 +240,69 @@ def test_row_round_robin_streaming(n_parts, in_part, n_in):
     op.close()
 
 
-@pytest.mark.parametrize("q", ["q1", "q2", "q3", "q4", "q5", "q6", "q7", "q8", "q9", "q11", "q12", "q14", "q15", "q16", "q17", "q18", "q19", "q20", "q21", "q22"])
+@pytest.mark.parametrize("q", ["q1", "q2", "q3", "q4", "q5", "q6", "q7", "q8", "q9", "q10", "q11", "q12", "q14", "q15", "q16", "q17", "q18", "q19", "q20", "q21", "q22"])
 def test_tpch_golden_on_gpu(q, golden):
     """whole plans through the C ABI on dbgen SF0.001 == the reference's own snapshot"""
     from datagen import tpch
+    from tests.test_oracle_golden import drop_unpinned
     tables = tpch.tables(0.001)
     got = plans.execute(plans.TPCH[q](), tables, gpu_op)
     assert got.schema.names == golden[q]["columns"]
-    assert render.rows(got) == golden[q]["rows"]
+    assert drop_unpinned(q, render.rows(got)) == drop_unpinned(q, golden[q]["rows"])
 
 
-@pytest.mark.parametrize("q", ["q2", "q3", "q4", "q5", "q7", "q8", "q9", "q11", "q12", "q13", "q14", "q15", "q16", "q17", "q19", "q20", "q21", "q22"])
+@pytest.mark.parametrize("q", ["q2", "q3", "q4", "q5", "q7", "q8", "q9", "q10", "q11", "q12", "q13", "q14", "q15", "q16", "q17", "q19", "q20", "q21", "q22"])
 def test_tpch_sf01_vs_oracle(q):
     from datagen import tpch
     tables = tpch.tables(0.1)
     plan = plans.TPCH[q]()
     got = plans.execute(plan, tables, gpu_op)
     want = plans.execute(plan, tables, oracle_op)
-    assert_same(got, want, ordered=(q != "q3"))   # Q3's top-10 may tie on (revenue, date): compare as sets
+    assert_same(got, want, ordered=(q not in ("q3", "q10")))   # top-k with possible ties on the sort key: compare as sets
+
+
+@pytest.mark.parametrize("mode", ["single", "two_phase"])
+@pytest.mark.parametrize("nulls", [False, True])
+def test_aggregate_with_a_group_key_wider_than_the_hash_table(mode, nulls):
+    """seven group keys / more than 64 packed key bytes: grouping by sorting (WideAggOp), several input batches, long strings and
+    NULL keys (NULL is a group of its own), every accumulator kind"""
+    rng = np.random.default_rng(5)
+    n = 30000
+    def maybe(a, typ):
+        mask = (rng.random(n) < 0.1) if nulls else None
+        return pa.array(a, type=typ, mask=mask)
+    words = [f"address-{i:03d}-" + "x" * (i % 29) for i in range(37)]
+    t = pa.table({
+        "k0": maybe(rng.integers(0, 5, n), pa.int64()),
+        "k1": maybe([f"Customer#{v:09d}" for v in rng.integers(0, 4, n)], pa.string_view()),
+        "k2": maybe([decimal.Decimal(int(v)) / 100 for v in rng.integers(-3, 3, n)], pa.decimal128(15, 2)),
+        "k3": maybe([f"{v:02d}-555-0100" for v in rng.integers(10, 13, n)], pa.string_view()),
+        "k4": maybe([["PERU", "CANADA", "UNITED KINGDOM"][v] for v in rng.integers(0, 3, n)], pa.string_view()),
+        "k5": maybe([words[v] for v in rng.integers(0, len(words), n)], pa.string_view()),
+        "k6": maybe(rng.integers(0, 2, n).astype(np.int32), pa.int32()),
+        "v": maybe([decimal.Decimal(int(v)) / 100 for v in rng.integers(-10**6, 10**6, n)], pa.decimal128(15, 2)),
+        "f": pa.array(rng.normal(size=n)),
+    })
+    keys = [f"k{i}" for i in range(7)]
+    aggs = [("sum", plans.col("v"), "sv", "Decimal128(15,2)"), ("avg", plans.col("v"), "av", "Decimal128(15,2)"), ("count", None, "c", None),
+            ("min", plans.col("v"), "mn", "Decimal128(15,2)"), ("sum", plans.col("f"), "sf", "Float64"), ("count", plans.col("v"), "cv", "Decimal128(15,2)")]
+    scan = plans.scan("t", t.schema.names)
+    node = plans.aggregate(scan, "single", keys, aggs) if mode == "single" else plans.two_phase(scan, keys, aggs)
+    def gpu_batched(spec, *ins):
+        from sail_b200 import engine
+        if spec["mode"] == "final_partitioned":
+            return gpu_op(spec, *ins)
+        op = engine.GpuExec(spec, [ins[0].schema])
+        for o in range(0, ins[0].num_rows, 7001):
+            op.push(ins[0].slice(o, 7001))
+        op.finish()
+        out = op.collect()
+        op.close()
+        return out
+    got = plans.execute(node, {"t": t}, gpu_batched)
+    want = plans.execute(node, {"t": t}, oracle_op)
+    assert got.num_rows == want.num_rows and got.num_rows > 1000
+    assert_same(got, want)
 
 
 @pytest.mark.parametrize("jt", ["left_semi", "left_anti"])
