@@ -2,6 +2,7 @@
 //
 // Replaces, for the GPU path, what arrow::ffi + a plain cudaMemcpy per buffer would do at the boundary the Rust shim
 // crosses per RecordBatch: Arrow's fixed widths are an in-memory format, not a wire format.
+#include <climits>
 #include "h2d.hpp"
 
 #include <sched.h>
@@ -70,17 +71,57 @@ uint32_t sg_scan_view_maxlen(const uint32_t* p, int64_t n);
 void sg_pack_i64(uint8_t* out, const int64_t* vals, int64_t stride, int64_t n, int64_t base, int w);
 void sg_pack_i32(uint8_t* out, const int32_t* vals, int64_t n, int32_t base, int w);
 void sg_pack_views(uint8_t* out, const uint8_t* views, int64_t n, uint32_t L);
+void sg_packchk_dec128(uint8_t* out, const int64_t* p, int64_t n, int64_t base, int w, int64_t* mn, int64_t* mx, uint64_t* bad);
+void sg_packchk_i64(uint8_t* out, const int64_t* p, int64_t n, int64_t base, int w, int64_t* mn, int64_t* mx);
+void sg_packchk_i32(uint8_t* out, const int32_t* p, int64_t n, int32_t base, int w, int32_t* mn, int32_t* mx);
+uint32_t sg_packchk_views(uint8_t* out, const uint8_t* views, int64_t n, uint32_t L);
 }
 namespace {
 
 static inline int width_for(unsigned long long range) { return range < (1ull << 8) ? 1 : range < (1ull << 16) ? 2 : range < (1ull << 32) ? 4 : 8; }
 
+// A guess of the piece's value range from 64 strided samples (prefetched together: one DRAM round trip).  The window of the
+// guessed width is centred on the sampled range and must be at least twice as wide, so that values the sample missed still fit.
+constexpr int N_SAMPLES = 64;
+struct Guess { bool ok; long long base; int w; };
+template <class T>
+static Guess guess_range(const T* p, int64_t n, int64_t stride, int max_w) {
+  const int64_t step = std::max<int64_t>(1, n / N_SAMPLES);
+  for (int64_t i = 0; i < n; i += step) __builtin_prefetch(p + i * stride);
+  long long mn = LLONG_MAX, mx = LLONG_MIN;
+  for (int64_t i = 0; i < n; i += step) { const long long v = (long long)p[i * stride]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+  const unsigned long long range = (unsigned long long)mx - (unsigned long long)mn;
+  if (range >= (1ull << 31)) return {false, 0, 0};
+  int w = 1;
+  while (w <= 4 && (2 * range + 2) > (w == 4 ? (1ull << 32) : (1ull << (8 * w)))) w *= 2;
+  if (w > max_w) return {false, 0, 0};
+  const unsigned long long window = w == 4 ? (1ull << 32) : (1ull << (8 * w));
+  const long long slack = (long long)((window - 1 - range) / 2);
+  if (mn < LLONG_MIN + slack) return {false, 0, 0};
+  return {true, mn - slack, w};
+}
+static inline bool fits(long long mn, long long mx, long long base, int w) {
+  if (mn < base) return false;
+  const unsigned long long top = (unsigned long long)mx - (unsigned long long)base;
+  return w >= 8 || top < (w == 4 ? (1ull << 32) : (1ull << (8 * w)));
+}
+static bool one_pass() { const char* e = getenv("SAILGPU_PACK_ONE_PASS"); return !(e && *e && atoi(e) == 0); }      // read per piece (A/B measurements)
+
 static Packed pack_piece(const HostStager::Item& it, uint8_t* out, bool narrow) {
   const int64_t n = it.n;
   if (narrow && n > 0 && it.kind == HostCol::Dec128) {
     const int64_t* p = reinterpret_cast<const int64_t*>(it.src);
-    int64_t mn, mx; uint64_t bad;
-    sg_scan_dec128(p, n, &mn, &mx, &bad);
+    int64_t mn, mx; uint64_t bad = 0;
+    bool scanned = false;
+    if (one_pass()) {
+      const Guess g = guess_range(p, n, 2, 4);
+      if (g.ok) {
+        sg_packchk_dec128(out, p, n, g.base, g.w, &mn, &mx, &bad);
+        if (!bad && fits(mn, mx, g.base, g.w)) return {ENC_INT, (size_t)n * g.w, g.base, g.w};
+        scanned = true;
+      }
+    }
+    if (!scanned) sg_scan_dec128(p, n, &mn, &mx, &bad);
     if (!bad) {
       const int w = width_for((unsigned long long)mx - (unsigned long long)mn);
       sg_pack_i64(out, p, 2, n, mn, w);
@@ -89,17 +130,47 @@ static Packed pack_piece(const HostStager::Item& it, uint8_t* out, bool narrow) 
   } else if (narrow && n > 0 && it.kind == HostCol::Int64) {
     const int64_t* p = reinterpret_cast<const int64_t*>(it.src);
     int64_t mn, mx;
-    sg_scan_i64(p, n, &mn, &mx);
+    bool scanned = false;
+    if (one_pass()) {
+      const Guess g = guess_range(p, n, 1, 4);
+      if (g.ok) {
+        sg_packchk_i64(out, p, n, g.base, g.w, &mn, &mx);
+        if (fits(mn, mx, g.base, g.w)) return {ENC_INT, (size_t)n * g.w, g.base, g.w};
+        scanned = true;
+      }
+    }
+    if (!scanned) sg_scan_i64(p, n, &mn, &mx);
     const int w = width_for((unsigned long long)mx - (unsigned long long)mn);
     if (w < 8) { sg_pack_i64(out, p, 1, n, mn, w); return {ENC_INT, (size_t)n * w, mn, w}; }
   } else if (narrow && n > 0 && it.kind == HostCol::Int32) {
     const int32_t* p = reinterpret_cast<const int32_t*>(it.src);
     int32_t mn, mx;
-    sg_scan_i32(p, n, &mn, &mx);
+    bool scanned = false;
+    if (one_pass()) {
+      const Guess g = guess_range(p, n, 1, 2);
+      if (g.ok && g.base >= INT32_MIN) {
+        sg_packchk_i32(out, p, n, (int32_t)g.base, g.w, &mn, &mx);
+        if (fits(mn, mx, g.base, g.w)) return {ENC_INT, (size_t)n * g.w, g.base, g.w};
+        scanned = true;
+      }
+    }
+    if (!scanned) sg_scan_i32(p, n, &mn, &mx);
     const int w = width_for((unsigned long long)((long long)mx - (long long)mn));
     if (w < 4) { sg_pack_i32(out, p, n, mn, w); return {ENC_INT, (size_t)n * w, (long long)mn, w}; }
   } else if (narrow && n > 0 && it.kind == HostCol::View16) {
-    const uint32_t L = sg_scan_view_maxlen(reinterpret_cast<const uint32_t*>(it.src), n);
+    const uint32_t* lens = reinterpret_cast<const uint32_t*>(it.src);
+    uint32_t L = 13;
+    if (one_pass()) {
+      const int64_t step = std::max<int64_t>(1, n / N_SAMPLES);
+      for (int64_t i = 0; i < n; i += step) __builtin_prefetch(lens + 4 * i);
+      uint32_t Ls = 0;
+      for (int64_t i = 0; i < n; i += step) Ls = std::max(Ls, lens[4 * i]);
+      if (Ls <= 12) {
+        L = sg_packchk_views(out, it.src, n, Ls);
+        if (L <= Ls) return {ENC_VIEW, (size_t)(1 + Ls) * (size_t)n, 0, (int)Ls};
+      }
+    }
+    if (L > 12) L = sg_scan_view_maxlen(lens, n);      // (a rejected one-pass attempt left the true maximum in L)
     if (L <= 12) { sg_pack_views(out, it.src, n, L); return {ENC_VIEW, (size_t)(1 + L) * (size_t)n, 0, (int)L}; }
   }
   const size_t bytes = (size_t)n * (size_t)it.width;

@@ -75,11 +75,13 @@ def main():
                 else:
                     os.environ[k] = v
 
-    run("default", {})
+    run("warm-up", {})
+    run("default (one pass, 64 Ki-row pieces)", {})
+    run("two passes (scan, then pack)", {"SAILGPU_PACK_ONE_PASS": "0"})
     run("raw bytes (no packing)", {"SAILGPU_H2D_PACK": "0"})
-    for th in (4, 8, 16, 24, 32):
+    for th in (8, 16, 32):
         run(f"threads={th}", {"SAILGPU_PACK_THREADS": str(th)})
-    for pr in (16384, 65536, 262144):
+    for pr in (32768, 131072, 262144):
         run(f"piece_rows={pr}", {"SAILGPU_PACK_PIECE_ROWS": str(pr)})
     run("host side only (dry)", {"SAILGPU_PACK_DRY": "1"})
     run("host side only (dry), threads=32", {"SAILGPU_PACK_DRY": "1", "SAILGPU_PACK_THREADS": "32"})
