@@ -410,6 +410,9 @@ def joins_leg(args, ctx, stream, local):
     dims_host = {"customer": tpch.customer(sf, ["c_custkey", "c_nationkey", "c_mktsegment"]).combine_chunks(),
                  "supplier": tpch.supplier(sf, ["s_suppkey", "s_nationkey"]).combine_chunks(), "nation": tpch.nation(), "region": tpch.region()}
     dims = {k: (engine.to_device(v, ctx), v.schema.names) for k, v in dims_host.items()}
+    # (Acero has no string_view kernels: the proxy reads the same dimension tables with Utf8 strings)
+    dims_acero = {"customer": tpch.customer(sf, ["c_custkey", "c_nationkey", "c_mktsegment"], strings="utf8").combine_chunks(),
+                  "supplier": dims_host["supplier"], "nation": tpch.nation("utf8"), "region": tpch.region("utf8")}
 
     def facts(first, n):
         o, l = tpch_gpu.generate_buffers(sf, first, n, OC, LC, local)
@@ -512,7 +515,7 @@ def joins_leg(args, ctx, stream, local):
             got = rows_of(run_gpu(mk(), dev))
             per_chunk[q].append(got)
             if ci == 0:
-                T = dict(dims_host)
+                T = dict(dims_acero)
                 T["orders"], T["lineitem"] = o.host_table(), l.host_table()
                 pa.set_cpu_count(host_cores())
                 t0 = time.perf_counter()
