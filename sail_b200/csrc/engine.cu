@@ -125,8 +125,38 @@ struct PipelineOp : Op {
     const uint64_t t0 = now_ns();
     m.input_rows += (uint64_t)b->rows; m.input_batches++;
     if (has_agg) { collect_heaps(*b); push_agg(b); }
+    else if (const std::vector<int>* cols = rename_only()) {
+      // a ProjectionExec of plain column references (the `expr=[_0@0 as #9, _3@1 as #12]` nodes over every scan in the reference's
+      // plans) moves no data: the output batch shares the input's buffers, as DataFusion's Arc-cloned arrays do
+      auto out = std::make_shared<DevBatch>();
+      out->rows = b->rows;
+      for (int c : *cols) out->cols.push_back(b->cols[(size_t)c]);
+      ready.push_back(out);
+    }
     else ready.push_back(run_stream(b));
     m.elapsed_compute_ns += now_ns() - t0;
+  }
+  // the input column of every output when the whole pipeline is projections of bare column references, else null
+  int rename_state = -1;      // -1: not analysed yet, 0: no, 1: yes
+  std::vector<int> rename_cols;
+  const std::vector<int>* rename_only() {
+    if (rename_state < 0) {
+      rename_state = 0;
+      std::vector<int> cur;
+      bool ok = !run.stages.empty();
+      for (size_t si = 0; ok && si < run.stages.size(); ++si) {
+        const StageSpec& st = run.stages[si];
+        if (st.kind != StageSpec::Projection) { ok = false; break; }
+        std::vector<int> next;
+        for (auto& e : st.exprs) {
+          if (e->kind != Expr::Col) { ok = false; break; }
+          next.push_back(si == 0 ? e->col : cur[(size_t)e->col]);
+        }
+        cur.swap(next);
+      }
+      if (ok) { rename_cols = cur; rename_state = 1; }
+    }
+    return rename_state == 1 ? &rename_cols : nullptr;
   }
   void finish(int input) override {
     SG_CHECK(input == 0, SAILGPU_ERR_INVALID, "operator has one input");

@@ -17,11 +17,12 @@ namespace {
 
 constexpr int64_t MAX_PIECE_ROWS = 256 * 1024;
 constexpr size_t SLOT_BYTES = (size_t)MAX_PIECE_ROWS * 16;     // 4 MiB: one piece of the widest column
-// rows per piece: SAILGPU_PACK_PIECE_ROWS (a multiple of 1024, at most 256 Ki) -- a piece is scanned and then packed, so it should
-// still be in the packing core's L2 when the second loop reads it
+// rows per piece: SAILGPU_PACK_PIECE_ROWS (a multiple of 1024, at most 256 Ki).  Every piece costs three driver calls (copy, expand
+// kernel, event) that serialise across the packer threads: 64 Ki-row pieces spent a third of the import there (55 vs 42 ms for a
+// 60 M-row batch, profiles/r02_h2d_probe.txt); the one-pass packer no longer needs the piece to stay in L2 for a second loop
 static int64_t piece_rows() {      // read per batch: A/B measurements in one process
   const char* e = getenv("SAILGPU_PACK_PIECE_ROWS");
-  const int64_t r = e && *e ? atoll(e) : 64 * 1024;
+  const int64_t r = e && *e ? atoll(e) : MAX_PIECE_ROWS;
   return std::max<int64_t>(1024, std::min<int64_t>(MAX_PIECE_ROWS, r / 1024 * 1024));
 }
 // SAILGPU_PACK_DRY=1 (measurements only): pieces are packed but neither copied nor expanded -- the host side of the ingest alone

@@ -302,7 +302,7 @@ def test_aggregate_with_a_group_key_wider_than_the_hash_table(mode, nulls):
     got = plans.execute(node, {"t": t}, gpu_batched)
     want = plans.execute(node, {"t": t}, oracle_op)
     assert got.num_rows == want.num_rows and got.num_rows > 1000
-    assert_same(got, want)
+    assert_same(got, want, float_cols=(11,))      # sum(f): Float64, summation order differs
 
 
 @pytest.mark.parametrize("jt", ["left_semi", "left_anti"])
