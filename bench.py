@@ -311,7 +311,7 @@ def exchange_leg(args, ctx, stream, rank, world, local):
     aggs = [("sum", {"col": 1}, "sum_qty", "Decimal128(15,2)"), ("count", None, "cnt", None)]
 
     def agg_spec(mode):
-        merging = mode != "partial"
+        merging = mode in ("final", "final_partitioned")
         return {"op": "aggregate", "mode": mode, "group_by": [{"expr": {"col": 0}, "name": "l_orderkey"}],
                 "aggs": [dict({"fn": fn, "name": nm, "input_type": it}, **({} if merging else {"args": [] if a is None else [a]})) for fn, a, nm, it in aggs]}
     chain = {"op": "chain", "ops": [agg_spec("partial"), {"op": "exchange", "mode": "hash", "exprs": [{"col": 0}]}, agg_spec("final_partitioned")]}

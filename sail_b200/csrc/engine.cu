@@ -102,6 +102,7 @@ void check_device_error(Ctx* ctx, uint32_t* dev_flag) {
 struct AggTable {
   BufPtr table, state, occ;
   uint64_t capacity = 0;
+  bool direct = false;        // direct-key protocol (vm.h AggParams::direct_key): `occ` is built on demand
 };
 
 struct PipelineOp : Op {
@@ -271,6 +272,20 @@ struct PipelineOp : Op {
     A.occ = static_cast<uint32_t*>(tab.occ->ptr);
     A.capacity_mask = tab.capacity - 1;
     A.n_groups = run.scal.n_groups();
+    A.direct_key = tab.direct ? 1 : 0;
+  }
+  // one never-null 8-byte key word: the table takes the direct-key protocol
+  static bool direct_eligible(const AggParams& A) {
+    return A.n_keys == 1 && A.key_words == 1 && !A.has_null_word && getenv("SAILGPU_NO_DIRECT_KEY") == nullptr;
+  }
+  // direct-key tables keep no list of occupied entries while they are filled: build it (extraction / re-hash / migration read it)
+  void build_occ(const AggTable& t, const AggParams& layout) {
+    if (!t.direct) return;
+    AggParams A = layout;
+    A.table = static_cast<uint8_t*>(t.table->ptr); A.occ = static_cast<uint32_t*>(t.occ->ptr); A.capacity_mask = t.capacity - 1;
+    BufPtr counter = dev_alloc_zero(ctx, 8);
+    SG_CUDA(launch_agg_build_occ(A, static_cast<unsigned long long*>(counter->ptr), ctx->stream));
+    m.kernel_launches++;
   }
 
   // (re)allocates the table with `cap` slots and moves the `groups` existing entries over
@@ -278,10 +293,13 @@ struct PipelineOp : Op {
     SG_CHECK(cap <= MAX_CAPACITY, SAILGPU_ERR_UNSUPPORTED, "aggregate needs more than 2^28 group slots");
     AggTable old = tab;
     tab.capacity = cap;
-    tab.table = dev_alloc(ctx, (size_t)cap * A0.entry_words * 8);
-    tab.state = dev_alloc_zero(ctx, (size_t)cap * 4);
-    tab.occ = dev_alloc(ctx, (size_t)cap * 4);
+    tab.direct = direct_eligible(A0);
+    tab.table = dev_alloc(ctx, (size_t)(cap + 1) * A0.entry_words * 8);
+    tab.state = tab.direct ? dev_alloc(ctx, 4) : dev_alloc_zero(ctx, (size_t)cap * 4);
+    tab.occ = dev_alloc(ctx, (size_t)(cap + 1) * 4);
+    if (tab.direct) { AggParams A = A0; fill_table(A); SG_CUDA(launch_agg_init_direct(A, ctx->stream)); m.kernel_launches++; }
     if (old.capacity && groups) {
+      build_occ(old, A0);
       AggParams A = A0;
       fill_table(A);
       SG_CUDA(cudaMemsetAsync(run.scal.n_groups(), 0, 8, ctx->stream));
@@ -375,11 +393,14 @@ struct PipelineOp : Op {
     check_device_error(ctx, run.scal.error());
     const uint64_t groups = read_n_groups();
     AggTable old = tab;
-    tab.table = dev_alloc(ctx, (size_t)tab.capacity * N.entry_words * 8);
-    tab.state = dev_alloc_zero(ctx, (size_t)tab.capacity * 4);
-    tab.occ = dev_alloc(ctx, (size_t)tab.capacity * 4);
+    build_occ(old, O);
+    tab.direct = direct_eligible(N);
+    tab.table = dev_alloc(ctx, (size_t)(tab.capacity + 1) * N.entry_words * 8);
+    tab.state = tab.direct ? dev_alloc(ctx, 4) : dev_alloc_zero(ctx, (size_t)tab.capacity * 4);
+    tab.occ = dev_alloc(ctx, (size_t)(tab.capacity + 1) * 4);
     AggParams A = N;
     fill_table(A);
+    if (tab.direct) { SG_CUDA(launch_agg_init_direct(A, ctx->stream)); m.kernel_launches++; }
     SG_CUDA(cudaMemsetAsync(run.scal.n_groups(), 0, 8, ctx->stream));
     SG_CUDA(launch_agg_migrate(A, M, static_cast<const uint8_t*>(old.table->ptr), static_cast<const uint32_t*>(old.occ->ptr), groups, run.scal.error(), ctx->stream));
     m.kernel_launches++;
@@ -494,6 +515,7 @@ struct PipelineOp : Op {
       out->cols.push_back(c);
     }
     if (!synth && rows > 0) {
+      build_occ(tab, A0);
       AggParams A = A0;
       fill_table(A);
       SG_CUDA(launch_agg_extract(A, X, groups, run.scal.error(), ctx->stream));

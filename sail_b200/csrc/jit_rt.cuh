@@ -107,6 +107,34 @@ __device__ __forceinline__ uint64_t i128_hi(i128 v) { return (uint64_t)((u128)v 
 // ================================================================================================
 template <class G>
 __device__ __forceinline__ uint64_t* jit_find_or_insert(const AggParams& A, const uint64_t (&kw)[MAX_KEY_WORDS], uint64_t h, uint32_t* err) {
+  if constexpr (G::KEY_WORDS == 1) {
+    if (A.direct_key) {          // direct-key protocol (vm.h): one CAS on the key word, no fence, no state word
+      const unsigned long long k = kw[0];
+      if (k == DIRECT_EMPTY_KEY) {
+        uint64_t* e = reinterpret_cast<uint64_t*>(A.table) + (A.capacity_mask + 1) * G::ENTRY_WORDS;
+        if (*reinterpret_cast<volatile unsigned long long*>(e) == 0ull && atomicCAS(reinterpret_cast<unsigned long long*>(e), 0ull, h | 1ull) == 0ull) atomicAdd(A.n_groups, 1ull);
+        return e;
+      }
+      uint64_t idx = h & A.capacity_mask;
+      for (uint64_t probes = 0; probes <= A.capacity_mask; ++probes) {
+        uint64_t* e = reinterpret_cast<uint64_t*>(A.table) + idx * G::ENTRY_WORDS;
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(e + 2);
+        if (cur == DIRECT_EMPTY_KEY) {
+          cur = atomicCAS(reinterpret_cast<unsigned long long*>(e + 2), DIRECT_EMPTY_KEY, k);
+          if (cur == DIRECT_EMPTY_KEY) {
+            e[0] = h | 1ull;
+            const unsigned m = __activemask();
+            if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(A.n_groups, (unsigned long long)__popc(m));
+            return e;
+          }
+        }
+        if (cur == k) return e;
+        idx = (idx + 1) & A.capacity_mask;
+      }
+      atomicOr(err, ERR_TABLE_FULL);
+      return nullptr;
+    }
+  }
   const uint32_t tag = (uint32_t)(h >> 34) << 2;
   uint64_t idx = h & A.capacity_mask;
   uint64_t probes = 0;

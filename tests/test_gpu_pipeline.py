@@ -244,6 +244,47 @@ def test_aggregate_many_groups_multi_batch_growth():
         assert_same(got, oracle_op(spec, whole))
 
 
+@pytest.mark.parametrize("late_nulls", [False, True])
+@pytest.mark.parametrize("ktype", ["int64", "date32", "decimal"])
+def test_aggregate_single_word_key_takes_the_direct_protocol(ktype, late_nulls):
+    """One never-null 8-byte key word: slots are claimed by a compare-and-swap on the key word itself (vm.h direct_key).  Covers the
+    sentinel value as a real key (INT64_MIN), growth with re-hashing over many batches, min/max identities, and a late batch with
+    NULL keys, which moves the table to the general layout (null-mask word) in the middle of the stream."""
+    from sail_b200 import engine
+    rng = np.random.default_rng(11)
+    n_batches, n = 12, 50000
+    batches = []
+    for b in range(n_batches):
+        k = rng.integers(-30000 * (b + 1), 30000 * (b + 1), n).astype(np.int64)
+        if ktype == "int64":
+            k[::997] = np.iinfo(np.int64).min
+            k[1::1999] = 0
+            karr = pa.array(k, mask=(rng.random(n) < 0.05) if (late_nulls and b >= 8) else None)
+        elif ktype == "date32":
+            karr = pa.array((k % 20000).astype(np.int32), type=pa.int32()).cast(pa.date32())
+            if late_nulls and b >= 8:
+                karr = pa.array(karr.to_pylist()[: n // 2] + [None] * (n - n // 2), type=pa.date32())
+        else:
+            vals = [decimal.Decimal(int(x)) / 100 for x in k]
+            if late_nulls and b >= 8:
+                vals[::13] = [None] * len(vals[::13])
+            karr = pa.array(vals, type=pa.decimal128(15, 2))
+        v = pa.array([decimal.Decimal(int(x)) / 100 for x in rng.integers(-10**7, 10**7, n)], type=pa.decimal128(15, 2))
+        i = pa.array(rng.integers(-1000, 1000, n).astype(np.int64))
+        batches.append(pa.table({"k": karr, "v": v, "i": i}))
+    whole = pa.concat_tables(batches)
+    spec = {"op": "aggregate", "mode": "single", "group_by": [{"expr": {"col": 0}, "name": "k"}],
+            "aggs": [{"fn": "sum", "args": [{"col": 1}], "name": "sv"}, {"fn": "count", "args": [], "name": "c"}, {"fn": "min", "args": [{"col": 1}], "name": "mn"},
+                     {"fn": "max", "args": [{"col": 2}], "name": "mx"}, {"fn": "avg", "args": [{"col": 1}], "name": "av"}, {"fn": "sum", "args": [{"col": 2}], "name": "si"}]}
+    op = engine.GpuExec(spec, [whole.schema])
+    for t in batches:
+        op.push(t)
+    op.finish()
+    got = op.collect()
+    op.close()
+    assert_same(got, oracle_op(spec, whole))
+
+
 @pytest.mark.parametrize("nulls", [False, True])
 @pytest.mark.parametrize("keys", [["b"], ["a"], ["a", "s"]])
 @pytest.mark.parametrize("first_limit", ["0", "40", "700"])
