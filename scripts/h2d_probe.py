@@ -75,9 +75,24 @@ def main():
                 else:
                     os.environ[k] = v
 
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        where = {}
+        for ci, c in enumerate(table.columns):
+            buf = c.chunks[0].buffers()[1]
+            for off in (0, buf.size // 2, buf.size - 1):
+                page = ctypes.c_void_p((buf.address + off) & ~4095)
+                st = ctypes.c_int(-1)
+                rc = libc.syscall(279, 0, ctypes.c_ulong(1), ctypes.byref(page), None, ctypes.byref(st), 0)
+                where[f"col{ci}@{off * 100 // max(1, buf.size)}%"] = st.value if rc == 0 else f"errno {ctypes.get_errno()}"
+        print(json.dumps({"numa_node_of_source_pages": where}), flush=True)
+    except Exception as e:      # noqa: BLE001
+        print(json.dumps({"numa_node_of_source_pages": str(e)}), flush=True)
     run("warm-up", {})
-    run("default (one pass, 64 Ki-row pieces)", {})
+    run("default (one pass, 256 Ki-row pieces, packers on the source's NUMA node)", {})
     run("two passes (scan, then pack)", {"SAILGPU_PACK_ONE_PASS": "0"})
+    run("packers not bound to the source's NUMA node", {"SAILGPU_PACK_NUMA": "0"})
     run("raw bytes (no packing)", {"SAILGPU_H2D_PACK": "0"})
     for th in (8, 16, 32):
         run(f"threads={th}", {"SAILGPU_PACK_THREADS": str(th)})
