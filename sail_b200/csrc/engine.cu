@@ -297,7 +297,7 @@ struct PipelineOp : Op {
     tab.table = dev_alloc(ctx, (size_t)(cap + 1) * A0.entry_words * 8);
     tab.state = tab.direct ? dev_alloc(ctx, 4) : dev_alloc_zero(ctx, (size_t)cap * 4);
     tab.occ = dev_alloc(ctx, (size_t)(cap + 1) * 4);
-    if (tab.direct) { AggParams A = A0; fill_table(A); SG_CUDA(launch_agg_init_direct(A, ctx->stream)); m.kernel_launches++; }
+    if (tab.direct) { run.ensure_scratch(); AggParams A = A0; fill_table(A); SG_CUDA(launch_agg_init_direct(A, ctx->stream)); m.kernel_launches++; }
     if (old.capacity && groups) {
       build_occ(old, A0);
       AggParams A = A0;
@@ -398,6 +398,7 @@ struct PipelineOp : Op {
     tab.table = dev_alloc(ctx, (size_t)(tab.capacity + 1) * N.entry_words * 8);
     tab.state = tab.direct ? dev_alloc(ctx, 4) : dev_alloc_zero(ctx, (size_t)tab.capacity * 4);
     tab.occ = dev_alloc(ctx, (size_t)(tab.capacity + 1) * 4);
+    run.ensure_scratch();
     AggParams A = N;
     fill_table(A);
     if (tab.direct) { SG_CUDA(launch_agg_init_direct(A, ctx->stream)); m.kernel_launches++; }
