@@ -274,9 +274,14 @@ struct PipelineOp : Op {
     A.n_groups = run.scal.n_groups();
     A.direct_key = tab.direct ? 1 : 0;
   }
-  // one never-null 8-byte key word: the table takes the direct-key protocol
+  // One never-null 8-byte key word: the table CAN take the direct-key protocol.  Opt-in (SAILGPU_DIRECT_KEY=1): measured on
+  // GROUP BY l_orderkey over SF10 (60 M rows -> 15 M groups) the insert kernel itself did not get faster without the fence and the
+  // counter round trip (6.25 vs 6.5 ms: it is bound by the per-row accumulator atomics that need their old value for the 128-bit
+  // carry), while initialising and scanning every ENTRY of the 64 M-slot table cost 4.3 ms more than the 4-byte state words of
+  // the general protocol (11.5 vs 8.4 ms per aggregation, profiles/README.md).
   static bool direct_eligible(const AggParams& A) {
-    return A.n_keys == 1 && A.key_words == 1 && !A.has_null_word && getenv("SAILGPU_NO_DIRECT_KEY") == nullptr;
+    const char* e = getenv("SAILGPU_DIRECT_KEY");
+    return A.n_keys == 1 && A.key_words == 1 && !A.has_null_word && e && *e && atoi(e) != 0;
   }
   // direct-key tables keep no list of occupied entries while they are filled: build it (extraction / re-hash / migration read it)
   void build_occ(const AggTable& t, const AggParams& layout) {

@@ -246,11 +246,14 @@ def test_aggregate_many_groups_multi_batch_growth():
 
 @pytest.mark.parametrize("late_nulls", [False, True])
 @pytest.mark.parametrize("ktype", ["int64", "date32", "decimal"])
-def test_aggregate_single_word_key_takes_the_direct_protocol(ktype, late_nulls):
-    """One never-null 8-byte key word: slots are claimed by a compare-and-swap on the key word itself (vm.h direct_key).  Covers the
+@pytest.mark.parametrize("direct", ["1", "0"])
+def test_aggregate_single_word_key_direct_protocol(ktype, late_nulls, direct, monkeypatch):
+    """One never-null 8-byte key word: with SAILGPU_DIRECT_KEY=1 slots are claimed by a compare-and-swap on the key word itself
+    (vm.h direct_key; opt-in, see engine.cu for the measurement); without it the general protocol runs the same input.  Covers the
     sentinel value as a real key (INT64_MIN), growth with re-hashing over many batches, min/max identities, and a late batch with
     NULL keys, which moves the table to the general layout (null-mask word) in the middle of the stream."""
     from sail_b200 import engine
+    monkeypatch.setenv("SAILGPU_DIRECT_KEY", direct)
     rng = np.random.default_rng(11)
     n_batches, n = 12, 50000
     batches = []
