@@ -199,8 +199,9 @@ struct PackPool {
   uint64_t epoch = 0;
   bool stop = false;
   std::string error;
-  // NUMA: the packers stream the producer's buffers, so they run on the CPUs of the node those pages live on (a remote-node
-  // reader gets about 60 % of the local bandwidth: 31 vs 52 ms for the host side of a 60 M-row batch, profiles/r02_h2d_probe.txt)
+  // NUMA (opt-in, SAILGPU_PACK_NUMA=1): run the packers on the CPUs of the node the producer's pages live on.  A process pinned to
+  // the WRONG node reads at ~60 % of the local bandwidth (52 vs 32 ms for the host side of a 60 M-row batch), but left alone the
+  // kernel's scheduler already keeps the packers near the data: binding measured 41.8 vs 38.6 ms unbound (profiles/r02_h2d_probe.txt)
   cpu_set_t allowed;                         // the process's affinity when the pool was created
   std::vector<cpu_set_t> node_cpus;          // allowed CPUs of every NUMA node (empty sets: unknown)
   std::atomic<int> want_node{-1};
@@ -309,7 +310,7 @@ static PackPool* pool_of(Ctx* ctx) {
   const char* nw = getenv("SAILGPU_H2D_PACK");
   p->narrow = !(nw && *nw && atoi(nw) == 0);
   p->workers.resize((size_t)n);
-  { const char* e = getenv("SAILGPU_PACK_NUMA"); if (!(e && *e && atoi(e) == 0)) p->read_topology(); }
+  { const char* e = getenv("SAILGPU_PACK_NUMA"); if (e && *e && atoi(e) != 0) p->read_topology(); }
   auto init_worker = [](PackPool::Worker& w) {
     SG_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     SG_CUDA(cudaEventCreateWithFlags(&w.done_ev, cudaEventDisableTiming));
