@@ -573,11 +573,97 @@ struct FilteredSemiJoinOp : Op {
   }
 };
 
+// ================================================================================================
+// LeftSemi / LeftAnti without a residual filter: DataFusion builds on the LEFT input whatever its size (CollectLeft), and TPC-H
+// Q18 / Q20 put a 60 M-row join result there against a probe side of a few dozen keys -- 6.4 ms of hash-table build at SF10 for a
+// 99-row probe.  Both inputs of these join types are complete before a single row can be emitted (the build rows come out after
+// the last probe batch), so the operator waits: probe batches are held while they stay below 1/8 of the build side, and if the
+// probe input ends that small the ROLES ARE EXCHANGED -- hash table on the probe keys, the big side streamed through a
+// RightSemi / RightAnti probe (same rows: a row of the left input qualifies iff its key has / has no partner on the right).
+// Otherwise the plain operator runs exactly as before.
+// ================================================================================================
+struct LazySemiJoinOp : Op {
+  Json spec;
+  std::unique_ptr<Op> inner;          // set once the decision is taken
+  std::vector<BatchPtr> bparts, pparts;
+  int64_t build_rows = 0, probe_rows = 0;
+  bool build_done = false, finished = false;
+  std::deque<BatchPtr> ready;
+
+  void drain() {
+    for (;;) {
+      BatchPtr b;
+      const bool more = inner->pull(&b);
+      if (b && b->rows > 0) ready.push_back(b);
+      if (!b || !more) break;
+    }
+  }
+  void commit_plain() {
+    inner = make_plain_join_op(ctx, spec, in_schemas);
+    for (auto& b : bparts) inner->push(0, b);
+    inner->finish(0);
+    bparts.clear();
+    for (auto& b : pparts) inner->push(1, b);
+    pparts.clear();
+  }
+  void push(int input, const BatchPtr& b) override {
+    if (input == 0) {
+      SG_CHECK(!build_done, SAILGPU_ERR_STATE, "build input already finished");
+      m.build_input_rows += (uint64_t)b->rows; m.build_input_batches++;
+      bparts.push_back(b); build_rows += b->rows;
+      return;
+    }
+    SG_CHECK(input == 1 && build_done, input == 1 ? SAILGPU_ERR_STATE : SAILGPU_ERR_INVALID, "hash_join: the build input must be finished before the probe input is pushed");
+    m.input_rows += (uint64_t)b->rows; m.input_batches++;
+    if (inner) { inner->push(1, b); return; }
+    pparts.push_back(b); probe_rows += b->rows;
+    if (probe_rows * 8 >= build_rows) commit_plain();          // not a small probe side: the plain operator takes over
+  }
+  void finish(int input) override {
+    if (input == 0) { build_done = true; return; }
+    if (!inner) {
+      // roles exchanged: {on: [[probe key, build key]], RightSemi/RightAnti}; the projection indexes the left input's columns in both forms
+      const std::string jt = spec.at("join_type").as_str();
+      std::vector<std::pair<std::string, Json>> o;
+      for (auto& kv : spec.o) {
+        if (kv.first == "join_type") { Json j; j.kind = Json::Str; j.s = jt == "left_semi" ? "right_semi" : "right_anti"; o.push_back({"join_type", j}); }
+        else if (kv.first == "on") {
+          Json on; on.kind = Json::Arr;
+          for (auto& pr : kv.second.a) { Json x; x.kind = Json::Arr; x.a = {pr.a[1], pr.a[0]}; on.a.push_back(x); }
+          o.push_back({"on", on});
+        } else o.push_back(kv);
+      }
+      Json sw; sw.kind = Json::Obj; sw.o = o;
+      inner = make_plain_join_op(ctx, sw, {in_schemas[1], in_schemas[0]});
+      for (auto& b : pparts) inner->push(0, b);
+      inner->finish(0);
+      pparts.clear();
+      for (auto& b : bparts) { inner->push(1, b); drain(); }
+      bparts.clear();
+      inner->finish(1);
+    } else inner->finish(1);
+    drain();
+    finished = true;
+    m.kernel_launches += inner->m.kernel_launches;
+  }
+  bool pull(BatchPtr* out) override {
+    *out = nullptr;
+    if (!ready.empty()) { *out = ready.front(); ready.pop_front(); m.output_rows += (uint64_t)(*out)->rows; m.output_batches++; }
+    return !ready.empty() || !finished;
+  }
+};
+
 std::unique_ptr<Op> make_join_op(Ctx* ctx, const Json& spec, const std::vector<Schema>& inputs) {
   SG_CHECK(inputs.size() == 2, SAILGPU_ERR_INVALID, "hash_join takes two inputs (build = left, probe = right)");
   const Json* jtj = spec.find("join_type");
   const std::string jt = jtj ? jtj->as_str() : "inner";
   const Json* fj = spec.find("filter");
+  if ((jt == "left_semi" || jt == "left_anti") && !(fj && !fj->is_null()) && getenv("SAILGPU_NO_JOIN_SWAP") == nullptr) {
+    auto plain = make_plain_join_op(ctx, spec, inputs);     // plan-time validation + output schema
+    auto op = std::make_unique<LazySemiJoinOp>();
+    op->ctx = ctx; op->kind = "hash_join"; op->in_schemas = inputs; op->out_schema = plain->out_schema; op->spec = spec;
+    return op;
+  }
   if (!((jt == "left_semi" || jt == "left_anti") && fj && !fj->is_null())) return make_plain_join_op(ctx, spec, inputs);
   // validates keys / projection / filter types exactly as the plain operator would (its output schema is ours)
   auto plain = make_plain_join_op(ctx, spec, inputs);

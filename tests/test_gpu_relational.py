@@ -261,6 +261,32 @@ def test_tpch_sf01_vs_oracle(q):
     assert_same(got, want, ordered=(q not in ("q3", "q10")))   # top-k with possible ties on the sort key: compare as sets
 
 
+@pytest.mark.parametrize("jt", ["left_semi", "left_anti"])
+@pytest.mark.parametrize("dups", [False, True])
+@pytest.mark.parametrize("probe_rows,probe_batches", [(60, 1), (60, 3), (0, 0), (40000, 4)])
+def test_semi_anti_join_exchanges_roles_for_a_small_probe_side(jt, dups, probe_rows, probe_batches):
+    """LeftSemi / LeftAnti (TPC-H Q18: a 60 M-row build side against 99 probe keys): with a probe input below 1/8 of the build side
+    the hash table goes on the probe keys and the big side streams through a RightSemi / RightAnti probe; larger probe inputs take
+    the plain operator after the held batches are replayed.  Two keys, NULL keys on both sides, projection, several batches."""
+    from sail_b200 import engine
+    l = left_table(30000, 81, dups, True)
+    r = right_table(max(probe_rows, 1), 82, 9000, True).slice(0, probe_rows)
+    spec = {"op": "hash_join", "join_type": jt, "mode": "collect_left", "on": [[0, 0], [1, 1]], "filter": None, "projection": [2, 0, 3]}
+    want = oracle_op(spec, l, r)
+    op = engine.GpuExec(spec, [l.schema, r.schema])
+    for o in range(0, l.num_rows, 7000):
+        op.push(l.slice(o, 7000), 0)
+    op.finish(0)
+    if probe_batches:
+        step = (probe_rows + probe_batches - 1) // probe_batches
+        for o in range(0, probe_rows, step):
+            op.push(r.slice(o, step), 1)
+    op.finish(1)
+    got = op.collect()
+    op.close()
+    assert_same(got, want)
+
+
 @pytest.mark.parametrize("mode", ["single", "two_phase"])
 @pytest.mark.parametrize("nulls", [False, True])
 def test_aggregate_with_a_group_key_wider_than_the_hash_table(mode, nulls):
