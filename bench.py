@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--sf", type=float, default=100.0, help="scale factor PER GPU (weak scaling)")
     ap.add_argument("--chunk-sf", type=float, default=10.0, help="rows of one resident Arrow batch, as a scale factor")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="host batches of the end-to-end leg (each chunk-sf big)")
-    ap.add_argument("--exchange-sf", type=float, default=30.0, help="per-GPU input of the all-to-all leg (N > 1)")
+    ap.add_argument("--exchange-sf", type=float, default=50.0, help="per-GPU input of the all-to-all leg (N > 1)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-exchange", action="store_true")
