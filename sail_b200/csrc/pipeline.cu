@@ -978,7 +978,11 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
     while (__syncthreads_or(miss && sm->hot_n < A.hot_groups)) {
       if (threadIdx.x == 0) sm->elect = NT;
       __syncthreads();
-      const bool want = miss && sm->hot_n < A.hot_groups;
+      // (the dictionary size is read once, before the barrier: the winner appends at that index.  Reading it again next to
+      // `elect` let the compiler fetch both words with one 64-bit load in EVERY thread, which racecheck rightly reports against
+      // the winner's store -- harmless, the losers never use the value, but there is no reason to keep it)
+      const int hot_cur = sm->hot_n;
+      const bool want = miss && hot_cur < A.hot_groups;
       if (want) atomicMin(&sm->elect, (int)threadIdx.x);
       __syncthreads();
       if (want && sm->elect == (int)threadIdx.x) {
@@ -986,7 +990,7 @@ __device__ __forceinline__ void sink_agg(const PipelineParams& P, const AggParam
           if (live[k] && gid[k] < 0) {
             uint64_t kw[HOT_KEY_WORDS];
             const uint64_t fp = pack_words(A, c, threadIdx.x + k * NT, kw);
-            const int g = sm->hot_n;
+            const int g = hot_cur;
             for (int w = 0; w < HOT_KEY_WORDS; ++w) H.keys[g * HOT_KEY_WORDS + w] = kw[w];
             H.fps[g] = fp;
             H.entry[g] = 0;
