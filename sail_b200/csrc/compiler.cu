@@ -527,6 +527,7 @@ void PipelineCompiler::finalize(CompiledPipeline& out, Ctx* ctx, int hot_wanted)
     J.agg.hot_groups = best_hot;
     if (out.cold_variant) { J.agg.cold_only = 1; J.agg.reg_path = 0; }
     if (best_hot < REG_GROUPS) J.agg.reg_path = 0;
+    for (ProbeParams* pp : probe_params) J.probes.push_back({pp->n_keys, pp->keys[0]});
     J.valid = true;
   }
   auto off = [&](uint32_t id) -> uint32_t { return id == NO_SLOT ? NO_SLOT : slots_.at(id).offset; };

@@ -103,6 +103,32 @@ __device__ __forceinline__ uint64_t i128_lo(i128 v) { return (uint64_t)(u128)v; 
 __device__ __forceinline__ uint64_t i128_hi(i128 v) { return (uint64_t)((u128)v >> 64); }
 
 // ================================================================================================
+// hash-join probe with one key of at most 8 bytes (pipeline.cu::vm_probe_narrow; table slot = {hash | 1, build row + 1})
+// ================================================================================================
+__device__ __forceinline__ int64_t jit_probe_narrow(const ProbeParams& P, uint64_t key, int width, bool act) {
+  if (!act) return -1;
+  const uint64_t h = mix64(0x243F6A8885A308D3ull ^ key);
+  const uint64_t tag = h | 1ull;
+  const uint8_t* bcol = P.build_keys[0];
+  const int bstride = P.build_stride[0];
+  uint64_t idx = (h >> 1) & P.capacity_mask;
+  int64_t row = -1;
+  for (;;) {
+    const ulonglong2 cur = *reinterpret_cast<const ulonglong2*>(P.table + idx * 16);
+    if (cur.x == 0) break;
+    if (cur.x == tag && load_key_word(bcol + ((int64_t)cur.y - 1) * bstride, width) == key) { row = (int64_t)cur.y - 1; break; }
+    idx = (idx + 1) & P.capacity_mask;
+  }
+  if (row >= 0 && P.visited) P.visited[row] = 1;
+  return row;
+}
+template <class T>
+__device__ __forceinline__ T jit_gather(uint64_t base, int64_t row) {
+  if (row < 0) return T{};
+  return *reinterpret_cast<const T*>(base + (uint64_t)row * sizeof(T));
+}
+
+// ================================================================================================
 // global group table (layout and protocol of pipeline.cu::agg_find_or_insert, constants from G)
 // ================================================================================================
 template <class G>
