@@ -67,13 +67,6 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
-// One 8-byte-or-narrower key word folded into the hash of a group-table / join-table key.  LOCALITY-PRESERVING: the 32 keys of an
-// aligned block land on 32 consecutive hash values (the block itself is scattered by mix64), so inputs that arrive clustered by
-// key -- fact tables sorted by their foreign key: lineitem by l_orderkey -- walk the table in runs instead of touching one DRAM
-// sector per row, and unclustered inputs lose nothing.  Used by every kernel that hashes keys for a table (pipeline.cu pack_key /
-// hash_packed_key / vm_probe_narrow, relational.cu raw_key_hash, the generated key_hash, jit_probe_narrow).  The PARTITION hash of
-// the exchange is a different function (partition_of, mirrored by the oracle) and is not affected.
-__host__ __device__ __forceinline__ uint64_t mix_key_word(uint64_t h, uint64_t v) { return mix64(h ^ (v >> 5)) + (v & 31ull); }
 
 // A resolved string view: len<=12 -> bytes inline; else {len, prefix, absolute device pointer}
 struct View { uint32_t len; uint32_t prefix; uint64_t rest; };

@@ -292,7 +292,7 @@ struct Emitter {
         else if (kk == K_B) bits = "(" + f + " ? 1ull : 0ull)";
         else throw Unsupported{"group key kind"};
         kwf << "    kw[" << w << "] = " << nul << " ? 0ull : " << bits << ";\n";
-        khf << "    h = mix_key_word(h, kw[" << w << "]);\n";
+        khf << "    h = mix64(h ^ kw[" << w << "]);\n";
         kef << "    eq = eq && a[" << w << "] == kw[" << w << "];\n";
         w += 1;
       }

@@ -107,7 +107,7 @@ __device__ __forceinline__ uint64_t i128_hi(i128 v) { return (uint64_t)((u128)v 
 // ================================================================================================
 __device__ __forceinline__ int64_t jit_probe_narrow(const ProbeParams& P, uint64_t key, int width, bool act) {
   if (!act) return -1;
-  const uint64_t h = mix_key_word(0x243F6A8885A308D3ull, key);
+  const uint64_t h = mix64(0x243F6A8885A308D3ull ^ key);
   const uint64_t tag = h | 1ull;
   const uint8_t* bcol = P.build_keys[0];
   const int bstride = P.build_stride[0];

@@ -302,7 +302,7 @@ __device__ __forceinline__ uint64_t pack_key(const KeyDesc* keys, int n_keys, in
       } else {
         uint64_t v = isnull ? 0 : load_key_word(p, d.width);
         k.w[w] = v;
-        h = mix_key_word(h, v);
+        h = mix64(h ^ v);
         w += 1;
       }
     }
@@ -403,7 +403,7 @@ __device__ __noinline__ void vm_probe_narrow(const ProbeParams& P, const TileCtx
     const int r = threadIdx.x + k * NT;
     act[k] = r < c.nrows && (pact == nullptr || pact[r]) && (pv == nullptr || pv[r]);     // NULL keys match nothing
     key[k] = load_key_word(pk + r * d.stride, d.width);
-    const uint64_t h = mix_key_word(0x243F6A8885A308D3ull, key[k]);
+    const uint64_t h = mix64(0x243F6A8885A308D3ull ^ key[k]);
     tag[k] = h | 1ull;
     s[k].x = 0; s[k].y = 0;
     if (act[k]) s[k] = *reinterpret_cast<const ulonglong2*>(P.table + ((h >> 1) & P.capacity_mask) * 16);
@@ -788,7 +788,7 @@ __device__ __forceinline__ uint64_t hash_packed_key(const AggParams& A, const Ke
       ulonglong2 v; v.x = key.w[w]; v.y = key.w[w + 1];
       h = mix64(h ^ (A.keys[i].is_view ? view_hash(v) : mix64(v.x ^ mix64(v.y))));
       w += 2;
-    } else { h = mix_key_word(h, key.w[w]); w += 1; }
+    } else { h = mix64(h ^ key.w[w]); w += 1; }
   }
   if (A.has_null_word) h = mix64(h ^ key.w[0]);
   return h;

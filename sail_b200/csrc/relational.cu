@@ -38,7 +38,7 @@ __device__ __forceinline__ uint64_t raw_key_hash(const RawKeyCol* keys, int n_ke
       h = mix64(h ^ (k.is_view ? view_hash(v) : mix64(v.x ^ mix64(v.y))));
     } else {
       uint64_t v = k.width == 8 ? *reinterpret_cast<const uint64_t*>(p) : k.width == 4 ? (uint64_t)*reinterpret_cast<const uint32_t*>(p) : (uint64_t)*p;
-      h = mix_key_word(h, v);
+      h = mix64(h ^ v);
     }
   }
   return h;
