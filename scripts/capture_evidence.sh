@@ -12,7 +12,10 @@ timeout 900 ncu --set full --import-source on --clock-control none -k regex:sg_j
 ncu -i /tmp/q1.ncu-rep --page raw --csv > $OUT/${R}_q1_jit_kernel_raw.csv 2>/dev/null
 ncu -i /tmp/q1.ncu-rep --page source --csv --print-source sass > /tmp/q1_source.csv 2>/dev/null
 python scripts/ncu_sass_summary.py /tmp/q1_source.csv 50 > $OUT/${R}_q1_jit_kernel_sass_top.txt 2>&1
-for f in sail_b200/_build/jit_cache/*.cubin; do echo "== $f"; cuobjdump --dump-resource-usage $f | grep -E "REG|Function"; cuobjdump -sass $f | grep -cE "UBLKCP"; cuobjdump -sass $f | grep -cE "SYNCS"; done > $OUT/${R}_jit_cubins.txt 2>&1
+set +x
+{ echo "# specialised kernels in sail_b200/_build/jit_cache after this run: resource usage (cuobjdump --dump-resource-usage), UBLKCP = TMA bulk copies, SYNCS = mbarrier instructions in the SASS"
+  for f in sail_b200/_build/jit_cache/*.cubin; do echo "$(basename $f)  $(cuobjdump --dump-resource-usage $f | grep -oE "REG:[0-9]+ STACK:[0-9]+ SHARED:[0-9]+")  UBLKCP=$(cuobjdump -sass $f | grep -cE "UBLKCP") SYNCS=$(cuobjdump -sass $f | grep -cE "SYNCS")"; done; } > $OUT/${R}_jit_cubins.txt 2>&1
+set -x
 timeout 600 python scripts/bench_ops.py 10 > $OUT/ops.log 2>/dev/null; tail -1 $OUT/ops.log > $OUT/${R}_ops_sf10.json
-timeout 900 python scripts/bench_tpch.py 10 > $OUT/${R}_tpch_sf10.txt 2>&1
+timeout 1200 python scripts/bench_tpch.py 10 > $OUT/${R}_tpch_sf10.txt 2>&1
 ls -la $OUT
