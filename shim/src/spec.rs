@@ -10,10 +10,11 @@ use datafusion::physical_expr::expressions::{BinaryExpr, CaseExpr, CastExpr, Col
 use datafusion::physical_expr::PhysicalExpr;
 use datafusion::physical_plan::aggregates::{AggregateExec, AggregateMode};
 use datafusion::physical_plan::filter::FilterExec;
-use datafusion::physical_plan::joins::{HashJoinExec, PartitionMode};
+use datafusion::physical_plan::joins::{HashJoinExec, NestedLoopJoinExec, PartitionMode};
 use datafusion::physical_plan::projection::ProjectionExec;
 use datafusion::physical_plan::repartition::RepartitionExec;
 use datafusion::physical_plan::sorts::sort::SortExec;
+use datafusion::physical_plan::sorts::sort_preserving_merge::SortPreservingMergeExec;
 use datafusion::physical_plan::{ExecutionPlan, Partitioning};
 use datafusion_common::{JoinType, ScalarValue};
 use serde_json::{json, Value};
@@ -168,6 +169,25 @@ pub fn sort(s: &SortExec) -> Option<Value> {
     Some(json!({"op": "sort", "keys": keys?, "fetch": s.fetch()}))
 }
 
+/// `NestedLoopJoinExec` (inner): what DataFusion plans for scalar subqueries compared with `<` / `>` (TPC-H Q11, Q22:
+/// test_tpch.plan.yaml:333,661).  The library takes the left input as the (small: at most 64 rows) build side.
+pub fn nested_loop_join(j: &NestedLoopJoinExec) -> Option<Value> {
+    if *j.join_type() != JoinType::Inner { return None; }
+    let n_left = j.left().schema().fields().len();
+    let filter = match j.filter() { Some(f) => remap_join_filter(f, n_left)?, None => Value::Null };
+    let projection = j.projection.as_ref().map(|p| json!(p)).unwrap_or(Value::Null);
+    Some(json!({"op": "nested_loop_join", "join_type": "inner", "filter": filter, "projection": projection}))
+}
+
+/// `SortPreservingMergeExec`: its single child has N sorted partitions; the GpuExec pushes every partition's batches as one run
+/// (`"runs": "batches"`) and pulls the merged stream.
+pub fn sort_preserving_merge(m: &SortPreservingMergeExec) -> Option<Value> {
+    let keys: Option<Vec<Value>> = m.expr().iter().map(|k| {
+        Some(json!({"expr": expr(&k.expr)?, "asc": !k.options.descending, "nulls_first": k.options.nulls_first}))
+    }).collect();
+    Some(json!({"op": "sort_preserving_merge", "keys": keys?, "fetch": m.fetch(), "runs": "batches"}))
+}
+
 pub fn repartition(r: &RepartitionExec) -> Option<Value> {
     match r.partitioning() {
         Partitioning::Hash(exprs, n) => {
@@ -186,6 +206,8 @@ pub fn of_plan(plan: &Arc<dyn ExecutionPlan>) -> Option<Value> {
     if let Some(x) = any.downcast_ref::<AggregateExec>() { return aggregate(x); }
     if let Some(x) = any.downcast_ref::<HashJoinExec>() { return hash_join(x); }
     if let Some(x) = any.downcast_ref::<SortExec>() { return sort(x); }
+    if let Some(x) = any.downcast_ref::<NestedLoopJoinExec>() { return nested_loop_join(x); }
+    if let Some(x) = any.downcast_ref::<SortPreservingMergeExec>() { return sort_preserving_merge(x); }
     if let Some(x) = any.downcast_ref::<RepartitionExec>() { return repartition(x); }
     None
 }
