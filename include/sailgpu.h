@@ -268,7 +268,7 @@ SAILGPU_API void sailgpu_host_free(sailgpu_ctx* ctx, void* p);
  *   SAILGPU_DIRECT_KEY=1          direct-key protocol for single-word group keys (measured slower end to end: off)
  *   SAILGPU_NO_JOIN_SWAP=1        never exchange the roles of a join's inputs;  SAILGPU_TOPK_MIN_ROWS=n  TopK selection threshold
  *   SAILGPU_PACK_THREADS=n        packer threads of the host ingest (default: the CPUs the cgroup grants, at most 32)
- *   SAILGPU_H2D_PACK=0 / SAILGPU_PACK_ONE_PASS=0 / SAILGPU_PACK_PIECE_ROWS=n / SAILGPU_PACK_NUMA=1 / SAILGPU_PACK_DRY=1   ingest A/B knobs
+ *   SAILGPU_H2D_PACK=0 / SAILGPU_PACK_ONE_PASS=0 / SAILGPU_PACK_PIECE_ROWS=n / SAILGPU_PACK_NUMA=0 / SAILGPU_PACK_DRY=1   ingest A/B knobs
  *   SAILGPU_PACKED_EXCHANGE=1     small exchange messages as one buffer per peer;  SAILGPU_AGG_MIN_CAPACITY=n  first group-table size */
 
 #endif /* SAILGPU_H */

@@ -199,9 +199,11 @@ struct PackPool {
   uint64_t epoch = 0;
   bool stop = false;
   std::string error;
-  // NUMA (opt-in, SAILGPU_PACK_NUMA=1): run the packers on the CPUs of the node the producer's pages live on.  A process pinned to
-  // the WRONG node reads at ~60 % of the local bandwidth (52 vs 32 ms for the host side of a 60 M-row batch), but left alone the
-  // kernel's scheduler already keeps the packers near the data: binding measured 41.8 vs 38.6 ms unbound (profiles/r02_h2d_probe.txt)
+  // NUMA (SAILGPU_PACK_NUMA=0 turns it off): the packers run on the CPUs of the node the producer's pages live on.  A reader on
+  // the other socket gets ~60 % of the local bandwidth (52 vs 32 ms for the host side of a 60 M-row batch).  In a small probe
+  // process the scheduler happens to keep the threads near the data and binding is neutral (37.7 vs 36.7 ms), but in bench.py --
+  // host tables first touched by the main thread, packers created later -- it is 75.8 vs 103.7 ms per two-batch step
+  // (profiles/README.md).
   cpu_set_t allowed;                         // the process's affinity when the pool was created
   std::vector<cpu_set_t> node_cpus;          // allowed CPUs of every NUMA node (empty sets: unknown)
   std::atomic<int> want_node{-1};
@@ -310,7 +312,7 @@ static PackPool* pool_of(Ctx* ctx) {
   const char* nw = getenv("SAILGPU_H2D_PACK");
   p->narrow = !(nw && *nw && atoi(nw) == 0);
   p->workers.resize((size_t)n);
-  { const char* e = getenv("SAILGPU_PACK_NUMA"); if (e && *e && atoi(e) != 0) p->read_topology(); }
+  { const char* e = getenv("SAILGPU_PACK_NUMA"); if (!(e && *e && atoi(e) == 0)) p->read_topology(); }
   auto init_worker = [](PackPool::Worker& w) {
     SG_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     SG_CUDA(cudaEventCreateWithFlags(&w.done_ev, cudaEventDisableTiming));

@@ -90,9 +90,9 @@ def main():
     except Exception as e:      # noqa: BLE001
         print(json.dumps({"numa_node_of_source_pages": str(e)}), flush=True)
     run("warm-up", {})
-    run("default (one pass, 256 Ki-row pieces)", {})
+    run("default (one pass, 256 Ki-row pieces, packers on the source's NUMA node)", {})
     run("two passes (scan, then pack)", {"SAILGPU_PACK_ONE_PASS": "0"})
-    run("packers bound to the source's NUMA node", {"SAILGPU_PACK_NUMA": "1"})
+    run("packers NOT bound to the source's NUMA node", {"SAILGPU_PACK_NUMA": "0"})
     run("raw bytes (no packing)", {"SAILGPU_H2D_PACK": "0"})
     for th in (8, 16, 32):
         run(f"threads={th}", {"SAILGPU_PACK_THREADS": str(th)})
