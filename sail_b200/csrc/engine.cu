@@ -535,7 +535,6 @@ struct PipelineOp : Op {
       }
     }
     SG_CUDA(cudaMemsetAsync(run.scal.nulls(0), 0, 8 * 20, ctx->stream));
-    SG_CHECK(X.n_cols <= 20 || true, SAILGPU_ERR_UNSUPPORTED, "");
     std::vector<unsigned long long> nulls((size_t)X.n_cols, 0);
     BufPtr nullctr = dev_alloc_zero(ctx, (size_t)X.n_cols * 8 + 8);
     for (int i = 0; i < X.n_cols; ++i) {
