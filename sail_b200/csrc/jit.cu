@@ -68,11 +68,10 @@ struct Emitter {
 
   Emitter(const CompiledPipeline& c, const JitPlan& p) : cp(c), J(c.jit), plan(p), tile(p.rpt * NT) {
     uint32_t off = 0;
-    const uint32_t ltile = (uint32_t)tile * (uint32_t)std::max(1, p.load);      // rows of one TMA stage
     for (size_t i = 0; i < J.inputs.size(); ++i) {
       const InputReg& r = J.inputs[i];
       input_index[r.slot] = (int)i;
-      const uint32_t b = r.width ? (uint32_t)r.width * ltile : ltile / 8;
+      const uint32_t b = r.width ? (uint32_t)r.width * tile : (uint32_t)tile / 8;
       in_off.push_back(off); in_bytes.push_back(b);
       off += align128(b);
     }
@@ -371,20 +370,19 @@ struct Emitter {
     std::string live = "inb";
     if (J.mask.is_imm) { if (!(J.mask.i0 & 1)) throw Unsupported{"constant FALSE predicate"}; }
     else if (J.mask.slot >= 0) live += " && " + operand((uint32_t)J.mask.slot, K_B, 1);
-    uint32_t stage_bytes = 0, tx = 0;      // tx: bytes of ONE tile (a stage of `nsub` tiles expects nsub * tx)
-    for (size_t i = 0; i < in_bytes.size(); ++i) { stage_bytes = in_off[i] + align128(in_bytes[i]); tx += in_bytes[i] / (uint32_t)std::max(1, plan.load); }
+    uint32_t stage_bytes = 0, tx = 0;
+    for (size_t i = 0; i < in_bytes.size(); ++i) { stage_bytes = in_off[i] + align128(in_bytes[i]); tx += in_bytes[i]; }
     std::ostringstream o;
     o << "#include \"jit_rt.cuh\"\nnamespace sg {\nstruct G {\n";
-    o << "  static constexpr int RPT = " << plan.rpt << ", STAGES = " << plan.stages << ", TILE = " << tile << ", LOAD = " << std::max(1, plan.load) << ", SINK = " << cp.sink << ", N_IN = " << J.inputs.size() << ";\n";
+    o << "  static constexpr int RPT = " << plan.rpt << ", STAGES = " << plan.stages << ", TILE = " << tile << ", SINK = " << cp.sink << ", N_IN = " << J.inputs.size() << ";\n";
     o << "  static constexpr uint32_t STAGE_BYTES = " << stage_bytes << "u, SCRATCH_BYTES = " << plan.scratch_bytes << "u, TX_BYTES = " << tx << "u;\n";
     o << "  struct Row {\n    bool live;\n";
     for (auto& f : fields) o << "    " << f.first << " " << f.second << ";\n";
     o << "  };\n";
-    o << "  static __device__ __forceinline__ void issue(uint8_t* st, const KernelArgs& K, int64_t row0, uint64_t* bar, uint32_t nsub) {\n";
+    o << "  static __device__ __forceinline__ void issue(uint8_t* st, const KernelArgs& K, int64_t row0, uint64_t* bar) {\n";
     for (size_t i = 0; i < J.inputs.size(); ++i) {
       const InputReg& r = J.inputs[i];
-      o << "    tma_load_1d(st + " << in_off[i] << ", K.P[0].in[" << i << "].data + " << (r.width ? "row0 * " + std::to_string(r.width) : std::string("(row0 >> 3)")) << ", "
-        << in_bytes[i] / (uint32_t)std::max(1, plan.load) << "u * nsub, bar);\n";
+      o << "    tma_load_1d(st + " << in_off[i] << ", K.P[0].in[" << i << "].data + " << (r.width ? "row0 * " + std::to_string(r.width) : std::string("(row0 >> 3)")) << ", " << in_bytes[i] << "u, bar);\n";
     }
     o << "  }\n";
     o << "  static __device__ __forceinline__ void copy_partial(uint8_t* st, const KernelArgs& K, int64_t row0, int nrows) {\n";
@@ -445,25 +443,8 @@ bool jit_plan(const CompiledPipeline& cp, size_t max_smem, JitPlan* plan) {
     if (tier > 0) p.scratch_bytes = align128((uint32_t)(32 + hot_g * (HOT_KEY_WORDS * 8 + 8) + (NT / 32) * hot_g * (1 + 2 * A.n_accs) * 8));
     target = tier == 0 ? 3 : 2; cap = tier == 0 ? 4 : 2;
   }
-  // Tiles per TMA stage.  One bulk copy per column per stage: with 256-row tiles that is 1-4 KB per copy, and the load path --
-  // not the arithmetic -- then bounds the kernel (seven 4 KB copies per tile streamed Q1's columns at 3.1 TB/s with four stages
-  // and 4.1 TB/s with two; 8 KB copies in the same shared memory reach 4.8 TB/s: profiles/README.md).  So a stage fetches the
-  // largest power-of-two run of tiles that still leaves the wanted number of CTAs per SM with TWO stages, and the per-tile
-  // compute loop walks the stage tile by tile.
   const int force_s = env_i("SAILGPU_JIT_STAGES", 0);
-  const int force_l = env_i("SAILGPU_JIT_LOAD", 0);
-  auto stage_of = [&](int load) { uint32_t b = 0; for (auto& r : J.inputs) b += align128(r.width ? (uint32_t)r.width * tile * (uint32_t)load : tile * (uint32_t)load / 8); return b; };
-  int chosen = 0, load = 1;
-  for (int l = 16; l >= 2 && !chosen; l >>= 1) {
-    if (force_l && l != force_l) continue;
-    const uint32_t st = stage_of(l);
-    if (st > 96 * 1024 && !force_l) continue;
-    const size_t smem = JIT_HDR_BYTES + p.scratch_bytes + 2 * (size_t)st;
-    if (smem > max_smem) continue;
-    const int ctas = (int)((228 * 1024) / (smem + 1024));
-    if ((ctas >= target || force_l) && (!force_s || force_s == 2)) { chosen = 2; load = l; stage = st; }
-  }
-  if (force_l == 1) chosen = 0;
+  int chosen = 0;
   for (int s = 4; s >= 2 && !chosen; --s) {
     if (force_s && s != force_s) continue;
     const size_t smem = JIT_HDR_BYTES + p.scratch_bytes + (size_t)s * stage;
@@ -476,8 +457,6 @@ bool jit_plan(const CompiledPipeline& cp, size_t max_smem, JitPlan* plan) {
     if (smem > max_smem) return false;
     chosen = 2;
   }
-  p.load = load;
-  p.stage_bytes = stage;
   p.stages = chosen;
   p.smem_bytes = JIT_HDR_BYTES + p.scratch_bytes + (size_t)chosen * stage;
   const int by_smem = std::max(1, (int)((228 * 1024) / (p.smem_bytes + 1024)));
@@ -701,7 +680,7 @@ std::shared_ptr<JitKernel> jit_get_kernel(const CompiledPipeline& cp, size_t max
   int per_sm = 0;
   rc = d.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k->func, NT, plan.smem_bytes);
   SG_CHECK(rc == 0 && per_sm >= 1, SAILGPU_ERR_CUDA, "specialised kernel cannot be resident: " + cu_err(rc));
-  k->rpt = plan.rpt; k->stages = plan.stages; k->load = plan.load; k->minb = plan.minb; k->smem_bytes = plan.smem_bytes; k->ctas_per_sm = per_sm; k->key = key;
+  k->rpt = plan.rpt; k->stages = plan.stages; k->minb = plan.minb; k->smem_bytes = plan.smem_bytes; k->ctas_per_sm = per_sm; k->key = key;
   g_kernels[key] = k;
   return k;
 }

@@ -11,7 +11,7 @@ constexpr size_t JIT_HDR_BYTES = 256;     // shared-memory header of a specialis
 struct JitKernel {
   void* module = nullptr;      // CUmodule
   void* func = nullptr;        // CUfunction
-  int rpt = 0, stages = 0, minb = 0, load = 1;
+  int rpt = 0, stages = 0, minb = 0;
   size_t smem_bytes = 0;
   int ctas_per_sm = 0;
   std::string key;
@@ -19,7 +19,6 @@ struct JitKernel {
 
 struct JitPlan {       // geometry chosen by the host for one pipeline
   int rpt = 2, stages = 2, minb = 2;
-  int load = 1;          // tiles per TMA stage: one bulk copy per column fetches `load` consecutive tiles (compute stays tile by tile)
   uint32_t stage_bytes = 0, scratch_bytes = 0;
   size_t smem_bytes = 0;
 };

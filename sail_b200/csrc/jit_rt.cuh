@@ -25,8 +25,7 @@ constexpr int JIT_NWARPS = NT / 32;
 struct JitSmem {
   uint64_t full[JIT_MAX_STAGES];       // "tile landed" (TMA transaction barrier, 1 arrival)
   uint64_t empty[JIT_MAX_STAGES];      // "stage released" (one arrival per warp)
-  long long tile_no[JIT_MAX_STAGES];   // first tile number of the stage (bit 62: partial stage, copied cooperatively); -1 = end
-  uint8_t tile_cnt[JIT_MAX_STAGES];    // tiles in the stage (1 .. G::LOAD <= 16)
+  long long tile_no[JIT_MAX_STAGES];   // tile number of the stage (bit 62: partial tile, copied cooperatively); -1 = end
   unsigned long long tile_base;        // COMPACT: exclusive prefix of the tile
   uint32_t warp_sums[33];
   uint32_t dict_n;                     // groups in the CTA dictionary (release/acquire)
@@ -821,10 +820,7 @@ __device__ __forceinline__ void jit_main(const KernelArgs& K) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t n_tiles = (P.n_rows + TILE - 1) / TILE;
   const bool dynamic = G::SINK == SINK_COMPACT && P.tile_offsets == nullptr;
-  // A position is one stage: G::LOAD consecutive tiles, or ONE tile of a tile list (re-launches over handed-back tiles)
-  constexpr int LOAD = G::LOAD;
-  const int64_t n_super = (n_tiles + LOAD - 1) / LOAD;
-  const int64_t n_pos = P.tile_list ? P.n_list : n_super;
+  const int64_t n_pos = P.tile_list ? P.n_list : n_tiles;
   const bool guarded = G::SINK == SINK_AGG && K.aux[0].agg.deferred != nullptr;
 
   if (tid == 0) {
@@ -842,34 +838,30 @@ __device__ __forceinline__ void jit_main(const KernelArgs& K) {
   auto produce = [&](int j) {
     const int s = j % S;
     long long tn = -1;
-    int nsub = 1;
     if (!stopped) {
       int64_t pos;
       if (dynamic) pos = (int64_t)atomicAdd(P.ticket, 1u);
       else { pos = next_pos; next_pos += gridDim.x; }
-      if (pos >= n_pos) stopped = true;
+      if (pos >= (dynamic ? n_tiles : n_pos)) stopped = true;
       else if (guarded && *reinterpret_cast<volatile unsigned long long*>(K.aux[0].agg.n_groups) > K.aux[0].agg.group_limit) {
-        // bounded table: hand the tiles this CTA still owns back to the host (as TILE numbers, whatever the stage size)
+        // bounded table: hand the tiles this CTA still owns back to the host
         const AggParams& A = K.aux[0].agg;
-        unsigned long long cnt = 0;
-        for (int64_t pp = pos; pp < n_pos; pp += gridDim.x) cnt += P.tile_list ? 1ull : (unsigned long long)min((int64_t)LOAD, n_tiles - pp * LOAD);
-        unsigned long long w = atomicAdd(A.n_deferred, cnt);
-        for (int64_t pp = pos; pp < n_pos; pp += gridDim.x) {
-          if (P.tile_list) A.deferred[w++] = P.tile_list[pp];
-          else for (int64_t t = pp * LOAD; t < min(n_tiles, pp * LOAD + LOAD); ++t) A.deferred[w++] = (uint32_t)t;
+        const int64_t cnt = (n_pos - pos + gridDim.x - 1) / gridDim.x;
+        const unsigned long long base = atomicAdd(A.n_deferred, (unsigned long long)cnt);
+        for (int64_t q = 0; q < cnt; ++q) {
+          const int64_t pp = pos + q * gridDim.x;
+          A.deferred[base + q] = P.tile_list ? P.tile_list[pp] : (uint32_t)pp;
         }
         stopped = true;
-      } else if (P.tile_list) tn = (long long)P.tile_list[pos];
-      else { tn = pos * LOAD; nsub = (int)min((int64_t)LOAD, n_tiles - tn); }
+      } else tn = (dynamic || !P.tile_list) ? pos : (long long)P.tile_list[pos];
     }
-    sm->tile_cnt[s] = (uint8_t)nsub;
     if (tn >= 0) {
       const int64_t row0 = tn * TILE;
-      if (P.n_rows - row0 >= (int64_t)nsub * TILE) {
+      if (P.n_rows - row0 >= TILE) {
         sm->tile_no[s] = tn;
         fence_proxy_async();
-        mbar_expect_tx(&sm->full[s], G::TX_BYTES * (uint32_t)nsub);
-        G::issue(ring + (size_t)s * G::STAGE_BYTES, K, row0, &sm->full[s], (uint32_t)nsub);
+        mbar_expect_tx(&sm->full[s], G::TX_BYTES);
+        G::issue(ring + (size_t)s * G::STAGE_BYTES, K, row0, &sm->full[s]);
       } else {
         sm->tile_no[s] = tn | JIT_PARTIAL;
         mbar_arrive(&sm->full[s]);
@@ -902,39 +894,34 @@ __device__ __forceinline__ void jit_main(const KernelArgs& K) {
     __syncwarp();
     const long long tn = sm->tile_no[s];
     if (tn < 0) break;
-    const int nsub = (int)sm->tile_cnt[s];
-    const int64_t tile0 = tn & ~JIT_PARTIAL;
+    const int64_t tile = tn & ~JIT_PARTIAL;
     const uint8_t* stg = ring + (size_t)s * G::STAGE_BYTES;
-    if (tn & JIT_PARTIAL) {       // the last stage of the batch: cooperative copy, zero-filled past the end
-      const int64_t row00 = tile0 * TILE;
+    const int64_t row0 = tile * TILE;
+    const int nrows = (int)min((int64_t)TILE, P.n_rows - row0);
+    if (tn & JIT_PARTIAL) {       // the last tile of the batch: cooperative copy, zero-filled past the end
       __syncthreads();
-      G::copy_partial(ring + (size_t)s * G::STAGE_BYTES, K, row00, (int)min((int64_t)nsub * TILE, P.n_rows - row00));
+      G::copy_partial(ring + (size_t)s * G::STAGE_BYTES, K, row0, nrows);
       __syncthreads();
     }
-    for (int sub = 0; sub < nsub; ++sub) {
-      const int64_t tile = tile0 + sub;
-      const int64_t row0 = tile * TILE;
-      const int nrows = (int)min((int64_t)TILE, P.n_rows - row0);
-      typename G::Row rows[G::RPT];
+    typename G::Row rows[G::RPT];
 #pragma unroll
-      for (int k = 0; k < G::RPT; ++k) {
-        const int r = tid + k * NT;
-        G::eval(stg, sub * TILE + r, r < nrows, K, rows[k]);
-      }
-      if constexpr (G::SINK == SINK_AGG) {
-        if constexpr (G::AGG_TIER == 2) jit_agg_reg_tile<G>(K, rows, sm, scratch, R);
-        else if constexpr (G::AGG_TIER == 1) jit_agg_dict_tile<G>(K, rows, sm, scratch);
-        else {
-          int gid[G::RPT];
+    for (int k = 0; k < G::RPT; ++k) {
+      const int r = tid + k * NT;
+      G::eval(stg, r, r < nrows, K, rows[k]);
+    }
+    if constexpr (G::SINK == SINK_AGG) {
+      if constexpr (G::AGG_TIER == 2) jit_agg_reg_tile<G>(K, rows, sm, scratch, R);
+      else if constexpr (G::AGG_TIER == 1) jit_agg_dict_tile<G>(K, rows, sm, scratch);
+      else {
+        int gid[G::RPT];
 #pragma unroll
-          for (int k = 0; k < G::RPT; ++k) gid[k] = -1;
-          jit_cold_rows<G>(K, rows, gid);
-        }
-      } else if constexpr (G::SINK == SINK_STORE) {
-        jit_store_tile<G>(K, rows, row0, nrows);
-      } else if constexpr (G::SINK == SINK_COMPACT) {
-        jit_compact_tile<G>(K, rows, sm, tile);
+        for (int k = 0; k < G::RPT; ++k) gid[k] = -1;
+        jit_cold_rows<G>(K, rows, gid);
       }
+    } else if constexpr (G::SINK == SINK_STORE) {
+      jit_store_tile<G>(K, rows, row0, nrows);
+    } else if constexpr (G::SINK == SINK_COMPACT) {
+      jit_compact_tile<G>(K, rows, sm, tile);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm->empty[s]);

@@ -239,7 +239,7 @@ struct PipelineRunner {
       // on a table-full reading that is up to two tiles old, so three tiles per CTA; a specialised kernel has its whole
       // stage ring in flight) and from the dictionary flushes
       const uint64_t cap = aux_host->agg.capacity_mask + 1;
-      const uint64_t in_flight = jk ? ((uint64_t)jk->stages + 1) * (uint64_t)std::max(1, jk->load) : 3ull;
+      const uint64_t in_flight = jk ? (uint64_t)jk->stages + 1 : 3ull;
       const uint64_t slack = std::min<uint64_t>(in_flight * (uint64_t)grid * (uint64_t)P.tile_rows, (uint64_t)P.n_rows) + (uint64_t)grid * (uint64_t)std::max(0, cp->agg.hot_groups);
       const uint64_t limit = std::min<uint64_t>(cap / 2 > slack ? cap / 2 - slack : 0, group_limit_cap);
       for (int st = 0; st < 2; ++st)
