@@ -1206,11 +1206,26 @@ struct WideAggOp : Op {
     S.idx_a = static_cast<uint32_t*>(ia->ptr); S.idx_b = static_cast<uint32_t*>(ib->ptr);
     S.kw_a = static_cast<uint64_t*>(ka->ptr); S.kw_b = static_cast<uint64_t*>(kbuf->ptr);
     S.hist = static_cast<uint32_t*>(hist->ptr); S.offs = static_cast<uint64_t*>(offs->ptr); S.scan_scratch = static_cast<uint64_t*>(scr->ptr);
+    // rows with equal keys next to each other: ordered by a 64-bit hash of the encoded key (8 radix digits whatever the key
+    // width); only if two different keys share a hash -- equal keys would then not be adjacent -- by the full key
     int sort_launches = 0;
-    SG_CUDA(radix_sort_indices(static_cast<const uint8_t*>(enc.keys->ptr), enc.key_bytes, n, S, static_cast<const uint32_t*>(enc.bits->ptr), ctx->stream, &sort_launches));
+    BufPtr hk = dev_alloc(ctx, (size_t)n * 8), all_bits = dev_alloc(ctx, 16 * 4), coll = dev_alloc_zero(ctx, 8);
+    SG_CUDA(cudaMemsetAsync(all_bits->ptr, 0xFF, 16 * 4, ctx->stream));
+    SG_CUDA(launch_key_hash(static_cast<const uint8_t*>(enc.keys->ptr), enc.key_bytes, n, static_cast<uint8_t*>(hk->ptr), ctx->stream));
+    SG_CUDA(radix_sort_indices(static_cast<const uint8_t*>(hk->ptr), 8, n, S, static_cast<const uint32_t*>(all_bits->ptr), ctx->stream, &sort_launches));
     // 3. runs of equal keys -> dense group numbers, one representative row per group
     BufPtr heads = dev_alloc(ctx, (size_t)n * 4), before = dev_alloc(ctx, (size_t)n * 8), scr2 = dev_alloc(ctx, 1026 * 8);
-    SG_CUDA(launch_group_heads(static_cast<const uint8_t*>(enc.keys->ptr), enc.key_bytes, S.idx_a, n, static_cast<uint32_t*>(heads->ptr), ctx->stream));
+    SG_CUDA(launch_group_heads(static_cast<const uint8_t*>(enc.keys->ptr), enc.key_bytes, S.idx_a, n, static_cast<uint32_t*>(heads->ptr),
+                               static_cast<const uint8_t*>(hk->ptr), static_cast<unsigned long long*>(coll->ptr), ctx->stream));
+    unsigned long long n_coll = 0;
+    SG_CUDA(cudaMemcpyAsync(&n_coll, coll->ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_coll != 0 || getenv("SAILGPU_WIDEAGG_FULL_SORT") != nullptr) {
+      int more = 0;
+      SG_CUDA(radix_sort_indices(static_cast<const uint8_t*>(enc.keys->ptr), enc.key_bytes, n, S, static_cast<const uint32_t*>(enc.bits->ptr), ctx->stream, &more));
+      SG_CUDA(launch_group_heads(static_cast<const uint8_t*>(enc.keys->ptr), enc.key_bytes, S.idx_a, n, static_cast<uint32_t*>(heads->ptr), nullptr, nullptr, ctx->stream));
+      sort_launches += more + 1;
+    }
     SG_CUDA(launch_exclusive_scan_u32(static_cast<const uint32_t*>(heads->ptr), n, static_cast<uint64_t*>(before->ptr), static_cast<uint64_t*>(scr2->ptr), ctx->stream));
     uint64_t n_groups = 0;
     SG_CUDA(cudaMemcpyAsync(&n_groups, static_cast<uint64_t*>(scr2->ptr) + std::min<int64_t>(1024, (n + 4095) / 4096), 8, cudaMemcpyDeviceToHost, ctx->stream));

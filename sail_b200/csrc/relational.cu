@@ -425,15 +425,40 @@ cudaError_t launch_merge_rank(const uint8_t* keys, int key_bytes, const int64_t*
   return cudaGetLastError();
 }
 
-// sort-based grouping (aggregates whose group key does not fit the hash table's packed key): rows in key order, `heads` marks
-// the first row of every run of equal encoded keys
-__global__ void group_heads_kernel(const uint8_t* __restrict__ keys, int key_bytes, const uint32_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ heads) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    heads[i] = (i == 0 || key_cmp(keys + (int64_t)idx[i] * key_bytes, keys + (int64_t)idx[i - 1] * key_bytes, key_bytes) != 0) ? 1u : 0u;
+// sort-based grouping (aggregates whose group key does not fit the hash table's packed key).  Rows are ordered by a 64-bit hash of
+// their encoded key (8 radix digits instead of one per key byte: Q10's keys are ~250 bytes); `heads` marks the first row of every
+// run of equal ENCODED keys.  Two different keys with one hash would make equal keys non-adjacent: *collisions counts adjacent
+// rows with equal hash and different keys, and the caller falls back to ordering by the full key when it is not zero.
+__global__ void key_hash_kernel(const uint8_t* __restrict__ keys, int key_bytes, int64_t n, uint8_t* __restrict__ out8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* k = keys + i * key_bytes;
+    uint64_t h = 0x243F6A8885A308D3ull;
+    int j = 0;
+    for (; j + 8 <= key_bytes; j += 8) { uint64_t w = 0; for (int b = 0; b < 8; ++b) w |= (uint64_t)k[j + b] << (8 * b); h = mix64(h ^ w); }
+    if (j < key_bytes) { uint64_t w = 0; for (int b = 0; j + b < key_bytes; ++b) w |= (uint64_t)k[j + b] << (8 * b); h = mix64(h ^ w ^ ((uint64_t)key_bytes << 56)); }
+    for (int b = 0; b < 8; ++b) out8[i * 8 + b] = (uint8_t)(h >> (56 - 8 * b));      // big-endian: memcmp order == numeric order
+  }
 }
-cudaError_t launch_group_heads(const uint8_t* keys, int key_bytes, const uint32_t* idx, int64_t n, uint32_t* heads, cudaStream_t s) {
+cudaError_t launch_key_hash(const uint8_t* keys, int key_bytes, int64_t n, uint8_t* out8, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  group_heads_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(keys, key_bytes, idx, n, heads);
+  key_hash_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(keys, key_bytes, n, out8);
+  return cudaGetLastError();
+}
+__global__ void group_heads_kernel(const uint8_t* __restrict__ keys, int key_bytes, const uint32_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ heads,
+                                   const uint8_t* __restrict__ hashes, unsigned long long* __restrict__ collisions) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    bool head = i == 0;
+    if (i > 0) {
+      head = key_cmp(keys + (int64_t)idx[i] * key_bytes, keys + (int64_t)idx[i - 1] * key_bytes, key_bytes) != 0;
+      if (head && hashes && key_cmp(hashes + (int64_t)idx[i] * 8, hashes + (int64_t)idx[i - 1] * 8, 8) == 0) atomicAdd(collisions, 1ull);
+    }
+    heads[i] = head ? 1u : 0u;
+  }
+}
+cudaError_t launch_group_heads(const uint8_t* keys, int key_bytes, const uint32_t* idx, int64_t n, uint32_t* heads, const uint8_t* hashes,
+                               unsigned long long* collisions, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  group_heads_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(keys, key_bytes, idx, n, heads, hashes, collisions);
   return cudaGetLastError();
 }
 // group number of every input row (dense, in key order) and one representative input row per group

@@ -290,9 +290,13 @@ def test_semi_anti_join_exchanges_roles_for_a_small_probe_side(jt, dups, probe_r
 
 @pytest.mark.parametrize("mode", ["single", "two_phase"])
 @pytest.mark.parametrize("nulls", [False, True])
-def test_aggregate_with_a_group_key_wider_than_the_hash_table(mode, nulls):
+@pytest.mark.parametrize("full_sort", [False, True])
+def test_aggregate_with_a_group_key_wider_than_the_hash_table(mode, nulls, full_sort, monkeypatch):
     """seven group keys / more than 64 packed key bytes: grouping by sorting (WideAggOp), several input batches, long strings and
-    NULL keys (NULL is a group of its own), every accumulator kind"""
+    NULL keys (NULL is a group of its own), every accumulator kind.  Rows are ordered by a 64-bit hash of the encoded key;
+    full_sort forces the path taken when two keys share a hash (ordering by the whole key)."""
+    if full_sort:
+        monkeypatch.setenv("SAILGPU_WIDEAGG_FULL_SORT", "1")
     rng = np.random.default_rng(5)
     n = 30000
     def maybe(a, typ):
