@@ -233,6 +233,12 @@ SAILGPU_API int32_t sailgpu_op_finish_input(sailgpu_op* op, int32_t input_idx);
  * operator needs more input before it can produce output it returns length 0, has_more 1. */
 SAILGPU_API int32_t sailgpu_op_pull(sailgpu_op* op, struct ArrowArray* out, int32_t* has_more);
 SAILGPU_API int32_t sailgpu_op_pull_device(sailgpu_op* op, struct ArrowDeviceArray* out, int32_t* has_more);
+/* The same batch as a HANDLE for the next GpuExec: `out` carries the length and a release callback but NO column arrays
+ * (n_children == 0); the batch stays in the library's internal HBM form -- string views are not rewritten into compact Arrow
+ * heaps, no stream is waited for -- and only sailgpu_op_push_device / sailgpu_exchange of this library instance can consume
+ * it (an operator of another context waits for the producing context's stream when it takes the handle).  This is what a
+ * GpuExec whose parent is a GpuExec pulls: the counterpart of DataFusion handing an Arc<RecordBatch> to the next operator. */
+SAILGPU_API int32_t sailgpu_op_pull_device_handle(sailgpu_op* op, struct ArrowDeviceArray* out, int32_t* has_more);
 
 /* For "repartition" operators: output batches of partition `part` only. */
 SAILGPU_API int32_t sailgpu_op_pull_partition(sailgpu_op* op, int32_t part, struct ArrowDeviceArray* out, int32_t* has_more);

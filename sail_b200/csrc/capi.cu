@@ -215,7 +215,8 @@ SAILGPU_API int32_t sailgpu_op_push_device(sailgpu_op* h, int32_t input_idx, str
     SG_CHECK(input_idx >= 0 && input_idx < (int)h->op->in_schemas.size(), SAILGPU_ERR_INVALID, "input index out of range");
     SG_CHECK(!h->input_finished[(size_t)input_idx], SAILGPU_ERR_STATE, "push after finish_input");
     SG_CHECK(batch && batch->array.release, SAILGPU_ERR_INVALID, "batch is null or released");
-    BatchPtr b = take_internal_batch(batch);
+    BatchPtr b = take_internal_batch(batch, &h->owner->ctx);
+    if (!b) { SG_CHECK(batch->array.n_children == (int64_t)h->op->in_schemas[(size_t)input_idx].size(), SAILGPU_ERR_INVALID, "device batch has no column arrays (a handle of another library instance?)"); }
     if (!b) { Trace t(&h->owner->ctx, "import_device_batch"); b = import_device_batch(&h->owner->ctx, h->op->in_schemas[(size_t)input_idx], batch); }
     Trace t2(&h->owner->ctx, "op.push");
     h->op->push(input_idx, b);
@@ -235,7 +236,7 @@ SAILGPU_API int32_t sailgpu_op_finish_input(sailgpu_op* h, int32_t input_idx) {
   });
 }
 
-static int32_t pull_common(sailgpu_op* h, int part, struct ArrowArray* host_out, struct ArrowDeviceArray* dev_out, int32_t* has_more) {
+static int32_t pull_common(sailgpu_op* h, int part, struct ArrowArray* host_out, struct ArrowDeviceArray* dev_out, int32_t* has_more, bool handle_only = false) {
   if (!h) return SAILGPU_ERR_INVALID;
   return guard(&h->last_error, [&] {
     CtxLock lk(h->owner->ctx.mu);
@@ -248,12 +249,13 @@ static int32_t pull_common(sailgpu_op* h, int part, struct ArrowArray* host_out,
     *has_more = more ? 1 : 0;
     if (!b) b = empty_batch(&h->owner->ctx, h->op->out_schema);
     if (host_out) export_host_batch(&h->owner->ctx, h->op->out_schema, b, host_out);
-    else export_device_batch(&h->owner->ctx, h->op->out_schema, b, dev_out);
+    else export_device_batch(&h->owner->ctx, h->op->out_schema, b, dev_out, handle_only);
   });
 }
 
 SAILGPU_API int32_t sailgpu_op_pull(sailgpu_op* h, struct ArrowArray* out, int32_t* has_more) { return pull_common(h, -1, out, nullptr, has_more); }
 SAILGPU_API int32_t sailgpu_op_pull_device(sailgpu_op* h, struct ArrowDeviceArray* out, int32_t* has_more) { return pull_common(h, -1, nullptr, out, has_more); }
+SAILGPU_API int32_t sailgpu_op_pull_device_handle(sailgpu_op* h, struct ArrowDeviceArray* out, int32_t* has_more) { return pull_common(h, -1, nullptr, out, has_more, true); }
 SAILGPU_API int32_t sailgpu_op_pull_partition(sailgpu_op* h, int32_t part, struct ArrowDeviceArray* out, int32_t* has_more) {
   if (part < 0) return SAILGPU_ERR_INVALID;
   return pull_common(h, part, nullptr, out, has_more);

@@ -275,6 +275,8 @@ struct ArrayPriv {
   std::vector<ArrowArray*> child_ptrs;
   std::vector<BufPtr> keep;                  // device export keeps HBM alive
   BatchPtr batch;                            // internal fast path for chained operators
+  Ctx* ctx = nullptr;                        // exporting context (a handle taken by another context waits for its stream)
+  bool opaque = false;                       // handle export: no Arrow children were materialised
 };
 void release_array(ArrowArray* a) {
   if (!a || !a->release) return;
@@ -428,21 +430,31 @@ void export_host_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, ArrowA
   out->children = p->child_ptrs.data();
 }
 
-void export_device_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, ArrowDeviceArray* out) {
+void export_device_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, ArrowDeviceArray* out, bool handle_only) {
   auto* p = new ArrayPriv();
   p->buffers.push_back(nullptr);
-  p->children.resize(schema.size());
-  p->child_ptrs.resize(schema.size());
-  for (size_t i = 0; i < schema.size(); ++i) {
-    p->children[i].release = nullptr;
-    export_column(ctx, schema[i], b->cols[i], &p->children[i], true);
-    p->child_ptrs[i] = &p->children[i];
-  }
   p->batch = b;
-  SG_CUDA(cudaStreamSynchronize(ctx->stream));   // consumer may use any stream: hand over completed data
-  init_array(&out->array, b->rows, 0, p);
-  out->array.n_children = (int64_t)schema.size();
-  out->array.children = p->child_ptrs.data();
+  p->ctx = ctx;
+  if (handle_only) {
+    // a HANDLE: the batch stays in the library's internal form (resolved string views, no compacted heaps, no Arrow child
+    // structs) and nothing is waited for -- only sailgpu_op_push_device of this library can consume it (take_internal_batch)
+    p->opaque = true;
+    init_array(&out->array, b->rows, 0, p);
+    out->array.n_children = 0;
+    out->array.children = nullptr;
+  } else {
+    p->children.resize(schema.size());
+    p->child_ptrs.resize(schema.size());
+    for (size_t i = 0; i < schema.size(); ++i) {
+      p->children[i].release = nullptr;
+      export_column(ctx, schema[i], b->cols[i], &p->children[i], true);
+      p->child_ptrs[i] = &p->children[i];
+    }
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));   // consumer may use any stream: hand over completed data
+    init_array(&out->array, b->rows, 0, p);
+    out->array.n_children = (int64_t)schema.size();
+    out->array.children = p->child_ptrs.data();
+  }
   out->device_id = ctx->device;
   out->device_type = ARROW_DEVICE_CUDA;
   out->sync_event = nullptr;
@@ -450,11 +462,15 @@ void export_device_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, Arro
 }
 
 // internal fast path: a device array we exported ourselves carries the batch
-BatchPtr take_internal_batch(ArrowDeviceArray* arr) {
+BatchPtr take_internal_batch(ArrowDeviceArray* arr, Ctx* consumer) {
   if (arr->array.release != release_array) return nullptr;
   auto* p = static_cast<ArrayPriv*>(arr->array.private_data);
   BatchPtr b = p->batch;
-  if (b) { arr->array.release(&arr->array); }
+  if (b) {
+    // a handle was not waited for at export: work queued on another context's stream must be complete before this one reads it
+    if (p->opaque && p->ctx && p->ctx != consumer) cudaStreamSynchronize(p->ctx->stream);
+    arr->array.release(&arr->array);
+  }
   return b;
 }
 

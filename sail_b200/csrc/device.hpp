@@ -152,7 +152,7 @@ BatchPtr import_device_batch(Ctx* ctx, const Schema& schema, ArrowDeviceArray* a
 // HBM -> host ArrowArray (malloc'ed buffers released by the consumer).
 void export_host_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, ArrowArray* out);
 // HBM -> ArrowDeviceArray sharing the buffers.
-void export_device_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, ArrowDeviceArray* out);
+void export_device_batch(Ctx* ctx, const Schema& schema, const BatchPtr& b, ArrowDeviceArray* out, bool handle_only = false);
 
 BatchPtr concat_batches(Ctx* ctx, const Schema& schema, const std::vector<BatchPtr>& parts);
 BatchPtr empty_batch(Ctx* ctx, const Schema& schema);

@@ -9,7 +9,7 @@
 
 namespace sg {
 
-BatchPtr take_internal_batch(ArrowDeviceArray* arr);   // device.cu
+BatchPtr take_internal_batch(ArrowDeviceArray* arr, Ctx* consumer);   // device.cu
 
 struct Metrics {
   uint64_t input_rows = 0, input_batches = 0, output_rows = 0, output_batches = 0;

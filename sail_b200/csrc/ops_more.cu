@@ -1958,7 +1958,7 @@ SAILGPU_API int32_t sailgpu_exchange(sailgpu_ctx* c, const struct ArrowSchema* s
     std::vector<BatchPtr> parts;
     for (int p = 0; p < n; ++p) {
       if (send[p].array.release == nullptr) { parts.push_back(empty_batch(ctx, schema)); continue; }   // nothing for rank p
-      BatchPtr b = take_internal_batch(&send[p]);
+      BatchPtr b = take_internal_batch(&send[p], ctx);
       if (!b) b = import_device_batch(ctx, schema, &send[p]);
       parts.push_back(b);
     }

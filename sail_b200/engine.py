@@ -84,6 +84,7 @@ def lib():
         L.sailgpu_op_finish_input.argtypes = [vp, i32]
         L.sailgpu_op_pull.argtypes = [vp, vp, ctypes.POINTER(i32)]
         L.sailgpu_op_pull_device.argtypes = [vp, vp, ctypes.POINTER(i32)]
+        L.sailgpu_op_pull_device_handle.argtypes = [vp, vp, ctypes.POINTER(i32)]
         L.sailgpu_op_pull_partition.argtypes = [vp, i32, vp, ctypes.POINTER(i32)]
         L.sailgpu_op_metrics.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
         L.sailgpu_op_metrics.restype = i64
@@ -277,12 +278,14 @@ class GpuExec:
         batch = pa.RecordBatch._import_from_c(ctypes.addressof(c), ctypes.addressof(sc))
         return batch, bool(more.value)
 
-    def pull_device(self, partition: int | None = None):
-        """-> (DeviceBatch, has_more)"""
+    def pull_device(self, partition: int | None = None, handle: bool = False):
+        """-> (DeviceBatch, has_more).  handle=True: sailgpu_op_pull_device_handle -- no Arrow column arrays are materialised; the
+        batch can only be pushed (once, not borrowed) into another operator of this library"""
         d = DeviceBatch(self.schema)
         more = ctypes.c_int32(0)
         if partition is None:
-            self._check(lib().sailgpu_op_pull_device(self._h, ctypes.addressof(d.c), ctypes.byref(more)))
+            fn = lib().sailgpu_op_pull_device_handle if handle else lib().sailgpu_op_pull_device
+            self._check(fn(self._h, ctypes.addressof(d.c), ctypes.byref(more)))
         else:
             self._check(lib().sailgpu_op_pull_partition(self._h, partition, ctypes.addressof(d.c), ctypes.byref(more)))
         d._live = True
@@ -303,10 +306,10 @@ class GpuExec:
                 break
         return pa.Table.from_batches(out, schema=self.schema)
 
-    def collect_device(self) -> list:
+    def collect_device(self, handle: bool = False) -> list:
         out = []
         while True:
-            d, more = self.pull_device()
+            d, more = self.pull_device(handle=handle)
             if d.num_rows or not more:
                 out.append(d)
             if not more:

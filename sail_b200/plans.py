@@ -175,7 +175,7 @@ def execute_gpu(node: Node, dev_tables: dict, ctx=None, stats: dict | None = Non
         for d in devs:
             op.push(d.borrow())
         op.finish()
-        out = op.collect_device()
+        out = op.collect_device(handle=True)
         for d in out:
             d.schema = op.schema
         op.close()
@@ -190,7 +190,7 @@ def execute_gpu(node: Node, dev_tables: dict, ctx=None, stats: dict | None = Non
         for b in batches:
             op.push(b, k)
         op.finish(k)
-    out = op.collect_device()
+    out = op.collect_device(handle=True)      # GpuExec -> GpuExec: the batch is handed on in its internal form
     for d in out:
         d.schema = op.schema
     if stats is not None:

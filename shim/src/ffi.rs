@@ -57,6 +57,7 @@ extern "C" {
     pub fn sailgpu_op_push_device(op: *mut SailGpuOp, input_idx: i32, batch: *mut FFI_ArrowDeviceArray) -> i32;
     pub fn sailgpu_op_finish_input(op: *mut SailGpuOp, input_idx: i32) -> i32;
     pub fn sailgpu_op_pull(op: *mut SailGpuOp, out: *mut FFI_ArrowArray, has_more: *mut i32) -> i32;
+    pub fn sailgpu_op_pull_device_handle(op: *mut SailGpuOp, out: *mut FFI_ArrowDeviceArray, has_more: *mut i32) -> i32;
     pub fn sailgpu_op_pull_device(op: *mut SailGpuOp, out: *mut FFI_ArrowDeviceArray, has_more: *mut i32) -> i32;
     pub fn sailgpu_op_pull_partition(op: *mut SailGpuOp, part: i32, out: *mut FFI_ArrowDeviceArray, has_more: *mut i32) -> i32;
     pub fn sailgpu_op_metrics(op: *mut SailGpuOp, json_buf: *mut c_char, cap: usize) -> i64;

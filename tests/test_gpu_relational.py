@@ -261,6 +261,28 @@ def test_tpch_sf01_vs_oracle(q):
     assert_same(got, want, ordered=(q not in ("q3", "q10")))   # top-k with possible ties on the sort key: compare as sets
 
 
+@pytest.mark.parametrize("q", ["q2", "q3", "q10", "q16", "q21"])
+def test_tpch_sf01_operator_chain_in_hbm(q):
+    """plans.execute_gpu: every operator hands its output to the next one as a device HANDLE (sailgpu_op_pull_device_handle:
+    internal form, no Arrow column arrays, no stream wait); only the final result is exported to the host.  Long strings
+    (names, addresses, comments) ride through joins, aggregates and sorts that way."""
+    from datagen import tpch
+    from sail_b200 import engine
+    tables = {k: v.combine_chunks() for k, v in tpch.tables(0.1).items()}
+    plan = plans.TPCH[q]()
+    dev = {k: (engine.to_device(v), v.schema.names) for k, v in tables.items()}
+    out = plans.execute_gpu(plan, dev)
+    ident = {"op": "projection", "exprs": [{"expr": {"col": i}, "name": n} for i, n in enumerate(out[0].schema.names)]}
+    op = engine.GpuExec(ident, [out[0].schema])
+    for d in out:
+        op.push(d)
+    op.finish()
+    got = op.collect()
+    op.close()
+    want = plans.execute(plan, tables, oracle_op)
+    assert_same(got, want, ordered=(q not in ("q3", "q10")))
+
+
 @pytest.mark.parametrize("jt", ["left_semi", "left_anti"])
 @pytest.mark.parametrize("dups", [False, True])
 @pytest.mark.parametrize("probe_rows,probe_batches", [(60, 1), (60, 3), (0, 0), (40000, 4)])
