@@ -338,7 +338,6 @@ ColumnPlan plan_parquet_column(const Field& f, const ParquetColumnDesc& c, int64
       SG_CHECK(have_dict, SAILGPU_ERR_INVALID, "parquet: dictionary-encoded page without a dictionary page");
       any_dict_page = true;
       segs.push_back(Segment{dense_done, 0, 1});
-      if (is_str) str_off.resize((size_t)(dense_done + non_null), 0);
       SG_CHECK(vals < body_end || non_null == 0, SAILGPU_ERR_INVALID, "parquet: empty dictionary-index stream");
       if (non_null > 0) {
         const int bw = vals[0];
@@ -350,6 +349,9 @@ ColumnPlan plan_parquet_column(const Field& f, const ParquetColumnDesc& c, int64
       any_plain_page = true;
       segs.push_back(Segment{dense_done, (int64_t)(vals - base), 0});
       if (is_str) {
+        // offsets are indexed by dense value number: values of earlier DICTIONARY pages get a zero (never read) -- filled
+        // only now, so that an all-dictionary chunk keeps no per-value host state at all
+        str_off.resize((size_t)dense_done, 0);
         const uint8_t* q = vals;
         for (int64_t i = 0; i < non_null; ++i) {
           SG_CHECK(q + 4 <= body_end, SAILGPU_ERR_INVALID, "parquet: BYTE_ARRAY value overruns its page");
