@@ -85,70 +85,121 @@ impl ExecutionPlan for GpuExec {
     fn metrics(&self) -> Option<MetricsSet> { Some(self.metrics.clone_inner()) }
 
     fn execute(&self, partition: usize, context: Arc<TaskContext>) -> Result<SendableRecordBatchStream> {
-        // `execute` is synchronous and must not block (SURVEY.md 8b "Threading"): create child streams only
-        let inputs = self.children.iter().map(|c| c.execute(partition, context.clone())).collect::<Result<Vec<_>>>()?;
-        let in_schemas: Vec<SchemaRef> = self.children.iter().map(|c| c.schema()).collect();
-        let (spec, schema, opts) = (self.spec.clone(), self.schema.clone(), self.options.clone());
+        // `execute` is synchronous and must not block (SURVEY.md 8b "Threading"): create child streams only.  A child that is a
+        // GpuExec itself is NOT executed as a RecordBatch stream: it is run inside this node's blocking task and hands its output
+        // over as device handles (sailgpu_op_pull_device_handle -> sailgpu_op_push_device), so the rows never leave HBM.
+        let inputs: Vec<Input> = self.children.iter().map(|c| match c.as_any().downcast_ref::<GpuExec>() {
+            Some(g) => Ok(Input::Gpu(g.clone_node(), context.clone())),
+            None => c.execute(partition, context.clone()).map(Input::Host),
+        }).collect::<Result<Vec<_>>>()?;
+        let node = self.clone_node();
+        let schema = self.schema.clone();
         let stream = futures::stream::once(async move {
             // CUDA synchronisation points block the calling thread: keep them off the tokio workers
-            tokio::task::spawn_blocking(move || run_operator(&spec, partition, inputs, in_schemas, schema, &opts))
-                .await
-                .map_err(|e| DataFusionError::Execution(format!("GpuExec task: {e}")))?
+            tokio::task::spawn_blocking(move || {
+                let ctx = GpuContext::create(node.options.device_for(partition))?;
+                let op = node.run(&ctx, partition, inputs)?;
+                pull_host(&op, &node.schema)
+            })
+            .await
+            .map_err(|e| DataFusionError::Execution(format!("GpuExec task: {e}")))?
         })
         .flat_map(|r| match r {
             Ok(batches) => futures::stream::iter(batches.into_iter().map(Ok)).boxed(),
             Err(e) => futures::stream::iter(vec![Err(e)]).boxed(),
         });
-        Ok(Box::pin(RecordBatchStreamAdapter::new(self.schema.clone(), stream)))
+        Ok(Box::pin(RecordBatchStreamAdapter::new(schema, stream)))
     }
 }
 
-struct OpHandle(*mut SailGpuOp);
+/// What feeds one input of a GpuExec
+enum Input {
+    Host(SendableRecordBatchStream),
+    /// a child GpuExec (and the task context its own host-side children are executed with)
+    Gpu(GpuExec, Arc<TaskContext>),
+}
+
+struct OpHandle { raw: *mut SailGpuOp, out_schema: FFI_ArrowSchema }
 unsafe impl Send for OpHandle {}
 impl Drop for OpHandle {
-    fn drop(&mut self) { unsafe { ffi::sailgpu_op_destroy(self.0) } } // idempotent cancel
+    fn drop(&mut self) { unsafe { ffi::sailgpu_op_destroy(self.raw) } } // idempotent cancel
 }
 
-/// push every input (input 0 first: the build side of a join), then pull until `has_more == 0`
-fn run_operator(spec: &str, partition: usize, mut inputs: Vec<SendableRecordBatchStream>, in_schemas: Vec<SchemaRef>,
-                out_schema: SchemaRef, opts: &GpuOptions) -> Result<Vec<RecordBatch>> {
-    let ctx = GpuContext::create(opts.device_for(partition))?;
-    let ffi_schemas: Vec<FFI_ArrowSchema> = in_schemas.iter().map(|s| FFI_ArrowSchema::try_from(s.as_ref())).collect::<std::result::Result<_, _>>()?;
-    let ptrs: Vec<*const FFI_ArrowSchema> = ffi_schemas.iter().map(|s| s as *const _).collect();
-    let cspec = CString::new(spec).map_err(|e| DataFusionError::Plan(e.to_string()))?;
-    let mut out_c = FFI_ArrowSchema::empty();
-    let mut raw = std::ptr::null_mut();
-    ffi::check(std::ptr::null(), unsafe {
-        ffi::sailgpu_op_create(ctx.0, cspec.as_ptr(), spec.len(), ptrs.as_ptr(), ptrs.len() as i32, partition as i32, &mut raw, &mut out_c)
-    })?;
-    let op = OpHandle(raw);
-    let rt = tokio::runtime::Handle::current();
-    for (i, input) in inputs.iter_mut().enumerate() {
-        // DataFusion streams 8192-row batches (application.yaml:247-251); a launch wants millions: coalesce before the copy
-        let mut pending: Vec<RecordBatch> = vec![];
-        let mut rows = 0usize;
-        let mut flush = |pending: &mut Vec<RecordBatch>| -> Result<()> {
-            if pending.is_empty() { return Ok(()); }
-            let batch = concat_batches(&pending[0].schema(), pending.iter())?;
-            pending.clear();
-            let (mut arr, _schema) = to_ffi(&StructArray::from(batch).to_data())?;
-            ffi::check(op.0, unsafe { ffi::sailgpu_op_push(op.0, i as i32, &mut arr as *mut FFI_ArrowArray) }) // takes ownership
-        };
-        while let Some(b) = rt.block_on(input.next()) {
-            let b = b?;
-            rows += b.num_rows();
-            pending.push(b);
-            if rows >= opts.coalesce_rows { flush(&mut pending)?; rows = 0; }
-        }
-        flush(&mut pending)?;
-        ffi::check(op.0, unsafe { ffi::sailgpu_op_finish_input(op.0, i as i32) })?;
+impl GpuExec {
+    fn clone_node(&self) -> GpuExec {
+        GpuExec { spec: self.spec.clone(), replaces: self.replaces.clone(), children: self.children.clone(), schema: self.schema.clone(),
+                  properties: self.properties.clone(), options: self.options.clone(), metrics: ExecutionPlanMetricsSet::new() }
     }
+
+    /// Creates the operator in `ctx`, feeds every input (input 0 first: the build side of a join) and returns it ready to be pulled.
+    /// Runs on a blocking thread.  GPU children run recursively in the SAME context: one stream, so a handle needs no event.
+    fn run(&self, ctx: &Arc<GpuContext>, partition: usize, inputs: Vec<Input>) -> Result<OpHandle> {
+        let in_schemas: Vec<SchemaRef> = self.children.iter().map(|c| c.schema()).collect();
+        let ffi_schemas: Vec<FFI_ArrowSchema> = in_schemas.iter().map(|s| FFI_ArrowSchema::try_from(s.as_ref())).collect::<std::result::Result<_, _>>()?;
+        let ptrs: Vec<*const FFI_ArrowSchema> = ffi_schemas.iter().map(|s| s as *const _).collect();
+        let cspec = CString::new(self.spec.as_str()).map_err(|e| DataFusionError::Plan(e.to_string()))?;
+        let mut out_c = FFI_ArrowSchema::empty();
+        let mut raw = std::ptr::null_mut();
+        ffi::check(std::ptr::null(), unsafe {
+            ffi::sailgpu_op_create(ctx.0, cspec.as_ptr(), self.spec.len(), ptrs.as_ptr(), ptrs.len() as i32, partition as i32, &mut raw, &mut out_c)
+        })?;
+        let op = OpHandle { raw, out_schema: out_c };
+        let rt = tokio::runtime::Handle::current();
+        for (i, input) in inputs.into_iter().enumerate() {
+            match input {
+                Input::Gpu(child, task_ctx) => {
+                    // the child's own inputs: host streams for DataFusion children, recursion for GPU children
+                    let grand: Vec<Input> = child.children.iter().map(|c| match c.as_any().downcast_ref::<GpuExec>() {
+                        Some(g) => Ok(Input::Gpu(g.clone_node(), task_ctx.clone())),
+                        None => c.execute(partition, task_ctx.clone()).map(Input::Host),
+                    }).collect::<Result<Vec<_>>>()?;
+                    let child_op = child.run(ctx, partition, grand)?;
+                    loop {
+                        let mut dev = ffi::FFI_ArrowDeviceArray::empty();
+                        let mut more = 0i32;
+                        ffi::check(child_op.raw, unsafe { ffi::sailgpu_op_pull_device_handle(child_op.raw, &mut dev, &mut more) })?;
+                        if dev.array_length() > 0 {
+                            ffi::check(op.raw, unsafe { ffi::sailgpu_op_push_device(op.raw, i as i32, &mut dev) })?; // takes ownership
+                        } else {
+                            dev.release();
+                        }
+                        if more == 0 { break; }
+                    }
+                }
+                Input::Host(mut stream) => {
+                    // DataFusion streams 8192-row batches (application.yaml:247-251); a launch wants millions: coalesce before the copy
+                    let mut pending: Vec<RecordBatch> = vec![];
+                    let mut rows = 0usize;
+                    let flush = |pending: &mut Vec<RecordBatch>| -> Result<()> {
+                        if pending.is_empty() { return Ok(()); }
+                        let batch = concat_batches(&pending[0].schema(), pending.iter())?;
+                        pending.clear();
+                        let (mut arr, _schema) = to_ffi(&StructArray::from(batch).to_data())?;
+                        ffi::check(op.raw, unsafe { ffi::sailgpu_op_push(op.raw, i as i32, &mut arr as *mut FFI_ArrowArray) }) // takes ownership
+                    };
+                    while let Some(b) = rt.block_on(stream.next()) {
+                        let b = b?;
+                        rows += b.num_rows();
+                        pending.push(b);
+                        if rows >= self.options.coalesce_rows { flush(&mut pending)?; rows = 0; }
+                    }
+                    flush(&mut pending)?;
+                }
+            }
+            ffi::check(op.raw, unsafe { ffi::sailgpu_op_finish_input(op.raw, i as i32) })?;
+        }
+        Ok(op)
+    }
+}
+
+/// pull until `has_more == 0`, importing every batch into host Arrow memory (the node's parent is a DataFusion operator)
+fn pull_host(op: &OpHandle, out_schema: &SchemaRef) -> Result<Vec<RecordBatch>> {
     let mut out = vec![];
     loop {
         let mut arr = FFI_ArrowArray::empty();
         let mut more = 0i32;
-        ffi::check(op.0, unsafe { ffi::sailgpu_op_pull(op.0, &mut arr, &mut more) })?;
-        let data = unsafe { from_ffi(arr, &out_c) }?;
+        ffi::check(op.raw, unsafe { ffi::sailgpu_op_pull(op.raw, &mut arr, &mut more) })?;
+        let data = unsafe { from_ffi(arr, &op.out_schema) }?;
         let batch = RecordBatch::from(StructArray::from(data)).with_schema(out_schema.clone())?;
         if batch.num_rows() > 0 || more == 0 { out.push(batch); }
         if more == 0 { break; }

@@ -24,6 +24,16 @@ pub struct FFI_ArrowDeviceArray {
     pub reserved: [i64; 3],
 }
 
+impl FFI_ArrowDeviceArray {
+    pub fn empty() -> Self {
+        Self { array: FFI_ArrowArray::empty(), device_id: -1, device_type: 0, sync_event: std::ptr::null_mut(), reserved: [0; 3] }
+    }
+    /// rows of the batch (the only field of a HANDLE a consumer outside the library may look at)
+    pub fn array_length(&self) -> usize { self.array.len() }
+    /// drops the batch: `FFI_ArrowArray`'s own Drop calls the release callback the library installed
+    pub fn release(self) { drop(self) }
+}
+
 pub const SAILGPU_OK: i32 = 0;
 pub const SAILGPU_ERR_INVALID: i32 = 1;
 pub const SAILGPU_ERR_UNSUPPORTED: i32 = 2;
