@@ -49,6 +49,8 @@ pub struct GpuExec {
     properties: Arc<PlanProperties>,
     options: GpuOptions,
     metrics: ExecutionPlanMetricsSet,
+    /// the DataFusion node this one replaced (kept so that the rewrite can take a replacement back: rewrite.rs consistent_partitioning)
+    original: Arc<dyn ExecutionPlan>,
 }
 
 impl GpuExec {
@@ -56,9 +58,14 @@ impl GpuExec {
     /// unchanged except where INTEGRATION.md section 2 says otherwise (hash_join reports no maintained input order).
     pub fn new(spec: String, template: &Arc<dyn ExecutionPlan>, children: Vec<Arc<dyn ExecutionPlan>>, options: GpuOptions) -> Self {
         Self { spec, replaces: template.name().to_string(), children, schema: template.schema(), properties: template.properties().clone(),
-               options, metrics: ExecutionPlanMetricsSet::new() }
+               options, metrics: ExecutionPlanMetricsSet::new(), original: template.clone() }
     }
     pub fn spec(&self) -> &str { &self.spec }
+    pub fn original(&self) -> &Arc<dyn ExecutionPlan> { &self.original }
+    /// `"filter"`, `"hash_join"`, `"repartition"`, ... (the spec's `op`)
+    pub fn op_kind(&self) -> String {
+        serde_json::from_str::<serde_json::Value>(&self.spec).ok().and_then(|v| v["op"].as_str().map(str::to_string)).unwrap_or_default()
+    }
 }
 
 impl DisplayAs for GpuExec {
@@ -80,7 +87,8 @@ impl ExecutionPlan for GpuExec {
     fn with_new_children(self: Arc<Self>, children: Vec<Arc<dyn ExecutionPlan>>) -> Result<Arc<dyn ExecutionPlan>> {
         if children.len() != self.children.len() { return internal_err!("GpuExec: wrong number of children"); }
         Ok(Arc::new(Self { spec: self.spec.clone(), replaces: self.replaces.clone(), children, schema: self.schema.clone(),
-                           properties: self.properties.clone(), options: self.options.clone(), metrics: ExecutionPlanMetricsSet::new() }))
+                           properties: self.properties.clone(), options: self.options.clone(), metrics: ExecutionPlanMetricsSet::new(),
+                           original: self.original.clone() }))
     }
     fn metrics(&self) -> Option<MetricsSet> { Some(self.metrics.clone_inner()) }
 
@@ -128,7 +136,8 @@ impl Drop for OpHandle {
 impl GpuExec {
     fn clone_node(&self) -> GpuExec {
         GpuExec { spec: self.spec.clone(), replaces: self.replaces.clone(), children: self.children.clone(), schema: self.schema.clone(),
-                  properties: self.properties.clone(), options: self.options.clone(), metrics: ExecutionPlanMetricsSet::new() }
+                  properties: self.properties.clone(), options: self.options.clone(), metrics: ExecutionPlanMetricsSet::new(),
+                  original: self.original.clone() }
     }
 
     /// Creates the operator in `ctx`, feeds every input (input 0 first: the build side of a join) and returns it ready to be pulled.

@@ -85,10 +85,50 @@ fn precompile(spec_text: &str, children: &[Arc<dyn ExecutionPlan>]) {
     }
 }
 
-/// A GPU `repartition` under a CPU consumer whose sibling input is partitioned by DataFusion (or the reverse) would break
-/// co-partitioning: such exchanges are turned back into their DataFusion nodes.
+/// Which engine computes the hash partitioning an input of a multi-input operator arrives in.
+#[derive(Clone, Copy, PartialEq, Eq)]
+enum Exchange { Gpu, DataFusion }
+
+/// The nearest hash exchange below `p`, looking through single-child nodes (filters, projections, partial aggregates, sorts keep
+/// the partitioning of their input); `None`: the input is not hash-partitioned by an exchange in this plan (e.g. a CollectLeft
+/// build side or a scan that is already partitioned).
+fn exchange_below(p: &Arc<dyn ExecutionPlan>) -> Option<Exchange> {
+    if let Some(g) = p.as_any().downcast_ref::<GpuExec>() {
+        if g.op_kind() == "repartition" { return Some(Exchange::Gpu); }
+    } else if let Some(r) = p.as_any().downcast_ref::<datafusion::physical_plan::repartition::RepartitionExec>() {
+        if matches!(r.partitioning(), datafusion::physical_plan::Partitioning::Hash(..)) { return Some(Exchange::DataFusion); }
+    }
+    let children = p.children();
+    if children.len() == 1 { exchange_below(children[0]) } else { None }
+}
+
+/// Turns the GPU hash exchange below `p` (if any, same search as `exchange_below`) back into the DataFusion node it replaced,
+/// keeping whatever sits under it.
+fn restore_exchange(p: &Arc<dyn ExecutionPlan>) -> Result<Arc<dyn ExecutionPlan>> {
+    if let Some(g) = p.as_any().downcast_ref::<GpuExec>() {
+        if g.op_kind() == "repartition" {
+            let kept: Vec<Arc<dyn ExecutionPlan>> = g.children().into_iter().cloned().collect();
+            return g.original().clone().with_new_children(kept);
+        }
+    }
+    let children = p.children();
+    if children.len() != 1 { return Ok(p.clone()); }
+    let restored = restore_exchange(children[0])?;
+    p.clone().with_new_children(vec![restored])
+}
+
+/// A GPU `repartition` under a consumer whose sibling input is partitioned by DataFusion (or the reverse) would break
+/// co-partitioning: libsailgpu's partition hash is its own, not DataFusion's `REPARTITION_RANDOM_STATE` ahash.  For every node
+/// with two or more inputs the exchanges below them must come from ONE engine; where they are mixed, the GPU exchanges are
+/// turned back into the DataFusion nodes they replaced (the operators above and below stay on the GPU).
 fn consistent_partitioning(plan: Arc<dyn ExecutionPlan>) -> Result<Arc<dyn ExecutionPlan>> {
-    // (the original DataFusion node is kept in `GpuExec::replaces` by the caller's bookkeeping; elided in this uncompiled sketch:
-    //  walk the plan, for every node with >= 2 hash-partitioned inputs require all or none of them to be GpuExec repartitions)
-    Ok(plan)
+    Ok(plan.transform_down(|node| {
+        let children: Vec<Arc<dyn ExecutionPlan>> = node.children().into_iter().cloned().collect();
+        if children.len() < 2 { return Ok(Transformed::no(node)); }
+        let kinds: Vec<Option<Exchange>> = children.iter().map(exchange_below).collect();
+        let mixed = kinds.contains(&Some(Exchange::Gpu)) && kinds.contains(&Some(Exchange::DataFusion));
+        if !mixed { return Ok(Transformed::no(node)); }
+        let restored = children.iter().map(restore_exchange).collect::<Result<Vec<_>>>()?;
+        Ok(Transformed::yes(node.with_new_children(restored)?))
+    })?.data)
 }
