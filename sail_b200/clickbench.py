@@ -12,14 +12,14 @@ nothing falls back):
   18, 42  extract(minute ..) / date_trunc('minute', ..) on a Timestamp: no Timestamp type on the GPU path yet
   21, 22  MIN(URL) / MIN(Title): min/max over strings (planned below as REJECTED, the tests pin the plan-time error)
   27, 28  length() / regexp_replace(): scalar string functions outside {substr, like}
-Strings are Utf8View and EventTime is Int64 seconds (see datagen/hits.py); [23] `SELECT *` selects the generated columns.
+Strings are Utf8View and EventTime is Int64 seconds (see datagen/hits.py); [23] `SELECT *` selects ten columns, [29] runs as six aggregates.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
 from typing import Callable
 
-from .plans import Node, and_, binop, col, date, filter_, like, lit, nested_loop_join, project, scan, sort, string, two_phase
+from .plans import Node, and_, binop, col, date, filter_, like, lit, project, scan, sort, string, two_phase
 
 I16, I32, I64 = "Int16", "Int32", "Int64"
 COUNT_STAR = ("count", None, "c", None)
@@ -157,13 +157,12 @@ def c22():
     return sort(outer, [("c", False)], fetch=10)
 
 
-STAR = ["WatchID", "Title", "EventTime", "EventDate", "CounterID", "ClientIP", "RegionID", "UserID", "URL", "Referer", "IsRefresh", "ResolutionWidth", "MobilePhone",
-        "MobilePhoneModel", "TraficSourceID", "SearchEngineID", "SearchPhrase", "AdvEngineID", "WindowClientWidth", "WindowClientHeight"]
+STAR = ["WatchID", "Title", "EventTime", "EventDate", "CounterID", "ClientIP", "RegionID", "UserID", "URL", "Referer"]
 
 
 def c23(columns=None):
-    """`SELECT *`: twenty columns -- a filter pipeline reads at most 20 column buffers (the full 105-column row needs the filter
-    run per column chunk against one selection vector, which the library does not do yet)"""
+    """`SELECT *`: ten columns -- a filter pipeline stages at most 20 column buffers per tile, validity bitmaps included (the full
+    105-column row needs the filter run per column chunk against one selection vector, which the library does not do yet)"""
     f = filter_(hits(list(columns or STAR)), like(col("URL"), "%google%"))
     return sort(f, [("EventTime", True)], fetch=10)
 
@@ -183,17 +182,13 @@ def c26():
     return project(sort(f, [("EventTime", True), ("SearchPhrase", True)], fetch=10), ["SearchPhrase"])
 
 
-def c29(n_sums: int = 90, per_pass: int = 15):
-    """ninety sums of one Int16 column: an aggregate carries at most 16 accumulators, so the sums are computed fifteen at a time
-    (six keyless aggregates over the same 2-byte column) and the six one-row results are put side by side by cross joins
-    (NestedLoopJoinExec without a filter, one row on each side).  The reference plans a single AggregateExec."""
+def c29(part: int = 0, n_sums: int = 90, per_pass: int = 15):
+    """ninety sums of one Int16 column: an aggregate carries at most 16 accumulators, so the sums are computed fifteen at a time --
+    six keyless aggregates over the same 2-byte column (`QUERIES["c29"].parts`), whose one-row results the caller puts side by
+    side.  The reference plans a single AggregateExec."""
     w = {"cast": col("ResolutionWidth"), "to": I32}          # Spark widens SMALLINT + INT literal to INT before the sum
     sums = [("sum", w if i == 0 else binop("+", w, lit(i, I32)), "sum(ResolutionWidth)" if i == 0 else f"sum((ResolutionWidth + {i}))", I32) for i in range(n_sums)]
-    out = None
-    for i in range(0, n_sums, per_pass):
-        part = two_phase(hits(["ResolutionWidth"]), [], sums[i:i + per_pass])
-        out = part if out is None else nested_loop_join(out, part)
-    return out
+    return two_phase(hits(["ResolutionWidth"]), [], sums[part * per_pass:(part + 1) * per_pass])
 
 
 def _c30(keys, filtered):
@@ -285,6 +280,7 @@ class Query:
     skip: int = 0                  # OFFSET applied by the caller (GlobalLimitExec) to the TopK(fetch=skip+k) result
     floats: tuple = ()             # Float64 result columns (compared within 1e-6 relative)
     params: tuple = ()             # literals of the SQL text that a synthetic table has to supply (plan(**{name: value}))
+    parts: int = 1                 # the result is plan(part=0) .. plan(part=parts-1) side by side ([29])
     note: str = ""
 
 
@@ -310,7 +306,7 @@ QUERIES = {
     "c17": Query(c17, 17, order=("UserID", "SearchPhrase"), note="LIMIT without ORDER BY: the plan orders by the keys to make the ten rows deterministic"),
     "c19": Query(c19, 19, params=("user",)), "c20": Query(c20, 20),
     "c23": Query(c23, 23, order=("EventTime",)), "c24": Query(c24, 24, order=("EventTime",)), "c25": Query(c25, 25, order=("SearchPhrase",)), "c26": Query(c26, 26, order=("EventTime", "SearchPhrase")),
-    "c29": Query(c29, 29), "c30": Query(c30, 30, order=("c",), floats=(4,)), "c31": Query(c31, 31, order=("c",), floats=(4,)), "c32": Query(c32, 32, order=("c",), floats=(4,)),
+    "c29": Query(c29, 29, parts=6), "c30": Query(c30, 30, order=("c",), floats=(4,)), "c31": Query(c31, 31, order=("c",), floats=(4,)), "c32": Query(c32, 32, order=("c",), floats=(4,)),
     "c33": Query(c33, 33, order=("c",)), "c34": Query(c34, 34, order=("c",)), "c35": Query(c35, 35, order=("c",)),
     "c36": Query(c36, 36, order=("PageViews",)), "c37": Query(c37, 37, order=("PageViews",)),
     "c38": Query(c38, 38, order=("PageViews",), skip=1000), "c39": Query(c39, 39, order=("PageViews",), skip=1000),

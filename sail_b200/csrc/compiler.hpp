@@ -339,6 +339,7 @@ class PipelineCompiler {
     return k;
   }
   void emit_outputs(CompiledPipeline& out) {
+    SG_CHECK((int)bindings_.size() <= MAX_OUTPUTS, SAILGPU_ERR_UNSUPPORTED, "more than " + std::to_string(MAX_OUTPUTS) + " output columns");
     for (auto& b : bindings_) {
       Val v = ensure_slot(compile(b));
       OutputCol o{}; o.slot = (uint32_t)v.slot; o.stride = (uint16_t)v.stride; o.valid_slot = v.vslot >= 0 ? (uint32_t)v.vslot : NO_SLOT;

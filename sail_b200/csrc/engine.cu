@@ -589,7 +589,7 @@ void pipeline_static_check(const Json& spec, const std::vector<Schema>& inputs) 
   static Ctx plan_ctx;
   std::unique_ptr<Op> op = make_op(&plan_ctx, spec, inputs, 0);
   PipelineOp* p = dynamic_cast<PipelineOp*>(op.get());
-  if (p == nullptr) return;
+  if (p == nullptr || p->rename_only()) return;       // a projection that only picks / renames columns passes buffers on: nothing to compile
   DevBatch shape;
   for (auto& f : inputs[0]) { DevColumn c; c.type = f.type; shape.cols.push_back(c); }
   p->run.compiled_for(shape, false);

@@ -842,6 +842,8 @@ std::unique_ptr<Op> make_nlj_op(Ctx* ctx, const Json& spec, const std::vector<Sc
     for (auto& x : pj->a) { const int i = (int)x.as_int(); SG_CHECK(i >= 0 && i < (int)op->joined.size(), SAILGPU_ERR_INVALID, "join projection index out of range"); op->projection.push_back(i); }
   } else for (size_t i = 0; i < op->joined.size(); ++i) op->projection.push_back((int)i);
   for (int i : op->projection) op->out_schema.push_back(op->joined[(size_t)i]);
+  // the joined rows are written by a streaming pipeline: its limit, reported while planning
+  SG_CHECK((int)op->out_schema.size() <= MAX_OUTPUTS, SAILGPU_ERR_UNSUPPORTED, "nested_loop_join: more than " + std::to_string(MAX_OUTPUTS) + " output columns");
   return op;
 }
 

@@ -1937,6 +1937,7 @@ __global__ void agg_extract_kernel(AggParams A, AggExtractParams X, uint64_t n_g
         }
         else if (o.width == 8) *reinterpret_cast<uint64_t*>(dst) = s[0];
         else if (o.width == 4) *reinterpret_cast<uint32_t*>(dst) = (uint32_t)s[0];
+        else if (o.width == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)s[0];      // Int16 / UInt16 group keys
         else *dst = (uint8_t)s[0];
       } else if (o.kind == 1) {
         const AccDesc& d = A.accs[o.a];
