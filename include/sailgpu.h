@@ -243,6 +243,18 @@ SAILGPU_API int32_t sailgpu_op_pull_device_handle(sailgpu_op* op, struct ArrowDe
 /* For "repartition" operators: output batches of partition `part` only. */
 SAILGPU_API int32_t sailgpu_op_pull_partition(sailgpu_op* op, int32_t part, struct ArrowDeviceArray* out, int32_t* has_more);
 
+/* Result sink.  Sail sends every result batch to the Spark Connect client as one self-contained Arrow
+ * IPC stream -- Schema message, one RecordBatch message, end-of-stream marker (`to_arrow_batch`,
+ * crates/sail-spark-connect/src/executor.rs:320-330: StreamWriter::try_new + write + finish).  sailgpu_ipc_stream frames a HOST
+ * batch that way (batch == NULL: schema and end-of-stream only) into a malloc'ed buffer the caller returns with
+ * sailgpu_ipc_free; it touches no device and needs no context.  sailgpu_op_pull_ipc is sailgpu_op_pull followed by that framing:
+ * what the root GpuExec of a plan hands to the executor instead of a RecordBatch.  Column types: those of "Types T" above plus
+ * Binary / LargeUtf8 / LargeBinary / BinaryView; nested and dictionary columns return SAILGPU_ERR_UNSUPPORTED. */
+SAILGPU_API int32_t sailgpu_ipc_stream(const struct ArrowSchema* schema, const struct ArrowArray* batch, uint8_t** data, size_t* len);
+SAILGPU_API int32_t sailgpu_op_pull_ipc(sailgpu_op* op, uint8_t** data, size_t* len, int64_t* rows, int32_t* has_more);
+SAILGPU_API const char* sailgpu_ipc_last_error(void);   /* message of the last failed sailgpu_ipc_stream on this thread */
+SAILGPU_API void sailgpu_ipc_free(uint8_t* data);
+
 /* All-to-all exchange of the n = world_size device batches in `send` (batch p goes to rank p);
  * on return `recv` holds the concatenation of what every rank sent to this rank.  NCCL
  * send/recv groups over NVLink; counts are exchanged first.  world_size 1 degenerates to a move. */

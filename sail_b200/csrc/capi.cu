@@ -261,6 +261,27 @@ SAILGPU_API int32_t sailgpu_op_pull_partition(sailgpu_op* h, int32_t part, struc
   return pull_common(h, part, nullptr, out, has_more);
 }
 
+// Result sink: the next output batch as one self-contained Arrow IPC stream (ipc.cpp), the bytes Sail's Spark Connect executor
+// sends for a result batch (crates/sail-spark-connect/src/executor.rs:320-330).  pull to the host + framing.
+SAILGPU_API int32_t sailgpu_op_pull_ipc(sailgpu_op* h, uint8_t** data, size_t* len, int64_t* rows, int32_t* has_more) {
+  if (!h || !data || !len || !has_more) return SAILGPU_ERR_INVALID;
+  struct ArrowArray batch;
+  memset(&batch, 0, sizeof(batch));
+  int32_t rc = pull_common(h, -1, &batch, nullptr, has_more);
+  if (rc != SAILGPU_OK) return rc;
+  struct ArrowSchema schema;
+  memset(&schema, 0, sizeof(schema));
+  rc = guard(&h->last_error, [&] { schema_to_arrow(h->op->out_schema, &schema); });
+  if (rc == SAILGPU_OK) {
+    rc = sailgpu_ipc_stream(&schema, &batch, data, len);
+    if (rc != SAILGPU_OK) h->last_error = sailgpu_ipc_last_error();
+    else if (rows) *rows = batch.length;
+  }
+  if (schema.release) schema.release(&schema);
+  if (batch.release) batch.release(&batch);
+  return rc;
+}
+
 SAILGPU_API int64_t sailgpu_op_metrics(sailgpu_op* h, char* json_buf, size_t cap) {
   if (!h) return -1;
   CtxLock lk(h->owner->ctx.mu);

@@ -98,6 +98,11 @@ def lib():
         L.sailgpu_comm_unique_id.argtypes = [ctypes.c_char_p]
         L.sailgpu_ctx_comm_init.argtypes = [vp, ctypes.c_char_p, i32, i32]
         L.sailgpu_exchange.argtypes = [vp, vp, vp, i32, vp]
+        L.sailgpu_ipc_stream.argtypes = [vp, vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+        L.sailgpu_op_pull_ipc.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(i64), ctypes.POINTER(i32)]
+        L.sailgpu_ipc_last_error.restype = ctypes.c_char_p
+        L.sailgpu_ipc_free.argtypes = [vp]
+        L.sailgpu_ipc_free.restype = None
         _lib = L
     return _lib
 
@@ -278,6 +283,16 @@ class GpuExec:
         batch = pa.RecordBatch._import_from_c(ctypes.addressof(c), ctypes.addressof(sc))
         return batch, bool(more.value)
 
+    def pull_ipc(self):
+        """-> (bytes of one Arrow IPC stream holding the next batch, rows, has_more): the result sink (sailgpu_op_pull_ipc)"""
+        data, n = ctypes.c_void_p(), ctypes.c_size_t(0)
+        rows, more = ctypes.c_int64(0), ctypes.c_int32(0)
+        self._check(lib().sailgpu_op_pull_ipc(self._h, ctypes.byref(data), ctypes.byref(n), ctypes.byref(rows), ctypes.byref(more)))
+        try:
+            return ctypes.string_at(data.value, n.value), rows.value, bool(more.value)
+        finally:
+            lib().sailgpu_ipc_free(data)
+
     def pull_device(self, partition: int | None = None, handle: bool = False):
         """-> (DeviceBatch, has_more).  handle=True: sailgpu_op_pull_device_handle -- no Arrow column arrays are materialised; the
         batch can only be pushed (once, not borrowed) into another operator of this library"""
@@ -327,6 +342,26 @@ class GpuExec:
                 self.close()
         except Exception:
             pass
+
+
+def ipc_stream(batch: pa.RecordBatch | None, schema: pa.Schema | None = None) -> bytes:
+    """A host batch framed as one self-contained Arrow IPC stream (sailgpu_ipc_stream; batch None: schema + end-of-stream only).
+    Needs no GPU and no context."""
+    sc = _export_schema(batch.schema if batch is not None else schema)
+    c = ArrowArrayC()
+    if batch is not None:
+        batch._export_to_c(ctypes.addressof(c))
+    data, n = ctypes.c_void_p(), ctypes.c_size_t(0)
+    try:
+        rc = lib().sailgpu_ipc_stream(ctypes.addressof(sc), ctypes.addressof(c) if batch is not None else None, ctypes.byref(data), ctypes.byref(n))
+        if rc != 0:
+            raise SailGpuError(rc, lib().sailgpu_ipc_last_error().decode())
+        return ctypes.string_at(data.value, n.value)
+    finally:
+        lib().sailgpu_ipc_free(data)
+        _release_schema(sc)
+        if batch is not None and c.release:
+            ctypes.CFUNCTYPE(None, ctypes.c_void_p)(c.release)(ctypes.addressof(c))
 
 
 def validate(spec: dict, inputs: list) -> pa.Schema:

@@ -73,6 +73,11 @@ extern "C" {
     pub fn sailgpu_op_metrics(op: *mut SailGpuOp, json_buf: *mut c_char, cap: usize) -> i64;
     pub fn sailgpu_last_error(op: *const SailGpuOp) -> *const c_char;
     pub fn sailgpu_op_destroy(op: *mut SailGpuOp);
+    /// result sink: one self-contained Arrow IPC stream per batch (what `to_arrow_batch` writes, executor.rs:320-330)
+    pub fn sailgpu_ipc_stream(schema: *const FFI_ArrowSchema, batch: *const FFI_ArrowArray, data: *mut *mut u8, len: *mut usize) -> i32;
+    pub fn sailgpu_op_pull_ipc(op: *mut SailGpuOp, data: *mut *mut u8, len: *mut usize, rows: *mut i64, has_more: *mut i32) -> i32;
+    pub fn sailgpu_ipc_last_error() -> *const c_char;
+    pub fn sailgpu_ipc_free(data: *mut u8);
     pub fn sailgpu_exchange(
         ctx: *mut SailGpuCtx, schema: *const FFI_ArrowSchema, send: *mut FFI_ArrowDeviceArray, n: i32,
         recv: *mut FFI_ArrowDeviceArray,
