@@ -1,4 +1,4 @@
-"""Regenerates tests/golden/tpch_plan_ops.json from the reference's plan snapshot
+"""Regenerates tests/golden/tpch_plan_ops.json (and clickbench_plan_ops.json, see clickbench()) from the reference's plan snapshot
 (python/pysail/tests/spark/__snapshots__/test_tpch.plan.yaml): per query, the operators that carry semantics -- join types of
 HashJoinExec / NestedLoopJoinExec, modes of AggregateExec, TopK fetch of SortExec.  Run in the build container only.
 
@@ -33,5 +33,26 @@ def main():
     print("wrote", DST, len(out))
 
 
+def clickbench():
+    """tests/golden/clickbench_plan_ops.json: per ClickBench query of the reference's plan snapshot (taken on an EMPTY hits table,
+    python/pysail/tests/spark/test_clickbench.py:122-158) the pieces that do not depend on table size -- TopK fetch,
+    GlobalLimitExec skip, and whether count(DISTINCT) is planned as two stacked aggregates (the inner one grouping by `alias1`)."""
+    src = "/root/reference/python/pysail/tests/spark/__snapshots__/test_clickbench.plan.yaml"
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "clickbench_plan_ops.json")
+    out = {}
+    for block in open(src).read().split("\n---\n"):
+        m = re.search(r'name: "test_clickbench_query_plan\[(\d+)\]"', block)
+        if not m:
+            continue
+        fetch = sorted({int(x) for x in re.findall(r"TopK\(fetch=(\d+)\)", block)})
+        skip = re.findall(r"GlobalLimitExec: skip=(\d+), fetch=(\d+)", block)
+        out[f"c{int(m.group(1))}"] = {"topk": fetch[0] if fetch else None, "skip": int(skip[0][0]) if skip else 0,
+                                     "limit": int(skip[0][1]) if skip else None, "two_level_distinct": "alias1" in block}
+    with open(dst, "w") as f:
+        json.dump({"source": "lakehq/sail python/pysail/tests/spark/__snapshots__/test_clickbench.plan.yaml", "queries": out}, f, indent=1, sort_keys=True)
+    print("wrote", dst, len(out))
+
+
 if __name__ == "__main__":
     main()
+    clickbench()

@@ -121,3 +121,28 @@ def test_coverage_statement():
     planned = {q.sql for q in cb.QUERIES.values()} | {q.sql for q in cb.REJECTED.values()} | set(cb.NOT_PLANNED)
     assert planned == set(range(43))
     assert len({q.sql for q in cb.QUERIES.values()}) == 37
+
+
+def test_limits_and_distinct_shapes_follow_the_reference_plans():
+    """what the reference's ClickBench plan snapshot fixes independently of table size (tests/golden/clickbench_plan_ops.json):
+    `LIMIT k OFFSET m` is TopK(fetch = m + k) under a GlobalLimitExec(skip = m), and count(DISTINCT x) alone in its SELECT is two
+    stacked aggregates grouping by `alias1`"""
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "clickbench_plan_ops.json")))["queries"]
+
+    def has_alias1(node):
+        return any(g["name"] == "alias1" for g in node.spec.get("group_by", [])) or any(has_alias1(c) for c in node.inputs)
+    for name, q in cb.QUERIES.items():
+        r = ref[f"c{q.sql}"]
+        plan = q.plan() if q.parts == 1 else q.plan(part=0)
+        top = cb.top_sort(plan)
+        if name == "c17":          # LIMIT without ORDER BY: the reference cuts the stream (GlobalLimitExec fetch=10), here the keys are ordered first
+            assert r["topk"] is None and r["limit"] == 10 and top.spec["fetch"] == 10
+            continue
+        assert (top.spec["fetch"] if top is not None else None) == r["topk"], name
+        assert q.skip == r["skip"], name
+        if r["two_level_distinct"]:
+            assert has_alias1(plan), name
+        else:
+            assert not has_alias1(plan) or name == "c9", name      # [09]: SingleDistinctToGroupBy rewrite instead of a distinct accumulator
