@@ -6,7 +6,7 @@ OUT=gpurun_out/evidence; mkdir -p $OUT
 R=${ROUND:-r02}
 timeout 1500 python bench.py > $OUT/${R}_bench_n1.json 2> $OUT/${R}_bench_n1.err
 timeout 600 python bench.py --impl reference > $OUT/${R}_bench_reference.json 2> $OUT/${R}_bench_reference.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${R}_launches_q1_bench.csv python bench.py --sf 20 --steps 3 --warmup 3 --skip-cpu --skip-e2e --skip-joins > $OUT/ncu_launches.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${R}_launches_q1_bench.csv python bench.py --sf 20 --steps 3 --warmup 3 --skip-cpu --skip-e2e --skip-joins --skip-suites > $OUT/ncu_launches.log 2>&1
 # launches of the specialised kernel in run_q1_once.py: one per repetition (the final aggregate and the sort are interpreted / small)
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:sg_jit_kernel --launch-skip 2 -c 1 -o /tmp/q1 python scripts/run_q1_once.py 10 4 > $OUT/ncu_q1.log 2>&1
 ncu -i /tmp/q1.ncu-rep --page raw --csv > $OUT/${R}_q1_jit_kernel_raw.csv 2>/dev/null
