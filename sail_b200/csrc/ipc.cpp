@@ -215,9 +215,12 @@ int64_t count_nulls(const ArrowArray* a) {
   if (a->null_count >= 0) return a->null_count;
   const uint8_t* v = a->n_buffers > 0 ? static_cast<const uint8_t*>(a->buffers[0]) : nullptr;
   if (!v) return 0;
-  int64_t valid = 0;
-  for (int64_t i = 0; i < a->length; ++i) { const int64_t j = a->offset + i; valid += (v[j >> 3] >> (j & 7)) & 1; }
-  return a->length - valid;
+  int64_t valid = 0, i = 0;
+  const int64_t n = a->length, o = a->offset;
+  for (; i < n && ((o + i) & 7); ++i) valid += (v[(o + i) >> 3] >> ((o + i) & 7)) & 1;          // up to a byte boundary
+  for (; i + 64 <= n; i += 64) { uint64_t w; memcpy(&w, v + ((o + i) >> 3), 8); valid += __builtin_popcountll(w); }
+  for (; i < n; ++i) valid += (v[(o + i) >> 3] >> ((o + i) & 7)) & 1;
+  return n - valid;
 }
 
 void write_batch_message(std::vector<uint8_t>& out, const ArrowSchema* s, const ArrowArray* batch, const std::vector<ColType>& types) {

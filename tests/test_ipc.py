@@ -108,3 +108,23 @@ def test_unsupported_columns_are_refused():
     with pytest.raises(engine.SailGpuError) as e:
         engine.ipc_stream(ts)
     assert e.value.code == 2 and "tsu" in str(e.value)
+
+
+@pytest.mark.parametrize("first,count", [(0, 1000), (3, 777), (64, 128), (5, 3)])
+def test_unknown_null_count_is_counted(first, count):
+    """a producer may leave null_count = -1 (Arrow C Data Interface): the RecordBatch's FieldNode needs the real count"""
+    import ctypes
+    rng = np.random.default_rng(first)
+    col = pa.array(rng.integers(0, 100, 1200), mask=rng.random(1200) < 0.3).slice(first, count)
+    batch = pa.record_batch([col], names=["x"])
+    sc, c = engine._export_schema(batch.schema), engine.ArrowArrayC()
+    batch._export_to_c(ctypes.addressof(c))
+    child = engine.ArrowArrayC.from_address(ctypes.cast(c.children, ctypes.POINTER(ctypes.c_void_p))[0])
+    child.null_count = -1
+    data, n = ctypes.c_void_p(), ctypes.c_size_t(0)
+    assert engine.lib().sailgpu_ipc_stream(ctypes.addressof(sc), ctypes.addressof(c), ctypes.byref(data), ctypes.byref(n)) == 0
+    out = pa.ipc.open_stream(ctypes.string_at(data.value, n.value)).read_all()
+    engine.lib().sailgpu_ipc_free(data)
+    engine._release_schema(sc)
+    ctypes.CFUNCTYPE(None, ctypes.c_void_p)(c.release)(ctypes.addressof(c))
+    assert out.column(0).null_count == col.null_count and out.equals(pa.Table.from_batches([batch]))
