@@ -559,11 +559,29 @@ def suite_legs(args):
     import tempfile
     out = {}
     env = {k: v for k, v in os.environ.items() if k != "SAILGPU_TIMING"}     # per-launch event timing is this file's own instrument
+
+    def run_bounded(cmd, limit):
+        """-> (exit code or None after the limit, stdout, stderr).  Output goes to files, not pipes, and a child that does not die
+        within ten seconds of being killed is left behind: this function returns after limit + 10 s whatever the child does."""
+        with tempfile.TemporaryFile("w+") as so, tempfile.TemporaryFile("w+") as se:
+            p = subprocess.Popen(cmd, stdout=so, stderr=se, cwd=ROOT, env=env)
+            try:
+                rc = p.wait(timeout=limit)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                try:
+                    p.wait(timeout=10)
+                except subprocess.TimeoutExpired:
+                    pass
+                rc = None
+            so.seek(0)
+            se.seek(0)
+            return rc, so.read(), se.read()
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_tpch.py"), f"{args.suite_sf:g}", "2"], capture_output=True, text=True, timeout=200, cwd=ROOT, env=env)
-        lines = [x for x in r.stdout.strip().splitlines() if x.startswith("{")]
+        rc, so, se = run_bounded([sys.executable, os.path.join(ROOT, "scripts", "bench_tpch.py"), f"{args.suite_sf:g}", "2"], 200)
+        lines = [x for x in so.strip().splitlines() if x.startswith("{")]
         if not lines:
-            raise RuntimeError(f"scripts/bench_tpch.py exited {r.returncode}: " + (r.stderr.strip().splitlines() or ["no output"])[-1])
+            raise RuntimeError(f"scripts/bench_tpch.py {'ran into its time limit' if rc is None else f'exited {rc}'}: " + (se.strip().splitlines() or ["no output"])[-1])
         d = json.loads(lines[-1])
         out["tpch22"] = {"workload": f"TPC-H 22 queries SF{args.suite_sf:g}, 1 GPU, referenced columns resident in HBM, every operator through the C ABI with device hand-off",
                          "n_queries": d["n_queries"], "total_ms": d["total_ms"], "ms": {k: v["ms"] for k, v in d["queries"].items()}, "hbm_bytes": d["hbm_bytes"],
@@ -573,11 +591,8 @@ def suite_legs(args):
     try:
         with tempfile.TemporaryDirectory() as tmp:
             path = os.path.join(tmp, "clickbench.jsonl")
-            try:
-                subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "clickbench_gpu.py"), "--out", path, "--parity-rows", "100000", "--timing-rows", "3000000",
-                                "--budget-s", "120"], capture_output=True, text=True, timeout=170, cwd=ROOT, env=env)
-            except subprocess.TimeoutExpired:
-                pass                                 # what it finished before the limit is in the file
+            run_bounded([sys.executable, os.path.join(ROOT, "scripts", "clickbench_gpu.py"), "--out", path, "--parity-rows", "100000", "--timing-rows", "3000000",
+                         "--budget-s", "120"], 170)                   # what it finished before the limit is in the file
             recs = [json.loads(x) for x in open(path) if x.strip()] if os.path.exists(path) else []
         if not recs:
             raise RuntimeError("scripts/clickbench_gpu.py produced no record")
