@@ -101,3 +101,31 @@ def test_exchange_and_chain_specs_validate_without_a_gpu():
              "aggs": [{"fn": "sum", "name": "sv", "input_type": "Decimal128(15,2)"}]}
     out = engine.validate(sdist.two_phase_chain(partial, final, [0]), [s])
     assert out.names == ["k", "sv"] and str(out.field(1).type) == "decimal128(25, 2)"
+
+
+def test_width_limits_of_one_operator_are_reported_at_plan_time():
+    """a streaming pipeline writes at most 24 output columns and an aggregate carries at most 16 accumulators (vm.h): both are
+    answered by sailgpu_spec_validate, not after the first batch arrived (ClickBench [29] met the first one at run time once)"""
+    wide = pa.schema([(f"c{i}", pa.int64()) for i in range(30)])
+    # picking / renaming columns passes buffers on: no limit
+    assert len(engine.validate({"op": "projection", "exprs": [{"expr": {"col": i}, "name": f"x{i}"} for i in range(30)]}, [wide])) == 30
+    computed = {"op": "projection", "exprs": [{"expr": plans.binop("+", {"col": i % 10}, plans.lit(i, "Int64")), "name": f"x{i}"} for i in range(25)]}
+    with pytest.raises(engine.SailGpuError) as e:
+        engine.validate(computed, [wide])
+    assert e.value.code == 2 and "24 output columns" in str(e.value)
+    computed["exprs"] = computed["exprs"][:24]
+    assert len(engine.validate(computed, [wide])) == 24
+    with pytest.raises(engine.SailGpuError) as e:
+        engine.validate({"op": "filter", "predicate": plans.binop(">", {"col": 0}, plans.lit(0, "Int64")), "projection": None}, [wide])
+    assert e.value.code == 2            # 30 columns: more than 20 column buffers staged per tile
+    half = pa.schema([(f"c{i}", pa.int64()) for i in range(13)])
+    other = pa.schema([(f"d{i}", pa.int64()) for i in range(13)])
+    with pytest.raises(engine.SailGpuError) as e:
+        engine.validate({"op": "nested_loop_join", "join_type": "inner", "filter": None, "projection": None}, [half, other])
+    assert e.value.code == 2 and "24 output columns" in str(e.value)
+    assert len(engine.validate({"op": "nested_loop_join", "join_type": "inner", "filter": None, "projection": list(range(24))}, [half, other])) == 24
+    sums = [{"fn": "sum", "args": [plans.binop("+", {"col": 0}, plans.lit(i, "Int64"))], "name": f"s{i}", "input_type": "Int64"} for i in range(17)]
+    with pytest.raises(engine.SailGpuError) as e:
+        engine.validate({"op": "aggregate", "mode": "single", "group_by": [], "aggs": sums}, [wide])
+    assert e.value.code == 2 and "16" in str(e.value)
+    assert len(engine.validate({"op": "aggregate", "mode": "single", "group_by": [], "aggs": sums[:16]}, [wide])) == 16
