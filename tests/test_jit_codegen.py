@@ -2,7 +2,8 @@
 ClickBench plans `sailgpu_jit_precompile` (no device, no NVRTC: source only, nothing is written to the kernel cache) either
 emits the CUDA source of the specialised kernel or says why the pipeline stays interpreted (SAILGPU_ERR_UNSUPPORTED).
 NVRTC-compiling all of them for sm_100a takes a minute and is what `__graft_entry__.build()` does for the bench pipelines;
-`scripts/` runs did it once for every ClickBench pipeline (152 kernels, no compile error)."""
+`scripts/jit_compile_all.py` does it for every ClickBench pipeline into a scratch cache (profiles/r02_jit_clickbench_compile.txt: 152
+kernels, no compile error)."""
 import json
 
 import pytest
